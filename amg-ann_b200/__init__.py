@@ -1,0 +1,429 @@
+"""amg-ann_b200: B200-native drop-in for the AMG-PCG theta-sweep hot path of
+MatteoCaldana/AMG-ANN (see DESIGN.md for scope, include/amgb.h for the C ABI).
+
+This Python layer is a thin mirror of the reference-facing interface on top of
+the C ABI, used by the tests and bench.py; the host-side product code for the
+reference's C++ drivers is host/amgb_shim.hpp.  Names follow the reference:
+
+  AdditionalData            deal.II PreconditionBoomerAMG::AdditionalData
+                            (ref common/amg_solver.h:20, t2 main.cpp:447-453)
+  PreconditionBoomerAMG     .initialize(A, data) / .vmult(dst, src)
+                            (ref common/amg_solver.h:39,48)
+  SolverControl, SolverCG   (ref common/amg_solver.h:33,38,54)
+  ViewMaker                 (ref common/view_maker.h:17-92)
+  amg_solve                 (ref common/amg_solver.h:22-92)
+
+Import name: the directory is `amg-ann_b200`; import it as `amg_ann_b200`
+through the loader module at the repository root.
+"""
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import gen
+from ._native import (AMGB_SYMBOLS, BoomerAMGDataStruct, amgb_lib, amgb_lib_path, c_f64p,
+                      c_i32p, c_i64p, c_u8p, gen_lib)
+
+__all__ = [
+    "AdditionalData", "RelaxationType", "Context", "SparseMatrix", "PreconditionBoomerAMG",
+    "SolverControl", "SolverCG", "NoConvergence", "ViewMaker", "amg_solve", "AmgbError", "gen",
+]
+
+AMGB_OK = 0
+AMGB_ERR_NO_CONVERGENCE = -6
+
+
+class AmgbError(RuntimeError):
+    def __init__(self, status, where, detail=""):
+        self.status = status
+        name = amgb_lib().amgb_status_string(status).decode()
+        super().__init__(f"{where}: {name} ({status}) {detail}")
+
+
+class NoConvergence(AmgbError):
+    """deal.II SolverControl::NoConvergence equivalent."""
+
+
+class RelaxationType:
+    """deal.II RelaxationType enum, same order (include/amgb.h)."""
+    Jacobi = 0
+    sequentialGaussSeidel = 1
+    seqboundaryGaussSeidel = 2
+    SORJacobi = 3
+    backwardSORJacobi = 4
+    symmetricSORJacobi = 5
+    l1scaledSORJacobi = 6
+    GaussianElimination = 7
+    l1GaussSeidel = 8
+    backwardl1GaussSeidel = 9
+    CG = 10
+    Chebyshev = 11
+    FCFJacobi = 12
+    l1scaledJacobi = 13
+    none = 14
+
+
+COARSEN_FALGOUT, COARSEN_PMIS = 6, 8
+INTERP_CLASSICAL = 0
+SMOOTHER_SUBSTITUTE, SMOOTHER_STRICT = 0, 1
+
+
+class AdditionalData:
+    """Same positional order as deal.II's constructor; the
+    reference passes the first five.  Keyword-only extras are the PCHYPRE
+    defaults made explicit (A.2)."""
+
+    def __init__(self, symmetric_operator=False, strong_threshold=0.25, max_row_sum=0.9,
+                 aggressive_coarsening_num_levels=0, output_details=False,
+                 relaxation_type_up=RelaxationType.SORJacobi,
+                 relaxation_type_down=RelaxationType.SORJacobi,
+                 relaxation_type_coarse=RelaxationType.GaussianElimination,
+                 n_sweeps_coarse=1, tol=0.0, max_iter=1, w_cycle=False, *,
+                 coarsen_type=COARSEN_PMIS, interp_type=INTERP_CLASSICAL, relax_order=1,
+                 n_sweeps=1, max_levels=25, max_coarse_size=9, relax_weight=1.0,
+                 smoother_policy=SMOOTHER_SUBSTITUTE, options_via_string=True,
+                 keep_setup_intermediates=False):
+        self.symmetric_operator = bool(symmetric_operator)
+        self.strong_threshold = float(strong_threshold)
+        self.max_row_sum = float(max_row_sum)
+        self.aggressive_coarsening_num_levels = int(aggressive_coarsening_num_levels)
+        self.output_details = bool(output_details)
+        self.relaxation_type_up = int(relaxation_type_up)
+        self.relaxation_type_down = int(relaxation_type_down)
+        self.relaxation_type_coarse = int(relaxation_type_coarse)
+        self.n_sweeps_coarse = int(n_sweeps_coarse)
+        self.tol = float(tol)
+        self.max_iter = int(max_iter)
+        self.w_cycle = bool(w_cycle)
+        self.coarsen_type = int(coarsen_type)
+        self.interp_type = int(interp_type)
+        self.relax_order = int(relax_order)
+        self.n_sweeps = int(n_sweeps)
+        self.max_levels = int(max_levels)
+        self.max_coarse_size = int(max_coarse_size)
+        self.relax_weight = float(relax_weight)
+        self.smoother_policy = int(smoother_policy)
+        self.options_via_string = bool(options_via_string)
+        self.keep_setup_intermediates = bool(keep_setup_intermediates)
+
+    def to_struct(self):
+        s = BoomerAMGDataStruct()
+        for name, _ in BoomerAMGDataStruct._fields_:
+            if name == "reserved":
+                continue
+            setattr(s, name, int(getattr(self, name)) if not isinstance(getattr(self, name), float)
+                    else getattr(self, name))
+        return s
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _chk(ctx_handle, rc, where):
+    if rc != AMGB_OK:
+        detail = ""
+        if ctx_handle:
+            detail = amgb_lib().amgb_last_error(ctx_handle).decode()
+        if rc == AMGB_ERR_NO_CONVERGENCE:
+            raise NoConvergence(rc, where, detail)
+        raise AmgbError(rc, where, detail)
+
+
+class Context:
+    """amgb_ctx: one CUDA device + stream.  stream: raw cudaStream_t (int) or None."""
+
+    def __init__(self, device_id=0, stream=None):
+        self._h = C.c_void_p()
+        rc = amgb_lib().amgb_ctx_create(C.byref(self._h), device_id, C.c_void_p(stream or 0))
+        if rc != AMGB_OK:
+            self._h = C.c_void_p()
+            raise AmgbError(rc, "amgb_ctx_create",
+                            "(a CUDA device is required: this library has no CPU path)")
+
+    def close(self):
+        if self._h:
+            amgb_lib().amgb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _chk(self._h, amgb_lib().amgb_ctx_synchronize(self._h), "amgb_ctx_synchronize")
+
+    def kernel_launches(self):
+        v = C.c_int64()
+        _chk(self._h, amgb_lib().amgb_ctx_kernel_launches(self._h, C.byref(v)), "kernel_launches")
+        return v.value
+
+    def reset_kernel_launches(self):
+        amgb_lib().amgb_ctx_reset_kernel_launches(self._h)
+
+    def enable_timers(self, on=True):
+        _chk(self._h, amgb_lib().amgb_ctx_enable_timers(self._h, int(on)), "enable_timers")
+
+    def reset_timers(self):
+        amgb_lib().amgb_ctx_reset_timers(self._h)
+
+    def timers(self):
+        L = amgb_lib()
+        out = {}
+        for f in range(L.amgb_timer_count()):
+            ms, cnt, by = C.c_double(), C.c_int64(), C.c_double()
+            _chk(self._h, L.amgb_ctx_get_timer(self._h, f, C.byref(ms), C.byref(cnt), C.byref(by)),
+                 "get_timer")
+            out[L.amgb_timer_name(f).decode()] = dict(ms=ms.value, launches=cnt.value,
+                                                       bytes=by.value)
+        return out
+
+
+class SparseMatrix:
+    """Device-resident CSR system matrix; stays resident across the theta sweep
+    (the reference re-converts it for every theta)."""
+
+    def __init__(self, ctx, rowptr, col, val):
+        self.ctx = ctx
+        self.rowptr = np.ascontiguousarray(rowptr)
+        self.col = np.ascontiguousarray(col, dtype=np.int32)
+        self.val = np.ascontiguousarray(val, dtype=np.float64)
+        self.n = len(self.rowptr) - 1
+        self._h = C.c_void_p()
+        L = amgb_lib()
+        if self.rowptr.dtype == np.int32:
+            rc = L.amgb_matrix_upload_csr(ctx._h, self.n, _p(self.rowptr, c_i32p),
+                                          _p(self.col, c_i32p), _p(self.val, c_f64p),
+                                          C.byref(self._h))
+        else:
+            self.rowptr = np.ascontiguousarray(self.rowptr, dtype=np.int64)
+            rc = L.amgb_matrix_upload_csr64(ctx._h, self.n, _p(self.rowptr, c_i64p),
+                                            _p(self.col, c_i32p), _p(self.val, c_f64p),
+                                            C.byref(self._h))
+        _chk(ctx._h, rc, "amgb_matrix_upload_csr")
+
+    @classmethod
+    def wrap_device(cls, ctx, n, nnz, rowptr_ptr, col_ptr, val_ptr):
+        self = cls.__new__(cls)
+        self.ctx, self.n = ctx, n
+        self._h = C.c_void_p()
+        rc = amgb_lib().amgb_matrix_wrap_device_csr(ctx._h, n, nnz, C.c_void_p(rowptr_ptr),
+                                                    C.c_void_p(col_ptr), C.c_void_p(val_ptr),
+                                                    C.byref(self._h))
+        _chk(ctx._h, rc, "amgb_matrix_wrap_device_csr")
+        return self
+
+    def m(self):
+        return self.n
+
+    def close(self):
+        if self._h:
+            amgb_lib().amgb_matrix_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def vmult(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(self.n)
+        _chk(self.ctx._h, amgb_lib().amgb_matrix_vmult(self.ctx._h, self._h, _p(y, c_f64p),
+                                                       _p(x, c_f64p)), "amgb_matrix_vmult")
+        return y
+
+
+class PreconditionBoomerAMG:
+    """ref common/amg_solver.h:39,48 -- `preconditioner.initialize(A, data)`."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        self.ctx = None
+
+    def initialize(self, matrix, data=None):
+        self.close()
+        data = data or AdditionalData()
+        s = data.to_struct()
+        self.ctx = matrix.ctx
+        rc = amgb_lib().amgb_precond_initialize(self.ctx._h, matrix._h, C.byref(s),
+                                                C.byref(self._h))
+        _chk(self.ctx._h, rc, "amgb_precond_initialize")
+
+    def close(self):
+        if self._h:
+            amgb_lib().amgb_precond_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def vmult(self, dst, src):
+        src = np.ascontiguousarray(src, dtype=np.float64)
+        assert dst.dtype == np.float64 and dst.flags.c_contiguous
+        _chk(self.ctx._h, amgb_lib().amgb_precond_vmult(self._h, _p(dst, c_f64p), _p(src, c_f64p)),
+             "amgb_precond_vmult")
+
+    @property
+    def num_levels(self):
+        v = C.c_int32()
+        _chk(self.ctx._h, amgb_lib().amgb_precond_num_levels(self._h, C.byref(v)), "num_levels")
+        return v.value
+
+    def level_stats(self):
+        cap = 64
+        nl = C.c_int32()
+        rows = np.empty(cap, dtype=np.int64)
+        nnz = np.empty(cap, dtype=np.int64)
+        sp = np.empty(cap)
+        g, o, m = C.c_double(), C.c_double(), C.c_double()
+        _chk(self.ctx._h, amgb_lib().amgb_precond_level_stats(
+            self._h, cap, C.byref(nl), _p(rows, c_i64p), _p(nnz, c_i64p), _p(sp, c_f64p),
+            C.byref(g), C.byref(o), C.byref(m)), "level_stats")
+        k = nl.value
+        return dict(rows=rows[:k].copy(), nnz=nnz[:k].copy(), sparsity=sp[:k].copy(),
+                    grid=g.value, operator=o.value, memory=m.value)
+
+    def effective_relax(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        _chk(self.ctx._h, amgb_lib().amgb_precond_effective_relax(self._h, C.byref(a), C.byref(b),
+                                                                  C.byref(c)), "effective_relax")
+        return a.value, b.value, c.value
+
+    def level_dims(self, level):
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _chk(self.ctx._h, amgb_lib().amgb_precond_level_dims(
+            self._h, level, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "level_dims")
+        return a.value, b.value, c.value, d.value
+
+    def strength_mask(self, level):
+        _, nnz, _, _ = self.level_dims(level)
+        out = np.empty(nnz, dtype=np.uint8)
+        _chk(self.ctx._h, amgb_lib().amgb_precond_get_strength_mask(self._h, level, _p(out, c_u8p)),
+             "get_strength_mask")
+        return out
+
+    def cf_marker(self, level):
+        n, _, _, _ = self.level_dims(level)
+        out = np.empty(n, dtype=np.int32)
+        _chk(self.ctx._h, amgb_lib().amgb_precond_get_cf_marker(self._h, level, _p(out, c_i32p)),
+             "get_cf_marker")
+        return out
+
+    def A(self, level):
+        n, nnz, _, _ = self.level_dims(level)
+        rp = np.empty(n + 1, dtype=np.int32)
+        cl = np.empty(nnz, dtype=np.int32)
+        vl = np.empty(nnz)
+        _chk(self.ctx._h, amgb_lib().amgb_precond_get_A_csr(self._h, level, _p(rp, c_i32p),
+                                                            _p(cl, c_i32p), _p(vl, c_f64p)),
+             "get_A_csr")
+        return rp, cl, vl
+
+    def P(self, level):
+        n, _, nc, nnzp = self.level_dims(level)
+        rp = np.empty(n + 1, dtype=np.int32)
+        cl = np.empty(nnzp, dtype=np.int32)
+        vl = np.empty(nnzp)
+        _chk(self.ctx._h, amgb_lib().amgb_precond_get_P_csr(self._h, level, _p(rp, c_i32p),
+                                                            _p(cl, c_i32p), _p(vl, c_f64p)),
+             "get_P_csr")
+        return rp, cl, vl, nc
+
+
+class SolverControl:
+    """deal.II SolverControl(max_steps, tol): `tol` is ABSOLUTE on the
+    preconditioned residual (ref common/amg_solver.h:33)."""
+
+    def __init__(self, max_steps=100, tol=1e-10):
+        self.max_steps = int(max_steps)
+        self.tol = float(tol)
+        self._last_step = 0
+        self._last_value = float("nan")
+        self.history = np.zeros(0)
+
+    def last_step(self):
+        return self._last_step
+
+    def last_value(self):
+        return self._last_value
+
+
+class SolverCG:
+    """ref common/amg_solver.h:38,54 -- `cg.solve(A, x, b, preconditioner)`."""
+
+    def __init__(self, solver_control):
+        self.control = solver_control
+
+    def solve(self, A, x, b, preconditioner):
+        assert x.dtype == np.float64 and x.flags.c_contiguous
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        cap = min(self.control.max_steps, 1 << 20) + 1
+        hist = np.zeros(cap)
+        nit = C.c_int64()
+        rc = amgb_lib().amgb_cg_solve(A.ctx._h, A._h, _p(x, c_f64p), _p(b, c_f64p),
+                                      preconditioner._h, self.control.max_steps,
+                                      self.control.tol, _p(hist, c_f64p), cap, C.byref(nit))
+        k = min(cap, nit.value + 1)
+        self.control._last_step = nit.value
+        self.control.history = hist[:k].copy()
+        self.control._last_value = float(hist[k - 1]) if k else float("nan")
+        _chk(A.ctx._h, rc, "amgb_cg_solve")
+
+
+class ViewMaker:
+    """ref common/view_maker.h:17-92."""
+
+    def __init__(self, vs):
+        self.view_size = int(vs)
+        vv = self.view_size ** 2
+        self.view = np.zeros(vv)
+        self.count = np.zeros(vv, dtype=np.int64)
+        self.max_pp = np.zeros(vv)
+        self.max_np = np.zeros(vv)
+        self.t_view_us = 0.0
+        self.t_device_us = 0.0
+
+    def make_view(self, A):
+        t = C.c_double()
+        t1 = time.perf_counter()
+        rc = amgb_lib().amgb_make_view(A.ctx._h, A._h, self.view_size, _p(self.view, c_f64p),
+                                       _p(self.count, c_i64p), _p(self.max_pp, c_f64p),
+                                       _p(self.max_np, c_f64p), C.byref(t))
+        self.t_view_us = (time.perf_counter() - t1) * 1e6
+        self.t_device_us = t.value
+        _chk(A.ctx._h, rc, "amgb_make_view")
+        return self
+
+
+def amg_solve(data, rtol, A, b, x):
+    """Python mirror of ref common/amg_solver.h:22-92: timed initialize + timed
+    cg.solve, returning the CSV fields as a dict instead of scraping stdout."""
+    control = SolverControl(A.m(), rtol)
+    cg = SolverCG(control)
+    prec = PreconditionBoomerAMG()
+    t1 = time.perf_counter()
+    prec.initialize(A, data)
+    A.ctx.synchronize()
+    t2 = time.perf_counter()
+    t3 = time.perf_counter()
+    cg.solve(A, x, b, prec)
+    t4 = time.perf_counter()
+    row = dict(theta=data.strong_threshold, maxrowsum=data.max_row_sum,
+               symop=int(data.symmetric_operator),
+               agg_nl=data.aggressive_coarsening_num_levels, tol=rtol,
+               t_amg_setup=int((t2 - t1) * 1e6), t_solve=int((t4 - t3) * 1e6),
+               niters=control.last_step(), p_res=control.history)
+    if data.output_details:
+        st = prec.level_stats()
+        row.update(nrows=st["rows"], nze=st["nnz"], sparsity=st["sparsity"], grid=st["grid"],
+                   operator=st["operator"], memory=st["memory"])
+    prec.close()
+    return row

@@ -1,0 +1,226 @@
+/*
+ * amgb.h -- C ABI of the B200-native AMG-PCG theta-sweep hot path.
+ *
+ * This is the drop-in boundary for the one path of MatteoCaldana/AMG-ANN that
+ * this library replaces.  Every entry point cites the
+ * reference call site it stands in for.  Reference paths are relative to
+ * code/data-generation/ of the reference tree.
+ *
+ *   reference call                                              replaced by
+ *   ----------------------------------------------------------  ---------------------------
+ *   PETScWrappers::MPI::SparseMatrix (PETSc AIJ, 1 rank)        amgb_matrix_upload_csr
+ *     built at testcase2-.../src/main.cpp:239-249
+ *   PreconditionBoomerAMG::AdditionalData                       amgb_boomeramg_data
+ *     common/amg_solver.h:20, t2 main.cpp:447-453
+ *   preconditioner.initialize(A, data)  common/amg_solver.h:48  amgb_precond_initialize
+ *   preconditioner.vmult (PCApply in CG) common/amg_solver.h:54 amgb_precond_vmult
+ *   SolverControl(n, tol) + SolverCG::solve  amg_solver.h:33,54 amgb_cg_solve
+ *   hypre setup printout scraped by BoomerAMGParser             amgb_precond_level_stats
+ *     common/parser.h:181-266, amg_solver.h:71-78
+ *   -ksp_monitor residuals scraped by PETScOutputParser         res_hist of amgb_cg_solve
+ *     common/parser.h:149-155, amg_solver.h:83-86
+ *   ViewMaker::make_view (MatGetRow loop) common/view_maker.h:26-74   amgb_make_view
+ *
+ * Conventions: plain pointers and sizes only; pointers are HOST pointers unless
+ * the name says _device; every function returns AMGB_OK (0) or a negative
+ * amgb_status; no exceptions cross the ABI; no hidden global state (everything
+ * hangs off an amgb_ctx; one ctx per host thread); there is NO CPU fallback:
+ * without a usable CUDA device amgb_ctx_create fails with AMGB_ERR_NO_DEVICE.
+ */
+#ifndef AMGB_H
+#define AMGB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMGB_VERSION 100
+
+typedef enum amgb_status {
+  AMGB_OK = 0,
+  AMGB_ERR_BAD_ARG = -1,
+  AMGB_ERR_NO_DEVICE = -2,      /* no CUDA device / driver: the library has no CPU path */
+  AMGB_ERR_CUDA = -3,           /* a CUDA runtime call failed; see amgb_last_error */
+  AMGB_ERR_OOM = -4,
+  AMGB_ERR_UNSUPPORTED = -5,    /* option exists in the reference API but not on device */
+  AMGB_ERR_NO_CONVERGENCE = -6, /* SolverControl::NoConvergence equivalent */
+  AMGB_ERR_BREAKDOWN = -7,      /* zero pivot / NaN in the iteration */
+  AMGB_ERR_RANGE = -8,          /* index out of range (level, buffer capacity) */
+  AMGB_ERR_COMM = -9            /* NCCL failure */
+} amgb_status;
+
+/* deal.II PETScWrappers::PreconditionBoomerAMG::AdditionalData::RelaxationType,
+ * same order as the deal.II enum. */
+typedef enum amgb_relaxation_type {
+  AMGB_RELAX_Jacobi = 0,
+  AMGB_RELAX_sequentialGaussSeidel = 1,
+  AMGB_RELAX_seqboundaryGaussSeidel = 2,
+  AMGB_RELAX_SORJacobi = 3,
+  AMGB_RELAX_backwardSORJacobi = 4,
+  AMGB_RELAX_symmetricSORJacobi = 5,
+  AMGB_RELAX_l1scaledSORJacobi = 6,
+  AMGB_RELAX_GaussianElimination = 7,
+  AMGB_RELAX_l1GaussSeidel = 8,
+  AMGB_RELAX_backwardl1GaussSeidel = 9,
+  AMGB_RELAX_CG = 10,
+  AMGB_RELAX_Chebyshev = 11,
+  AMGB_RELAX_FCFJacobi = 12,
+  AMGB_RELAX_l1scaledJacobi = 13,
+  AMGB_RELAX_None = 14
+} amgb_relaxation_type;
+
+/* hypre coarsen_type / interp_type numbers (PETSc -pc_hypre_boomeramg_coarsen_type). */
+enum { AMGB_COARSEN_CLJP = 0, AMGB_COARSEN_FALGOUT = 6, AMGB_COARSEN_PMIS = 8 };
+enum { AMGB_INTERP_CLASSICAL = 0, AMGB_INTERP_DIRECT = 3, AMGB_INTERP_EXT_I = 6 };
+
+/* What to do when the requested smoother is inherently sequential on one rank
+ * (the reference default: hybrid symmetric Gauss-Seidel, hypre relax type 6). */
+enum {
+  AMGB_SMOOTHER_SUBSTITUTE = 0, /* run C/F-ordered l1-scaled Jacobi instead (hypre's own GPU choice) */
+  AMGB_SMOOTHER_STRICT = 1      /* return AMGB_ERR_UNSUPPORTED */
+};
+
+/*
+ * Parameter pack of initialize().  The first twelve fields are deal.II's
+ * AdditionalData field for field, in constructor order (the reference passes the
+ * first five: t2 main.cpp:447-453, t3 main.cpp:458-464).  The rest are the PETSc
+ * PCHYPRE defaults that deal.II leaves implicit, made
+ * explicit so they can be pinned in tests.  Fill with amgb_boomeramg_data_default.
+ */
+typedef struct amgb_boomeramg_data {
+  int32_t symmetric_operator;               /* default 0 (reference always passes 1) */
+  double strong_threshold;                  /* theta, default 0.25 */
+  double max_row_sum;                       /* default 0.9 */
+  uint32_t aggressive_coarsening_num_levels;/* default 0; >0 is AMGB_ERR_UNSUPPORTED for now */
+  int32_t output_details;                   /* collect level statistics */
+  int32_t relaxation_type_up;               /* amgb_relaxation_type, default SORJacobi */
+  int32_t relaxation_type_down;
+  int32_t relaxation_type_coarse;           /* default GaussianElimination */
+  uint32_t n_sweeps_coarse;                 /* default 1 */
+  double tol;                               /* default 0.0 */
+  uint32_t max_iter;                        /* default 1 */
+  int32_t w_cycle;                          /* default 0 */
+  /* ---- explicit PCHYPRE/hypre knobs ---- */
+  int32_t coarsen_type;       /* AMGB_COARSEN_*; device default PMIS (Falgout is serial) */
+  int32_t interp_type;        /* AMGB_INTERP_*; default classical modified */
+  int32_t relax_order;        /* 1 = C/F relaxation (PCHYPRE default) */
+  uint32_t n_sweeps;          /* grid sweeps down and up, default 1 */
+  int32_t max_levels;         /* default 25 */
+  int32_t max_coarse_size;    /* default 9 */
+  double relax_weight;        /* default 1.0 (Jacobi-type smoothers) */
+  int32_t smoother_policy;    /* AMGB_SMOOTHER_SUBSTITUTE / _STRICT */
+  int32_t options_via_string; /* 1: theta and max_row_sum are rounded through
+                                 std::to_string (6 decimals) as deal.II forwards
+                                 them to PETSc (Appendix A.1, hard part H4) */
+  int32_t keep_setup_intermediates; /* 1: keep strength masks etc. for the parity accessors */
+  int32_t reserved[7];
+} amgb_boomeramg_data;
+
+typedef struct amgb_ctx amgb_ctx;
+typedef struct amgb_matrix amgb_matrix;
+typedef struct amgb_precond amgb_precond;
+
+/* ---- context ------------------------------------------------------------ */
+/* device_id: CUDA ordinal.  stream: a cudaStream_t to enqueue on (e.g. the
+ * caller's current stream), or NULL to let the context create its own. */
+int amgb_ctx_create(amgb_ctx** out, int device_id, void* stream);
+int amgb_ctx_destroy(amgb_ctx* ctx);
+int amgb_ctx_synchronize(amgb_ctx* ctx);
+/* Last error text of this context (never NULL). */
+const char* amgb_last_error(const amgb_ctx* ctx);
+const char* amgb_status_string(int status);
+int amgb_version(void);
+/* Number of kernels of this library launched on ctx since creation / last reset. */
+int amgb_ctx_kernel_launches(const amgb_ctx* ctx, int64_t* count);
+int amgb_ctx_reset_kernel_launches(amgb_ctx* ctx);
+
+/* ---- matrix (resident across the theta sweep) ---------------------------- */
+/* CSR with ascending column ids per row and a stored diagonal in every row
+ * (PETSc AIJ as deal.II builds it).  rowptr has n+1 entries.  The 32-bit variant
+ * matches PetscInt of a default PETSc build. */
+int amgb_matrix_upload_csr(amgb_ctx* ctx, int64_t n, const int32_t* rowptr,
+                           const int32_t* col, const double* val, amgb_matrix** out);
+int amgb_matrix_upload_csr64(amgb_ctx* ctx, int64_t n, const int64_t* rowptr,
+                             const int32_t* col, const double* val, amgb_matrix** out);
+/* Wrap CSR arrays that already live in device memory (no copy; caller keeps ownership). */
+int amgb_matrix_wrap_device_csr(amgb_ctx* ctx, int64_t n, int64_t nnz,
+                                const int32_t* rowptr_device, const int32_t* col_device,
+                                const double* val_device, amgb_matrix** out);
+int amgb_matrix_destroy(amgb_matrix* A);
+int amgb_matrix_dims(const amgb_matrix* A, int64_t* n, int64_t* nnz);
+/* y = A x (host vectors); the plain SpMV, exposed for parity tests. */
+int amgb_matrix_vmult(amgb_ctx* ctx, const amgb_matrix* A, double* y, const double* x);
+
+/* ---- preconditioner ------------------------------------------------------ */
+int amgb_boomeramg_data_default(amgb_boomeramg_data* data);
+/* ref common/amg_solver.h:48.  Builds the whole hierarchy on the device. */
+int amgb_precond_initialize(amgb_ctx* ctx, const amgb_matrix* A,
+                            const amgb_boomeramg_data* data, amgb_precond** out);
+int amgb_precond_destroy(amgb_precond* P);
+/* dst = M^{-1} src: one V(1,1) cycle from a zero initial guess (PCApply_HYPRE). */
+int amgb_precond_vmult(amgb_precond* P, double* dst, const double* src);
+int amgb_precond_vmult_device(amgb_precond* P, double* dst_device, const double* src_device);
+
+/* Level statistics: what BoomerAMGParser scrapes (common/parser.h:248-256).
+ * Arrays need capacity >= max_levels. */
+int amgb_precond_num_levels(const amgb_precond* P, int32_t* n_levels);
+int amgb_precond_level_stats(const amgb_precond* P, int32_t capacity, int32_t* n_levels,
+                             int64_t* rows, int64_t* nnz, double* sparsity,
+                             double* grid_complexity, double* operator_complexity,
+                             double* memory_complexity);
+/* hypre relax type actually run on the device for down/up/coarse (after the
+ * smoother policy was applied). */
+int amgb_precond_effective_relax(const amgb_precond* P, int32_t* down, int32_t* up,
+                                 int32_t* coarse);
+
+/* Parity accessors (integer outputs must be bit-exact vs the oracle).
+ * level 0 is the finest.  Query sizes with amgb_precond_level_dims first. */
+int amgb_precond_level_dims(const amgb_precond* P, int32_t level, int64_t* n,
+                            int64_t* nnz_A, int64_t* n_coarse, int64_t* nnz_P);
+int amgb_precond_get_strength_mask(const amgb_precond* P, int32_t level, uint8_t* mask /*nnz_A*/);
+int amgb_precond_get_cf_marker(const amgb_precond* P, int32_t level, int32_t* cf /*n*/);
+int amgb_precond_get_A_csr(const amgb_precond* P, int32_t level, int32_t* rowptr,
+                           int32_t* col, double* val);
+int amgb_precond_get_P_csr(const amgb_precond* P, int32_t level, int32_t* rowptr,
+                           int32_t* col, double* val);
+
+/* ---- PCG ----------------------------------------------------------------- */
+/* ref common/amg_solver.h:33,38,54 and SURVEY.md Appendix A.4: PETSc KSPCG, left
+ * preconditioning, stops when the PRECONDITIONED residual norm ||M^{-1} r||_2 is
+ * <= abs_tol (absolute!), initial guess x honoured.  res_hist receives
+ * min(hist_cap, n_iters+1) norms (entry 0 = before the first step).  Returns
+ * AMGB_ERR_NO_CONVERGENCE if max_steps is hit (x and the history are still
+ * written). */
+int amgb_cg_solve(amgb_ctx* ctx, const amgb_matrix* A, double* x, const double* b,
+                  amgb_precond* P, int64_t max_steps, double abs_tol, double* res_hist,
+                  int64_t hist_cap, int64_t* n_iters);
+/* Same with x and b already on the device. */
+int amgb_cg_solve_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_device,
+                         const double* b_device, amgb_precond* P, int64_t max_steps,
+                         double abs_tol, double* res_hist, int64_t hist_cap,
+                         int64_t* n_iters);
+
+/* ---- pooling ------------------------------------------------------------- */
+/* ref common/view_maker.h:26-74.  Outputs are V*V row-major (V*bin_row+bin_col);
+ * count is integer-exact, max_pp/max_np are order-independent hence exact,
+ * sum is accumulated in a fixed tree over the CSR order.  t_us (may be NULL)
+ * receives the device time of the pass in microseconds. */
+int amgb_make_view(amgb_ctx* ctx, const amgb_matrix* A, int32_t view_size, double* sum,
+                   int64_t* count, double* max_pp, double* max_np, double* t_us);
+
+/* ---- measurement hooks (bench.py) ---------------------------------------- */
+/* Per-kernel-family device time accumulated with CUDA events on the context's
+ * stream while profiling is enabled.  Families: see amgb_timer_name. */
+int amgb_ctx_enable_timers(amgb_ctx* ctx, int enable);
+int amgb_ctx_reset_timers(amgb_ctx* ctx);
+int amgb_timer_count(void);
+const char* amgb_timer_name(int family);
+int amgb_ctx_get_timer(amgb_ctx* ctx, int family, double* total_ms, int64_t* launches,
+                       double* algorithmic_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMGB_H */

@@ -1,0 +1,226 @@
+// Internal structures shared by the translation units of libamgb.so.
+// Nothing here is part of the ABI (include/amgb.h is).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "amgb.h"
+
+namespace amgb {
+
+// Kernel families for the measurement hooks (amgb_timer_name).
+enum Family : int {
+  F_SPMV = 0,      // y = A x (+ fused dot) on the system matrix
+  F_SMOOTH,        // Jacobi-type half sweeps
+  F_RESIDUAL,      // r = f - A u
+  F_RESTRICT,      // f_c = P^T r
+  F_PROLONG,       // u += P e
+  F_VEC,           // PCG vector kernels (axpy, dots, finalize)
+  F_COARSE,        // dense coarsest-grid solve
+  F_STRENGTH,      // setup: strength of connection
+  F_COARSEN,       // setup: PMIS rounds
+  F_INTERP,        // setup: interpolation
+  F_TRANSPOSE,     // setup: P -> P^T
+  F_SPGEMM,        // setup: Galerkin products
+  F_SCAN,          // setup: prefix sums / compaction helpers
+  F_AUX,           // setup: l1 norms, diag, SELL conversion
+  F_POOL,          // pooling
+  F_COUNT
+};
+
+struct TimerRec {
+  cudaEvent_t a, b;
+  int family;
+  double bytes;
+};
+
+}  // namespace amgb
+
+struct amgb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  size_t l2_bytes = 0;
+  std::string err;
+  int64_t launches = 0;
+  bool timers_on = false;
+  std::vector<amgb::TimerRec> recs;
+  std::vector<cudaEvent_t> free_events;
+  double fam_ms[amgb::F_COUNT] = {0};
+  int64_t fam_launches[amgb::F_COUNT] = {0};
+  double fam_bytes[amgb::F_COUNT] = {0};
+  // small pinned staging area for device->host scalars
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+};
+
+namespace amgb {
+
+int set_error(amgb_ctx* ctx, int status, const char* fmt, ...);
+int cuda_fail(amgb_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
+
+#define AMGB_CUDA(ctx, call)                                                  \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess) return amgb::cuda_fail((ctx), e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define AMGB_TRY(expr)            \
+  do {                            \
+    int rc__ = (expr);            \
+    if (rc__ != AMGB_OK) return rc__; \
+  } while (0)
+
+// Stream-ordered device buffer.
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  amgb_ctx* ctx = nullptr;
+  bool owns = true;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) {
+      release();
+      p = o.p; n = o.n; ctx = o.ctx; owns = o.owns;
+      o.p = nullptr; o.n = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  int alloc(amgb_ctx* c, size_t count) {
+    release();
+    ctx = c;
+    owns = true;
+    n = count;
+    if (count == 0) return AMGB_OK;
+    cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), c->stream);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      n = 0;
+      (void)cudaGetLastError();
+      return set_error(c, e == cudaErrorMemoryAllocation ? AMGB_ERR_OOM : AMGB_ERR_CUDA,
+                       "cudaMallocAsync(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+    }
+    return AMGB_OK;
+  }
+  int alloc_zero(amgb_ctx* c, size_t count) {
+    AMGB_TRY(alloc(c, count));
+    if (count) AMGB_CUDA(c, cudaMemsetAsync(p, 0, count * sizeof(T), c->stream));
+    return AMGB_OK;
+  }
+  void wrap(amgb_ctx* c, T* ptr, size_t count) {
+    release();
+    ctx = c; p = ptr; n = count; owns = false;
+  }
+  void release() {
+    if (p && owns && ctx) cudaFreeAsync(p, ctx->stream);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct DeviceCsr {
+  int64_t n = 0, ncols = 0, nnz = 0;
+  DevBuf<int32_t> rp, col;
+  DevBuf<double> val;
+};
+
+// SELL-32 copy of a level operator for the solve phase.
+struct DeviceSell {
+  int64_t n = 0, nslices = 0, padded = 0;
+  DevBuf<int64_t> slice_off;  // nslices+1
+  DevBuf<int32_t> col;        // padded, column-major within a slice
+  DevBuf<double> val;
+  bool ready = false;
+};
+
+struct Level {
+  DeviceCsr A;          // level 0 aliases the user's matrix (no copy)
+  DeviceCsr P, R;       // prolongator and its explicit transpose
+  DevBuf<uint8_t> mask; // strength mask aligned with A (kept for parity accessors)
+  DevBuf<int32_t> cf;   // +1 / -1 / -3 as returned by the coarsening
+  DevBuf<int32_t> diag_idx;
+  DevBuf<double> inv_relax; // 1/l1 (type 18) or 1/diag (type 0); 0 where the row is skipped
+  DevBuf<double> u, f, tmp, tmp2;
+  int64_t n_coarse = 0;
+};
+
+int64_t div_up(int64_t a, int64_t b);
+
+// Launch bookkeeping: counts the launch, optionally brackets it with events.
+struct LaunchScope {
+  amgb_ctx* ctx;
+  bool timed;
+  TimerRec rec;
+  LaunchScope(amgb_ctx* c, int family, double bytes);
+  ~LaunchScope();
+};
+
+// Kernel names with template commas must be parenthesised at the call site.
+template <class... KArgs, class... Args>
+inline void launch_kernel(amgb_ctx* ctx, int family, double bytes, void (*kernel)(KArgs...),
+                          dim3 grid, dim3 block, size_t smem, Args... args) {
+  LaunchScope scope(ctx, family, bytes);
+  kernel<<<grid, block, smem, ctx->stream>>>(args...);
+}
+
+#define AMGB_LAUNCH(ctx, family, bytes, kernel, grid, block, smem, ...)                       \
+  amgb::launch_kernel((ctx), (family), (double)(bytes), kernel, dim3(grid), dim3(block), (smem), \
+                      __VA_ARGS__)
+
+#define AMGB_CHECK_LAUNCH(ctx)                                          \
+  do {                                                                  \
+    cudaError_t e__ = cudaGetLastError();                               \
+    if (e__ != cudaSuccess)                                             \
+      return amgb::cuda_fail((ctx), e__, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+// ---- shared device-side helpers implemented in amgb_core.cu ----
+// exclusive scan of int32 counts (n entries) into out (n+1 entries, out[n] = total).
+int exclusive_scan_i32(amgb_ctx* ctx, const int32_t* in, int32_t* out, int64_t n);
+// total on host (synchronises the stream)
+int read_i32(amgb_ctx* ctx, const int32_t* dptr, int32_t* host);
+int read_i64(amgb_ctx* ctx, const int64_t* dptr, int64_t* host);
+
+}  // namespace amgb
+
+struct amgb_matrix {
+  amgb_ctx* ctx = nullptr;
+  amgb::DeviceCsr A;
+};
+
+struct amgb_precond {
+  amgb_ctx* ctx = nullptr;
+  const amgb_matrix* mat = nullptr;
+  amgb_boomeramg_data data;
+  double theta_eff = 0.25, mrs_eff = 0.9;
+  int relax_down = 18, relax_up = 18, relax_coarse = 9;
+  std::vector<amgb::Level> lv;
+  amgb::DevBuf<double> dense;  // coarsest operator, LU in place (row-major)
+  bool dense_ok = false;
+  // statistics
+  std::vector<int64_t> st_rows, st_nnz, st_nnzP;
+  // captured V-cycle
+  cudaGraphExec_t vcycle_graph = nullptr;
+};
+
+namespace amgb {
+// amgb_setup.cu
+int build_hierarchy(amgb_precond* P);
+// amgb_solve.cu
+int level_aux(amgb_precond* P, int level);
+int finish_solve_setup(amgb_precond* P);
+int vcycle_apply(amgb_precond* P, double* z_dev, const double* r_dev);
+int spmv(amgb_ctx* ctx, const DeviceCsr& A, const double* x, double* y, int family);
+void destroy_solve_state(amgb_precond* P);
+}  // namespace amgb

@@ -1,0 +1,990 @@
+// AMG setup on the device: strength of connection, PMIS C/F splitting,
+// modified classical interpolation, explicit transpose and the Galerkin triple
+// product as two hash SpGEMMs.  This replaces hypre_BoomerAMGSetup reached from
+// `preconditioner.initialize(system_matrix, data)` (ref common/amg_solver.h:48);
+// the algorithms are restated in SURVEY.md Appendix A.3 and, operation for
+// operation, in oracle/amg_oracle.cpp, against which the integer outputs are
+// bit-exact and the weights/operators bit-identical.
+//
+// Bit-exactness rules used throughout (hard parts H3/H5/H6 of SURVEY.md 7.3):
+//  * every multiply that feeds an add is written __dmul_rn/__dadd_rn so nvcc can
+//    not contract it into an FMA (the oracle is built with -ffp-contract=off);
+//  * sums whose result feeds a comparison (row sums, interpolation sums, SpGEMM
+//    accumulators) are accumulated in the same sequential order as the oracle:
+//    ascending column within a row, ascending k for C(i,c) = sum_k a_ik b_kc.
+#include <algorithm>
+#include <cstring>
+
+#include "amgb_internal.cuh"
+
+namespace amgb {
+
+constexpr int kBlock = 256;
+
+// ---------------------------------------------------------------------------
+// Strength (hypre_BoomerAMGCreateS).  One thread per row, sequential in the
+// oracle's order: diagonal first, then off-diagonals left to right.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+strength_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                const double* __restrict__ val, double theta, double max_row_sum,
+                uint8_t* __restrict__ mask, int32_t* __restrict__ has_strong) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const int b = rp[i], e = rp[i + 1];
+  double diag = 0.0;
+  for (int k = b; k < e; ++k)
+    if (col[k] == i) diag = val[k];
+  double row_scale = 0.0, row_sum = diag;
+  if (diag < 0) {
+    for (int k = b; k < e; ++k)
+      if (col[k] != i) {
+        const double v = val[k];
+        row_scale = row_scale < v ? v : row_scale;
+        row_sum = __dadd_rn(row_sum, v);
+      }
+  } else {
+    for (int k = b; k < e; ++k)
+      if (col[k] != i) {
+        const double v = val[k];
+        row_scale = v < row_scale ? v : row_scale;
+        row_sum = __dadd_rn(row_sum, v);
+      }
+  }
+  int any = 0;
+  const bool all_weak = fabs(row_sum) > __dmul_rn(fabs(diag), max_row_sum) && max_row_sum < 1.0;
+  const double thr = __dmul_rn(theta, row_scale);
+  for (int k = b; k < e; ++k) {
+    uint8_t m = 0;
+    if (!all_weak && col[k] != i) {
+      const double v = val[k];
+      m = diag < 0 ? (v > thr) : (v < thr);
+    }
+    mask[k] = m;
+    any |= m;
+  }
+  has_strong[i] = any;
+}
+
+// ---------------------------------------------------------------------------
+// PMIS (hypre_BoomerAMGCoarsenPMIS, one rank).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double hypre_rand_at(int64_t i) {
+  // hypre_Rand after hypre_SeedRand(2747): seed_{i} = 2747 * 16807^(i+1) mod (2^31-1)
+  const unsigned long long m = 2147483647ull;
+  unsigned long long e = (unsigned long long)i + 1ull, base = 16807ull, r = 2747ull;
+  while (e) {
+    if (e & 1ull) r = (r * base) % m;
+    base = (base * base) % m;
+    e >>= 1;
+  }
+  return (double)r / 2147483647.0;
+}
+
+__global__ void __launch_bounds__(kBlock)
+pmis_influence_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                      const uint8_t* __restrict__ mask, int32_t* __restrict__ influence) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  for (int k = rp[i]; k < rp[i + 1]; ++k)
+    if (mask[k]) atomicAdd(&influence[col[k]], 1);
+}
+
+__global__ void __launch_bounds__(kBlock)
+pmis_init_kernel(int64_t n, const int32_t* __restrict__ influence, const int32_t* __restrict__ has_strong,
+                 double* __restrict__ measure, int32_t* __restrict__ cf) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  double m = (double)influence[i] + hypre_rand_at(i);
+  int c = 0;
+  if (!has_strong[i]) {
+    c = -3;  // special F point: no strong connections
+    m = 0.0;
+  } else if (m < 1.0) {
+    c = -1;  // nobody depends on it
+    m = 0.0;
+  }
+  measure[i] = m;
+  cf[i] = c;
+}
+
+// tentative independent-set membership: undecided points with measure > 1
+__global__ void __launch_bounds__(kBlock)
+pmis_mark_kernel(int64_t n, const int32_t* __restrict__ cf, const double* __restrict__ measure,
+                 int32_t* __restrict__ mark) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  mark[i] = (cf[i] == 0 && measure[i] > 1.0) ? 1 : 0;
+}
+
+// hypre_BoomerAMGIndepSet: along every strong connection i -> j between two
+// candidates the smaller measure is knocked out (writes of 0 only: benign race,
+// result independent of scheduling).
+__global__ void __launch_bounds__(kBlock)
+pmis_knockout_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                     const uint8_t* __restrict__ mask, const int32_t* __restrict__ cf,
+                     const double* __restrict__ measure, int32_t* __restrict__ mark) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  if (cf[i] != 0) return;
+  const double mi = measure[i];
+  if (!(mi > 1.0)) return;
+  bool lose = false;
+  for (int k = rp[i]; k < rp[i + 1]; ++k) {
+    if (!mask[k]) continue;
+    const int j = col[k];
+    const double mj = measure[j];
+    if (mj > 1.0) {
+      if (mi > mj) mark[j] = 0;
+      else if (mj > mi) lose = true;
+    }
+  }
+  if (lose) mark[i] = 0;
+}
+
+__global__ void __launch_bounds__(kBlock)
+pmis_set_c_kernel(int64_t n, const int32_t* __restrict__ mark, int32_t* __restrict__ cf) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  if (cf[i] == 0 && mark[i]) cf[i] = 1;
+}
+
+// undecided points that strongly depend on a C point become F; decided points
+// leave the graph (measure = 0); counts the points still undecided.
+__global__ void __launch_bounds__(kBlock)
+pmis_set_f_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                  const uint8_t* __restrict__ mask, int32_t* __restrict__ cf,
+                  double* __restrict__ measure, int32_t* __restrict__ undecided) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  int und = 0;
+  if (i < n) {
+    int c = cf[i];
+    if (c == 0) {
+      for (int k = rp[i]; k < rp[i + 1]; ++k)
+        if (mask[k] && cf[col[k]] > 0) {  // cf of others only moves 0 -> -1 here, never to > 0
+          c = -1;
+          break;
+        }
+      if (c != 0) cf[i] = c;
+    }
+    if (c != 0) measure[i] = 0.0; else und = 1;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, und);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(undecided, __popc(b));
+}
+
+__global__ void __launch_bounds__(kBlock)
+cpoint_flag_kernel(int64_t n, const int32_t* __restrict__ cf, int32_t* __restrict__ flag) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i < n) flag[i] = cf[i] > 0 ? 1 : 0;
+}
+
+static int coarsen_pmis(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const int32_t* has_strong,
+                        int32_t* cf) {
+  const int64_t n = A.n;
+  const unsigned grid = (unsigned)div_up(n, kBlock);
+  DevBuf<int32_t> influence, mark, undecided;
+  DevBuf<double> measure;
+  AMGB_TRY(influence.alloc_zero(ctx, n));
+  AMGB_TRY(mark.alloc(ctx, n));
+  AMGB_TRY(measure.alloc(ctx, n));
+  AMGB_TRY(undecided.alloc(ctx, 1));
+  const double row_bytes = 5.0 * A.nnz + 4.0 * (n + 1);
+  AMGB_LAUNCH(ctx, F_COARSEN, row_bytes, pmis_influence_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p, mask,
+              influence.p);
+  AMGB_LAUNCH(ctx, F_COARSEN, 20.0 * n, pmis_init_kernel, grid, kBlock, 0, n, influence.p, has_strong,
+              measure.p, cf);
+  AMGB_CHECK_LAUNCH(ctx);
+  for (int round = 0; round < 100000; ++round) {
+    AMGB_CUDA(ctx, cudaMemsetAsync(undecided.p, 0, sizeof(int32_t), ctx->stream));
+    AMGB_LAUNCH(ctx, F_COARSEN, 16.0 * n, pmis_mark_kernel, grid, kBlock, 0, n, cf, measure.p, mark.p);
+    AMGB_LAUNCH(ctx, F_COARSEN, row_bytes, pmis_knockout_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p, mask,
+                cf, measure.p, mark.p);
+    AMGB_LAUNCH(ctx, F_COARSEN, 12.0 * n, pmis_set_c_kernel, grid, kBlock, 0, n, mark.p, cf);
+    AMGB_LAUNCH(ctx, F_COARSEN, row_bytes, pmis_set_f_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p, mask, cf,
+                measure.p, undecided.p);
+    AMGB_CHECK_LAUNCH(ctx);
+    int32_t und = 0;
+    AMGB_TRY(read_i32(ctx, undecided.p, &und));
+    if (und == 0) return AMGB_OK;
+  }
+  return set_error(ctx, AMGB_ERR_BREAKDOWN, "PMIS did not terminate");
+}
+
+// ---------------------------------------------------------------------------
+// Interpolation type 0, modified classical (hypre_BoomerAMGBuildInterp).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+interp_count_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                    const uint8_t* __restrict__ mask, const int32_t* __restrict__ cf,
+                    int32_t* __restrict__ count) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  int c = 0;
+  if (cf[i] > 0) {
+    c = 1;
+  } else {
+    for (int k = rp[i]; k < rp[i + 1]; ++k)
+      if (mask[k] && cf[col[k]] > 0) ++c;
+  }
+  count[i] = c;
+}
+
+// position of coarse column cc in the sorted slice pcol[0..len), or -1
+__device__ __forceinline__ int find_sorted(const int32_t* pcol, int len, int cc) {
+  int lo = 0, hi = len;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (pcol[mid] < cc) lo = mid + 1; else hi = mid;
+  }
+  return (lo < len && pcol[lo] == cc) ? lo : -1;
+}
+
+__global__ void __launch_bounds__(128)
+interp_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                   const double* __restrict__ val, const uint8_t* __restrict__ mask,
+                   const int32_t* __restrict__ cf, const int32_t* __restrict__ f2c,
+                   const int32_t* __restrict__ prp, int32_t* __restrict__ pcol, double* __restrict__ pval) {
+  const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (i >= n) return;
+  const int jb = prp[i];
+  const int len = prp[i + 1] - jb;
+  if (cf[i] > 0) {
+    pcol[jb] = f2c[i];
+    pval[jb] = 1.0;
+    return;
+  }
+  const int b = rp[i], e = rp[i + 1];
+  double diagonal = 0.0;
+  {
+    int w = jb;
+    for (int k = b; k < e; ++k) {
+      const int i1 = col[k];
+      if (i1 == (int)i) diagonal = val[k];
+      else if (mask[k] && cf[i1] > 0) {
+        pcol[w] = f2c[i1];
+        pval[w] = 0.0;
+        ++w;
+      }
+    }
+  }
+  int32_t* myc = pcol + jb;
+  double* myv = pval + jb;
+  int seen_c = 0;
+  for (int k = b; k < e; ++k) {
+    const int i1 = col[k];
+    if (i1 == (int)i) continue;
+    const double a = val[k];
+    const int c1 = cf[i1];
+    const bool strong = mask[k] != 0;
+    if (strong && c1 > 0) {
+      myv[seen_c] = __dadd_rn(myv[seen_c], a);
+      ++seen_c;
+    } else if (strong && c1 != -3) {
+      // strong F neighbour: distribute a_ik over the C points i and k share
+      const int b1 = rp[i1], e1 = rp[i1 + 1];
+      double dk = 0.0;
+      for (int k1 = b1; k1 < e1; ++k1)
+        if (col[k1] == i1) dk = val[k1];
+      const double sgn = dk < 0 ? -1.0 : 1.0;
+      double sum = 0.0;
+      for (int k1 = b1; k1 < e1; ++k1) {
+        const int i2 = col[k1];
+        const double v = val[k1];
+        if (sgn * v < 0 && cf[i2] > 0 && find_sorted(myc, len, f2c[i2]) >= 0) sum = __dadd_rn(sum, v);
+      }
+      if (sum != 0) {
+        const double distribute = a / sum;
+        for (int k1 = b1; k1 < e1; ++k1) {
+          const int i2 = col[k1];
+          const double v = val[k1];
+          if (sgn * v < 0 && cf[i2] > 0) {
+            const int pos = find_sorted(myc, len, f2c[i2]);
+            if (pos >= 0) myv[pos] = __dadd_rn(myv[pos], __dmul_rn(distribute, v));
+          }
+        }
+      } else {
+        diagonal = __dadd_rn(diagonal, a);
+      }
+    } else if (c1 != -3) {
+      diagonal = __dadd_rn(diagonal, a);  // weak connection
+    }
+  }
+  if (diagonal == 0.0) {
+    for (int t = 0; t < len; ++t) myv[t] = 0.0;
+  } else {
+    const double nd = -diagonal;
+    for (int t = 0; t < len; ++t) myv[t] = myv[t] / nd;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Explicit transpose R = P^T with rows sorted by fine index.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+transpose_count_kernel(int64_t nnz, const int32_t* __restrict__ pcol, int32_t* __restrict__ count) {
+  const int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (k < nnz) atomicAdd(&count[pcol[k]], 1);
+}
+
+__global__ void __launch_bounds__(kBlock)
+transpose_fill_kernel(int64_t n, const int32_t* __restrict__ prp, const int32_t* __restrict__ pcol,
+                      const double* __restrict__ pval, const int32_t* __restrict__ rrp,
+                      int32_t* __restrict__ cursor, int32_t* __restrict__ rcol, double* __restrict__ rval) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  for (int k = prp[i]; k < prp[i + 1]; ++k) {
+    const int c = pcol[k];
+    const int w = rrp[c] + atomicAdd(&cursor[c], 1);
+    rcol[w] = (int)i;
+    rval[w] = pval[k];
+  }
+}
+
+// the atomic fill leaves each row in arbitrary order: insertion sort per row
+__global__ void __launch_bounds__(kBlock)
+sort_rows_kernel(int64_t n, const int32_t* __restrict__ rp, int32_t* __restrict__ col,
+                 double* __restrict__ val) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const int b = rp[i], e = rp[i + 1];
+  for (int a = b + 1; a < e; ++a) {
+    const int c = col[a];
+    const double v = val[a];
+    int t = a - 1;
+    while (t >= b && col[t] > c) {
+      col[t + 1] = col[t];
+      val[t + 1] = val[t];
+      --t;
+    }
+    col[t + 1] = c;
+    val[t + 1] = v;
+  }
+}
+
+static int transpose_csr(amgb_ctx* ctx, const DeviceCsr& P, DeviceCsr& R) {
+  R.n = P.ncols;
+  R.ncols = P.n;
+  R.nnz = P.nnz;
+  DevBuf<int32_t> count, cursor;
+  AMGB_TRY(count.alloc_zero(ctx, R.n));
+  AMGB_TRY(cursor.alloc_zero(ctx, R.n));
+  AMGB_TRY(R.rp.alloc(ctx, R.n + 1));
+  AMGB_TRY(R.col.alloc(ctx, R.nnz));
+  AMGB_TRY(R.val.alloc(ctx, R.nnz));
+  if (P.nnz > 0)
+    AMGB_LAUNCH(ctx, F_TRANSPOSE, 8.0 * P.nnz, transpose_count_kernel, (unsigned)div_up(P.nnz, kBlock), kBlock,
+                0, P.nnz, P.col.p, count.p);
+  AMGB_TRY(exclusive_scan_i32(ctx, count.p, R.rp.p, R.n));
+  AMGB_LAUNCH(ctx, F_TRANSPOSE, 24.0 * P.nnz + 4.0 * P.n, transpose_fill_kernel, (unsigned)div_up(P.n, kBlock),
+              kBlock, 0, P.n, P.rp.p, P.col.p, P.val.p, R.rp.p, cursor.p, R.col.p, R.val.p);
+  AMGB_LAUNCH(ctx, F_TRANSPOSE, 24.0 * R.nnz + 4.0 * R.n, sort_rows_kernel, (unsigned)div_up(R.n, kBlock),
+              kBlock, 0, R.n, R.rp.p, R.col.p, R.val.p);
+  AMGB_CHECK_LAUNCH(ctx);
+  return AMGB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// SpGEMM C = A*B: two-phase hash (count, then fill), G lanes per output row,
+// hash tables in shared memory with a global-memory path for oversized rows.
+// Numeric phase: k (entries of A's row) is walked sequentially and the lanes of
+// the group spread over B's row k, whose columns are distinct, so every C(i,c)
+// accumulates a_ik*b_kc in ascending k exactly like the oracle's Gustavson loop.
+// Rows are finally sorted by column with a bitonic network over the table.
+// ---------------------------------------------------------------------------
+constexpr int kSpThreads = 128;
+constexpr unsigned kEmpty = 0xffffffffu;
+
+__device__ __forceinline__ unsigned group_mask(int G) {
+  return G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+}
+
+__device__ __forceinline__ int hash_slot(unsigned key, int lgH) {
+  return lgH == 0 ? 0 : (int)((key * 2654435761u) >> (32 - lgH));
+}
+
+__device__ __forceinline__ int ceil_log2(int v) {  // smallest l with (1<<l) >= v, v >= 1
+  return v <= 1 ? 0 : 32 - __clz(v - 1);
+}
+
+// insert key; returns 1 if it was not present, 0 if it was, -1 if the table is full
+__device__ __forceinline__ int hash_insert(unsigned* keys, int H, int lgH, unsigned key) {
+  int h = hash_slot(key, lgH);
+  for (int probes = 0; probes < H; ++probes) {
+    const unsigned old = atomicCAS(&keys[h], kEmpty, key);
+    if (old == kEmpty) return 1;
+    if (old == key) return 0;
+    h = (h + 1) & (H - 1);
+  }
+  return -1;
+}
+
+template <int G>
+__device__ __forceinline__ int group_sum(int v, unsigned gm) {
+#pragma unroll
+  for (int d = G / 2; d > 0; d >>= 1) v += __shfl_xor_sync(gm, v, d);
+  return v;
+}
+
+// upper bound on the number of entries of row i of A*B
+template <int G>
+__device__ __forceinline__ int row_upper_bound(int b, int e, int gl, unsigned gm,
+                                               const int32_t* __restrict__ acol,
+                                               const int32_t* __restrict__ brp) {
+  int ub = 0;
+  for (int k = b + gl; k < e; k += G) {
+    const int kk = acol[k];
+    ub += brp[kk + 1] - brp[kk];
+  }
+  return group_sum<G>(ub, gm);
+}
+
+// number of distinct columns of row i of A*B, or -1 if the table overflowed
+template <int G>
+__device__ __forceinline__ int symbolic_row(unsigned* keys, int H, int lgH, int b, int e, int gl,
+                                            unsigned gm, const int32_t* __restrict__ acol,
+                                            const int32_t* __restrict__ brp,
+                                            const int32_t* __restrict__ bcol) {
+  for (int t = gl; t < H; t += G) keys[t] = kEmpty;
+  __syncwarp(gm);
+  int cnt = 0, fail = 0;
+  for (int k = b; k < e; ++k) {
+    const int kk = acol[k];
+    const int bb = brp[kk], be = brp[kk + 1];
+    for (int m = bb + gl; m < be; m += G) {
+      const int r = hash_insert(keys, H, lgH, (unsigned)bcol[m]);
+      if (r < 0) { fail = 1; break; }
+      cnt += r;
+    }
+    if (__any_sync(gm, fail)) {  // group-uniform: the table is full
+      fail = 1;
+      break;
+    }
+  }
+  __syncwarp(gm);
+  cnt = group_sum<G>(cnt, gm);
+  return fail ? -1 : cnt;
+}
+
+// CAP: shared-memory table capacity per row group (power of two).
+template <int G, int CAP>
+__global__ void __launch_bounds__(kSpThreads)
+spgemm_symbolic_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
+                       const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
+                       int32_t* __restrict__ count, int32_t* __restrict__ ovf_rows,
+                       int32_t* __restrict__ ovf_info /* [0]=count [1]=max ub */) {
+  extern __shared__ unsigned smem_keys[];
+  const int g = threadIdx.x / G, gl = threadIdx.x % G;
+  const unsigned gm = group_mask(G);
+  const int64_t i = (int64_t)blockIdx.x * (kSpThreads / G) + g;
+  if (i >= n) return;
+  unsigned* keys = smem_keys + (size_t)g * CAP;
+  const int b = arp[i], e = arp[i + 1];
+  const int ub = row_upper_bound<G>(b, e, gl, gm, acol, brp);
+  if (ub == 0) {
+    if (gl == 0) count[i] = 0;
+    return;
+  }
+  // ub overestimates the distinct count a lot in a Galerkin product, so rows
+  // whose bound does not fit still try the full shared-memory table; a full
+  // table is detected by the probe limit and the row takes the global path.
+  int lgH = ceil_log2(2 * ub);
+  if (lgH < 5) lgH = 5;
+  if ((1 << lgH) > CAP) lgH = ceil_log2(CAP);
+  const int cnt = symbolic_row<G>(keys, 1 << lgH, lgH, b, e, gl, gm, acol, brp, bcol);
+  if (gl == 0) {
+    if (cnt < 0) {
+      const int w = atomicAdd(&ovf_info[0], 1);
+      ovf_rows[w] = (int)i;
+      atomicMax(&ovf_info[1], ub);
+      count[i] = 0;
+    } else {
+      count[i] = cnt;
+    }
+  }
+}
+
+// oversized rows: one warp per row from the overflow list, table in global memory
+__global__ void __launch_bounds__(kSpThreads)
+spgemm_symbolic_global_kernel(const int32_t* __restrict__ ovf_rows, int novf, int H, int lgH,
+                              unsigned* __restrict__ tables, const int32_t* __restrict__ arp,
+                              const int32_t* __restrict__ acol, const int32_t* __restrict__ brp,
+                              const int32_t* __restrict__ bcol, int32_t* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * kSpThreads + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * kSpThreads) >> 5;
+  unsigned* keys = tables + (size_t)warp * H;
+  for (int idx = warp; idx < novf; idx += nwarps) {
+    const int i = ovf_rows[idx];
+    const int cnt = symbolic_row<32>(keys, H, lgH, arp[i], arp[i + 1], lane, 0xffffffffu, acol, brp, bcol);
+    if (lane == 0) count[i] = cnt;
+    __syncwarp();
+  }
+}
+
+template <int G>
+__device__ __forceinline__ void numeric_row(unsigned* keys, double* vals, int H, int lgH, int b, int e,
+                                            int gl, unsigned gm, const int32_t* __restrict__ acol,
+                                            const double* __restrict__ aval,
+                                            const int32_t* __restrict__ brp,
+                                            const int32_t* __restrict__ bcol,
+                                            const double* __restrict__ bval, int out_b, int out_n,
+                                            int32_t* __restrict__ ccol, double* __restrict__ cval) {
+  for (int t = gl; t < H; t += G) keys[t] = kEmpty;
+  __syncwarp(gm);
+  for (int k = b; k < e; ++k) {
+    const int kk = acol[k];
+    const double a = aval[k];
+    const int bb = brp[kk], be = brp[kk + 1];
+    for (int m = bb + gl; m < be; m += G) {
+      const unsigned key = (unsigned)bcol[m];
+      const double prod = __dmul_rn(a, bval[m]);
+      int h = hash_slot(key, lgH);
+      for (;;) {
+        const unsigned old = atomicCAS(&keys[h], kEmpty, key);
+        if (old == kEmpty) {
+          vals[h] = __dadd_rn(0.0, prod);
+          break;
+        }
+        if (old == key) {
+          vals[h] = __dadd_rn(vals[h], prod);
+          break;
+        }
+        h = (h + 1) & (H - 1);
+      }
+    }
+    __syncwarp(gm);  // orders the accumulation over k
+  }
+  // bitonic sort of the whole table by key (empty = 0xffffffff sorts last)
+  for (int kk = 2; kk <= H; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int t = gl; t < H; t += G) {
+        const int x = t ^ j;
+        if (x > t) {
+          const unsigned kt = keys[t], kx = keys[x];
+          const bool up = (t & kk) == 0;
+          if ((kt > kx) == up && kt != kx) {
+            keys[t] = kx;
+            keys[x] = kt;
+            const double vt = vals[t];
+            vals[t] = vals[x];
+            vals[x] = vt;
+          }
+        }
+      }
+      __syncwarp(gm);
+    }
+  }
+  for (int t = gl; t < out_n; t += G) {
+    ccol[out_b + t] = (int)keys[t];
+    cval[out_b + t] = vals[t];
+  }
+  __syncwarp(gm);
+}
+
+template <int G, int CAP>
+__global__ void __launch_bounds__(kSpThreads)
+spgemm_numeric_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
+                      const double* __restrict__ aval, const int32_t* __restrict__ brp,
+                      const int32_t* __restrict__ bcol, const double* __restrict__ bval,
+                      const int32_t* __restrict__ crp, int32_t* __restrict__ ccol,
+                      double* __restrict__ cval, int32_t* __restrict__ ovf_rows,
+                      int32_t* __restrict__ ovf_info) {
+  extern __shared__ unsigned char smem_raw[];
+  const int g = threadIdx.x / G, gl = threadIdx.x % G;
+  const unsigned gm = group_mask(G);
+  const int64_t i = (int64_t)blockIdx.x * (kSpThreads / G) + g;
+  if (i >= n) return;
+  const int out_b = crp[i], out_n = crp[i + 1] - out_b;
+  if (out_n == 0) return;
+  int lgH = ceil_log2(2 * out_n);
+  if (lgH < 5) lgH = 5;
+  if ((1 << lgH) > CAP) {
+    if (gl == 0) {
+      const int w = atomicAdd(&ovf_info[0], 1);
+      ovf_rows[w] = (int)i;
+      atomicMax(&ovf_info[1], out_n);
+    }
+    return;
+  }
+  constexpr int kGroups = kSpThreads / G;
+  double* vals = reinterpret_cast<double*>(smem_raw) + (size_t)g * CAP;
+  unsigned* keys = reinterpret_cast<unsigned*>(smem_raw + sizeof(double) * (size_t)kGroups * CAP) + (size_t)g * CAP;
+  numeric_row<G>(keys, vals, 1 << lgH, lgH, arp[i], arp[i + 1], gl, gm, acol, aval, brp, bcol, bval, out_b,
+                 out_n, ccol, cval);
+}
+
+__global__ void __launch_bounds__(kSpThreads)
+spgemm_numeric_global_kernel(const int32_t* __restrict__ ovf_rows, int novf, int H, int lgH,
+                             unsigned* __restrict__ key_tables, double* __restrict__ val_tables,
+                             const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
+                             const double* __restrict__ aval, const int32_t* __restrict__ brp,
+                             const int32_t* __restrict__ bcol, const double* __restrict__ bval,
+                             const int32_t* __restrict__ crp, int32_t* __restrict__ ccol,
+                             double* __restrict__ cval) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * kSpThreads + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * kSpThreads) >> 5;
+  unsigned* keys = key_tables + (size_t)warp * H;
+  double* vals = val_tables + (size_t)warp * H;
+  for (int idx = warp; idx < novf; idx += nwarps) {
+    const int i = ovf_rows[idx];
+    const int out_b = crp[i], out_n = crp[i + 1] - out_b;
+    numeric_row<32>(keys, vals, H, lgH, arp[i], arp[i + 1], lane, 0xffffffffu, acol, aval, brp, bcol, bval,
+                    out_b, out_n, ccol, cval);
+  }
+}
+
+template <int G, int CAP_SYM, int CAP_NUM>
+static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C) {
+  const int64_t n = A.n;
+  C.n = n;
+  C.ncols = B.ncols;
+  DevBuf<int32_t> count, ovf_rows, ovf_info;
+  AMGB_TRY(count.alloc(ctx, n));
+  AMGB_TRY(ovf_rows.alloc(ctx, n));
+  AMGB_TRY(ovf_info.alloc_zero(ctx, 2));
+  AMGB_TRY(C.rp.alloc(ctx, n + 1));
+  constexpr int kGroups = kSpThreads / G;
+  const unsigned grid = (unsigned)div_up(n, kGroups);
+  const double in_bytes = 12.0 * A.nnz + 4.0 * A.n + 12.0 * B.nnz + 4.0 * B.n;
+  const int fb_blocks = ctx->sm_count * 2;
+  const int fb_warps = fb_blocks * kSpThreads / 32;
+  {
+    auto kern = spgemm_symbolic_kernel<G, CAP_SYM>;
+    const size_t smem = sizeof(unsigned) * (size_t)kGroups * CAP_SYM;
+    AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, kern, grid, kSpThreads, smem, n, A.rp.p, A.col.p, B.rp.p, B.col.p,
+                count.p, ovf_rows.p, ovf_info.p);
+    AMGB_CHECK_LAUNCH(ctx);
+    int32_t* info = (int32_t*)ctx->pinned;
+    AMGB_CUDA(ctx, cudaMemcpyAsync(info, ovf_info.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int novf = info[0], max_ub = info[1];
+    if (novf > 0) {
+      int lgH = 5;
+      const long long want = std::min<long long>(2ll * max_ub, 2ll * B.ncols);
+      while ((1ll << lgH) < want) ++lgH;
+      const int H = 1 << lgH;
+      DevBuf<unsigned> tables;
+      AMGB_TRY(tables.alloc(ctx, (size_t)fb_warps * H));
+      AMGB_LAUNCH(ctx, F_SPGEMM, 0.0, spgemm_symbolic_global_kernel, fb_blocks, kSpThreads, 0, ovf_rows.p, novf,
+                  H, lgH, tables.p, A.rp.p, A.col.p, B.rp.p, B.col.p, count.p);
+      AMGB_CHECK_LAUNCH(ctx);
+    }
+  }
+  AMGB_TRY(exclusive_scan_i32(ctx, count.p, C.rp.p, n));
+  int32_t nnz = 0;
+  AMGB_TRY(read_i32(ctx, C.rp.p + n, &nnz));
+  C.nnz = nnz;
+  AMGB_TRY(C.col.alloc(ctx, nnz));
+  AMGB_TRY(C.val.alloc(ctx, nnz));
+  AMGB_CUDA(ctx, cudaMemsetAsync(ovf_info.p, 0, 2 * sizeof(int32_t), ctx->stream));
+  {
+    auto kern = spgemm_numeric_kernel<G, CAP_NUM>;
+    const size_t smem = (sizeof(unsigned) + sizeof(double)) * (size_t)kGroups * CAP_NUM;
+    AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes + 12.0 * nnz + 4.0 * n, kern, grid, kSpThreads, smem, n, A.rp.p, A.col.p,
+                A.val.p, B.rp.p, B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p, ovf_rows.p, ovf_info.p);
+    AMGB_CHECK_LAUNCH(ctx);
+    int32_t* info = (int32_t*)ctx->pinned;
+    AMGB_CUDA(ctx, cudaMemcpyAsync(info, ovf_info.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int novf = info[0], max_n = info[1];
+    if (novf > 0) {
+      int lgH = 5;
+      while ((1ll << lgH) < 2ll * max_n) ++lgH;
+      const int H = 1 << lgH;
+      DevBuf<unsigned> kt;
+      DevBuf<double> vt;
+      AMGB_TRY(kt.alloc(ctx, (size_t)fb_warps * H));
+      AMGB_TRY(vt.alloc(ctx, (size_t)fb_warps * H));
+      AMGB_LAUNCH(ctx, F_SPGEMM, 0.0, spgemm_numeric_global_kernel, fb_blocks, kSpThreads, 0, ovf_rows.p, novf, H,
+                  lgH, kt.p, vt.p, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p);
+      AMGB_CHECK_LAUNCH(ctx);
+    }
+  }
+  return AMGB_OK;
+}
+
+static int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C) {
+  const double avg_b = B.n > 0 ? double(B.nnz) / double(B.n) : 0.0;
+  if (avg_b <= 8.0) return spgemm_impl<8, 1024, 512>(ctx, A, B, C);
+  return spgemm_impl<32, 4096, 2048>(ctx, A, B, C);
+}
+
+// deal.II forwards theta / max_row_sum to PETSc through std::to_string (6 decimals)
+static double option_roundtrip(double v) { return std::strtod(std::to_string(v).c_str(), nullptr); }
+
+static int hypre_relax_type(int dealii_type, bool symmetric_operator) {
+  switch (dealii_type) {
+    case AMGB_RELAX_Jacobi: return 0;
+    case AMGB_RELAX_sequentialGaussSeidel: return 1;
+    case AMGB_RELAX_seqboundaryGaussSeidel: return 2;
+    case AMGB_RELAX_SORJacobi: return symmetric_operator ? 6 : 3;
+    case AMGB_RELAX_backwardSORJacobi: return 4;
+    case AMGB_RELAX_symmetricSORJacobi: return 6;
+    case AMGB_RELAX_l1scaledSORJacobi: return 8;
+    case AMGB_RELAX_GaussianElimination: return 9;
+    case AMGB_RELAX_l1GaussSeidel: return 13;
+    case AMGB_RELAX_backwardl1GaussSeidel: return 14;
+    case AMGB_RELAX_CG: return 15;
+    case AMGB_RELAX_Chebyshev: return 16;
+    case AMGB_RELAX_FCFJacobi: return 17;
+    case AMGB_RELAX_l1scaledJacobi: return 18;
+    default: return -1;
+  }
+}
+
+static int resolve_options(amgb_precond* P) {
+  amgb_ctx* ctx = P->ctx;
+  const amgb_boomeramg_data& d = P->data;
+  if (d.aggressive_coarsening_num_levels != 0)
+    return set_error(ctx, AMGB_ERR_UNSUPPORTED, "aggressive coarsening is not available on the device yet");
+  if (d.coarsen_type != AMGB_COARSEN_PMIS)
+    return set_error(ctx, AMGB_ERR_UNSUPPORTED,
+                     "coarsen_type %d: only PMIS (8) runs on the device (Falgout/RS is sequential)",
+                     d.coarsen_type);
+  if (d.interp_type != AMGB_INTERP_CLASSICAL)
+    return set_error(ctx, AMGB_ERR_UNSUPPORTED, "interp_type %d not available", d.interp_type);
+  if (d.max_levels < 1) return set_error(ctx, AMGB_ERR_BAD_ARG, "max_levels < 1");
+  P->theta_eff = d.options_via_string ? option_roundtrip(d.strong_threshold) : d.strong_threshold;
+  P->mrs_eff = d.options_via_string ? option_roundtrip(d.max_row_sum) : d.max_row_sum;
+  const bool sym = d.symmetric_operator != 0;
+  int types[3] = {hypre_relax_type(d.relaxation_type_down, sym), hypre_relax_type(d.relaxation_type_up, sym),
+                  hypre_relax_type(d.relaxation_type_coarse, sym)};
+  for (int t = 0; t < 3; ++t) {
+    const bool jacobi_like = types[t] == 0 || types[t] == 18;
+    const bool ok = jacobi_like || (t == 2 && types[t] == 9);
+    if (ok) continue;
+    const bool sequential = types[t] == 1 || types[t] == 2 || types[t] == 3 || types[t] == 4 || types[t] == 6 ||
+                            types[t] == 8 || types[t] == 13 || types[t] == 14;
+    if (sequential && d.smoother_policy == AMGB_SMOOTHER_SUBSTITUTE) {
+      types[t] = 18;  // l1-scaled Jacobi, C/F ordered when relax_order == 1
+      continue;
+    }
+    return set_error(ctx, AMGB_ERR_UNSUPPORTED, "relaxation type (hypre %d) not available on the device",
+                     types[t]);
+  }
+  if (types[0] != types[1])
+    return set_error(ctx, AMGB_ERR_UNSUPPORTED, "different up/down smoothers are not supported");
+  P->relax_down = types[0];
+  P->relax_up = types[1];
+  P->relax_coarse = types[2];
+  return AMGB_OK;
+}
+
+int build_hierarchy(amgb_precond* P) {
+  amgb_ctx* ctx = P->ctx;
+  AMGB_TRY(resolve_options(P));
+  const amgb_boomeramg_data& d = P->data;
+  const DeviceCsr& A0 = P->mat->A;
+  P->lv.clear();
+  P->lv.emplace_back();
+  {
+    Level& L = P->lv[0];
+    L.A.n = A0.n;
+    L.A.ncols = A0.ncols;
+    L.A.nnz = A0.nnz;
+    L.A.rp.wrap(ctx, A0.rp.p, A0.rp.n);
+    L.A.col.wrap(ctx, A0.col.p, A0.col.n);
+    L.A.val.wrap(ctx, A0.val.p, A0.val.n);
+  }
+  P->lv.reserve(d.max_levels + 1);
+  for (int level = 0;; ++level) {
+    Level& L = P->lv[level];
+    const int64_t n = L.A.n;
+    if (level == d.max_levels - 1 || n <= d.max_coarse_size) break;
+    const unsigned grid = (unsigned)div_up(n, kBlock);
+    DevBuf<int32_t> has_strong;
+    AMGB_TRY(L.mask.alloc(ctx, L.A.nnz));
+    AMGB_TRY(has_strong.alloc(ctx, n));
+    AMGB_TRY(L.cf.alloc(ctx, n));
+    AMGB_LAUNCH(ctx, F_STRENGTH, 13.0 * L.A.nnz + 8.0 * n, strength_kernel, grid, kBlock, 0, n, L.A.rp.p,
+                L.A.col.p, L.A.val.p, P->theta_eff, P->mrs_eff, L.mask.p, has_strong.p);
+    AMGB_CHECK_LAUNCH(ctx);
+    AMGB_TRY(coarsen_pmis(ctx, L.A, L.mask.p, has_strong.p, L.cf.p));
+    // coarse numbering: ascending fine index of the C points
+    DevBuf<int32_t> flag, f2c;
+    AMGB_TRY(flag.alloc(ctx, n));
+    AMGB_TRY(f2c.alloc(ctx, n + 1));
+    AMGB_LAUNCH(ctx, F_INTERP, 8.0 * n, cpoint_flag_kernel, grid, kBlock, 0, n, L.cf.p, flag.p);
+    AMGB_TRY(exclusive_scan_i32(ctx, flag.p, f2c.p, n));
+    int32_t nc = 0;
+    AMGB_TRY(read_i32(ctx, f2c.p + n, &nc));
+    if (nc == 0 || nc == n) {
+      // coarsening stalled: this level is the coarsest
+      L.mask.release();
+      L.cf.release();
+      break;
+    }
+    L.n_coarse = nc;
+    // interpolation
+    DevBuf<int32_t> pcount;
+    AMGB_TRY(pcount.alloc(ctx, n));
+    AMGB_LAUNCH(ctx, F_INTERP, 5.0 * L.A.nnz + 12.0 * n, interp_count_kernel, grid, kBlock, 0, n, L.A.rp.p,
+                L.A.col.p, L.mask.p, L.cf.p, pcount.p);
+    L.P.n = n;
+    L.P.ncols = nc;
+    AMGB_TRY(L.P.rp.alloc(ctx, n + 1));
+    AMGB_TRY(exclusive_scan_i32(ctx, pcount.p, L.P.rp.p, n));
+    int32_t nnzp = 0;
+    AMGB_TRY(read_i32(ctx, L.P.rp.p + n, &nnzp));
+    L.P.nnz = nnzp;
+    AMGB_TRY(L.P.col.alloc(ctx, nnzp));
+    AMGB_TRY(L.P.val.alloc(ctx, nnzp));
+    AMGB_LAUNCH(ctx, F_INTERP, 13.0 * L.A.nnz + 12.0 * nnzp + 16.0 * n, interp_fill_kernel,
+                (unsigned)div_up(n, 128), 128, 0, n, L.A.rp.p, L.A.col.p, L.A.val.p, L.mask.p, L.cf.p, f2c.p,
+                L.P.rp.p, L.P.col.p, L.P.val.p);
+    AMGB_CHECK_LAUNCH(ctx);
+    AMGB_TRY(transpose_csr(ctx, L.P, L.R));
+    // Galerkin product A_c = R (A P)
+    DeviceCsr T;
+    AMGB_TRY(spgemm(ctx, L.A, L.P, T));
+    P->lv.emplace_back();
+    Level& Lc = P->lv[level + 1];
+    AMGB_TRY(spgemm(ctx, P->lv[level].R, T, Lc.A));
+    if (!d.keep_setup_intermediates) P->lv[level].mask.release();
+  }
+  P->st_rows.clear();
+  P->st_nnz.clear();
+  P->st_nnzP.clear();
+  for (auto& L : P->lv) {
+    P->st_rows.push_back(L.A.n);
+    P->st_nnz.push_back(L.A.nnz);
+    P->st_nnzP.push_back(L.P.nnz);
+  }
+  AMGB_TRY(finish_solve_setup(P));
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMGB_OK;
+}
+
+}  // namespace amgb
+
+using namespace amgb;
+
+extern "C" {
+
+int amgb_precond_initialize(amgb_ctx* ctx, const amgb_matrix* A, const amgb_boomeramg_data* data,
+                            amgb_precond** out) {
+  if (!ctx || !A || !data || !out) return AMGB_ERR_BAD_ARG;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  amgb_precond* P = new amgb_precond;
+  P->ctx = ctx;
+  P->mat = A;
+  P->data = *data;
+  const int rc = build_hierarchy(P);
+  if (rc != AMGB_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    (void)cudaGetLastError();
+    delete P;
+    return rc;
+  }
+  *out = P;
+  return AMGB_OK;
+}
+
+int amgb_precond_destroy(amgb_precond* P) {
+  if (!P) return AMGB_OK;
+  cudaSetDevice(P->ctx->device);
+  destroy_solve_state(P);
+  delete P;
+  return AMGB_OK;
+}
+
+int amgb_precond_num_levels(const amgb_precond* P, int32_t* n_levels) {
+  if (!P || !n_levels) return AMGB_ERR_BAD_ARG;
+  *n_levels = (int32_t)P->lv.size();
+  return AMGB_OK;
+}
+
+int amgb_precond_level_stats(const amgb_precond* P, int32_t capacity, int32_t* n_levels, int64_t* rows,
+                             int64_t* nnz, double* sparsity, double* grid_complexity,
+                             double* operator_complexity, double* memory_complexity) {
+  if (!P) return AMGB_ERR_BAD_ARG;
+  const int nl = (int)P->lv.size();
+  if (n_levels) *n_levels = nl;
+  if (capacity < nl) return AMGB_ERR_RANGE;
+  double sr = 0, sa = 0, sp = 0;
+  for (int l = 0; l < nl; ++l) {
+    if (rows) rows[l] = P->st_rows[l];
+    if (nnz) nnz[l] = P->st_nnz[l];
+    if (sparsity) sparsity[l] = double(P->st_nnz[l]) / (double(P->st_rows[l]) * double(P->st_rows[l]));
+    sr += double(P->st_rows[l]);
+    sa += double(P->st_nnz[l]);
+    sp += double(P->st_nnzP[l]);
+  }
+  if (grid_complexity) *grid_complexity = sr / double(P->st_rows[0]);
+  if (operator_complexity) *operator_complexity = sa / double(P->st_nnz[0]);
+  if (memory_complexity) *memory_complexity = (sa + sp) / double(P->st_nnz[0]);
+  return AMGB_OK;
+}
+
+int amgb_precond_effective_relax(const amgb_precond* P, int32_t* down, int32_t* up, int32_t* coarse) {
+  if (!P) return AMGB_ERR_BAD_ARG;
+  if (down) *down = P->relax_down;
+  if (up) *up = P->relax_up;
+  if (coarse) *coarse = P->relax_coarse;
+  return AMGB_OK;
+}
+
+int amgb_precond_level_dims(const amgb_precond* P, int32_t level, int64_t* n, int64_t* nnz_A,
+                            int64_t* n_coarse, int64_t* nnz_P) {
+  if (!P) return AMGB_ERR_BAD_ARG;
+  if (level < 0 || level >= (int)P->lv.size()) return AMGB_ERR_RANGE;
+  const Level& L = P->lv[level];
+  if (n) *n = L.A.n;
+  if (nnz_A) *nnz_A = L.A.nnz;
+  if (n_coarse) *n_coarse = L.P.ncols;
+  if (nnz_P) *nnz_P = L.P.nnz;
+  return AMGB_OK;
+}
+
+static int d2h(amgb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return AMGB_OK;
+  AMGB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMGB_OK;
+}
+
+int amgb_precond_get_strength_mask(const amgb_precond* P, int32_t level, uint8_t* mask) {
+  if (!P || !mask) return AMGB_ERR_BAD_ARG;
+  if (level < 0 || level >= (int)P->lv.size()) return AMGB_ERR_RANGE;
+  const Level& L = P->lv[level];
+  if (!L.mask.p)
+    return set_error(P->ctx, AMGB_ERR_RANGE, "no strength mask kept for level %d (set keep_setup_intermediates)", level);
+  cudaSetDevice(P->ctx->device);
+  return d2h(P->ctx, mask, L.mask.p, L.A.nnz);
+}
+
+int amgb_precond_get_cf_marker(const amgb_precond* P, int32_t level, int32_t* cf) {
+  if (!P || !cf) return AMGB_ERR_BAD_ARG;
+  if (level < 0 || level >= (int)P->lv.size()) return AMGB_ERR_RANGE;
+  const Level& L = P->lv[level];
+  if (!L.cf.p) return set_error(P->ctx, AMGB_ERR_RANGE, "level %d is the coarsest: no C/F splitting", level);
+  cudaSetDevice(P->ctx->device);
+  return d2h(P->ctx, cf, L.cf.p, L.A.n * sizeof(int32_t));
+}
+
+static int get_csr(amgb_ctx* ctx, const DeviceCsr& M, int32_t* rowptr, int32_t* col, double* val) {
+  cudaSetDevice(ctx->device);
+  if (rowptr) AMGB_TRY(d2h(ctx, rowptr, M.rp.p, (M.n + 1) * sizeof(int32_t)));
+  if (col) AMGB_TRY(d2h(ctx, col, M.col.p, M.nnz * sizeof(int32_t)));
+  if (val) AMGB_TRY(d2h(ctx, val, M.val.p, M.nnz * sizeof(double)));
+  return AMGB_OK;
+}
+
+int amgb_precond_get_A_csr(const amgb_precond* P, int32_t level, int32_t* rowptr, int32_t* col, double* val) {
+  if (!P) return AMGB_ERR_BAD_ARG;
+  if (level < 0 || level >= (int)P->lv.size()) return AMGB_ERR_RANGE;
+  return get_csr(P->ctx, P->lv[level].A, rowptr, col, val);
+}
+
+int amgb_precond_get_P_csr(const amgb_precond* P, int32_t level, int32_t* rowptr, int32_t* col, double* val) {
+  if (!P) return AMGB_ERR_BAD_ARG;
+  if (level < 0 || level + 1 >= (int)P->lv.size()) return AMGB_ERR_RANGE;
+  return get_csr(P->ctx, P->lv[level].P, rowptr, col, val);
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI, against
+the CPU oracle on the same seeded inputs.  Integer outputs bit-exact, operators
+bit-identical, residual histories to 1e-10 relative, iterations within +-1
+(BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import amg_ann_b200 as ab
+from helpers import device_data, poisson, random_spd_csr
+from oracle import binding as orc
+
+pytestmark = pytest.mark.gpu
+
+RES_RTOL = 1e-10  # north_star: residual history agrees to 1e-10 relative
+
+
+def _both(ctx, s, data):
+    A = ab.SparseMatrix(ctx, s.rowptr32(), s.col, s.val)
+    P = ab.PreconditionBoomerAMG()
+    P.initialize(A, data)
+    H = orc.Hierarchy(s.rowptr32(), s.col, s.val, data.to_struct())
+    return A, P, H
+
+
+def _assert_hierarchy_identical(P, H):
+    assert P.num_levels == H.num_levels
+    for l in range(H.num_levels):
+        assert P.level_dims(l) == H.level_dims(l), l
+        rp, cl, vl = P.A(l)
+        rpo, clo, vlo = H.A(l)
+        assert np.array_equal(rp, rpo) and np.array_equal(cl, clo), f"A pattern level {l}"
+        assert np.array_equal(vl, vlo), f"A values level {l}: max diff {abs(vl - vlo).max()}"
+        if l + 1 < H.num_levels:
+            assert np.array_equal(P.strength_mask(l), H.strength_mask(l)), f"mask level {l}"
+            assert np.array_equal(P.cf_marker(l), H.cf_marker(l)), f"cf level {l}"
+            prp, pcl, pvl, nc = P.P(l)
+            orp, ocl, ovl, onc = H.P(l)
+            assert nc == onc and np.array_equal(prp, orp) and np.array_equal(pcl, ocl), f"P pattern {l}"
+            assert np.array_equal(pvl, ovl), f"P values level {l}"
+
+
+def test_spmv_matches_oracle(gpu_ctx):
+    s = poisson(12, contrast=3.0)
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    x = np.random.default_rng(0).standard_normal(s.n)
+    y = A.vmult(x)
+    yo = orc.spmv(s.rowptr32(), s.col, s.val, x)
+    assert np.abs(y - yo).max() <= 1e-13 * np.abs(yo).max()
+    # 64-bit row pointers take the same path
+    A64 = ab.SparseMatrix(gpu_ctx, s.rowptr, s.col, s.val)
+    assert np.array_equal(A64.vmult(x), y)
+
+
+@pytest.mark.parametrize("m,theta,contrast", [(8, 0.25, 0.0), (12, 0.5, 0.0), (12, 0.25, 6.0),
+                                              (16, 0.7, 3.0), (10, 0.05, 0.0), (10, 0.95, 6.0)])
+def test_setup_is_bit_exact(gpu_ctx, m, theta, contrast):
+    s = poisson(m, contrast=contrast)
+    A, P, H = _both(gpu_ctx, s, device_data(theta))
+    _assert_hierarchy_identical(P, H)
+    st, so = P.level_stats(), H.stats()
+    assert np.array_equal(st["rows"], so["rows"]) and np.array_equal(st["nnz"], so["nnz"])
+    assert (st["grid"], st["operator"], st["memory"]) == (so["grid"], so["operator"], so["memory"])
+
+
+def test_setup_theta_at_exact_tie(gpu_ctx):
+    # H3: corner/edge couplings of the uniform stencil are in ratio 0.5 exactly
+    s = ab.gen.poisson_q1(10)
+    A, P, H = _both(gpu_ctx, s, device_data(0.5))
+    _assert_hierarchy_identical(P, H)
+
+
+def test_setup_unstructured_ragged_rows(gpu_ctx):
+    M = random_spd_csr(2000, 0.004, 3)
+    class S:  # minimal System look-alike
+        n = M.shape[0]; col = M.indices; val = M.data
+        def rowptr32(self): return M.indptr.astype(np.int32)
+    A, P, H = _both(gpu_ctx, S(), device_data(0.25))
+    _assert_hierarchy_identical(P, H)
+
+
+def test_setup_elasticity(gpu_ctx):
+    young = 10.0 ** ab.gen.checkerboard_epsv(2, 3, 2.0)
+    s = ab.gen.elasticity_q1(6, 2, 3, young)
+    A, P, H = _both(gpu_ctx, s, device_data(0.5))
+    _assert_hierarchy_identical(P, H)
+
+
+def test_vmult_matches_oracle(gpu_ctx):
+    s = poisson(12, contrast=2.0)
+    A, P, H = _both(gpu_ctx, s, device_data(0.25))
+    r = np.random.default_rng(1).standard_normal(s.n)
+    z = np.empty(s.n)
+    P.vmult(z, r)
+    zo = H.vmult(r)
+    assert np.abs(z - zo).max() <= 1e-12 * np.abs(zo).max()
+
+
+@pytest.mark.parametrize("m,theta,contrast", [(12, 0.25, 0.0), (16, 0.5, 6.0), (20, 0.25, 3.0)])
+def test_pcg_residual_history_and_iterations(gpu_ctx, m, theta, contrast):
+    s = poisson(m, contrast=contrast)
+    A, P, H = _both(gpu_ctx, s, device_data(theta))
+    ctl = ab.SolverControl(s.n, 1e-8)
+    x = s.x0.copy()
+    ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+    rc, xo, nit, hist = H.cg_solve(s.rhs, s.x0, abs_tol=1e-8)
+    assert rc == 0 and abs(ctl.last_step() - nit) <= 1
+    k = min(len(hist), len(ctl.history))
+    assert (np.abs(ctl.history[:k] - hist[:k]) <= RES_RTOL * hist[:k]).all()
+    assert np.abs(x - xo).max() <= 1e-9 * np.abs(xo).max()
+    assert ctl.last_value() <= 1e-8
+
+
+def test_jacobi_smoother_and_no_cf_relaxation(gpu_ctx):
+    s = ab.gen.poisson_q1(10)
+    R = ab.RelaxationType
+    data = device_data(0.25, relaxation_type_up=R.Jacobi, relaxation_type_down=R.Jacobi,
+                       relax_weight=0.6, relax_order=0)
+    A, P, H = _both(gpu_ctx, s, data)
+    assert P.effective_relax() == H.effective_relax() == (0, 0, 9)
+    ctl = ab.SolverControl(s.n, 1e-8)
+    x = s.x0.copy()
+    ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+    rc, xo, nit, hist = H.cg_solve(s.rhs, s.x0, abs_tol=1e-8)
+    assert abs(ctl.last_step() - nit) <= 1
+    k = min(len(hist), len(ctl.history))
+    assert (np.abs(ctl.history[:k] - hist[:k]) <= RES_RTOL * hist[:k]).all()
+
+
+def test_reference_default_smoother_is_substituted_or_rejected(gpu_ctx):
+    s = ab.gen.poisson_q1(8)
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    P = ab.PreconditionBoomerAMG()
+    # the reference's 5-argument construction (t2 main.cpp:447-453)
+    P.initialize(A, ab.AdditionalData(True, 0.25, 0.9, 0, True))
+    assert P.effective_relax() == (18, 18, 9)
+    with pytest.raises(ab.AmgbError) as e:
+        P.initialize(A, ab.AdditionalData(True, 0.25, 0.9, 0, True, smoother_policy=ab.SMOOTHER_STRICT))
+    assert e.value.status == -5
+    with pytest.raises(ab.AmgbError):
+        P.initialize(A, ab.AdditionalData(True, 0.25, 0.9, 2, True))  # aggressive levels
+
+
+def test_no_convergence_is_reported(gpu_ctx):
+    s = ab.gen.poisson_q1(8)
+    A, P, H = _both(gpu_ctx, s, device_data(0.25))
+    ctl = ab.SolverControl(2, 1e-30)
+    x = s.x0.copy()
+    with pytest.raises(ab.NoConvergence):
+        ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+    assert ctl.last_step() == 2 and len(ctl.history) == 3
+    ctl = ab.SolverControl(10, 1e30)  # absolute tolerance: stops before the first step
+    ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+    assert ctl.last_step() == 0
+
+
+@pytest.mark.parametrize("m,V,contrast", [(6, 5, 0.0), (10, 75, 2.0), (14, 50, 6.0), (3, 100, 0.0)])
+def test_pooling_parity(gpu_ctx, m, V, contrast):
+    s = poisson(m, contrast=contrast)
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    vm = ab.ViewMaker(V).make_view(A)
+    so, co, ppo, npo = orc.make_view(s.rowptr32(), s.col, s.val, V)
+    assert np.array_equal(vm.count, co) and vm.count.sum() == s.nnz
+    assert np.array_equal(vm.max_pp, ppo) and np.array_equal(vm.max_np, npo)
+    assert np.allclose(vm.view, so, rtol=0, atol=1e-13 * np.abs(s.val).sum())
+
+
+def test_theta_sweep_reuses_resident_matrix(gpu_ctx):
+    # ref t2 main.cpp:440-467: independent solves sharing one matrix
+    s = poisson(10, contrast=3.0)
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    for th in ab.gen.theta_sweep(0.05, 0.96, 0.15):
+        x = s.x0.copy()
+        row = ab.amg_solve(device_data(th), 1e-8, A, s.rhs, x)
+        H = orc.Hierarchy(s.rowptr32(), s.col, s.val, device_data(th).to_struct())
+        rc, xo, nit, hist = H.cg_solve(s.rhs, s.x0, abs_tol=1e-8)
+        assert abs(row["niters"] - nit) <= 1
+        assert list(row["nrows"]) == list(H.stats()["rows"])
+        assert list(row["nze"]) == list(H.stats()["nnz"])
+
+
+def test_full_size_properties_config1(gpu_ctx):
+    """BASELINE config 1 (m=100, 1.03M DoFs): size-independent properties."""
+    s = ab.gen.poisson_q1(100)
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    P = ab.PreconditionBoomerAMG()
+    P.initialize(A, device_data(0.25))
+    st = P.level_stats()
+    assert st["rows"][0] == 1030301 and st["nnz"][0] == 27270901
+    assert (np.diff(st["rows"]) < 0).all() and st["rows"][-1] <= 9
+    # level-0 mask: strong count per interior row = 20 (edges + corners), H3
+    mk = P.strength_mask(0)
+    rp = s.rowptr32()
+    N = 101
+    c = (N // 2) * (1 + N + N * N)
+    assert mk[rp[c]:rp[c + 1]].sum() == 20
+    cf = P.cf_marker(0)
+    assert (cf > 0).sum() == st["rows"][1]
+    # coarse operator symmetric away from Dirichlet couplings: A_c row sums bounded
+    ctl = ab.SolverControl(s.n, 1e-8)
+    x = s.x0.copy()
+    ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+    assert ctl.last_step() < 60 and ctl.history[-1] <= 1e-8
+    # true residual of the returned solution
+    r = s.rhs - A.vmult(x)
+    assert np.linalg.norm(r) <= 1e-6 * np.linalg.norm(s.rhs)
+    # pooled image: count sums to nnz, sum channel sums to A.sum()
+    vm = ab.ViewMaker(75).make_view(A)
+    assert vm.count.sum() == s.nnz
+    assert vm.view.sum() == pytest.approx(s.val.sum(), abs=1e-9 * np.abs(s.val).sum())
+    assert vm.max_pp.max() == s.val.max() and vm.max_np.max() == -s.val.min()

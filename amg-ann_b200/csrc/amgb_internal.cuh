@@ -30,6 +30,10 @@ enum Family : int {
   F_SCAN,          // setup: prefix sums / compaction helpers
   F_AUX,           // setup: l1 norms, diag, SELL conversion
   F_POOL,          // pooling
+  F_SMOOTH_L0,     // level-0 share of F_SMOOTH etc. (fine-grid roofline numbers)
+  F_RESIDUAL_L0,
+  F_RESTRICT_L0,
+  F_PROLONG_L0,
   F_COUNT
 };
 

@@ -298,6 +298,7 @@ struct CycleVecs {
 
 static int half_sweep(amgb_precond* P, Level& L, const double* f, const double* u_in, double* u_out,
                       int pts) {
+  const bool fine = &L == &P->lv[0];
   EpiJacobi epi{f, u_in, L.inv_relax.p, L.cf.p, u_out, P->data.relax_weight, L.cf.p ? pts : 0};
   // bytes: the rows touched; for a C/F half sweep roughly the selected share.
   // Reported as the full-sweep formula of SURVEY.md 8(d) scaled by the share of
@@ -309,7 +310,7 @@ static int half_sweep(amgb_precond* P, Level& L, const double* f, const double* 
     share = pts > 0 ? c : 1.0 - c;
   }
   const double bytes = share * csr_bytes(L.A) + 32.0 * L.A.n;
-  return launch_rows(P->ctx, L.A, u_in, epi, F_SMOOTH, bytes);
+  return launch_rows(P->ctx, L.A, u_in, epi, fine ? F_SMOOTH_L0 : F_SMOOTH, bytes);
 }
 
 // One hypre_BoomerAMGRelaxIF call; the result ends in `u` (L.tmp is scratch).
@@ -343,14 +344,15 @@ static int cycle(amgb_precond* P, int l, double* u, const double* f) {
   }
   for (unsigned s = 0; s < P->data.n_sweeps; ++s) AMGB_TRY(relax_if(P, L, f, u, 1));
   // residual into tmp, restriction into the coarse rhs
-  AMGB_TRY(launch_rows(ctx, L.A, u, EpiResidual{f, L.tmp.p}, F_RESIDUAL, csr_bytes(L.A) + 24.0 * L.A.n));
+  AMGB_TRY(launch_rows(ctx, L.A, u, EpiResidual{f, L.tmp.p}, l == 0 ? F_RESIDUAL_L0 : F_RESIDUAL,
+                       csr_bytes(L.A) + 24.0 * L.A.n));
   Level& C = P->lv[l + 1];
-  AMGB_TRY(launch_rows(ctx, L.R, L.tmp.p, EpiStore{C.f.p}, F_RESTRICT,
+  AMGB_TRY(launch_rows(ctx, L.R, L.tmp.p, EpiStore{C.f.p}, l == 0 ? F_RESTRICT_L0 : F_RESTRICT,
                        csr_bytes(L.R) + 8.0 * L.A.n + 8.0 * C.A.n));
   AMGB_CUDA(ctx, cudaMemsetAsync(C.u.p, 0, C.A.n * sizeof(double), ctx->stream));
   AMGB_TRY(cycle(P, l + 1, C.u.p, C.f.p));
   if (P->data.w_cycle && l + 1 < nl - 1) AMGB_TRY(cycle(P, l + 1, C.u.p, C.f.p));
-  AMGB_TRY(launch_rows(ctx, L.P, C.u.p, EpiAdd{u}, F_PROLONG,
+  AMGB_TRY(launch_rows(ctx, L.P, C.u.p, EpiAdd{u}, l == 0 ? F_PROLONG_L0 : F_PROLONG,
                        csr_bytes(L.P) + 8.0 * C.A.n + 16.0 * L.A.n));
   for (unsigned s = 0; s < P->data.n_sweeps; ++s) AMGB_TRY(relax_if(P, L, f, u, 2));
   return AMGB_OK;

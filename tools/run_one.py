@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Run one (matrix, theta) pass of the hot path on cuda:0 -- the small command
+profiled under ncu (profiles/README.md).  --mode setup|solve|full|pool"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import amg_ann_b200 as ab  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--m", type=int, default=100)
+ap.add_argument("--theta", type=float, default=0.25)
+ap.add_argument("--contrast", type=float, default=6.0)
+ap.add_argument("--mode", default="full")
+ap.add_argument("--repeat", type=int, default=1)
+ap.add_argument("--max-steps", type=int, default=0)
+args = ap.parse_args()
+
+epsv = ab.gen.checkerboard_epsv(4, 3, args.contrast)
+s = ab.gen.poisson_q1(args.m, 4, 3, epsv)
+R = ab.RelaxationType
+data = ab.AdditionalData(True, args.theta, 0.9, 0, True, relaxation_type_up=R.l1scaledJacobi,
+                         relaxation_type_down=R.l1scaledJacobi)
+ctx = ab.Context(0)
+A = ab.SparseMatrix(ctx, s.rowptr32(), s.col, s.val)
+for rep in range(args.repeat):
+    if args.mode == "pool":
+        vm = ab.ViewMaker(75).make_view(A)
+        print(f"pool: device {vm.t_device_us:.1f} us, count sum {vm.count.sum()}")
+        continue
+    P = ab.PreconditionBoomerAMG()
+    t0 = time.perf_counter()
+    P.initialize(A, data)
+    ctx.synchronize()
+    t1 = time.perf_counter()
+    st = P.level_stats()
+    msg = f"setup {1e3 * (t1 - t0):.1f} ms levels {list(st['rows'])} opcx {st['operator']:.3f}"
+    if args.mode in ("solve", "full"):
+        ctl = ab.SolverControl(args.max_steps or s.n, 1e-8)
+        x = s.x0.copy()
+        t2 = time.perf_counter()
+        try:
+            ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+        except ab.NoConvergence:
+            pass
+        t3 = time.perf_counter()
+        msg += f" | solve {1e3 * (t3 - t2):.1f} ms iters {ctl.last_step()} res {ctl.last_value():.3e}"
+    print(msg)
+    P.close()
+print("kernel launches", ctx.kernel_launches())

@@ -182,6 +182,23 @@ class Context:
         return out
 
 
+    def level_timers(self, max_levels=32):
+        """{family: [dict(ms, launches, bytes) per level]} for launches timed with timers on."""
+        L = amgb_lib()
+        out = {}
+        for f in range(L.amgb_timer_count()):
+            rows = []
+            for lv in range(max_levels):
+                ms, cnt, by = C.c_double(), C.c_int64(), C.c_double()
+                L.amgb_ctx_get_timer_level(self._h, f, lv, C.byref(ms), C.byref(cnt), C.byref(by))
+                rows.append(dict(ms=ms.value, launches=cnt.value, bytes=by.value))
+            while rows and rows[-1]["launches"] == 0:
+                rows.pop()
+            if rows:
+                out[L.amgb_timer_name(f).decode()] = rows
+        return out
+
+
 class SparseMatrix:
     """Device-resident CSR system matrix; stays resident across the theta sweep
     (the reference re-converts it for every theta)."""

@@ -89,6 +89,7 @@ AMGB_SYMBOLS = [
     "amgb_precond_get_A_csr", "amgb_precond_get_P_csr", "amgb_cg_solve",
     "amgb_cg_solve_device", "amgb_make_view", "amgb_ctx_enable_timers",
     "amgb_ctx_reset_timers", "amgb_timer_count", "amgb_timer_name", "amgb_ctx_get_timer",
+    "amgb_ctx_get_timer_level",
 ]
 
 
@@ -150,5 +151,6 @@ def amgb_lib():
         _sig(L.amgb_timer_count, C.c_int)
         _sig(L.amgb_timer_name, C.c_char_p, C.c_int)
         _sig(L.amgb_ctx_get_timer, C.c_int, vp, C.c_int, c_f64p, c_i64p, c_f64p)
+        _sig(L.amgb_ctx_get_timer_level, C.c_int, vp, C.c_int, C.c_int, c_f64p, c_i64p, c_f64p)
         _amgb = L
     return _amgb

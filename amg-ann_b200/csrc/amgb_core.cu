@@ -34,6 +34,7 @@ LaunchScope::LaunchScope(amgb_ctx* c, int family, double bytes) : ctx(c), timed(
     timed = true;
     rec.family = family;
     rec.bytes = bytes;
+    rec.level = ctx->cur_level < 0 ? 0 : (ctx->cur_level >= kTimerLevels ? kTimerLevels - 1 : ctx->cur_level);
     auto get = [&](cudaEvent_t* ev) {
       if (!ctx->free_events.empty()) {
         *ev = ctx->free_events.back();
@@ -60,7 +61,12 @@ static void drain_timers(amgb_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& r : ctx->recs) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) ctx->fam_ms[r.family] += ms;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ctx->fam_ms[r.family] += ms;
+      ctx->lvl_ms[r.family][r.level] += ms;
+      ctx->lvl_bytes[r.family][r.level] += r.bytes;
+      ctx->lvl_launches[r.family][r.level] += 1;
+    }
     ctx->free_events.push_back(r.a);
     ctx->free_events.push_back(r.b);
   }
@@ -324,6 +330,11 @@ int amgb_ctx_reset_timers(amgb_ctx* ctx) {
     ctx->fam_ms[f] = 0;
     ctx->fam_launches[f] = 0;
     ctx->fam_bytes[f] = 0;
+    for (int l = 0; l < kTimerLevels; ++l) {
+      ctx->lvl_ms[f][l] = 0;
+      ctx->lvl_bytes[f][l] = 0;
+      ctx->lvl_launches[f][l] = 0;
+    }
   }
   return AMGB_OK;
 }
@@ -341,6 +352,16 @@ int amgb_ctx_get_timer(amgb_ctx* ctx, int family, double* total_ms, int64_t* lau
   if (total_ms) *total_ms = ctx->fam_ms[family];
   if (launches) *launches = ctx->fam_launches[family];
   if (algorithmic_bytes) *algorithmic_bytes = ctx->fam_bytes[family];
+  return AMGB_OK;
+}
+
+int amgb_ctx_get_timer_level(amgb_ctx* ctx, int family, int level, double* total_ms, int64_t* launches,
+                             double* algorithmic_bytes) {
+  if (!ctx || family < 0 || family >= F_COUNT || level < 0 || level >= kTimerLevels) return AMGB_ERR_BAD_ARG;
+  drain_timers(ctx);
+  if (total_ms) *total_ms = ctx->lvl_ms[family][level];
+  if (launches) *launches = ctx->lvl_launches[family][level];
+  if (algorithmic_bytes) *algorithmic_bytes = ctx->lvl_bytes[family][level];
   return AMGB_OK;
 }
 

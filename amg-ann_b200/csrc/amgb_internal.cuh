@@ -40,8 +40,11 @@ enum Family : int {
 struct TimerRec {
   cudaEvent_t a, b;
   int family;
+  int level;
   double bytes;
 };
+
+constexpr int kTimerLevels = 32;
 
 }  // namespace amgb
 
@@ -59,6 +62,11 @@ struct amgb_ctx {
   double fam_ms[amgb::F_COUNT] = {0};
   int64_t fam_launches[amgb::F_COUNT] = {0};
   double fam_bytes[amgb::F_COUNT] = {0};
+  // per (family, level) device time while timers are on; cur_level tags launches
+  int cur_level = 0;
+  double lvl_ms[amgb::F_COUNT][amgb::kTimerLevels] = {{0}};
+  double lvl_bytes[amgb::F_COUNT][amgb::kTimerLevels] = {{0}};
+  int64_t lvl_launches[amgb::F_COUNT][amgb::kTimerLevels] = {{0}};
   // small pinned staging area for device->host scalars
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -139,24 +147,34 @@ struct DeviceCsr {
   DevBuf<double> val;
 };
 
-// SELL-32 copy of a level operator for the solve phase.
-struct DeviceSell {
-  int64_t n = 0, nslices = 0, padded = 0;
-  DevBuf<int64_t> slice_off;  // nslices+1
-  DevBuf<int32_t> col;        // padded, column-major within a slice
+// SELL-32 (sliced ELLPACK, slice height = one warp) operator of the solve phase.
+// With T lanes per row a slice (= one warp) holds 32/T rows; entry j of local row
+// q lives at 32*slice_ptr[slice] + 32*(j/T) + q*T + j%T, so one warp-wide load is
+// always 32 consecutive elements.  Padding entries have val = 0 and a valid col.  Rows/columns are in the C/F-permuted
+// ("new") numbering of the level, see DESIGN.md "Solve-phase layout".
+struct Sell {
+  int64_t n = 0, ncols = 0, nslices = 0, nnz = 0, padded = 0;
+  int T = 1;  // lanes cooperating on one row (1,2,...,32); a slice holds 32/T rows
+  DevBuf<int32_t> slice_ptr;  // nslices+1, in units of 32 elements
+  DevBuf<int32_t> col;
   DevBuf<double> val;
-  bool ready = false;
+  double csr_bytes() const { return 12.0 * nnz + 4.0 * (n + 1); }
 };
 
 struct Level {
+  // ---- setup representation (CSR, original numbering of the level) ----
   DeviceCsr A;          // level 0 aliases the user's matrix (no copy)
   DeviceCsr P, R;       // prolongator and its explicit transpose
   DevBuf<uint8_t> mask; // strength mask aligned with A (kept for parity accessors)
   DevBuf<int32_t> cf;   // +1 / -1 / -3 as returned by the coarsening
-  DevBuf<int32_t> diag_idx;
-  DevBuf<double> inv_relax; // 1/l1 (type 18) or 1/diag (type 0); 0 where the row is skipped
-  DevBuf<double> u, f, tmp, tmp2;
+  DevBuf<int32_t> f2c;  // exclusive scan of the C flags (n+1): coarse index of a C point
   int64_t n_coarse = 0;
+  // ---- solve representation (SELL-32, C points first) ----
+  DevBuf<int32_t> perm;      // new -> old
+  DevBuf<int32_t> inv_perm;  // old -> new
+  Sell As, Ps, Rs;
+  DevBuf<double> inv_relax;  // new order: 1/l1 (type 18) or 1/diag (type 0); 0 = skip row
+  DevBuf<double> u, f, tmp;  // new order
 };
 
 int64_t div_up(int64_t a, int64_t b);
@@ -214,16 +232,22 @@ struct amgb_precond {
   bool dense_ok = false;
   // statistics
   std::vector<int64_t> st_rows, st_nnz, st_nnzP;
-  // captured V-cycle
+  // captured V-cycle (valid for the (z, r) pointer pair below)
   cudaGraphExec_t vcycle_graph = nullptr;
+  double* graph_z = nullptr;
+  const double* graph_r = nullptr;
+  bool use_graph = true;
+  int64_t graph_kernels = 0;  // kernels inside the captured graph (launch accounting)
+  int64_t graph_fam_launches[amgb::F_COUNT] = {0};
+  double graph_fam_bytes[amgb::F_COUNT] = {0};
 };
 
 namespace amgb {
 // amgb_setup.cu
 int build_hierarchy(amgb_precond* P);
 // amgb_solve.cu
-int level_aux(amgb_precond* P, int level);
 int finish_solve_setup(amgb_precond* P);
+// z = M^{-1} r with z, r in the level-0 permuted numbering
 int vcycle_apply(amgb_precond* P, double* z_dev, const double* r_dev);
 int spmv(amgb_ctx* ctx, const DeviceCsr& A, const double* x, double* y, int family);
 void destroy_solve_state(amgb_precond* P);

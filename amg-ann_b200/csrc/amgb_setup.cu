@@ -28,13 +28,15 @@ constexpr int kBlock = 256;
 __global__ void __launch_bounds__(kBlock)
 strength_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
                 const double* __restrict__ val, double theta, double max_row_sum,
-                uint8_t* __restrict__ mask, int32_t* __restrict__ has_strong) {
+                uint8_t* __restrict__ mask, int32_t* __restrict__ has_strong,
+                double* __restrict__ diagv) {
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
   const int b = rp[i], e = rp[i + 1];
   double diag = 0.0;
   for (int k = b; k < e; ++k)
     if (col[k] == i) diag = val[k];
+  diagv[i] = diag;
   double row_scale = 0.0, row_sum = diag;
   if (diag < 0) {
     for (int k = b; k < e; ++k)
@@ -240,81 +242,156 @@ __device__ __forceinline__ int find_sorted(const int32_t* pcol, int len, int cc)
   return (lo < len && pcol[lo] == cc) ? lo : -1;
 }
 
-__global__ void __launch_bounds__(128)
+// One warp per row.  Row i's entries are walked in order (the oracle's order);
+// for a strong F neighbour k the warp reads row k cooperatively (coalesced), the
+// qualifying entries are found with a ballot and summed in lane (= column)
+// order, and each qualifying lane then updates its own, distinct, P entry.  The
+// P row holds FINE column ids while it is being built (sorted ascending, so
+// membership is a binary search) and is renumbered at the end.
+__global__ void __launch_bounds__(kBlock)
 interp_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
                    const double* __restrict__ val, const uint8_t* __restrict__ mask,
                    const int32_t* __restrict__ cf, const int32_t* __restrict__ f2c,
-                   const int32_t* __restrict__ prp, int32_t* __restrict__ pcol, double* __restrict__ pval) {
-  const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+                   const double* __restrict__ diagv, const int32_t* __restrict__ prp, int32_t* pcol,
+                   double* pval) {
+  const int64_t i = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= n) return;
+  const unsigned full = 0xffffffffu;
   const int jb = prp[i];
   const int len = prp[i + 1] - jb;
   if (cf[i] > 0) {
-    pcol[jb] = f2c[i];
-    pval[jb] = 1.0;
+    if (lane == 0) {
+      pcol[jb] = f2c[i];
+      pval[jb] = 1.0;
+    }
     return;
   }
   const int b = rp[i], e = rp[i + 1];
-  double diagonal = 0.0;
-  {
-    int w = jb;
-    for (int k = b; k < e; ++k) {
-      const int i1 = col[k];
-      if (i1 == (int)i) diagonal = val[k];
-      else if (mask[k] && cf[i1] > 0) {
-        pcol[w] = f2c[i1];
-        pval[w] = 0.0;
-        ++w;
-      }
-    }
-  }
   int32_t* myc = pcol + jb;
   double* myv = pval + jb;
-  int seen_c = 0;
-  for (int k = b; k < e; ++k) {
-    const int i1 = col[k];
-    if (i1 == (int)i) continue;
-    const double a = val[k];
-    const int c1 = cf[i1];
-    const bool strong = mask[k] != 0;
-    if (strong && c1 > 0) {
-      myv[seen_c] = __dadd_rn(myv[seen_c], a);
-      ++seen_c;
-    } else if (strong && c1 != -3) {
-      // strong F neighbour: distribute a_ik over the C points i and k share
-      const int b1 = rp[i1], e1 = rp[i1 + 1];
-      double dk = 0.0;
-      for (int k1 = b1; k1 < e1; ++k1)
-        if (col[k1] == i1) dk = val[k1];
-      const double sgn = dk < 0 ? -1.0 : 1.0;
-      double sum = 0.0;
-      for (int k1 = b1; k1 < e1; ++k1) {
-        const int i2 = col[k1];
-        const double v = val[k1];
-        if (sgn * v < 0 && cf[i2] > 0 && find_sorted(myc, len, f2c[i2]) >= 0) sum = __dadd_rn(sum, v);
+  // phase 0: diagonal, and the strong C neighbours (fine ids) in row order
+  double diagonal = 0.0;
+  {
+    int base = 0;
+    for (int kb = b; kb < e; kb += 32) {
+      const int k = kb + lane;
+      bool isc = false;
+      int i1 = -1;
+      double a = 0.0;
+      if (k < e) {
+        i1 = col[k];
+        a = val[k];
+        isc = i1 != (int)i && mask[k] && cf[i1] > 0;
       }
-      if (sum != 0) {
-        const double distribute = a / sum;
-        for (int k1 = b1; k1 < e1; ++k1) {
-          const int i2 = col[k1];
-          const double v = val[k1];
-          if (sgn * v < 0 && cf[i2] > 0) {
-            const int pos = find_sorted(myc, len, f2c[i2]);
-            if (pos >= 0) myv[pos] = __dadd_rn(myv[pos], __dmul_rn(distribute, v));
-          }
-        }
-      } else {
-        diagonal = __dadd_rn(diagonal, a);
+      const unsigned dm = __ballot_sync(full, k < e && i1 == (int)i);
+      if (dm) diagonal = __shfl_sync(full, a, __ffs(dm) - 1);
+      const unsigned cm = __ballot_sync(full, isc);
+      if (isc) {
+        const int pos = base + __popc(cm & ((1u << lane) - 1u));
+        myc[pos] = i1;
+        myv[pos] = 0.0;
       }
-    } else if (c1 != -3) {
-      diagonal = __dadd_rn(diagonal, a);  // weak connection
+      base += __popc(cm);
     }
   }
-  if (diagonal == 0.0) {
-    for (int t = 0; t < len; ++t) myv[t] = 0.0;
-  } else {
-    const double nd = -diagonal;
-    for (int t = 0; t < len; ++t) myv[t] = myv[t] / nd;
+  __syncwarp();
+  // phase 1: entries of row i in order
+  int seen_c = 0;
+  for (int kb = b; kb < e; kb += 32) {
+    const int k = kb + lane;
+    int my_i1 = -1, my_c1 = -3, my_strong = 0;
+    double my_a = 0.0;
+    if (k < e) {
+      my_i1 = col[k];
+      my_a = val[k];
+      my_strong = mask[k];
+      my_c1 = cf[my_i1];
+    }
+    const int cnt = min(32, e - kb);
+    for (int t = 0; t < cnt; ++t) {
+      const int i1 = __shfl_sync(full, my_i1, t);
+      const double a = __shfl_sync(full, my_a, t);
+      const int strong = __shfl_sync(full, my_strong, t);
+      const int c1 = __shfl_sync(full, my_c1, t);
+      if (i1 == (int)i) continue;
+      if (strong && c1 > 0) {
+        if (lane == 0) myv[seen_c] = __dadd_rn(myv[seen_c], a);
+        ++seen_c;
+        __syncwarp();
+      } else if (strong && c1 != -3) {
+        // strong F neighbour: distribute a_ik over the C points i and k share
+        const int b1 = rp[i1], e1 = rp[i1 + 1];
+        const double sgn = diagv[i1] < 0 ? -1.0 : 1.0;
+        double sum = 0.0;
+        if (e1 - b1 <= 32) {
+          // the usual case: row k fits one warp-wide read, the qualifying
+          // entries stay in registers between the sum and the distribution
+          const int k1 = b1 + lane;
+          double v = 0.0;
+          int pos = -1;
+          if (k1 < e1) {
+            v = val[k1];
+            if (sgn * v < 0) {
+              const int i2 = col[k1];
+              if (cf[i2] > 0) pos = find_sorted(myc, len, i2);
+            }
+          }
+          for (unsigned m = __ballot_sync(full, pos >= 0); m; m &= m - 1)
+            sum = __dadd_rn(sum, __shfl_sync(full, v, __ffs(m) - 1));
+          if (sum != 0) {
+            const double distribute = a / sum;
+            if (pos >= 0) myv[pos] = __dadd_rn(myv[pos], __dmul_rn(distribute, v));
+            __syncwarp();
+          } else {
+            diagonal = __dadd_rn(diagonal, a);
+          }
+        } else {
+          for (int k1b = b1; k1b < e1; k1b += 32) {
+            const int k1 = k1b + lane;
+            double v = 0.0;
+            bool q = false;
+            if (k1 < e1) {
+              v = val[k1];
+              if (sgn * v < 0) {
+                const int i2 = col[k1];
+                q = cf[i2] > 0 && find_sorted(myc, len, i2) >= 0;
+              }
+            }
+            for (unsigned m = __ballot_sync(full, q); m; m &= m - 1)
+              sum = __dadd_rn(sum, __shfl_sync(full, v, __ffs(m) - 1));
+          }
+          if (sum != 0) {
+            const double distribute = a / sum;
+            for (int k1b = b1; k1b < e1; k1b += 32) {
+              const int k1 = k1b + lane;
+              if (k1 < e1) {
+                const double v = val[k1];
+                if (sgn * v < 0) {
+                  const int i2 = col[k1];
+                  if (cf[i2] > 0) {
+                    const int pos = find_sorted(myc, len, i2);
+                    if (pos >= 0) myv[pos] = __dadd_rn(myv[pos], __dmul_rn(distribute, v));
+                  }
+                }
+              }
+            }
+            __syncwarp();
+          } else {
+            diagonal = __dadd_rn(diagonal, a);
+          }
+        }
+      } else if (c1 != -3) {
+        diagonal = __dadd_rn(diagonal, a);  // weak connection
+      }
+    }
+  }
+  __syncwarp();
+  // phase 2: scale, renumber to coarse ids
+  const double nd = -diagonal;
+  for (int t = lane; t < len; t += 32) {
+    myv[t] = diagonal == 0.0 ? 0.0 : myv[t] / nd;
+    myc[t] = f2c[myc[t]];
   }
 }
 
@@ -472,7 +549,7 @@ __global__ void __launch_bounds__(kSpThreads)
 spgemm_symbolic_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
                        const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
                        int32_t* __restrict__ count, int32_t* __restrict__ ovf_rows,
-                       int32_t* __restrict__ ovf_info /* [0]=count [1]=max ub */) {
+                       int32_t* __restrict__ ovf_info /* [0]=count [1]=max ub */, int min_ub) {
   extern __shared__ unsigned smem_keys[];
   const int g = threadIdx.x / G, gl = threadIdx.x % G;
   const unsigned gm = group_mask(G);
@@ -481,6 +558,7 @@ spgemm_symbolic_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t
   unsigned* keys = smem_keys + (size_t)g * CAP;
   const int b = arp[i], e = arp[i + 1];
   const int ub = row_upper_bound<G>(b, e, gl, gm, acol, brp);
+  if (ub <= min_ub) return;  // counted by the product-list kernel
   if (ub == 0) {
     if (gl == 0) count[i] = 0;
     return;
@@ -589,12 +667,13 @@ spgemm_numeric_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t*
                       const int32_t* __restrict__ bcol, const double* __restrict__ bval,
                       const int32_t* __restrict__ crp, int32_t* __restrict__ ccol,
                       double* __restrict__ cval, int32_t* __restrict__ ovf_rows,
-                      int32_t* __restrict__ ovf_info) {
+                      int32_t* __restrict__ ovf_info, int min_ub) {
   extern __shared__ unsigned char smem_raw[];
   const int g = threadIdx.x / G, gl = threadIdx.x % G;
   const unsigned gm = group_mask(G);
   const int64_t i = (int64_t)blockIdx.x * (kSpThreads / G) + g;
   if (i >= n) return;
+  if (min_ub >= 0 && row_upper_bound<G>(arp[i], arp[i + 1], gl, gm, acol, brp) <= min_ub) return;
   const int out_b = crp[i], out_n = crp[i + 1] - out_b;
   if (out_n == 0) return;
   int lgH = ceil_log2(2 * out_n);
@@ -635,8 +714,165 @@ spgemm_numeric_global_kernel(const int32_t* __restrict__ ovf_rows, int novf, int
   }
 }
 
+// ---------------------------------------------------------------------------
+// Product-list path for C = A*B with short B rows (A*P).  One warp per row:
+//  * the lanes take one entry k of A's row each and append their products
+//    (column, a_ik*b_kc) to a shared-memory list at offsets given by a warp
+//    prefix sum of the B-row lengths, so the list is in ascending k;
+//  * the distinct columns are found by inserting the list into a small hash
+//    table (parallel, order-free) and every product remembers its slot;
+//  * the list is then scanned once, lane L accumulating the products whose slot
+//    is congruent to L mod 32: no two lanes share a slot and every C(i,c) sums in
+//    ascending k -- bit-identical to the oracle -- without a barrier per k;
+//  * occupied slots are compacted to the output in slot order.  The result row
+//    is NOT sorted by column: it is only used as the inner operand T of
+//    R*(A*P), whose value does not depend on T's column order.
+// Rows with more than LCAP products are left to the generic hash kernels.
+// ---------------------------------------------------------------------------
+constexpr int kListWarps = 4;
+
+template <int LCAP>
+struct ListSmem {
+  unsigned keys[2 * LCAP];
+  double acc[2 * LCAP];
+  double lv[LCAP];
+  int lc[LCAP];
+};
+
+// builds the product list of row i; returns ub (total products), or -1 if > LCAP
+template <int LCAP, bool NUMERIC>
+__device__ __forceinline__ int list_build(ListSmem<LCAP>& sm, int b, int e, int lane,
+                                          const int32_t* __restrict__ acol, const double* __restrict__ aval,
+                                          const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
+                                          const double* __restrict__ bval) {
+  const unsigned full = 0xffffffffu;
+  int ub = 0;
+  for (int kb = b; kb < e; kb += 32) {
+    const int k = kb + lane;
+    int l = 0;
+    if (k < e) {
+      const int kk = acol[k];
+      l = brp[kk + 1] - brp[kk];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) l += __shfl_xor_sync(full, l, d);
+    ub += l;
+  }
+  if (ub > LCAP) return -1;
+  int base = 0;
+  for (int kb = b; kb < e; kb += 32) {
+    const int k = kb + lane;
+    int bb = 0, l = 0;
+    double a = 0.0;
+    if (k < e) {
+      const int kk = acol[k];
+      bb = brp[kk];
+      l = brp[kk + 1] - bb;
+      if (NUMERIC) a = aval[k];
+    }
+    int incl = l;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(full, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int off = base + incl - l;
+    for (int m = 0; m < l; ++m) {
+      sm.lc[off + m] = bcol[bb + m];
+      if (NUMERIC) sm.lv[off + m] = __dmul_rn(a, bval[bb + m]);
+    }
+    base += __shfl_sync(full, incl, 31);
+  }
+  return ub;
+}
+
+template <int LCAP>
+__global__ void __launch_bounds__(kListWarps * 32)
+spgemm_list_symbolic_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
+                            const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
+                            int32_t* __restrict__ count, int32_t* __restrict__ big_rows) {
+  extern __shared__ __align__(16) unsigned char list_raw[];
+  ListSmem<LCAP>& sm = reinterpret_cast<ListSmem<LCAP>*>(list_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * kListWarps + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int ub = list_build<LCAP, false>(sm, arp[i], arp[i + 1], lane, acol, nullptr, brp, bcol, nullptr);
+  if (ub < 0) {
+    if (lane == 0) {
+      count[i] = 0;
+      atomicAdd(big_rows, 1);
+    }
+    return;
+  }
+  int lgH = ceil_log2(2 * ub);
+  if (lgH < 5) lgH = 5;
+  const int H = 1 << lgH;
+  for (int t = lane; t < H; t += 32) sm.keys[t] = kEmpty;
+  __syncwarp();
+  int cnt = 0;
+  for (int t = lane; t < ub; t += 32) cnt += hash_insert(sm.keys, H, lgH, (unsigned)sm.lc[t]) > 0 ? 1 : 0;
+  cnt = group_sum<32>(cnt, 0xffffffffu);
+  if (lane == 0) count[i] = cnt;
+}
+
+template <int LCAP>
+__global__ void __launch_bounds__(kListWarps * 32)
+spgemm_list_numeric_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
+                           const double* __restrict__ aval, const int32_t* __restrict__ brp,
+                           const int32_t* __restrict__ bcol, const double* __restrict__ bval,
+                           const int32_t* __restrict__ crp, int32_t* __restrict__ ccol,
+                           double* __restrict__ cval) {
+  extern __shared__ __align__(16) unsigned char list_raw[];
+  ListSmem<LCAP>& sm = reinterpret_cast<ListSmem<LCAP>*>(list_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  const int64_t i = (int64_t)blockIdx.x * kListWarps + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int ub = list_build<LCAP, true>(sm, arp[i], arp[i + 1], lane, acol, aval, brp, bcol, bval);
+  if (ub <= 0) return;  // empty, or left to the generic kernels
+  int lgH = ceil_log2(2 * ub);
+  if (lgH < 5) lgH = 5;
+  const int H = 1 << lgH;
+  for (int t = lane; t < H; t += 32) {
+    sm.keys[t] = kEmpty;
+    sm.acc[t] = 0.0;
+  }
+  __syncwarp();
+  // slot of every product (parallel, order-free)
+  for (int t = lane; t < ub; t += 32) {
+    const unsigned key = (unsigned)sm.lc[t];
+    int h = hash_slot(key, lgH);
+    for (;;) {
+      const unsigned old = atomicCAS(&sm.keys[h], kEmpty, key);
+      if (old == kEmpty || old == key) break;
+      h = (h + 1) & (H - 1);
+    }
+    sm.lc[t] = h;
+  }
+  __syncwarp();
+  // ordered accumulation: lane owns the slots congruent to it mod 32
+  for (int t = 0; t < ub; ++t) {
+    const int h = sm.lc[t];
+    if ((h & 31) == lane) sm.acc[h] = __dadd_rn(sm.acc[h], sm.lv[t]);
+  }
+  __syncwarp();
+  // compaction in slot order
+  int out = crp[i];
+  for (int tb = 0; tb < H; tb += 32) {
+    const unsigned key = sm.keys[tb + lane];
+    const bool occ = key != kEmpty;
+    const unsigned om = __ballot_sync(full, occ);
+    if (occ) {
+      const int w = out + __popc(om & ((1u << lane) - 1u));
+      ccol[w] = (int)key;
+      cval[w] = sm.acc[tb + lane];
+    }
+    out += __popc(om);
+  }
+}
+
 template <int G, int CAP_SYM, int CAP_NUM>
-static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C) {
+static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, int list_cap = 0) {
   const int64_t n = A.n;
   C.n = n;
   C.ncols = B.ncols;
@@ -650,12 +886,41 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
   const double in_bytes = 12.0 * A.nnz + 4.0 * A.n + 12.0 * B.nnz + 4.0 * B.n;
   const int fb_blocks = ctx->sm_count * 2;
   const int fb_warps = fb_blocks * kSpThreads / 32;
-  {
+  const int min_ub = list_cap > 0 ? list_cap : -1;
+  bool run_generic = true;
+  const unsigned lgrid = (unsigned)div_up(n, kListWarps);
+  if (list_cap > 0) {
+    DevBuf<int32_t> big;
+    AMGB_TRY(big.alloc_zero(ctx, 1));
+    if (list_cap == 128) {
+      auto k = spgemm_list_symbolic_kernel<128>;
+      const size_t sm = sizeof(ListSmem<128>) * kListWarps;
+      AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, k, lgrid, kListWarps * 32, sm, n, A.rp.p, A.col.p, B.rp.p, B.col.p,
+                  count.p, big.p);
+    } else if (list_cap == 256) {
+      auto k = spgemm_list_symbolic_kernel<256>;
+      const size_t sm = sizeof(ListSmem<256>) * kListWarps;
+      AMGB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, k, lgrid, kListWarps * 32, sm, n, A.rp.p, A.col.p, B.rp.p, B.col.p,
+                  count.p, big.p);
+    } else {
+      auto k = spgemm_list_symbolic_kernel<512>;
+      const size_t sm = sizeof(ListSmem<512>) * kListWarps;
+      AMGB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, k, lgrid, kListWarps * 32, sm, n, A.rp.p, A.col.p, B.rp.p, B.col.p,
+                  count.p, big.p);
+    }
+    AMGB_CHECK_LAUNCH(ctx);
+    int32_t nbig = 0;
+    AMGB_TRY(read_i32(ctx, big.p, &nbig));
+    run_generic = nbig > 0;
+  }
+  if (run_generic) {
     auto kern = spgemm_symbolic_kernel<G, CAP_SYM>;
     const size_t smem = sizeof(unsigned) * (size_t)kGroups * CAP_SYM;
     AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, kern, grid, kSpThreads, smem, n, A.rp.p, A.col.p, B.rp.p, B.col.p,
-                count.p, ovf_rows.p, ovf_info.p);
+                count.p, ovf_rows.p, ovf_info.p, min_ub);
     AMGB_CHECK_LAUNCH(ctx);
     int32_t* info = (int32_t*)ctx->pinned;
     AMGB_CUDA(ctx, cudaMemcpyAsync(info, ovf_info.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -680,12 +945,34 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
   AMGB_TRY(C.col.alloc(ctx, nnz));
   AMGB_TRY(C.val.alloc(ctx, nnz));
   AMGB_CUDA(ctx, cudaMemsetAsync(ovf_info.p, 0, 2 * sizeof(int32_t), ctx->stream));
-  {
+  if (list_cap > 0) {
+    const double bytes = in_bytes + 12.0 * nnz + 4.0 * n;
+    if (list_cap == 128) {
+      auto k = spgemm_list_numeric_kernel<128>;
+      const size_t sm = sizeof(ListSmem<128>) * kListWarps;
+      AMGB_LAUNCH(ctx, F_SPGEMM, bytes, k, lgrid, kListWarps * 32, sm, n, A.rp.p, A.col.p, A.val.p, B.rp.p,
+                  B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p);
+    } else if (list_cap == 256) {
+      auto k = spgemm_list_numeric_kernel<256>;
+      const size_t sm = sizeof(ListSmem<256>) * kListWarps;
+      AMGB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      AMGB_LAUNCH(ctx, F_SPGEMM, bytes, k, lgrid, kListWarps * 32, sm, n, A.rp.p, A.col.p, A.val.p, B.rp.p,
+                  B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p);
+    } else {
+      auto k = spgemm_list_numeric_kernel<512>;
+      const size_t sm = sizeof(ListSmem<512>) * kListWarps;
+      AMGB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      AMGB_LAUNCH(ctx, F_SPGEMM, bytes, k, lgrid, kListWarps * 32, sm, n, A.rp.p, A.col.p, A.val.p, B.rp.p,
+                  B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p);
+    }
+    AMGB_CHECK_LAUNCH(ctx);
+  }
+  if (run_generic) {
     auto kern = spgemm_numeric_kernel<G, CAP_NUM>;
     const size_t smem = (sizeof(unsigned) + sizeof(double)) * (size_t)kGroups * CAP_NUM;
     AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes + 12.0 * nnz + 4.0 * n, kern, grid, kSpThreads, smem, n, A.rp.p, A.col.p,
-                A.val.p, B.rp.p, B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p, ovf_rows.p, ovf_info.p);
+                A.val.p, B.rp.p, B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p, ovf_rows.p, ovf_info.p, min_ub);
     AMGB_CHECK_LAUNCH(ctx);
     int32_t* info = (int32_t*)ctx->pinned;
     AMGB_CUDA(ctx, cudaMemcpyAsync(info, ovf_info.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -707,10 +994,17 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
   return AMGB_OK;
 }
 
-static int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C) {
+// sorted = false: the caller does not need ascending columns (inner operand of R*(A*P))
+static int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, bool sorted) {
+  const double avg_a = A.n > 0 ? double(A.nnz) / double(A.n) : 0.0;
   const double avg_b = B.n > 0 ? double(B.nnz) / double(B.n) : 0.0;
-  if (avg_b <= 8.0) return spgemm_impl<8, 1024, 512>(ctx, A, B, C);
-  return spgemm_impl<32, 4096, 2048>(ctx, A, B, C);
+  int list_cap = 0;
+  if (!sorted && avg_b <= 8.0) {
+    const double est = 2.5 * avg_a * avg_b;
+    list_cap = est <= 128.0 ? 128 : (est <= 256.0 ? 256 : 512);
+  }
+  if (avg_b <= 8.0) return spgemm_impl<8, 1024, 512>(ctx, A, B, C, list_cap);
+  return spgemm_impl<32, 4096, 2048>(ctx, A, B, C, list_cap);
 }
 
 // deal.II forwards theta / max_row_sum to PETSc through std::to_string (6 decimals)
@@ -794,18 +1088,22 @@ int build_hierarchy(amgb_precond* P) {
   for (int level = 0;; ++level) {
     Level& L = P->lv[level];
     const int64_t n = L.A.n;
+    ctx->cur_level = level;
     if (level == d.max_levels - 1 || n <= d.max_coarse_size) break;
     const unsigned grid = (unsigned)div_up(n, kBlock);
     DevBuf<int32_t> has_strong;
+    DevBuf<double> diagv;
     AMGB_TRY(L.mask.alloc(ctx, L.A.nnz));
     AMGB_TRY(has_strong.alloc(ctx, n));
+    AMGB_TRY(diagv.alloc(ctx, n));
     AMGB_TRY(L.cf.alloc(ctx, n));
     AMGB_LAUNCH(ctx, F_STRENGTH, 13.0 * L.A.nnz + 8.0 * n, strength_kernel, grid, kBlock, 0, n, L.A.rp.p,
-                L.A.col.p, L.A.val.p, P->theta_eff, P->mrs_eff, L.mask.p, has_strong.p);
+                L.A.col.p, L.A.val.p, P->theta_eff, P->mrs_eff, L.mask.p, has_strong.p, diagv.p);
     AMGB_CHECK_LAUNCH(ctx);
     AMGB_TRY(coarsen_pmis(ctx, L.A, L.mask.p, has_strong.p, L.cf.p));
     // coarse numbering: ascending fine index of the C points
-    DevBuf<int32_t> flag, f2c;
+    DevBuf<int32_t> flag;
+    DevBuf<int32_t>& f2c = L.f2c;
     AMGB_TRY(flag.alloc(ctx, n));
     AMGB_TRY(f2c.alloc(ctx, n + 1));
     AMGB_LAUNCH(ctx, F_INTERP, 8.0 * n, cpoint_flag_kernel, grid, kBlock, 0, n, L.cf.p, flag.p);
@@ -816,6 +1114,7 @@ int build_hierarchy(amgb_precond* P) {
       // coarsening stalled: this level is the coarsest
       L.mask.release();
       L.cf.release();
+      L.f2c.release();
       break;
     }
     L.n_coarse = nc;
@@ -834,16 +1133,16 @@ int build_hierarchy(amgb_precond* P) {
     AMGB_TRY(L.P.col.alloc(ctx, nnzp));
     AMGB_TRY(L.P.val.alloc(ctx, nnzp));
     AMGB_LAUNCH(ctx, F_INTERP, 13.0 * L.A.nnz + 12.0 * nnzp + 16.0 * n, interp_fill_kernel,
-                (unsigned)div_up(n, 128), 128, 0, n, L.A.rp.p, L.A.col.p, L.A.val.p, L.mask.p, L.cf.p, f2c.p,
-                L.P.rp.p, L.P.col.p, L.P.val.p);
+                (unsigned)div_up(n * 32, kBlock), kBlock, 0, n, L.A.rp.p, L.A.col.p, L.A.val.p, L.mask.p, L.cf.p, f2c.p,
+                diagv.p, L.P.rp.p, L.P.col.p, L.P.val.p);
     AMGB_CHECK_LAUNCH(ctx);
     AMGB_TRY(transpose_csr(ctx, L.P, L.R));
     // Galerkin product A_c = R (A P)
     DeviceCsr T;
-    AMGB_TRY(spgemm(ctx, L.A, L.P, T));
+    AMGB_TRY(spgemm(ctx, L.A, L.P, T, false));
     P->lv.emplace_back();
     Level& Lc = P->lv[level + 1];
-    AMGB_TRY(spgemm(ctx, P->lv[level].R, T, Lc.A));
+    AMGB_TRY(spgemm(ctx, P->lv[level].R, T, Lc.A, true));
     if (!d.keep_setup_intermediates) P->lv[level].mask.release();
   }
   P->st_rows.clear();
@@ -854,6 +1153,7 @@ int build_hierarchy(amgb_precond* P) {
     P->st_nnz.push_back(L.A.nnz);
     P->st_nnzP.push_back(L.P.nnz);
   }
+  ctx->cur_level = 0;
   AMGB_TRY(finish_solve_setup(P));
   AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return AMGB_OK;

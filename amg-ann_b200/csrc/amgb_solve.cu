@@ -1,6 +1,7 @@
-// Solve phase: CSR SpMV family with fused epilogues (plain, residual,
-// Jacobi-type C/F half sweep, SpMV+dot, prolong-correct), the V(1,1) cycle
-// driver, the dense coarsest-grid solve and PCG with device-resident scalars.
+// Solve phase: SELL-32 operators in a C/F-permuted numbering, SpMV family with
+// fused epilogues (plain, residual, Jacobi-type C/F half sweep, SpMV+dot,
+// prolong-correct), the V(1,1) cycle driver captured in a CUDA graph, the dense
+// coarsest-grid solve and PCG with device-resident scalars.
 //
 // Reference semantics being replaced (all inside hypre/PETSc):
 //   hypre_ParCSRMatrixMatvec{,T}, hypre_BoomerAMGRelax (types 0 / 18 with C/F
@@ -8,8 +9,16 @@
 //   hypre_GaussElimSolve, KSPSolve_CG driven by deal.II's SolverControl;
 //   call sites ref common/amg_solver.h:48,54.
 //
-// Every kernel here is HBM-bound; algorithmic bytes per launch follow
-// SURVEY.md 8(d) and are passed to AMGB_LAUNCH for the roofline report.
+// Layout (DESIGN.md "Solve-phase layout"): on every level the unknowns are
+// renumbered C points first (ascending), then F points (ascending).  Operators
+// are stored as SELL-32: a warp owns 32 consecutive rows, entry j of the 32 rows
+// is one contiguous 256 B (values) + 128 B (columns) segment, so every matrix
+// load is a full-line coalesced request and there is no row reduction.  A C/F
+// half sweep is then a contiguous slice range with no idle lanes, and the second
+// half sweep reads the freshly relaxed set from the output buffer through a
+// split-source gather (col < n_C ? x_lo : x_hi), which removes all full-vector
+// copies.  All kernels are HBM-bound; algorithmic bytes per launch follow
+// SURVEY.md 8(d) (defined on plain CSR) and go to the roofline report.
 #include <cmath>
 #include <cstring>
 
@@ -18,82 +27,15 @@
 namespace amgb {
 
 constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
 
 // ---------------------------------------------------------------------------
-// CSR row kernel: LANES threads cooperate on one row, coalesced val/col loads,
-// shuffle reduction, epilogue functor decides what to do with (row, A_row . x).
+// Plain CSR SpMV on the user's matrix (amgb_matrix_vmult, parity tests only).
 // ---------------------------------------------------------------------------
-struct EpiStore {
-  double* y;
-  __device__ bool active(int64_t) const { return true; }
-  __device__ void store(int64_t row, double s) const { y[row] = s; }
-  __device__ void skip(int64_t) const {}
-};
-
-struct EpiResidual {  // r = f - A u
-  const double* f;
-  double* r;
-  __device__ bool active(int64_t) const { return true; }
-  __device__ void store(int64_t row, double s) const { r[row] = f[row] - s; }
-  __device__ void skip(int64_t) const {}
-};
-
-struct EpiAdd {  // u += P e
-  double* u;
-  __device__ bool active(int64_t) const { return true; }
-  __device__ void store(int64_t row, double s) const { u[row] += s; }
-  __device__ void skip(int64_t) const {}
-};
-
-// Jacobi-type half sweep, out-of-place: rows with cf == pts (or all rows if
-// pts == 0) get out = u + w (f - A u) inv_relax, the others are copied.
-struct EpiJacobi {
-  const double* f;
-  const double* u;
-  const double* inv_relax;
-  const int32_t* cf;  // -3 counts as -1 (end of hypre_BoomerAMGBuildInterp)
-  double* out;
-  double w;
-  int pts;
-  __device__ bool active(int64_t row) const {
-    if (pts == 0) return true;
-    const int c = cf[row];
-    return pts > 0 ? c > 0 : c < 0;
-  }
-  __device__ void store(int64_t row, double s) const {
-    out[row] = u[row] + w * (f[row] - s) * inv_relax[row];
-  }
-  __device__ void skip(int64_t row) const { out[row] = u[row]; }
-};
-
-template <int LANES, class Epi>
-__global__ void __launch_bounds__(kBlock)
-csr_rows_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
-                const double* __restrict__ val, const double* __restrict__ x, Epi epi) {
-  const int64_t row = ((int64_t)blockIdx.x * kBlock + threadIdx.x) / LANES;
-  const int lane = threadIdx.x % LANES;
-  double s = 0.0;
-  bool act = false;
-  if (row < n) {
-    act = epi.active(row);
-    if (act) {
-      const int b = rp[row], e = rp[row + 1];
-      for (int k = b + lane; k < e; k += LANES) s += val[k] * x[col[k]];
-    }
-  }
-#pragma unroll
-  for (int d = LANES / 2; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d, LANES);
-  if (lane == 0 && row < n) {
-    if (act) epi.store(row, s); else epi.skip(row);
-  }
-}
-
-// SpMV with fused dot: w = A p and partial[blockIdx] = sum over the block's rows of p_i w_i.
 template <int LANES>
 __global__ void __launch_bounds__(kBlock)
-csr_spmv_dot_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
-                    const double* __restrict__ val, const double* __restrict__ x,
-                    double* __restrict__ y, double* __restrict__ partial) {
+csr_spmv_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y) {
   const int64_t row = ((int64_t)blockIdx.x * kBlock + threadIdx.x) / LANES;
   const int lane = threadIdx.x % LANES;
   double s = 0.0;
@@ -103,109 +45,322 @@ csr_spmv_dot_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __
   }
 #pragma unroll
   for (int d = LANES / 2; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d, LANES);
-  double c = 0.0;
-  if (lane == 0 && row < n) {
-    y[row] = s;
-    c = x[row] * s;
+  if (lane == 0 && row < n) y[row] = s;
+}
+
+int spmv(amgb_ctx* ctx, const DeviceCsr& A, const double* x, double* y, int family) {
+  if (A.n == 0) return AMGB_OK;
+  const double avg = double(A.nnz) / double(A.n);
+  const double bytes = 12.0 * A.nnz + 4.0 * (A.n + 1) + 8.0 * A.ncols + 8.0 * A.n;
+  if (avg <= 12.0) {
+    AMGB_LAUNCH(ctx, family, bytes, csr_spmv_kernel<4>, (unsigned)div_up(A.n * 4, kBlock), kBlock, 0, A.n,
+                A.rp.p, A.col.p, A.val.p, x, y);
+  } else if (avg <= 48.0) {
+    AMGB_LAUNCH(ctx, family, bytes, csr_spmv_kernel<8>, (unsigned)div_up(A.n * 8, kBlock), kBlock, 0, A.n,
+                A.rp.p, A.col.p, A.val.p, x, y);
+  } else {
+    AMGB_LAUNCH(ctx, family, bytes, csr_spmv_kernel<32>, (unsigned)div_up(A.n * 32, kBlock), kBlock, 0, A.n,
+                A.rp.p, A.col.p, A.val.p, x, y);
   }
-  // fixed-tree block reduction (deterministic for a given n)
+  AMGB_CHECK_LAUNCH(ctx);
+  return AMGB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C/F permutation and CSR -> SELL-32 conversion (once per level, end of setup).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+build_perm_kernel(int64_t n, const int32_t* __restrict__ cf, const int32_t* __restrict__ f2c, int nC,
+                  int32_t* __restrict__ perm, int32_t* __restrict__ inv_perm) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  int ni = (int)i;
+  if (cf) {
+    const int rank = f2c[i];  // number of C points before i
+    ni = cf[i] > 0 ? rank : nC + ((int)i - rank);
+  }
+  inv_perm[i] = ni;
+  perm[ni] = (int)i;
+}
+
+// one warp per slice of 32/T rows: width = ceil(longest row / T), in 32-element units
+template <int T>
+__global__ void __launch_bounds__(kBlock)
+sell_width_kernel(int64_t n, int64_t nslices, const int32_t* __restrict__ perm,
+                  const int32_t* __restrict__ rp, int32_t* __restrict__ width) {
+  const int64_t s = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= nslices) return;
+  const int64_t row = s * (32 / T) + lane / T;
+  int len = 0;
+  if (row < n) {
+    const int old = perm ? perm[row] : (int)row;
+    len = rp[old + 1] - rp[old];
+  }
+  len = (len + T - 1) / T;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, d));
+  if (lane == 0) width[s] = len;
+}
+
+template <int T>
+__global__ void __launch_bounds__(kBlock)
+sell_fill_kernel(int64_t n, int64_t ncols, int64_t nslices, const int32_t* __restrict__ perm,
+                 const int32_t* __restrict__ colmap, const int32_t* __restrict__ rp,
+                 const int32_t* __restrict__ col, const double* __restrict__ val,
+                 const int32_t* __restrict__ slice_ptr, int32_t* __restrict__ scol,
+                 double* __restrict__ sval) {
+  const int64_t s = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= nslices) return;
+  const int64_t row = s * (32 / T) + lane / T;
+  const int t = lane % T;
+  int b = 0, len = 0;
+  if (row < n) {
+    const int old = perm ? perm[row] : (int)row;
+    b = rp[old];
+    len = rp[old + 1] - b;
+  }
+  const int w = slice_ptr[s + 1] - slice_ptr[s];
+  const int64_t base = (int64_t)slice_ptr[s] * 32 + lane;
+  const int pad_col = row < ncols ? (int)row : 0;
+  for (int ju = 0; ju < w; ++ju) {
+    const int j = ju * T + t;
+    int c = pad_col;
+    double v = 0.0;
+    if (j < len) {
+      c = col[b + j];
+      if (colmap) c = colmap[c];
+      v = val[b + j];
+    }
+    scol[base + (int64_t)ju * 32] = c;
+    sval[base + (int64_t)ju * 32] = v;
+  }
+}
+
+// lanes per row: 1 on big regular levels (pure streaming, no reduction), more
+// where rows are long or the level is too small to hide a serial row walk
+static int pick_T(const DeviceCsr& A) {
+  const double avg = A.n > 0 ? double(A.nnz) / double(A.n) : 1.0;
+  if (A.n >= (1 << 20) && avg <= 32.0) return 1;
+  if (A.n < 8192) return avg > 2.0 ? 32 : 1;
+  int T = 1;
+  while (T < 32 && T * 8 < avg) T <<= 1;
+  return T;
+}
+
+#define AMGB_DISPATCH_T(T_, CALL)     \
+  switch (T_) {                       \
+    case 1: { constexpr int TT = 1; CALL; } break;   \
+    case 2: { constexpr int TT = 2; CALL; } break;   \
+    case 4: { constexpr int TT = 4; CALL; } break;   \
+    case 8: { constexpr int TT = 8; CALL; } break;   \
+    case 16: { constexpr int TT = 16; CALL; } break; \
+    default: { constexpr int TT = 32; CALL; } break; \
+  }
+
+static int csr_to_sell(amgb_ctx* ctx, const DeviceCsr& A, const int32_t* row_perm, const int32_t* colmap,
+                       Sell& S) {
+  S.n = A.n;
+  S.ncols = A.ncols;
+  S.nnz = A.nnz;
+  S.T = pick_T(A);
+  S.nslices = div_up(A.n * S.T, 32);
+  DevBuf<int32_t> width;
+  AMGB_TRY(width.alloc(ctx, S.nslices));
+  AMGB_TRY(S.slice_ptr.alloc(ctx, S.nslices + 1));
+  const unsigned grid = (unsigned)div_up(S.nslices * 32, kBlock);
+  AMGB_DISPATCH_T(S.T, AMGB_LAUNCH(ctx, F_AUX, 8.0 * A.n, sell_width_kernel<TT>, grid, kBlock, 0, A.n,
+                                   S.nslices, row_perm, A.rp.p, width.p));
+  AMGB_TRY(exclusive_scan_i32(ctx, width.p, S.slice_ptr.p, S.nslices));
+  int32_t total = 0;
+  AMGB_TRY(read_i32(ctx, S.slice_ptr.p + S.nslices, &total));
+  S.padded = (int64_t)total * 32;
+  AMGB_TRY(S.col.alloc(ctx, S.padded));
+  AMGB_TRY(S.val.alloc(ctx, S.padded));
+  AMGB_DISPATCH_T(S.T, AMGB_LAUNCH(ctx, F_AUX, 12.0 * A.nnz + 12.0 * S.padded, sell_fill_kernel<TT>, grid,
+                                   kBlock, 0, A.n, A.ncols, S.nslices, row_perm, colmap, A.rp.p, A.col.p,
+                                   A.val.p, S.slice_ptr.p, S.col.p, S.val.p));
+  AMGB_CHECK_LAUNCH(ctx);
+  return AMGB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// SELL row kernel.  One warp per slice, T lanes per row.  The gather source is
+// split: columns < split come from x_lo, the others from x_hi (the two are the
+// same array for ordinary products).  Epilogue functors decide what happens to
+// (row, A_row . x).
+// ---------------------------------------------------------------------------
+struct EpiStore {
+  double* y;
+  __device__ __forceinline__ void store(int row, double s) const { y[row] = s; }
+};
+
+struct EpiResidual {  // r = f - A u
+  const double* f;
+  double* r;
+  __device__ __forceinline__ void store(int row, double s) const { r[row] = f[row] - s; }
+};
+
+struct EpiAdd {  // u += P e
+  double* u;
+  __device__ __forceinline__ void store(int row, double s) const { u[row] += s; }
+};
+
+struct EpiJacobi {  // out = u_old + w (f - A u) inv_relax  (hypre relax types 0 / 18)
+  const double* f;
+  const double* u_old;
+  const double* inv_relax;
+  double* out;
+  double w;
+  __device__ __forceinline__ void store(int row, double s) const {
+    out[row] = u_old[row] + w * (f[row] - s) * inv_relax[row];
+  }
+};
+
+// STREAM: evict-first loads for operators that are far larger than L2; small
+// levels use plain loads so that they stay L2-resident across V-cycles.
+template <bool STREAM, class V>
+__device__ __forceinline__ V ld_mat(const V* p) {
+  if constexpr (STREAM) return __ldcs(p);
+  else return __ldg(p);
+}
+
+template <bool STREAM>
+__device__ __forceinline__ double sell_lane_dot(int w, int64_t base, const int32_t* __restrict__ col,
+                                                const double* __restrict__ val,
+                                                const double* __restrict__ x_lo,
+                                                const double* __restrict__ x_hi, int split) {
+  double s0 = 0.0, s1 = 0.0;
+  int j = 0;
+  // two independent accumulators, 4 loads in flight per array
+  for (; j + 4 <= w; j += 4) {
+    const int64_t p = base + (int64_t)j * 32;
+    const int c0 = ld_mat<STREAM>(col + p), c1 = ld_mat<STREAM>(col + p + 32),
+              c2 = ld_mat<STREAM>(col + p + 64), c3 = ld_mat<STREAM>(col + p + 96);
+    const double v0 = ld_mat<STREAM>(val + p), v1 = ld_mat<STREAM>(val + p + 32),
+                 v2 = ld_mat<STREAM>(val + p + 64), v3 = ld_mat<STREAM>(val + p + 96);
+    const double x0 = c0 < split ? x_lo[c0] : x_hi[c0];
+    const double x1 = c1 < split ? x_lo[c1] : x_hi[c1];
+    const double x2 = c2 < split ? x_lo[c2] : x_hi[c2];
+    const double x3 = c3 < split ? x_lo[c3] : x_hi[c3];
+    s0 += v0 * x0;
+    s1 += v1 * x1;
+    s0 += v2 * x2;
+    s1 += v3 * x3;
+  }
+  for (; j < w; ++j) {
+    const int64_t p = base + (int64_t)j * 32;
+    const int c = ld_mat<STREAM>(col + p);
+    const double v = ld_mat<STREAM>(val + p);
+    s0 += v * (c < split ? x_lo[c] : x_hi[c]);
+  }
+  return s0 + s1;
+}
+
+template <int T, class Epi>
+__global__ void __launch_bounds__(kBlock)
+sell_rows_kernel(int s_begin, int s_end, int row_lo, int row_hi, const int32_t* __restrict__ slice_ptr,
+                 const int32_t* __restrict__ col, const double* __restrict__ val,
+                 const double* __restrict__ x_lo, const double* __restrict__ x_hi, int split, Epi epi) {
+  const int s = s_begin + (int)(((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5);
+  if (s >= s_end) return;
+  const int lane = threadIdx.x & 31;
+  const int row = s * (32 / T) + lane / T;
+  const bool act = row >= row_lo && row < row_hi;
+  double sum = 0.0;
+  if (act) {
+    const int sp = slice_ptr[s];
+    const int w = slice_ptr[s + 1] - sp;
+    sum = sell_lane_dot<T == 1>(w, (int64_t)sp * 32 + lane, col, val, x_lo, x_hi, split);
+  }
+#pragma unroll
+  for (int d = T / 2; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if (act && lane % T == 0) epi.store(row, sum);
+}
+
+// w = A p fused with the partial dot (p, w): one partial per block, fixed tree.
+template <int T>
+__global__ void __launch_bounds__(kBlock)
+sell_spmv_dot_kernel(int nslices, int n, const int32_t* __restrict__ slice_ptr,
+                     const int32_t* __restrict__ col, const double* __restrict__ val,
+                     const double* __restrict__ x, double* __restrict__ y, double* __restrict__ partial) {
+  const int s = (int)(((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  const int row = s * (32 / T) + lane / T;
+  const bool act = s < nslices && row < n;
+  double sum = 0.0;
+  if (act) {
+    const int sp = slice_ptr[s];
+    const int w = slice_ptr[s + 1] - sp;
+    sum = sell_lane_dot<T == 1>(w, (int64_t)sp * 32 + lane, col, val, x, x, 0);
+  }
+#pragma unroll
+  for (int d = T / 2; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  double c = 0.0;
+  if (act && lane % T == 0) {
+    y[row] = sum;
+    c = x[row] * sum;
+  }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
-  __shared__ double ws[kBlock / 32];
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __shared__ double ws[kWarps];
+  if (lane == 0) ws[threadIdx.x >> 5] = c;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < kBlock / 32; ++i) t += ws[i];
+    for (int i = 0; i < kWarps; ++i) t += ws[i];
     partial[blockIdx.x] = t;
   }
 }
 
-static int pick_lanes(const DeviceCsr& A) {
-  const double avg = A.n > 0 ? double(A.nnz) / double(A.n) : 1.0;
-  int lanes = 1;
-  while (lanes < 32 && lanes * 4 < avg) lanes <<= 1;
-  return lanes;
-}
-
 template <class Epi>
-static int launch_rows(amgb_ctx* ctx, const DeviceCsr& A, const double* x, Epi epi, int family,
-                       double bytes) {
-  if (A.n == 0) return AMGB_OK;
-  const int lanes = pick_lanes(A);
-  const unsigned grid = (unsigned)div_up(A.n * lanes, kBlock);
-  switch (lanes) {
-    case 1: AMGB_LAUNCH(ctx, family, bytes, (csr_rows_kernel<1, Epi>), grid, kBlock, 0, A.n, A.rp.p, A.col.p, A.val.p, x, epi); break;
-    case 2: AMGB_LAUNCH(ctx, family, bytes, (csr_rows_kernel<2, Epi>), grid, kBlock, 0, A.n, A.rp.p, A.col.p, A.val.p, x, epi); break;
-    case 4: AMGB_LAUNCH(ctx, family, bytes, (csr_rows_kernel<4, Epi>), grid, kBlock, 0, A.n, A.rp.p, A.col.p, A.val.p, x, epi); break;
-    case 8: AMGB_LAUNCH(ctx, family, bytes, (csr_rows_kernel<8, Epi>), grid, kBlock, 0, A.n, A.rp.p, A.col.p, A.val.p, x, epi); break;
-    case 16: AMGB_LAUNCH(ctx, family, bytes, (csr_rows_kernel<16, Epi>), grid, kBlock, 0, A.n, A.rp.p, A.col.p, A.val.p, x, epi); break;
-    default: AMGB_LAUNCH(ctx, family, bytes, (csr_rows_kernel<32, Epi>), grid, kBlock, 0, A.n, A.rp.p, A.col.p, A.val.p, x, epi); break;
-  }
-  AMGB_CHECK_LAUNCH(ctx);
-  return AMGB_OK;
-}
-
-// plain CSR bytes, rp = 4 B.
-static double csr_bytes(const DeviceCsr& A) { return 12.0 * A.nnz + 4.0 * (A.n + 1); }
-
-int spmv(amgb_ctx* ctx, const DeviceCsr& A, const double* x, double* y, int family) {
-  return launch_rows(ctx, A, x, EpiStore{y}, family, csr_bytes(A) + 8.0 * A.ncols + 8.0 * A.n);
-}
-
-static int spmv_dot(amgb_ctx* ctx, const DeviceCsr& A, const double* x, double* y, double* partial,
-                    int64_t* nblocks) {
-  const int lanes = pick_lanes(A);
-  const unsigned grid = (unsigned)div_up(A.n * lanes, kBlock);
-  *nblocks = grid;
-  const double bytes = csr_bytes(A) + 16.0 * A.n;
-  switch (lanes) {
-    case 1: AMGB_LAUNCH(ctx, F_SPMV, bytes, csr_spmv_dot_kernel<1>, grid, kBlock, 0, A.n, A.rp.p, A.col.p, A.val.p, x, y, partial); break;
-    case 2: AMGB_LAUNCH(ctx, F_SPMV, bytes, csr_spmv_dot_kernel<2>, grid, kBlock, 0, A.n, A.rp.p, A.col.p, A.val.p, x, y, partial); break;
-    case 4: AMGB_LAUNCH(ctx, F_SPMV, bytes, csr_spmv_dot_kernel<4>, grid, kBlock, 0, A.n, A.rp.p, A.col.p, A.val.p, x, y, partial); break;
-    case 8: AMGB_LAUNCH(ctx, F_SPMV, bytes, csr_spmv_dot_kernel<8>, grid, kBlock, 0, A.n, A.rp.p, A.col.p, A.val.p, x, y, partial); break;
-    case 16: AMGB_LAUNCH(ctx, F_SPMV, bytes, csr_spmv_dot_kernel<16>, grid, kBlock, 0, A.n, A.rp.p, A.col.p, A.val.p, x, y, partial); break;
-    default: AMGB_LAUNCH(ctx, F_SPMV, bytes, csr_spmv_dot_kernel<32>, grid, kBlock, 0, A.n, A.rp.p, A.col.p, A.val.p, x, y, partial); break;
-  }
+static int launch_sell(amgb_ctx* ctx, const Sell& S, int row_lo, int row_hi, const double* x_lo,
+                       const double* x_hi, int split, Epi epi, int family, double bytes) {
+  if (row_hi <= row_lo) return AMGB_OK;
+  const int rps = 32 / S.T;
+  const int s_begin = row_lo / rps, s_end = (int)div_up(row_hi, rps);
+  const unsigned grid = (unsigned)div_up((int64_t)(s_end - s_begin) * 32, kBlock);
+  AMGB_DISPATCH_T(S.T, AMGB_LAUNCH(ctx, family, bytes, (sell_rows_kernel<TT, Epi>), grid, kBlock, 0, s_begin,
+                                   s_end, row_lo, row_hi, S.slice_ptr.p, S.col.p, S.val.p, x_lo, x_hi, split,
+                                   epi));
   AMGB_CHECK_LAUNCH(ctx);
   return AMGB_OK;
 }
 
 // ---------------------------------------------------------------------------
-// Level auxiliaries: diagonal position, 1/l1 or 1/diag for the smoother.
+// Level auxiliaries in the new numbering: 1/l1 or 1/diag for the smoother.
 // ---------------------------------------------------------------------------
+template <int T>
 __global__ void __launch_bounds__(kBlock)
-level_aux_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
-                 const double* __restrict__ val, int relax_type, double* __restrict__ inv_relax) {
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
+sell_aux_kernel(int nslices, int n, const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ col,
+                const double* __restrict__ val, int relax_type, double* __restrict__ inv_relax) {
+  const int s = (int)(((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (s >= nslices) return;
+  const int row = s * (32 / T) + lane / T;
   double diag = 0.0, l1 = 0.0;
-  for (int k = rp[i]; k < rp[i + 1]; ++k) {
-    const double v = val[k];
-    if (col[k] == i) diag = v;
-    l1 += fabs(v);
+  if (row < n) {
+    const int sp = slice_ptr[s];
+    const int w = slice_ptr[s + 1] - sp;
+    const int64_t base = (int64_t)sp * 32 + lane;
+    for (int j = 0; j < w; ++j) {
+      const double v = val[base + (int64_t)j * 32];
+      if (col[base + (int64_t)j * 32] == row && v != 0.0) diag = v;
+      l1 += fabs(v);
+    }
   }
-  double inv = 0.0;  // rows with a zero diagonal are skipped (hypre_BoomerAMGRelax)
-  if (diag != 0.0) inv = relax_type == 18 ? 1.0 / l1 : 1.0 / diag;
-  inv_relax[i] = inv;
-}
-
-int level_aux(amgb_precond* P, int level) {
-  amgb_ctx* ctx = P->ctx;
-  Level& L = P->lv[level];
-  const int64_t n = L.A.n;
-  AMGB_TRY(L.inv_relax.alloc(ctx, n));
-  // one smoother family per hierarchy: down == up is enforced at initialize
-  AMGB_LAUNCH(ctx, F_AUX, csr_bytes(L.A) + 8.0 * n, level_aux_kernel, (unsigned)div_up(n, kBlock), kBlock,
-              0, n, L.A.rp.p, L.A.col.p, L.A.val.p, P->relax_down, L.inv_relax.p);
-  AMGB_CHECK_LAUNCH(ctx);
-  AMGB_TRY(L.tmp.alloc(ctx, n));
-  if (level > 0) {
-    AMGB_TRY(L.u.alloc(ctx, n));
-    AMGB_TRY(L.f.alloc(ctx, n));
+#pragma unroll
+  for (int d = T / 2; d > 0; d >>= 1) {
+    diag += __shfl_xor_sync(0xffffffffu, diag, d);  // exactly one lane holds the diagonal
+    l1 += __shfl_xor_sync(0xffffffffu, l1, d);
   }
-  return AMGB_OK;
+  if (row < n && lane % T == 0) {
+    double inv = 0.0;  // rows with a zero diagonal are skipped (hypre_BoomerAMGRelax)
+    if (diag != 0.0) inv = relax_type == 18 ? 1.0 / l1 : 1.0 / diag;
+    inv_relax[row] = inv;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -279,7 +434,8 @@ static int setup_dense(amgb_precond* P) {
   if (P->relax_coarse != 9 || C.A.n > kMaxDenseCoarse) return AMGB_OK;
   const int64_t n = C.A.n;
   AMGB_TRY(P->dense.alloc_zero(ctx, n * n));
-  AMGB_LAUNCH(ctx, F_COARSE, csr_bytes(C.A), csr_to_dense_kernel, (unsigned)div_up(n, 128), 128, 0, n,
+  // the coarsest level has no C/F splitting: its permutation is the identity
+  AMGB_LAUNCH(ctx, F_COARSE, 12.0 * C.A.nnz, csr_to_dense_kernel, (unsigned)div_up(n, 128), 128, 0, n,
               C.A.rp.p, C.A.col.p, C.A.val.p, P->dense.p);
   AMGB_LAUNCH(ctx, F_COARSE, 8.0 * n * n, dense_factor_kernel, 1, kBlock, 0, (int)n, P->dense.p);
   AMGB_CHECK_LAUNCH(ctx);
@@ -287,82 +443,194 @@ static int setup_dense(amgb_precond* P) {
   return AMGB_OK;
 }
 
+int finish_solve_setup(amgb_precond* P) {
+  amgb_ctx* ctx = P->ctx;
+  const int nl = (int)P->lv.size();
+  // 1. permutations (C points first) on every level
+  for (int l = 0; l < nl; ++l) {
+    Level& L = P->lv[l];
+    const int64_t n = L.A.n;
+    AMGB_TRY(L.perm.alloc(ctx, n));
+    AMGB_TRY(L.inv_perm.alloc(ctx, n));
+    AMGB_LAUNCH(ctx, F_AUX, 16.0 * n, build_perm_kernel, (unsigned)div_up(n, kBlock), kBlock, 0, n,
+                (const int32_t*)L.cf.p, (const int32_t*)L.f2c.p, (int)L.n_coarse, L.perm.p, L.inv_perm.p);
+    AMGB_CHECK_LAUNCH(ctx);
+  }
+  // 2. operators: A (rows, cols permuted), P (fine rows, coarse cols), R = P^T
+  for (int l = 0; l < nl; ++l) {
+    Level& L = P->lv[l];
+    const int64_t n = L.A.n;
+    ctx->cur_level = l;
+    AMGB_TRY(csr_to_sell(ctx, L.A, L.perm.p, L.inv_perm.p, L.As));
+    if (l + 1 < nl) {
+      Level& C = P->lv[l + 1];
+      AMGB_TRY(csr_to_sell(ctx, L.P, L.perm.p, C.inv_perm.p, L.Ps));
+      AMGB_TRY(csr_to_sell(ctx, L.R, C.perm.p, L.inv_perm.p, L.Rs));
+      L.R.rp.release();
+      L.R.col.release();
+      L.R.val.release();
+      if (!P->data.keep_setup_intermediates) {
+        L.P.rp.release();
+        L.P.col.release();
+        L.P.val.release();
+      }
+    }
+    AMGB_TRY(L.inv_relax.alloc(ctx, n));
+    AMGB_DISPATCH_T(L.As.T, AMGB_LAUNCH(ctx, F_AUX, L.As.csr_bytes() + 8.0 * n, sell_aux_kernel<TT>,
+                                        (unsigned)div_up(L.As.nslices * 32, kBlock), kBlock, 0,
+                                        (int)L.As.nslices, (int)n, L.As.slice_ptr.p, L.As.col.p, L.As.val.p,
+                                        P->relax_down, L.inv_relax.p));
+    AMGB_CHECK_LAUNCH(ctx);
+    AMGB_TRY(L.tmp.alloc(ctx, n));
+    if (l > 0) {
+      AMGB_TRY(L.u.alloc(ctx, n));
+      AMGB_TRY(L.f.alloc(ctx, n));
+    }
+    L.f2c.release();
+  }
+  ctx->cur_level = 0;
+  return setup_dense(P);
+}
+
 // ---------------------------------------------------------------------------
 // V-cycle (hypre_BoomerAMGCycle): pre-smooth, residual, restrict, recurse,
 // prolong-correct, post-smooth; C/F ordering per hypre_BoomerAMGRelaxIF.
 // ---------------------------------------------------------------------------
-struct CycleVecs {
-  double* u;
-  const double* f;
-};
-
-static int half_sweep(amgb_precond* P, Level& L, const double* f, const double* u_in, double* u_out,
-                      int pts) {
-  const bool fine = &L == &P->lv[0];
-  EpiJacobi epi{f, u_in, L.inv_relax.p, L.cf.p, u_out, P->data.relax_weight, L.cf.p ? pts : 0};
-  // bytes: the rows touched; for a C/F half sweep roughly the selected share.
-  // Reported as the full-sweep formula of SURVEY.md 8(d) scaled by the share of
-  // rows relaxed is not knowable cheaply; count vectors fully and the matrix by
-  // share = n_coarse/n (C) or 1 - n_coarse/n (F).
-  double share = 1.0;
-  if (epi.pts != 0 && L.A.n > 0) {
-    const double c = double(L.n_coarse) / double(L.A.n);
-    share = pts > 0 ? c : 1.0 - c;
-  }
-  const double bytes = share * csr_bytes(L.A) + 32.0 * L.A.n;
-  return launch_rows(P->ctx, L.A, u_in, epi, fine ? F_SMOOTH_L0 : F_SMOOTH, bytes);
-}
-
-// One hypre_BoomerAMGRelaxIF call; the result ends in `u` (L.tmp is scratch).
-static int relax_if(amgb_precond* P, Level& L, const double* f, double* u, int cycle_param) {
-  if (P->data.relax_order == 1 && cycle_param < 3 && L.cf.p) {
-    const int p0 = cycle_param < 2 ? 1 : -1;
-    AMGB_TRY(half_sweep(P, L, f, u, L.tmp.p, p0));
-    AMGB_TRY(half_sweep(P, L, f, L.tmp.p, u, -p0));
+// One hypre_BoomerAMGRelaxIF call.  Reads `u`, leaves the relaxed vector in `out`.
+static int relax_if(amgb_precond* P, int l, const double* f, const double* u, double* out, int cycle_param) {
+  Level& L = P->lv[l];
+  amgb_ctx* ctx = P->ctx;
+  ctx->cur_level = l;
+  const int n = (int)L.A.n, nC = (int)L.n_coarse;
+  const double w = P->data.relax_weight;
+  const int fam = l == 0 ? F_SMOOTH_L0 : F_SMOOTH;
+  const double mat = L.As.csr_bytes();
+  EpiJacobi epi{f, u, L.inv_relax.p, out, w};
+  if (P->data.relax_order == 1 && cycle_param < 3 && nC > 0 && nC < n) {
+    const double share_c = double(nC) / double(n);
+    // half sweep = the rows touched + 4 vectors on those rows
+    const double bytes_c = share_c * mat + 32.0 * nC, bytes_f = (1.0 - share_c) * mat + 32.0 * (n - nC);
+    if (cycle_param < 2) {  // down: C then F
+      AMGB_TRY(launch_sell(ctx, L.As, 0, nC, u, u, 0, epi, fam, bytes_c));
+      AMGB_TRY(launch_sell(ctx, L.As, nC, n, out, u, nC, epi, fam, bytes_f));
+    } else {  // up: F then C
+      AMGB_TRY(launch_sell(ctx, L.As, nC, n, u, u, 0, epi, fam, bytes_f));
+      AMGB_TRY(launch_sell(ctx, L.As, 0, nC, u, out, nC, epi, fam, bytes_c));
+    }
   } else {
-    AMGB_TRY(half_sweep(P, L, f, u, L.tmp.p, 0));
-    AMGB_CUDA(P->ctx, cudaMemcpyAsync(u, L.tmp.p, L.A.n * sizeof(double), cudaMemcpyDeviceToDevice,
-                                      P->ctx->stream));
+    AMGB_TRY(launch_sell(ctx, L.As, 0, n, u, u, 0, epi, fam, mat + 32.0 * n));
   }
   return AMGB_OK;
 }
 
-static int cycle(amgb_precond* P, int l, double* u, const double* f) {
+// On entry `u` holds the initial guess, `alt` is scratch of the same size; on
+// exit the result is in `u` (the two pointers are swapped as needed).
+static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double* f) {
   amgb_ctx* ctx = P->ctx;
   Level& L = P->lv[l];
   const int nl = (int)P->lv.size();
+  const int n = (int)L.A.n;
   if (l == nl - 1) {
     if (P->relax_coarse == 9 && P->dense_ok) {
-      AMGB_LAUNCH(ctx, F_COARSE, 8.0 * L.A.n * L.A.n, dense_solve_kernel, 1, kBlock, 0, (int)L.A.n,
-                  P->dense.p, f, u);
+      AMGB_LAUNCH(ctx, F_COARSE, 8.0 * n * n, dense_solve_kernel, 1, kBlock, 0, n, P->dense.p, f, u);
       AMGB_CHECK_LAUNCH(ctx);
     } else {
       const unsigned sweeps = P->data.n_sweeps_coarse ? P->data.n_sweeps_coarse : 1u;
-      for (unsigned s = 0; s < sweeps; ++s) AMGB_TRY(relax_if(P, L, f, u, 3));
+      for (unsigned s = 0; s < sweeps; ++s) {
+        AMGB_TRY(relax_if(P, l, f, u, alt, 3));
+        std::swap(u, alt);
+      }
     }
     return AMGB_OK;
   }
-  for (unsigned s = 0; s < P->data.n_sweeps; ++s) AMGB_TRY(relax_if(P, L, f, u, 1));
-  // residual into tmp, restriction into the coarse rhs
-  AMGB_TRY(launch_rows(ctx, L.A, u, EpiResidual{f, L.tmp.p}, l == 0 ? F_RESIDUAL_L0 : F_RESIDUAL,
-                       csr_bytes(L.A) + 24.0 * L.A.n));
+  for (unsigned s = 0; s < P->data.n_sweeps; ++s) {
+    AMGB_TRY(relax_if(P, l, f, u, alt, 1));
+    std::swap(u, alt);
+  }
+  // residual into the scratch buffer, restriction into the coarse rhs
+  ctx->cur_level = l;
+  AMGB_TRY(launch_sell(ctx, L.As, 0, n, u, u, 0, EpiResidual{f, alt}, l == 0 ? F_RESIDUAL_L0 : F_RESIDUAL,
+                       L.As.csr_bytes() + 24.0 * n));
   Level& C = P->lv[l + 1];
-  AMGB_TRY(launch_rows(ctx, L.R, L.tmp.p, EpiStore{C.f.p}, l == 0 ? F_RESTRICT_L0 : F_RESTRICT,
-                       csr_bytes(L.R) + 8.0 * L.A.n + 8.0 * C.A.n));
-  AMGB_CUDA(ctx, cudaMemsetAsync(C.u.p, 0, C.A.n * sizeof(double), ctx->stream));
-  AMGB_TRY(cycle(P, l + 1, C.u.p, C.f.p));
-  if (P->data.w_cycle && l + 1 < nl - 1) AMGB_TRY(cycle(P, l + 1, C.u.p, C.f.p));
-  AMGB_TRY(launch_rows(ctx, L.P, C.u.p, EpiAdd{u}, l == 0 ? F_PROLONG_L0 : F_PROLONG,
-                       csr_bytes(L.P) + 8.0 * C.A.n + 16.0 * L.A.n));
-  for (unsigned s = 0; s < P->data.n_sweeps; ++s) AMGB_TRY(relax_if(P, L, f, u, 2));
+  const int ncrs = (int)C.A.n;
+  AMGB_TRY(launch_sell(ctx, L.Rs, 0, ncrs, alt, alt, 0, EpiStore{C.f.p}, l == 0 ? F_RESTRICT_L0 : F_RESTRICT,
+                       L.Rs.csr_bytes() + 8.0 * n + 8.0 * ncrs));
+  AMGB_CUDA(ctx, cudaMemsetAsync(C.u.p, 0, (size_t)ncrs * sizeof(double), ctx->stream));
+  double* cu = C.u.p;
+  double* calt = C.tmp.p;
+  AMGB_TRY(cycle(P, l + 1, cu, calt, C.f.p));
+  if (P->data.w_cycle && l + 1 < nl - 1) AMGB_TRY(cycle(P, l + 1, cu, calt, C.f.p));
+  ctx->cur_level = l;
+  AMGB_TRY(launch_sell(ctx, L.Ps, 0, n, cu, cu, 0, EpiAdd{u}, l == 0 ? F_PROLONG_L0 : F_PROLONG,
+                       L.Ps.csr_bytes() + 8.0 * ncrs + 16.0 * n));
+  for (unsigned s = 0; s < P->data.n_sweeps; ++s) {
+    AMGB_TRY(relax_if(P, l, f, u, alt, 2));
+    std::swap(u, alt);
+  }
   return AMGB_OK;
 }
 
-int vcycle_apply(amgb_precond* P, double* z_dev, const double* r_dev) {
+static int vcycle_launches(amgb_precond* P, double* z, const double* r) {
   amgb_ctx* ctx = P->ctx;
-  AMGB_CUDA(ctx, cudaMemsetAsync(z_dev, 0, P->lv[0].A.n * sizeof(double), ctx->stream));
+  const size_t n = (size_t)P->lv[0].A.n;
+  AMGB_CUDA(ctx, cudaMemsetAsync(z, 0, n * sizeof(double), ctx->stream));
+  double* u = z;
+  double* alt = P->lv[0].tmp.p;
   const unsigned iters = P->data.max_iter ? P->data.max_iter : 1u;
-  for (unsigned it = 0; it < iters; ++it) AMGB_TRY(cycle(P, 0, z_dev, r_dev));
+  for (unsigned it = 0; it < iters; ++it) AMGB_TRY(cycle(P, 0, u, alt, r));
+  if (u != z) AMGB_CUDA(ctx, cudaMemcpyAsync(z, u, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->cur_level = 0;
+  return AMGB_OK;
+}
+
+int vcycle_apply(amgb_precond* P, double* z, const double* r) {
+  amgb_ctx* ctx = P->ctx;
+  if (!P->use_graph || ctx->timers_on) return vcycle_launches(P, z, r);
+  if (P->vcycle_graph && (P->graph_z != z || P->graph_r != r)) destroy_solve_state(P);
+  if (!P->vcycle_graph) {
+    // capture the whole cycle once: on the small levels it is launch-latency bound
+    const int64_t before = ctx->launches;
+    int64_t fam_before[F_COUNT];
+    double bytes_before[F_COUNT];
+    for (int f = 0; f < F_COUNT; ++f) {
+      fam_before[f] = ctx->fam_launches[f];
+      bytes_before[f] = ctx->fam_bytes[f];
+    }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      (void)cudaGetLastError();
+      P->use_graph = false;
+      return vcycle_launches(P, z, r);
+    }
+    const int rc = vcycle_launches(P, z, r);
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    P->graph_kernels = ctx->launches - before;
+    for (int f = 0; f < F_COUNT; ++f) {
+      P->graph_fam_launches[f] = ctx->fam_launches[f] - fam_before[f];
+      P->graph_fam_bytes[f] = ctx->fam_bytes[f] - bytes_before[f];
+      ctx->fam_launches[f] = fam_before[f];
+      ctx->fam_bytes[f] = bytes_before[f];
+    }
+    ctx->launches = before;
+    if (rc != AMGB_OK || ce != cudaSuccess || !graph ||
+        cudaGraphInstantiate(&P->vcycle_graph, graph, 0) != cudaSuccess) {
+      (void)cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      P->vcycle_graph = nullptr;
+      P->use_graph = false;
+      if (rc != AMGB_OK) return rc;
+      return vcycle_launches(P, z, r);
+    }
+    cudaGraphDestroy(graph);
+    P->graph_z = z;
+    P->graph_r = r;
+  }
+  AMGB_CUDA(ctx, cudaGraphLaunch(P->vcycle_graph, ctx->stream));
+  ctx->launches += P->graph_kernels;
+  for (int f = 0; f < F_COUNT; ++f) {
+    ctx->fam_launches[f] += P->graph_fam_launches[f];
+    ctx->fam_bytes[f] += P->graph_fam_bytes[f];
+  }
   return AMGB_OK;
 }
 
@@ -371,11 +639,8 @@ void destroy_solve_state(amgb_precond* P) {
     cudaGraphExecDestroy(P->vcycle_graph);
     P->vcycle_graph = nullptr;
   }
-}
-
-int finish_solve_setup(amgb_precond* P) {
-  for (int l = 0; l < (int)P->lv.size(); ++l) AMGB_TRY(level_aux(P, l));
-  return setup_dense(P);
+  P->graph_z = nullptr;
+  P->graph_r = nullptr;
 }
 
 // ---------------------------------------------------------------------------
@@ -397,7 +662,7 @@ __device__ __forceinline__ double block_sum(double c, double* ws) {
   double t = 0.0;
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int i = 0; i < kBlock / 32; ++i) t += ws[i];
+    for (int i = 0; i < kWarps; ++i) t += ws[i];
   }
   __syncthreads();
   return t;  // valid in thread 0
@@ -406,7 +671,7 @@ __device__ __forceinline__ double block_sum(double c, double* ws) {
 __global__ void __launch_bounds__(kBlock)
 dot2_kernel(int64_t n, const double* __restrict__ z, const double* __restrict__ r,
             double* __restrict__ pzz, double* __restrict__ pzr) {
-  __shared__ double ws[kBlock / 32];
+  __shared__ double ws[kWarps];
   const int64_t base = (int64_t)blockIdx.x * kDotChunk;
   double a = 0.0, b = 0.0;
 #pragma unroll
@@ -439,7 +704,7 @@ __device__ double ordered_sum(const double* __restrict__ p, int64_t m, double* w
 
 __global__ void __launch_bounds__(kBlock)
 finalize_alpha_kernel(const double* __restrict__ partial, int64_t m, double* sc, int* fl) {
-  __shared__ double ws[kBlock / 32];
+  __shared__ double ws[kWarps];
   const double pw = ordered_sum(partial, m, ws);
   if (threadIdx.x == 0) {
     sc[2] = pw;
@@ -456,7 +721,7 @@ finalize_alpha_kernel(const double* __restrict__ partial, int64_t m, double* sc,
 __global__ void __launch_bounds__(kBlock)
 finalize_beta_kernel(const double* __restrict__ pzz, const double* __restrict__ pzr, int64_t m,
                      double* sc, int* fl, double* hist, int64_t hist_cap, double abs_tol, int first) {
-  __shared__ double ws[kBlock / 32];
+  __shared__ double ws[kWarps];
   const double zz = ordered_sum(pzz, m, ws);
   const double zr = ordered_sum(pzr, m, ws);
   if (threadIdx.x == 0) {
@@ -499,18 +764,38 @@ axpy2_kernel(int64_t n, const double* __restrict__ p, const double* __restrict__
   r[i] -= alpha * w[i];
 }
 
+// out[k] = in[perm[k]]  /  out[perm[k]] = in[k]
+__global__ void __launch_bounds__(kBlock)
+gather_kernel(int64_t n, const int32_t* __restrict__ perm, const double* __restrict__ in,
+              double* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (k < n) out[k] = in[perm[k]];
+}
+
+__global__ void __launch_bounds__(kBlock)
+scatter_kernel(int64_t n, const int32_t* __restrict__ perm, const double* __restrict__ in,
+               double* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (k < n) out[perm[k]] = in[k];
+}
+
 struct PcgFlags {
   int done, iters, status, pad;
 };
 
-static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x, const double* b, amgb_precond* P,
-                     int64_t max_steps, double abs_tol, double* res_hist, int64_t hist_cap,
+// x, b in the USER numbering (device); everything inside runs in the permuted one.
+static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const double* b_user,
+                     amgb_precond* P, int64_t max_steps, double abs_tol, double* res_hist, int64_t hist_cap,
                      int64_t* n_iters) {
   const int64_t n = A->A.n;
-  if (P->lv.empty() || P->lv[0].A.n != n)
+  if (P->lv.empty() || P->lv[0].A.n != n || P->mat != A)
     return set_error(ctx, AMGB_ERR_BAD_ARG, "preconditioner was initialised for another matrix");
-  DevBuf<double> r, z, p, w, sc, hist, pa, pb;
+  Level& L0 = P->lv[0];
+  const Sell& As = L0.As;
+  DevBuf<double> x, b, r, z, p, w, sc, hist, pa, pb;
   DevBuf<int> fl;
+  AMGB_TRY(x.alloc(ctx, n));
+  AMGB_TRY(b.alloc(ctx, n));
   AMGB_TRY(r.alloc(ctx, n));
   AMGB_TRY(z.alloc(ctx, n));
   AMGB_TRY(p.alloc(ctx, n));
@@ -522,13 +807,16 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x, const doubl
   if (cap < 1) cap = 1;
   AMGB_TRY(hist.alloc_zero(ctx, cap));
   const int64_t dot_blocks = div_up(n, kDotChunk);
-  const int64_t spmv_blocks = div_up(n * 32, kBlock);  // upper bound for any LANES
+  const int64_t spmv_blocks = div_up(As.nslices * 32, kBlock);
   AMGB_TRY(pa.alloc(ctx, spmv_blocks > dot_blocks ? spmv_blocks : dot_blocks));
   AMGB_TRY(pb.alloc(ctx, dot_blocks));
   const unsigned vgrid = (unsigned)div_up(n, kBlock);
 
+  AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, gather_kernel, vgrid, kBlock, 0, n, L0.perm.p, x_user, x.p);
+  AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, gather_kernel, vgrid, kBlock, 0, n, L0.perm.p, b_user, b.p);
   // r = b - A x ; z = M^{-1} r ; dp = ||z|| ; beta = (z, r)
-  AMGB_TRY(launch_rows(ctx, A->A, x, EpiResidual{b, r.p}, F_RESIDUAL, csr_bytes(A->A) + 24.0 * n));
+  AMGB_TRY(launch_sell(ctx, As, 0, (int)n, x.p, x.p, 0, EpiResidual{b.p, r.p}, F_RESIDUAL_L0,
+                       As.csr_bytes() + 24.0 * n));
   AMGB_TRY(vcycle_apply(P, z.p, r.p));
   AMGB_LAUNCH(ctx, F_VEC, 16.0 * n, dot2_kernel, (unsigned)dot_blocks, kBlock, 0, n, z.p, r.p, pa.p, pb.p);
   AMGB_LAUNCH(ctx, F_VEC, 16.0 * dot_blocks, finalize_beta_kernel, 1, kBlock, 0, pa.p, pb.p, dot_blocks,
@@ -544,10 +832,12 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x, const doubl
   int64_t it = 0;
   while (!hf->done && it < max_steps) {
     AMGB_LAUNCH(ctx, F_VEC, 24.0 * n, update_p_kernel, vgrid, kBlock, 0, n, z.p, p.p, sc.p, it == 0 ? 1 : 0);
-    int64_t nb = 0;
-    AMGB_TRY(spmv_dot(ctx, A->A, p.p, w.p, pa.p, &nb));
-    AMGB_LAUNCH(ctx, F_VEC, 8.0 * nb, finalize_alpha_kernel, 1, kBlock, 0, pa.p, nb, sc.p, fl.p);
-    AMGB_LAUNCH(ctx, F_VEC, 48.0 * n, axpy2_kernel, vgrid, kBlock, 0, n, p.p, w.p, x, r.p, sc.p);
+    AMGB_DISPATCH_T(As.T, AMGB_LAUNCH(ctx, F_SPMV, As.csr_bytes() + 16.0 * n, sell_spmv_dot_kernel<TT>,
+                                      (unsigned)spmv_blocks, kBlock, 0, (int)As.nslices, (int)n,
+                                      As.slice_ptr.p, As.col.p, As.val.p, p.p, w.p, pa.p));
+    AMGB_LAUNCH(ctx, F_VEC, 8.0 * spmv_blocks, finalize_alpha_kernel, 1, kBlock, 0, pa.p, spmv_blocks, sc.p,
+                fl.p);
+    AMGB_LAUNCH(ctx, F_VEC, 48.0 * n, axpy2_kernel, vgrid, kBlock, 0, n, p.p, w.p, x.p, r.p, sc.p);
     AMGB_CHECK_LAUNCH(ctx);
     AMGB_TRY(vcycle_apply(P, z.p, r.p));
     AMGB_LAUNCH(ctx, F_VEC, 16.0 * n, dot2_kernel, (unsigned)dot_blocks, kBlock, 0, n, z.p, r.p, pa.p, pb.p);
@@ -560,16 +850,43 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x, const doubl
   *n_iters = hf->iters;
   const int status = hf->status;
   const bool done = hf->done != 0;
+  const int iters = hf->iters;
+  AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, scatter_kernel, vgrid, kBlock, 0, n, L0.perm.p, x.p, x_user);
+  AMGB_CHECK_LAUNCH(ctx);
   if (res_hist && hist_cap > 0) {
-    int64_t k = hf->iters + 1;
+    int64_t k = iters + 1;
     if (k > cap) k = cap;
     AMGB_CUDA(ctx, cudaMemcpyAsync(res_hist, hist.p, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
-  if (status != 0) return set_error(ctx, status, "PCG breakdown at iteration %d", hf->iters);
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // the graph was captured for this call's (z, r): drop it before they are freed
+  destroy_solve_state(P);
+  if (status != 0) return set_error(ctx, status, "PCG breakdown at iteration %d", iters);
   if (!done)
     return set_error(ctx, AMGB_ERR_NO_CONVERGENCE, "PCG did not reach %g in %lld steps", abs_tol,
                      (long long)max_steps);
+  return AMGB_OK;
+}
+
+// z_user = M^{-1} r_user with both vectors in the user numbering (device)
+static int vmult_user(amgb_precond* P, double* dst, const double* src) {
+  amgb_ctx* ctx = P->ctx;
+  Level& L0 = P->lv[0];
+  const int64_t n = L0.A.n;
+  const unsigned vgrid = (unsigned)div_up(n, kBlock);
+  DevBuf<double> r, z;
+  AMGB_TRY(r.alloc(ctx, n));
+  AMGB_TRY(z.alloc(ctx, n));
+  AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, gather_kernel, vgrid, kBlock, 0, n, L0.perm.p, src, r.p);
+  AMGB_CHECK_LAUNCH(ctx);
+  const bool g = P->use_graph;
+  P->use_graph = false;  // one-off buffers: not worth a capture
+  const int rc = vcycle_apply(P, z.p, r.p);
+  P->use_graph = g;
+  AMGB_TRY(rc);
+  AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, scatter_kernel, vgrid, kBlock, 0, n, L0.perm.p, z.p, dst);
+  AMGB_CHECK_LAUNCH(ctx);
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return AMGB_OK;
 }
 
@@ -582,7 +899,7 @@ extern "C" {
 int amgb_precond_vmult_device(amgb_precond* P, double* dst_device, const double* src_device) {
   if (!P || !dst_device || !src_device) return AMGB_ERR_BAD_ARG;
   cudaSetDevice(P->ctx->device);
-  return vcycle_apply(P, dst_device, src_device);
+  return vmult_user(P, dst_device, src_device);
 }
 
 int amgb_precond_vmult(amgb_precond* P, double* dst, const double* src) {
@@ -594,7 +911,7 @@ int amgb_precond_vmult(amgb_precond* P, double* dst, const double* src) {
   AMGB_TRY(d.alloc(ctx, n));
   AMGB_TRY(s.alloc(ctx, n));
   AMGB_CUDA(ctx, cudaMemcpyAsync(s.p, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  AMGB_TRY(vcycle_apply(P, d.p, s.p));
+  AMGB_TRY(vmult_user(P, d.p, s.p));
   AMGB_CUDA(ctx, cudaMemcpyAsync(dst, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return AMGB_OK;

@@ -222,7 +222,10 @@ def run_gpu(args):
     n, nnz = s.n, s.nnz
     rp32 = s.rowptr32()
 
-    stream = torch.cuda.current_stream()
+    # a real (non-legacy) stream shared by torch and the library, so the CUDA
+    # events below are recorded on the stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx = ab.Context(local, stream.cuda_stream)
 
     # ---- device-resident inputs for `value`

@@ -219,6 +219,10 @@ int amgb_timer_count(void);
 const char* amgb_timer_name(int family);
 int amgb_ctx_get_timer(amgb_ctx* ctx, int family, double* total_ms, int64_t* launches,
                        double* algorithmic_bytes);
+/* Same, restricted to the launches made for one multigrid level (0 = finest; only
+ * launches timed while the timers were enabled are counted here). */
+int amgb_ctx_get_timer_level(amgb_ctx* ctx, int family, int level, double* total_ms,
+                             int64_t* launches, double* algorithmic_bytes);
 
 #ifdef __cplusplus
 }

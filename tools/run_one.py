@@ -18,6 +18,7 @@ ap.add_argument("--contrast", type=float, default=6.0)
 ap.add_argument("--mode", default="full")
 ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--max-steps", type=int, default=0)
+ap.add_argument("--timers", action="store_true", help="per-family CUDA-event timers (disables the V-cycle graph)")
 args = ap.parse_args()
 
 epsv = ab.gen.checkerboard_epsv(4, 3, args.contrast)
@@ -28,6 +29,9 @@ data = ab.AdditionalData(True, args.theta, 0.9, 0, True, relaxation_type_up=R.l1
 ctx = ab.Context(0)
 A = ab.SparseMatrix(ctx, s.rowptr32(), s.col, s.val)
 for rep in range(args.repeat):
+    if args.timers and rep == args.repeat - 1:
+        ctx.enable_timers(True)
+        ctx.reset_timers()
     if args.mode == "pool":
         vm = ab.ViewMaker(75).make_view(A)
         print(f"pool: device {vm.t_device_us:.1f} us, count sum {vm.count.sum()}")
@@ -52,3 +56,17 @@ for rep in range(args.repeat):
     print(msg)
     P.close()
 print("kernel launches", ctx.kernel_launches())
+if args.timers:
+    t = ctx.timers()
+    tot = sum(v["ms"] for v in t.values())
+    for k, v in sorted(t.items(), key=lambda kv: -kv[1]["ms"]):
+        if v["launches"]:
+            print(f"  {k:12s} {v['ms']:9.2f} ms {100 * v['ms'] / tot:5.1f}% {v['launches']:6d} launches "
+                  f"{v['bytes'] / max(v['ms'], 1e-9) / 1e6:8.1f} GB/s  {1e3 * v['ms'] / v['launches']:8.1f} us/launch")
+    print("per level (ms | GB/s | launches):")
+    for fam, rows in ctx.level_timers().items():
+        if fam.endswith("_l0"):
+            continue
+        cells = [f"L{l}: {r['ms']:.2f}|{r['bytes'] / max(r['ms'], 1e-9) / 1e6:.0f}|{r['launches']}"
+                 for l, r in enumerate(rows) if r["launches"]]
+        print(f"  {fam:10s} " + "  ".join(cells))

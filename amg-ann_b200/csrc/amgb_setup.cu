@@ -13,7 +13,9 @@
 //    accumulators) are accumulated in the same sequential order as the oracle:
 //    ascending column within a row, ascending k for C(i,c) = sum_k a_ik b_kc.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "amgb_internal.cuh"
 
@@ -1174,6 +1176,7 @@ int amgb_precond_initialize(amgb_ctx* ctx, const amgb_matrix* A, const amgb_boom
   P->ctx = ctx;
   P->mat = A;
   P->data = *data;
+  if (std::getenv("AMGB_NO_GRAPH")) P->use_graph = false;  // profiling aid: plain launches
   const int rc = build_hierarchy(P);
   if (rc != AMGB_OK) {
     cudaStreamSynchronize(ctx->stream);

@@ -394,35 +394,118 @@ __global__ void __launch_bounds__(kBlock) dense_factor_kernel(int n, double* __r
   }
 }
 
+// Large coarsest grids (coarsening stalled): one elimination step k as two
+// grid-wide kernels.  Every entry still receives its updates in ascending k with
+// two roundings each, so the factors equal the sequential loop bit for bit.
 __global__ void __launch_bounds__(kBlock)
+dense_step_factors_kernel(int n, int k, double* __restrict__ M, double* __restrict__ fac) {
+  const int j = k + 1 + blockIdx.x * kBlock + threadIdx.x;
+  if (j >= n) return;
+  const double pivot = M[(int64_t)k * n + k];
+  double f = 0.0;
+  if (pivot != 0.0) {
+    const double mjk = M[(int64_t)j * n + k];
+    if (mjk != 0.0) {
+      f = mjk / pivot;
+      M[(int64_t)j * n + k] = f;
+    }
+  }
+  fac[j] = f;
+}
+
+__global__ void __launch_bounds__(kBlock)
+dense_step_update_kernel(int n, int k, double* __restrict__ M, const double* __restrict__ fac) {
+  const int m = k + 1 + blockIdx.x * kBlock + threadIdx.x;
+  const int j = k + 1 + blockIdx.y;
+  if (m >= n) return;
+  const double f = fac[j];
+  if (f != 0.0)
+    M[(int64_t)j * n + m] = __dsub_rn(M[(int64_t)j * n + m], __dmul_rn(f, M[(int64_t)k * n + m]));
+}
+
+// Blocked forward/back substitution with the factors of hypre_gselim: 32-wide
+// diagonal blocks are solved by one warp with shuffles, the panel below/above
+// by one thread per row walking the block's columns in order.  Per entry of x
+// the sequence of updates (ascending k forward, descending k backward, two
+// roundings each) is the sequential one.
+constexpr int kDenseThreads = 512;
+
+__global__ void __launch_bounds__(kDenseThreads)
 dense_solve_kernel(int n, const double* __restrict__ M, const double* __restrict__ f,
                    double* __restrict__ x) {
-  for (int i = threadIdx.x; i < n; i += kBlock) x[i] = f[i];
-  __syncthreads();
-  for (int k = 0; k + 1 < n; ++k) {
-    if (M[(int64_t)k * n + k] != 0.0) {
-      const double xk = x[k];
-      for (int j = k + 1 + threadIdx.x; j < n; j += kBlock) {
-        const double l = M[(int64_t)j * n + k];
-        if (l != 0.0) x[j] = __dsub_rn(x[j], __dmul_rn(l, xk));
+  extern __shared__ double xs[];        // n entries
+  __shared__ double D[32][33];          // current diagonal block
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned full = 0xffffffffu;
+  for (int i = tid; i < n; i += kDenseThreads) xs[i] = f[i];
+  // forward elimination: x[j] -= L[j,k] x[k], k ascending
+  for (int kb = 0; kb < n; kb += 32) {
+    const int kend = min(kb + 32, n), bw = kend - kb;
+    for (int t = tid; t < 32 * 32; t += kDenseThreads) {
+      const int r = t >> 5, c = t & 31;
+      D[r][c] = (r < bw && c < bw) ? M[(int64_t)(kb + r) * n + kb + c] : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double xv = lane < bw ? xs[kb + lane] : 0.0;
+      for (int k = 0; k < bw; ++k) {
+        const double xk = __shfl_sync(full, xv, k);
+        if (D[k][k] != 0.0 && lane > k && lane < bw) {
+          const double l = D[lane][k];
+          if (l != 0.0) xv = __dsub_rn(xv, __dmul_rn(l, xk));
+        }
       }
+      if (lane < bw) xs[kb + lane] = xv;
+    }
+    __syncthreads();
+    for (int j = kend + tid; j < n; j += kDenseThreads) {
+      double lrow[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) lrow[k] = k < bw ? M[(int64_t)j * n + kb + k] : 0.0;
+      double xv = xs[j];
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k < bw && D[k][k] != 0.0 && lrow[k] != 0.0) xv = __dsub_rn(xv, __dmul_rn(lrow[k], xs[kb + k]));
+      xs[j] = xv;
     }
     __syncthreads();
   }
-  for (int k = n - 1; k > 0; --k) {
-    const double d = M[(int64_t)k * n + k];
-    if (d != 0.0) {
-      if (threadIdx.x == 0) x[k] = x[k] / d;
-      __syncthreads();
-      const double xk = x[k];
-      for (int j = threadIdx.x; j < k; j += kBlock) {
-        const double u = M[(int64_t)j * n + k];
-        if (u != 0.0) x[j] = __dsub_rn(x[j], __dmul_rn(xk, u));
-      }
+  // back substitution: x[k] /= U[k,k]; x[j] -= x[k] U[j,k], k descending
+  for (int khi = n; khi > 0;) {
+    const int klo = max(khi - 32, 0), bw = khi - klo;
+    for (int t = tid; t < 32 * 32; t += kDenseThreads) {
+      const int r = t >> 5, c = t & 31;
+      D[r][c] = (r < bw && c < bw) ? M[(int64_t)(klo + r) * n + klo + c] : 0.0;
     }
     __syncthreads();
+    if (warp == 0) {
+      double xv = lane < bw ? xs[klo + lane] : 0.0;
+      for (int k = bw - 1; k >= 0; --k) {
+        const double d = D[k][k];
+        if (d != 0.0 && lane == k) xv = xv / d;
+        const double xk = __shfl_sync(full, xv, k);
+        if (d != 0.0 && lane < k) {
+          const double u = D[lane][k];
+          if (u != 0.0) xv = __dsub_rn(xv, __dmul_rn(xk, u));
+        }
+      }
+      if (lane < bw) xs[klo + lane] = xv;
+    }
+    __syncthreads();
+    for (int j = tid; j < klo; j += kDenseThreads) {
+      double urow[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) urow[k] = k < bw ? M[(int64_t)j * n + klo + k] : 0.0;
+      double xv = xs[j];
+#pragma unroll
+      for (int k = 31; k >= 0; --k)
+        if (k < bw && D[k][k] != 0.0 && urow[k] != 0.0) xv = __dsub_rn(xv, __dmul_rn(xs[klo + k], urow[k]));
+      xs[j] = xv;
+    }
+    __syncthreads();
+    khi = klo;
   }
-  if (threadIdx.x == 0 && n > 0 && M[0] != 0.0) x[0] = x[0] / M[0];
+  for (int i = tid; i < n; i += kDenseThreads) x[i] = xs[i];
 }
 
 constexpr int64_t kMaxDenseCoarse = 1024;  // same limit as the oracle
@@ -437,7 +520,19 @@ static int setup_dense(amgb_precond* P) {
   // the coarsest level has no C/F splitting: its permutation is the identity
   AMGB_LAUNCH(ctx, F_COARSE, 12.0 * C.A.nnz, csr_to_dense_kernel, (unsigned)div_up(n, 128), 128, 0, n,
               C.A.rp.p, C.A.col.p, C.A.val.p, P->dense.p);
-  AMGB_LAUNCH(ctx, F_COARSE, 8.0 * n * n, dense_factor_kernel, 1, kBlock, 0, (int)n, P->dense.p);
+  if (n <= 96) {
+    AMGB_LAUNCH(ctx, F_COARSE, 8.0 * n * n, dense_factor_kernel, 1, kBlock, 0, (int)n, P->dense.p);
+  } else {
+    DevBuf<double> fac;
+    AMGB_TRY(fac.alloc(ctx, n));
+    for (int k = 0; k + 1 < (int)n; ++k) {
+      const int rem = (int)n - k - 1;
+      AMGB_LAUNCH(ctx, F_COARSE, 16.0 * rem, dense_step_factors_kernel, (unsigned)div_up(rem, kBlock), kBlock, 0,
+                  (int)n, k, P->dense.p, fac.p);
+      AMGB_LAUNCH(ctx, F_COARSE, 16.0 * rem * rem, dense_step_update_kernel,
+                  dim3((unsigned)div_up(rem, kBlock), (unsigned)rem), kBlock, 0, (int)n, k, P->dense.p, fac.p);
+    }
+  }
   AMGB_CHECK_LAUNCH(ctx);
   P->dense_ok = true;
   return AMGB_OK;
@@ -532,7 +627,8 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
   const int n = (int)L.A.n;
   if (l == nl - 1) {
     if (P->relax_coarse == 9 && P->dense_ok) {
-      AMGB_LAUNCH(ctx, F_COARSE, 8.0 * n * n, dense_solve_kernel, 1, kBlock, 0, n, P->dense.p, f, u);
+      AMGB_LAUNCH(ctx, F_COARSE, 8.0 * n * n, dense_solve_kernel, 1, kDenseThreads, (size_t)n * sizeof(double), n,
+                  P->dense.p, f, u);
       AMGB_CHECK_LAUNCH(ctx);
     } else {
       const unsigned sweeps = P->data.n_sweeps_coarse ? P->data.n_sweeps_coarse : 1u;

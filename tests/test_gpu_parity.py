@@ -208,3 +208,28 @@ def test_full_size_properties_config1(gpu_ctx):
     assert vm.count.sum() == s.nnz
     assert vm.view.sum() == pytest.approx(s.val.sum(), abs=1e-9 * np.abs(s.val).sum())
     assert vm.max_pp.max() == s.val.max() and vm.max_np.max() == -s.val.min()
+
+
+@pytest.mark.parametrize("m,max_levels", [(12, 2), (16, 3), (12, 1), (6, 2)])
+def test_truncated_hierarchy_dense_or_relaxed_coarsest(gpu_ctx, m, max_levels):
+    """max_levels cuts the hierarchy: the coarsest grid is then large.  <= 1024 rows:
+    Gaussian elimination (grid-parallel factorisation + blocked substitution must
+    reproduce the sequential hypre_gselim order); larger: smoother sweeps."""
+    s = poisson(m, contrast=3.0)
+    A, P, H = _both(gpu_ctx, s, device_data(0.25, max_levels=max_levels))
+    assert P.num_levels == H.num_levels == max_levels
+    r = np.random.default_rng(5).standard_normal(s.n)
+    z = np.empty(s.n)
+    P.vmult(z, r)
+    zo = H.vmult(r)
+    assert np.abs(z - zo).max() <= 1e-11 * np.abs(zo).max()
+    ctl = ab.SolverControl(400, 1e-8)
+    x = s.x0.copy()
+    try:
+        ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+    except ab.NoConvergence:
+        pass
+    rc, xo, nit, hist = H.cg_solve(s.rhs, s.x0, max_steps=400, abs_tol=1e-8)
+    assert abs(ctl.last_step() - nit) <= 1
+    k = min(len(hist), len(ctl.history), 60)
+    assert (np.abs(ctl.history[:k] - hist[:k]) <= 1e-9 * hist[:k]).all()

@@ -226,40 +226,49 @@ __device__ __forceinline__ V ld_mat(const V* p) {
   else return __ldg(p);
 }
 
-template <bool STREAM>
+// SPLIT: columns < split are gathered from x_lo, the others from x_hi (second
+// C/F half sweep); otherwise a single source, one load per entry.
+template <bool STREAM, bool SPLIT>
 __device__ __forceinline__ double sell_lane_dot(int w, int64_t base, const int32_t* __restrict__ col,
                                                 const double* __restrict__ val,
                                                 const double* __restrict__ x_lo,
                                                 const double* __restrict__ x_hi, int split) {
+  constexpr int U = 8;  // entries in flight per lane and array
   double s0 = 0.0, s1 = 0.0;
   int j = 0;
-  // two independent accumulators, 4 loads in flight per array
-  for (; j + 4 <= w; j += 4) {
+  for (; j + U <= w; j += U) {
     const int64_t p = base + (int64_t)j * 32;
-    const int c0 = ld_mat<STREAM>(col + p), c1 = ld_mat<STREAM>(col + p + 32),
-              c2 = ld_mat<STREAM>(col + p + 64), c3 = ld_mat<STREAM>(col + p + 96);
-    const double v0 = ld_mat<STREAM>(val + p), v1 = ld_mat<STREAM>(val + p + 32),
-                 v2 = ld_mat<STREAM>(val + p + 64), v3 = ld_mat<STREAM>(val + p + 96);
-    const double x0 = c0 < split ? x_lo[c0] : x_hi[c0];
-    const double x1 = c1 < split ? x_lo[c1] : x_hi[c1];
-    const double x2 = c2 < split ? x_lo[c2] : x_hi[c2];
-    const double x3 = c3 < split ? x_lo[c3] : x_hi[c3];
-    s0 += v0 * x0;
-    s1 += v1 * x1;
-    s0 += v2 * x2;
-    s1 += v3 * x3;
+    int c[U];
+    double v[U], x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = ld_mat<STREAM>(col + p + u * 32);
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = ld_mat<STREAM>(val + p + u * 32);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double* src = x_hi;
+      if (SPLIT) src = c[u] < split ? x_lo : x_hi;
+      x[u] = src[c[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < U; u += 2) {
+      s0 += v[u] * x[u];
+      s1 += v[u + 1] * x[u + 1];
+    }
   }
   for (; j < w; ++j) {
     const int64_t p = base + (int64_t)j * 32;
     const int c = ld_mat<STREAM>(col + p);
     const double v = ld_mat<STREAM>(val + p);
-    s0 += v * (c < split ? x_lo[c] : x_hi[c]);
+    const double* src = x_hi;
+    if (SPLIT) src = c < split ? x_lo : x_hi;
+    s0 += v * src[c];
   }
   return s0 + s1;
 }
 
-template <int T, class Epi>
-__global__ void __launch_bounds__(kBlock)
+template <int T, bool SPLIT, class Epi>
+__global__ void __launch_bounds__(kBlock, 4)  // <= 64 registers: room for 8 loads in flight per array
 sell_rows_kernel(int s_begin, int s_end, int row_lo, int row_hi, const int32_t* __restrict__ slice_ptr,
                  const int32_t* __restrict__ col, const double* __restrict__ val,
                  const double* __restrict__ x_lo, const double* __restrict__ x_hi, int split, Epi epi) {
@@ -272,7 +281,7 @@ sell_rows_kernel(int s_begin, int s_end, int row_lo, int row_hi, const int32_t* 
   if (act) {
     const int sp = slice_ptr[s];
     const int w = slice_ptr[s + 1] - sp;
-    sum = sell_lane_dot<T == 1>(w, (int64_t)sp * 32 + lane, col, val, x_lo, x_hi, split);
+    sum = sell_lane_dot<T == 1, SPLIT>(w, (int64_t)sp * 32 + lane, col, val, x_lo, x_hi, split);
   }
 #pragma unroll
   for (int d = T / 2; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
@@ -293,7 +302,7 @@ sell_spmv_dot_kernel(int nslices, int n, const int32_t* __restrict__ slice_ptr,
   if (act) {
     const int sp = slice_ptr[s];
     const int w = slice_ptr[s + 1] - sp;
-    sum = sell_lane_dot<T == 1>(w, (int64_t)sp * 32 + lane, col, val, x, x, 0);
+    sum = sell_lane_dot<T == 1, false>(w, (int64_t)sp * 32 + lane, col, val, x, x, 0);
   }
 #pragma unroll
   for (int d = T / 2; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
@@ -322,9 +331,15 @@ static int launch_sell(amgb_ctx* ctx, const Sell& S, int row_lo, int row_hi, con
   const int rps = 32 / S.T;
   const int s_begin = row_lo / rps, s_end = (int)div_up(row_hi, rps);
   const unsigned grid = (unsigned)div_up((int64_t)(s_end - s_begin) * 32, kBlock);
-  AMGB_DISPATCH_T(S.T, AMGB_LAUNCH(ctx, family, bytes, (sell_rows_kernel<TT, Epi>), grid, kBlock, 0, s_begin,
-                                   s_end, row_lo, row_hi, S.slice_ptr.p, S.col.p, S.val.p, x_lo, x_hi, split,
-                                   epi));
+  if (x_lo != x_hi) {
+    AMGB_DISPATCH_T(S.T, AMGB_LAUNCH(ctx, family, bytes, (sell_rows_kernel<TT, true, Epi>), grid, kBlock, 0,
+                                     s_begin, s_end, row_lo, row_hi, S.slice_ptr.p, S.col.p, S.val.p, x_lo,
+                                     x_hi, split, epi));
+  } else {
+    AMGB_DISPATCH_T(S.T, AMGB_LAUNCH(ctx, family, bytes, (sell_rows_kernel<TT, false, Epi>), grid, kBlock, 0,
+                                     s_begin, s_end, row_lo, row_hi, S.slice_ptr.p, S.col.p, S.val.p, x_lo,
+                                     x_hi, split, epi));
+  }
   AMGB_CHECK_LAUNCH(ctx);
   return AMGB_OK;
 }

@@ -72,3 +72,38 @@ def test_reference_harness_runs_unmodified_on_the_device(gpu_ctx, tmp_path):
         assert np.allclose(pres, mine["p_res"], rtol=2e-12, atol=0)
         assert float(f[10]) == pytest.approx(mine["grid"], abs=1e-6)
         assert float(f[11]) == pytest.approx(mine["operator"], abs=1e-6)
+
+
+def test_cpp_datagen_driver_writes_the_reference_csv_schema(gpu_ctx, tmp_path):
+    """amg-ann_b200/host/amgb_datagen (C++ host code on the C ABI) vs the Python mirror."""
+    exe = os.path.join(os.path.dirname(HERE), "amg-ann_b200", "host", "amgb_datagen")
+    out = tmp_path / "stats.csv"
+    r = subprocess.run([exe, "--m", "12", "--pattern-size", "2", "--mode", "3", "--contrast", "3",
+                        "--theta", "0.05,0.96,0.3", "--out", str(out)], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = list(csv.reader(open(out)))
+    assert rows[0][:3] == ["setting", "dim", "ndof"] and rows[0][-3:] == ["t_solve", "niters", "p_res"]
+    s = poisson(12, contrast=3.0)
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    assert len(rows) == 5
+    for row, th in zip(rows[1:], ab.gen.theta_sweep(0.05, 0.96, 0.3)):
+        assert int(row[2]) == s.n
+        f = row[10:]
+        assert float(f[0]) == th
+        x = s.x0.copy()
+        mine = ab.amg_solve(ab.AdditionalData(True, th, 0.9, 0, True), 1e-8, A, s.rhs, x)
+        assert [int(float(v)) for v in f[7].split(",")] == [int(v) for v in mine["nrows"]]
+        assert int(f[13]) == mine["niters"]
+        assert np.array_equal(np.array([float(v) for v in f[14].split(",")]), mine["p_res"])  # %.17e round trip
+    # pooled image mode + several systems over host threads
+    out2 = tmp_path / "views.csv"
+    r = subprocess.run([exe, "--m", "8", "--pattern-size", "2", "--mode", "3", "--seed", "5", "--make-view", "1",
+                        "--view-size", "10", "--systems", "4", "--threads", "2", "--out", str(out2)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = list(csv.reader(open(out2)))
+    assert len(rows) == 5
+    for row in rows[1:]:
+        cnt = np.array([int(float(v)) for v in row[13].split(",")])
+        assert cnt.sum() == (3 * 8 + 1) ** 3 and int(row[11]) == 10

@@ -40,9 +40,9 @@ def test_device_pooling_equals_reference_viewmaker_golden(gpu_ctx, name):
                     reason="oracle/_ref/ref_harness_gpu not built (needs /root/reference at build time)")
 def test_reference_harness_runs_unmodified_on_the_device(gpu_ctx, tmp_path):
     m, ps, mode, contrast, V = 12, 2, 3, 3.0, 20
-    out = tmp_path / "stats.csv"
+    out = tmp_path / "stats.csv"  # relative name: the reference's redirector prepends "./" (redirector.h:30)
     r = subprocess.run([os.path.join(REFDIR, "ref_harness_gpu"), str(m), str(ps), str(mode), str(contrast),
-                        "0.05,0.96,0.3", str(V), str(out)], capture_output=True, text=True, cwd=tmp_path,
+                        "0.05,0.96,0.3", str(V), "stats.csv"], capture_output=True, text=True, cwd=tmp_path,
                        timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     rows = list(csv.reader(open(out)))

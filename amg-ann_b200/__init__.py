@@ -420,6 +420,9 @@ class ViewMaker:
         return self
 
 
+from . import dist  # noqa: E402  (row-partitioned front end; needs the names above)
+
+
 def amg_solve(data, rtol, A, b, x):
     """Python mirror of ref common/amg_solver.h:22-92: timed initialize + timed
     cg.solve, returning the CSV fields as a dict instead of scraping stdout."""

@@ -90,6 +90,13 @@ AMGB_SYMBOLS = [
     "amgb_cg_solve_device", "amgb_make_view", "amgb_ctx_enable_timers",
     "amgb_ctx_reset_timers", "amgb_timer_count", "amgb_timer_name", "amgb_ctx_get_timer",
     "amgb_ctx_get_timer_level",
+    # row-partitioned path
+    "amgb_nccl_unique_id", "amgb_comm_create_nccl", "amgb_local_group_create",
+    "amgb_local_group_destroy", "amgb_comm_create_local", "amgb_comm_destroy", "amgb_comm_rank",
+    "amgb_comm_size", "amgb_dist_matrix_create", "amgb_dist_matrix_destroy",
+    "amgb_dist_precond_initialize", "amgb_dist_cg_solve", "amgb_dist_cg_solve_device",
+    "amgb_dist_precond_level_dims", "amgb_dist_precond_get_cf_marker",
+    "amgb_dist_precond_get_A_rows", "amgb_dist_precond_get_P_rows",
 ]
 
 
@@ -152,5 +159,27 @@ def amgb_lib():
         _sig(L.amgb_timer_name, C.c_char_p, C.c_int)
         _sig(L.amgb_ctx_get_timer, C.c_int, vp, C.c_int, c_f64p, c_i64p, c_f64p)
         _sig(L.amgb_ctx_get_timer_level, C.c_int, vp, C.c_int, C.c_int, c_f64p, c_i64p, c_f64p)
+        _sig(L.amgb_nccl_unique_id, C.c_int, vp, C.c_int)
+        _sig(L.amgb_comm_create_nccl, C.c_int, vp, C.c_int, C.c_int, vp, C.POINTER(vp))
+        _sig(L.amgb_local_group_create, C.c_int, C.c_int, C.POINTER(vp))
+        _sig(L.amgb_local_group_destroy, C.c_int, vp)
+        _sig(L.amgb_comm_create_local, C.c_int, vp, C.c_int, C.POINTER(vp))
+        _sig(L.amgb_comm_destroy, C.c_int, vp)
+        _sig(L.amgb_comm_rank, C.c_int, vp)
+        _sig(L.amgb_comm_size, C.c_int, vp)
+        _sig(L.amgb_dist_matrix_create, C.c_int, vp, vp, C.c_int64, C.c_int64, C.c_int64, c_i64p,
+             c_i32p, c_f64p, C.POINTER(vp))
+        _sig(L.amgb_dist_matrix_destroy, C.c_int, vp)
+        _sig(L.amgb_dist_precond_initialize, C.c_int, vp, vp, C.POINTER(BoomerAMGDataStruct),
+             C.POINTER(vp))
+        _sig(L.amgb_dist_cg_solve, C.c_int, vp, c_f64p, c_f64p, vp, C.c_int64, C.c_double, c_f64p,
+             C.c_int64, c_i64p)
+        _sig(L.amgb_dist_cg_solve_device, C.c_int, vp, vp, vp, vp, C.c_int64, C.c_double, c_f64p,
+             C.c_int64, c_i64p)
+        _sig(L.amgb_dist_precond_level_dims, C.c_int, vp, C.c_int32, c_i64p, c_i64p, c_i64p, c_i64p,
+             c_i64p, c_i64p, c_i64p)
+        _sig(L.amgb_dist_precond_get_cf_marker, C.c_int, vp, C.c_int32, c_i32p)
+        _sig(L.amgb_dist_precond_get_A_rows, C.c_int, vp, C.c_int32, c_i32p, c_i32p, c_f64p)
+        _sig(L.amgb_dist_precond_get_P_rows, C.c_int, vp, C.c_int32, c_i32p, c_i32p, c_f64p)
         _amgb = L
     return _amgb

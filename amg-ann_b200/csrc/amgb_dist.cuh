@@ -1,0 +1,99 @@
+// Row-partitioned (multi-GPU) path: data structures shared by amgb_dist.cu (index
+// spaces, exchange plans, ghost rows, the partitioned setup driver) and amgb_solve.cu
+// (partitioned V-cycle and PCG).  Design: DESIGN.md "Row partition".
+//
+// Every rank owns a contiguous range of global rows on every level.  The setup runs the
+// SAME kernels as the single-device path on the rank's *extended* index space
+//     E = owned points  U  H1 (non-owned columns of owned rows, rows fetched in full)
+//                       U  H2 (non-owned columns of those ghost rows; points only)
+// numbered by ascending global id, so every ordered sum (row sums, interpolation sums,
+// SpGEMM accumulators) sees its terms in the global order and the owned outputs are
+// bit-identical to the single-device ones for any number of ranks.  Per-point state of
+// non-owned points (measures, C/F markers, coarse ids) is refreshed from the owners after
+// every step that changes it.
+#pragma once
+
+#include <vector>
+
+#include "amgb_comm.cuh"
+#include "amgb_internal.cuh"
+
+namespace amgb {
+
+// Who sends what for per-point arrays over one index space of this rank.
+struct HaloPlan {
+  int size = 1, rank = 0;
+  int64_t n_space = 0, own_begin = 0, n_own = 0;
+  std::vector<int64_t> recv_off, recv_cnt;  // per owner: contiguous run of my index space
+  std::vector<int64_t> send_off, send_cnt;  // per peer: run of send_idx
+  DevBuf<int32_t> send_idx;                 // my indices whose values the peers need
+  int64_t send_total = 0, recv_total = 0;
+  DevBuf<char> sendbuf;                     // 8 bytes per entry
+};
+
+// Rows owned by this rank with GLOBAL column ids: the canonical form a level is handed
+// over in (level 0: the user's slab; level l+1: the owned rows of the Galerkin product).
+struct OwnedCsr {
+  int64_t n_global = 0, g0 = 0;  // global size, first owned global row
+  DeviceCsr M;                   // M.n = owned rows, M.col = global ids, ascending
+  std::vector<int64_t> starts;   // size+1 range starts of all ranks
+};
+
+struct DistLevel {
+  OwnedCsr own;              // owned rows, global columns (kept for the accessors)
+  int64_t next = 0, o0 = 0;  // extended space size, first owned extended index
+  int64_t nloc = 0;
+  DevBuf<int32_t> gid;       // extended -> global id (ascending)
+  HaloPlan plan;             // per-point state over E
+  DeviceCsr Pown;            // owned rows of P (rows over E), GLOBAL coarse column ids
+  int64_t nc_global = 0, nc_own = 0, c0 = 0;  // coarse sizes, my first global coarse id
+  std::vector<int64_t> cstarts;
+  DevBuf<int32_t> tc_gid;    // compact coarse column space of Phat / That: index -> global coarse id
+  int64_t nct = 0, tc0 = 0;  // its size, and the compact index of my first owned coarse point
+  // solve phase (amgb_solve.cu)
+  int64_t nhalo = 0;
+  HaloPlan vplan;            // vectors in the solve numbering: [owned C | owned F | halo]
+  DevBuf<int32_t> colmap;    // extended -> solve index (-1: not referenced)
+};
+
+}  // namespace amgb
+
+struct amgb_dist_matrix {
+  amgb_ctx* ctx = nullptr;
+  amgb_comm* comm = nullptr;
+  amgb::OwnedCsr own;
+};
+
+// Distributed state hanging off an amgb_precond (null on a single device).
+struct amgb_dist_state {
+  amgb_comm* comm = nullptr;
+  const amgb_dist_matrix* mat = nullptr;
+  std::vector<amgb::DistLevel> dl;
+  // coarsest level, replicated
+  int64_t coarse_n = 0;
+  std::vector<int64_t> coarse_starts;
+  amgb::DevBuf<double> coarse_f, coarse_x;  // full-length staging
+  amgb::DevBuf<double> red;                 // PCG reduction staging (device)
+};
+
+namespace amgb {
+
+// amgb_dist.cu
+int plan_sync(amgb_ctx* ctx, amgb_comm* comm, HaloPlan& pl, void* per_point, int elem_bytes);
+// values of my owned points, taken from lo (index < split) or hi, sent to the peers' halo
+// regions of dst (dst's non-owned runs); lo/hi/dst are over the plan's index space
+int plan_sync_split(amgb_ctx* ctx, amgb_comm* comm, HaloPlan& pl, const double* lo, const double* hi, int split,
+                    double* dst);
+int build_hierarchy_dist(amgb_precond* P);
+// amgb_solve.cu
+int finish_solve_setup_dist(amgb_precond* P);
+// plan for vectors whose non-owned part is the sorted id list `halo_gid` stored at
+// [n_own, n_own + n_halo); owners translate a requested id g to own_index[g - g0]
+int build_vector_plan(amgb_ctx* ctx, amgb_comm* comm, const int32_t* halo_gid, int64_t n_halo, int64_t n_own,
+                      const std::vector<int64_t>& starts, const int32_t* own_index, HaloPlan& pl);
+// every rank's owned rows, on every rank (coarsest level)
+int allgather_rows(amgb_ctx* ctx, amgb_comm* comm, const OwnedCsr& own, DeviceCsr& full);
+int allgather_f64(amgb_ctx* ctx, amgb_comm* comm, const std::vector<int64_t>& starts, const double* mine,
+                  double* full);
+
+}  // namespace amgb

@@ -175,6 +175,9 @@ struct Level {
   Sell As, Ps, Rs;
   DevBuf<double> inv_relax;  // new order: 1/l1 (type 18) or 1/diag (type 0); 0 = skip row
   DevBuf<double> u, f, tmp;  // new order
+  // solve-phase sizes: rows relaxed here and vector length (= rows + halo in the
+  // row-partitioned path; both equal A.n on a single device)
+  int64_t n_solve = 0, n_vec = 0;
 };
 
 int64_t div_up(int64_t a, int64_t b);
@@ -192,6 +195,7 @@ struct LaunchScope {
 template <class... KArgs, class... Args>
 inline void launch_kernel(amgb_ctx* ctx, int family, double bytes, void (*kernel)(KArgs...),
                           dim3 grid, dim3 block, size_t smem, Args... args) {
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return;  // empty index range (e.g. a rank without rows)
   LaunchScope scope(ctx, family, bytes);
   kernel<<<grid, block, smem, ctx->stream>>>(args...);
 }
@@ -221,8 +225,12 @@ struct amgb_matrix {
   amgb::DeviceCsr A;
 };
 
+struct amgb_dist_state;  // amgb_dist.cuh: row-partitioned state (null on a single device)
+void amgb_dist_state_destroy(amgb_dist_state* s);
+
 struct amgb_precond {
   amgb_ctx* ctx = nullptr;
+  amgb_dist_state* dist = nullptr;
   const amgb_matrix* mat = nullptr;
   amgb_boomeramg_data data;
   double theta_eff = 0.25, mrs_eff = 0.9;
@@ -243,7 +251,33 @@ struct amgb_precond {
 };
 
 namespace amgb {
-// amgb_setup.cu
+// Hooks of the row-partitioned path into the setup stages (null on a single device).
+// The stages run unchanged on the rank's extended index space (owned points plus ghost
+// layers, ordered by global id); the hooks refresh the entries of non-owned points from
+// their owners and make the global decisions global.
+struct DistHooks {
+  virtual ~DistHooks() {}
+  virtual int sync_i32(int32_t* per_point) = 0;
+  virtual int sync_f64(double* per_point) = 0;
+  virtual int allreduce_sum(int64_t* v) = 0;
+  int64_t own_begin = 0, own_end = 0;  // owned points in the extended numbering
+  const int32_t* gid = nullptr;        // extended -> global id
+};
+
+// amgb_setup.cu: the setup stages, shared by the single-device and the partitioned driver
+int run_strength(amgb_ctx* ctx, const DeviceCsr& A, double theta, double max_row_sum, uint8_t* mask,
+                 int32_t* has_strong, double* diagv);
+int coarsen_pmis(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const int32_t* has_strong, int32_t* cf,
+                 DistHooks* hooks);
+// f2c <- exclusive scan of the C flags (n+1 entries); returns the number of C points
+int number_coarse_points(amgb_ctx* ctx, int64_t n, const int32_t* cf, int32_t* f2c, int32_t* n_coarse);
+// classical modified interpolation for rows [row_begin,row_end) (other rows stay empty);
+// col_id[fine] is the coarse column id written for a C point (f2c, or global coarse ids)
+int build_interp(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const int32_t* cf, const int32_t* col_id,
+                 const double* diagv, int64_t row_begin, int64_t row_end, int64_t n_coarse_cols, DeviceCsr& P);
+int transpose_csr(amgb_ctx* ctx, const DeviceCsr& P, DeviceCsr& R);
+int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, bool sorted);
+int resolve_options(amgb_precond* P);
 int build_hierarchy(amgb_precond* P);
 // amgb_solve.cu
 int finish_solve_setup(amgb_precond* P);

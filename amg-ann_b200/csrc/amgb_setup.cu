@@ -96,10 +96,12 @@ pmis_influence_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* 
 
 __global__ void __launch_bounds__(kBlock)
 pmis_init_kernel(int64_t n, const int32_t* __restrict__ influence, const int32_t* __restrict__ has_strong,
-                 double* __restrict__ measure, int32_t* __restrict__ cf) {
+                 const int32_t* __restrict__ gid, double* __restrict__ measure, int32_t* __restrict__ cf) {
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
-  double m = (double)influence[i] + hypre_rand_at(i);
+  // the random part depends on the GLOBAL index only, so the splitting is the same for
+  // any number of devices (SURVEY.md 8e "Determinism")
+  double m = (double)influence[i] + hypre_rand_at(gid ? (int64_t)gid[i] : i);
   int c = 0;
   if (!has_strong[i]) {
     c = -3;  // special F point: no strong connections
@@ -158,7 +160,8 @@ pmis_set_c_kernel(int64_t n, const int32_t* __restrict__ mark, int32_t* __restri
 __global__ void __launch_bounds__(kBlock)
 pmis_set_f_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
                   const uint8_t* __restrict__ mask, int32_t* __restrict__ cf,
-                  double* __restrict__ measure, int32_t* __restrict__ undecided) {
+                  double* __restrict__ measure, int32_t* __restrict__ undecided, int64_t own_begin,
+                  int64_t own_end) {
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   int und = 0;
   if (i < n) {
@@ -171,7 +174,7 @@ pmis_set_f_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __re
         }
       if (c != 0) cf[i] = c;
     }
-    if (c != 0) measure[i] = 0.0; else und = 1;
+    if (c != 0) measure[i] = 0.0; else und = (i >= own_begin && i < own_end) ? 1 : 0;
   }
   const unsigned b = __ballot_sync(0xffffffffu, und);
   if ((threadIdx.x & 31) == 0 && b) atomicAdd(undecided, __popc(b));
@@ -183,9 +186,10 @@ cpoint_flag_kernel(int64_t n, const int32_t* __restrict__ cf, int32_t* __restric
   if (i < n) flag[i] = cf[i] > 0 ? 1 : 0;
 }
 
-static int coarsen_pmis(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const int32_t* has_strong,
-                        int32_t* cf) {
+int coarsen_pmis(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const int32_t* has_strong, int32_t* cf,
+                 DistHooks* hooks) {
   const int64_t n = A.n;
+  const int64_t own_begin = hooks ? hooks->own_begin : 0, own_end = hooks ? hooks->own_end : n;
   const unsigned grid = (unsigned)div_up(n, kBlock);
   DevBuf<int32_t> influence, mark, undecided;
   DevBuf<double> measure;
@@ -197,19 +201,33 @@ static int coarsen_pmis(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, 
   AMGB_LAUNCH(ctx, F_COARSEN, row_bytes, pmis_influence_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p, mask,
               influence.p);
   AMGB_LAUNCH(ctx, F_COARSEN, 20.0 * n, pmis_init_kernel, grid, kBlock, 0, n, influence.p, has_strong,
-              measure.p, cf);
+              hooks ? hooks->gid : (const int32_t*)nullptr, measure.p, cf);
   AMGB_CHECK_LAUNCH(ctx);
+  if (hooks) {  // influence counts / states of ghost points come from their owners
+    AMGB_TRY(hooks->sync_f64(measure.p));
+    AMGB_TRY(hooks->sync_i32(cf));
+  }
   for (int round = 0; round < 100000; ++round) {
     AMGB_CUDA(ctx, cudaMemsetAsync(undecided.p, 0, sizeof(int32_t), ctx->stream));
     AMGB_LAUNCH(ctx, F_COARSEN, 16.0 * n, pmis_mark_kernel, grid, kBlock, 0, n, cf, measure.p, mark.p);
     AMGB_LAUNCH(ctx, F_COARSEN, row_bytes, pmis_knockout_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p, mask,
                 cf, measure.p, mark.p);
     AMGB_LAUNCH(ctx, F_COARSEN, 12.0 * n, pmis_set_c_kernel, grid, kBlock, 0, n, mark.p, cf);
+    if (hooks) AMGB_TRY(hooks->sync_i32(cf));
     AMGB_LAUNCH(ctx, F_COARSEN, row_bytes, pmis_set_f_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p, mask, cf,
-                measure.p, undecided.p);
+                measure.p, undecided.p, own_begin, own_end);
     AMGB_CHECK_LAUNCH(ctx);
+    if (hooks) {
+      AMGB_TRY(hooks->sync_i32(cf));
+      AMGB_TRY(hooks->sync_f64(measure.p));
+    }
     int32_t und = 0;
     AMGB_TRY(read_i32(ctx, undecided.p, &und));
+    if (hooks) {
+      int64_t total = und;
+      AMGB_TRY(hooks->allreduce_sum(&total));
+      und = total > 0 ? 1 : 0;
+    }
     if (und == 0) return AMGB_OK;
   }
   return set_error(ctx, AMGB_ERR_BREAKDOWN, "PMIS did not terminate");
@@ -221,11 +239,13 @@ static int coarsen_pmis(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, 
 __global__ void __launch_bounds__(kBlock)
 interp_count_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
                     const uint8_t* __restrict__ mask, const int32_t* __restrict__ cf,
-                    int32_t* __restrict__ count) {
+                    int32_t* __restrict__ count, int64_t row_begin, int64_t row_end) {
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
   int c = 0;
-  if (cf[i] > 0) {
+  if (i < row_begin || i >= row_end) {
+    c = 0;
+  } else if (cf[i] > 0) {
     c = 1;
   } else {
     for (int k = rp[i]; k < rp[i + 1]; ++k)
@@ -255,8 +275,8 @@ interp_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __r
                    const double* __restrict__ val, const uint8_t* __restrict__ mask,
                    const int32_t* __restrict__ cf, const int32_t* __restrict__ f2c,
                    const double* __restrict__ diagv, const int32_t* __restrict__ prp, int32_t* pcol,
-                   double* pval) {
-  const int64_t i = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
+                   double* pval, int64_t row_begin) {
+  const int64_t i = row_begin + (((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= n) return;
   const unsigned full = 0xffffffffu;
@@ -441,7 +461,7 @@ sort_rows_kernel(int64_t n, const int32_t* __restrict__ rp, int32_t* __restrict_
   }
 }
 
-static int transpose_csr(amgb_ctx* ctx, const DeviceCsr& P, DeviceCsr& R) {
+int transpose_csr(amgb_ctx* ctx, const DeviceCsr& P, DeviceCsr& R) {
   R.n = P.ncols;
   R.ncols = P.n;
   R.nnz = P.nnz;
@@ -997,7 +1017,7 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
 }
 
 // sorted = false: the caller does not need ascending columns (inner operand of R*(A*P))
-static int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, bool sorted) {
+int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, bool sorted) {
   const double avg_a = A.n > 0 ? double(A.nnz) / double(A.n) : 0.0;
   const double avg_b = B.n > 0 ? double(B.nnz) / double(B.n) : 0.0;
   int list_cap = 0;
@@ -1007,6 +1027,47 @@ static int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceC
   }
   if (avg_b <= 8.0) return spgemm_impl<8, 1024, 512>(ctx, A, B, C, list_cap);
   return spgemm_impl<32, 4096, 2048>(ctx, A, B, C, list_cap);
+}
+
+// ---- setup stages as host functions (shared with the row-partitioned driver) ----
+int run_strength(amgb_ctx* ctx, const DeviceCsr& A, double theta, double max_row_sum, uint8_t* mask,
+                 int32_t* has_strong, double* diagv) {
+  AMGB_LAUNCH(ctx, F_STRENGTH, 13.0 * A.nnz + 8.0 * A.n, strength_kernel, (unsigned)div_up(A.n, kBlock), kBlock, 0,
+              A.n, A.rp.p, A.col.p, A.val.p, theta, max_row_sum, mask, has_strong, diagv);
+  AMGB_CHECK_LAUNCH(ctx);
+  return AMGB_OK;
+}
+
+int number_coarse_points(amgb_ctx* ctx, int64_t n, const int32_t* cf, int32_t* f2c, int32_t* n_coarse) {
+  DevBuf<int32_t> flag;
+  AMGB_TRY(flag.alloc(ctx, n));
+  AMGB_LAUNCH(ctx, F_INTERP, 8.0 * n, cpoint_flag_kernel, (unsigned)div_up(n, kBlock), kBlock, 0, n, cf, flag.p);
+  AMGB_TRY(exclusive_scan_i32(ctx, flag.p, f2c, n));
+  return read_i32(ctx, f2c + n, n_coarse);
+}
+
+int build_interp(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const int32_t* cf, const int32_t* col_id,
+                 const double* diagv, int64_t row_begin, int64_t row_end, int64_t n_coarse_cols, DeviceCsr& P) {
+  const int64_t n = A.n;
+  DevBuf<int32_t> pcount;
+  AMGB_TRY(pcount.alloc(ctx, n));
+  AMGB_LAUNCH(ctx, F_INTERP, 5.0 * A.nnz + 12.0 * n, interp_count_kernel, (unsigned)div_up(n, kBlock), kBlock, 0, n,
+              A.rp.p, A.col.p, mask, cf, pcount.p, row_begin, row_end);
+  P.n = n;
+  P.ncols = n_coarse_cols;
+  AMGB_TRY(P.rp.alloc(ctx, n + 1));
+  AMGB_TRY(exclusive_scan_i32(ctx, pcount.p, P.rp.p, n));
+  int32_t nnzp = 0;
+  AMGB_TRY(read_i32(ctx, P.rp.p + n, &nnzp));
+  P.nnz = nnzp;
+  AMGB_TRY(P.col.alloc(ctx, nnzp));
+  AMGB_TRY(P.val.alloc(ctx, nnzp));
+  const int64_t rows = row_end - row_begin;
+  AMGB_LAUNCH(ctx, F_INTERP, 13.0 * A.nnz + 12.0 * nnzp + 16.0 * n, interp_fill_kernel,
+              (unsigned)div_up(rows * 32, kBlock), kBlock, 0, row_end, A.rp.p, A.col.p, A.val.p, mask, cf, col_id,
+              diagv, P.rp.p, P.col.p, P.val.p, row_begin);
+  AMGB_CHECK_LAUNCH(ctx);
+  return AMGB_OK;
 }
 
 // deal.II forwards theta / max_row_sum to PETSc through std::to_string (6 decimals)
@@ -1032,7 +1093,7 @@ static int hypre_relax_type(int dealii_type, bool symmetric_operator) {
   }
 }
 
-static int resolve_options(amgb_precond* P) {
+int resolve_options(amgb_precond* P) {
   amgb_ctx* ctx = P->ctx;
   const amgb_boomeramg_data& d = P->data;
   if (d.aggressive_coarsening_num_levels != 0)
@@ -1092,26 +1153,18 @@ int build_hierarchy(amgb_precond* P) {
     const int64_t n = L.A.n;
     ctx->cur_level = level;
     if (level == d.max_levels - 1 || n <= d.max_coarse_size) break;
-    const unsigned grid = (unsigned)div_up(n, kBlock);
     DevBuf<int32_t> has_strong;
     DevBuf<double> diagv;
     AMGB_TRY(L.mask.alloc(ctx, L.A.nnz));
     AMGB_TRY(has_strong.alloc(ctx, n));
     AMGB_TRY(diagv.alloc(ctx, n));
     AMGB_TRY(L.cf.alloc(ctx, n));
-    AMGB_LAUNCH(ctx, F_STRENGTH, 13.0 * L.A.nnz + 8.0 * n, strength_kernel, grid, kBlock, 0, n, L.A.rp.p,
-                L.A.col.p, L.A.val.p, P->theta_eff, P->mrs_eff, L.mask.p, has_strong.p, diagv.p);
-    AMGB_CHECK_LAUNCH(ctx);
-    AMGB_TRY(coarsen_pmis(ctx, L.A, L.mask.p, has_strong.p, L.cf.p));
+    AMGB_TRY(run_strength(ctx, L.A, P->theta_eff, P->mrs_eff, L.mask.p, has_strong.p, diagv.p));
+    AMGB_TRY(coarsen_pmis(ctx, L.A, L.mask.p, has_strong.p, L.cf.p, nullptr));
     // coarse numbering: ascending fine index of the C points
-    DevBuf<int32_t> flag;
-    DevBuf<int32_t>& f2c = L.f2c;
-    AMGB_TRY(flag.alloc(ctx, n));
-    AMGB_TRY(f2c.alloc(ctx, n + 1));
-    AMGB_LAUNCH(ctx, F_INTERP, 8.0 * n, cpoint_flag_kernel, grid, kBlock, 0, n, L.cf.p, flag.p);
-    AMGB_TRY(exclusive_scan_i32(ctx, flag.p, f2c.p, n));
+    AMGB_TRY(L.f2c.alloc(ctx, n + 1));
     int32_t nc = 0;
-    AMGB_TRY(read_i32(ctx, f2c.p + n, &nc));
+    AMGB_TRY(number_coarse_points(ctx, n, L.cf.p, L.f2c.p, &nc));
     if (nc == 0 || nc == n) {
       // coarsening stalled: this level is the coarsest
       L.mask.release();
@@ -1120,24 +1173,7 @@ int build_hierarchy(amgb_precond* P) {
       break;
     }
     L.n_coarse = nc;
-    // interpolation
-    DevBuf<int32_t> pcount;
-    AMGB_TRY(pcount.alloc(ctx, n));
-    AMGB_LAUNCH(ctx, F_INTERP, 5.0 * L.A.nnz + 12.0 * n, interp_count_kernel, grid, kBlock, 0, n, L.A.rp.p,
-                L.A.col.p, L.mask.p, L.cf.p, pcount.p);
-    L.P.n = n;
-    L.P.ncols = nc;
-    AMGB_TRY(L.P.rp.alloc(ctx, n + 1));
-    AMGB_TRY(exclusive_scan_i32(ctx, pcount.p, L.P.rp.p, n));
-    int32_t nnzp = 0;
-    AMGB_TRY(read_i32(ctx, L.P.rp.p + n, &nnzp));
-    L.P.nnz = nnzp;
-    AMGB_TRY(L.P.col.alloc(ctx, nnzp));
-    AMGB_TRY(L.P.val.alloc(ctx, nnzp));
-    AMGB_LAUNCH(ctx, F_INTERP, 13.0 * L.A.nnz + 12.0 * nnzp + 16.0 * n, interp_fill_kernel,
-                (unsigned)div_up(n * 32, kBlock), kBlock, 0, n, L.A.rp.p, L.A.col.p, L.A.val.p, L.mask.p, L.cf.p, f2c.p,
-                diagv.p, L.P.rp.p, L.P.col.p, L.P.val.p);
-    AMGB_CHECK_LAUNCH(ctx);
+    AMGB_TRY(build_interp(ctx, L.A, L.mask.p, L.cf.p, L.f2c.p, diagv.p, 0, n, nc, L.P));
     AMGB_TRY(transpose_csr(ctx, L.P, L.R));
     // Galerkin product A_c = R (A P)
     DeviceCsr T;
@@ -1192,6 +1228,8 @@ int amgb_precond_destroy(amgb_precond* P) {
   if (!P) return AMGB_OK;
   cudaSetDevice(P->ctx->device);
   destroy_solve_state(P);
+  if (P->dist) amgb_dist_state_destroy(P->dist);
+  P->dist = nullptr;
   delete P;
   return AMGB_OK;
 }

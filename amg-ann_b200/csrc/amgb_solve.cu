@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "amgb_dist.cuh"
 #include "amgb_internal.cuh"
 
 namespace amgb {
@@ -525,16 +526,16 @@ dense_solve_kernel(int n, const double* __restrict__ M, const double* __restrict
 
 constexpr int64_t kMaxDenseCoarse = 1024;  // same limit as the oracle
 
-static int setup_dense(amgb_precond* P) {
+// CA: the whole coarsest operator (on the row-partitioned path: gathered from all ranks)
+static int setup_dense_from(amgb_precond* P, const DeviceCsr& CA) {
   amgb_ctx* ctx = P->ctx;
-  Level& C = P->lv.back();
   P->dense_ok = false;
-  if (P->relax_coarse != 9 || C.A.n > kMaxDenseCoarse) return AMGB_OK;
-  const int64_t n = C.A.n;
+  if (P->relax_coarse != 9 || CA.n > kMaxDenseCoarse) return AMGB_OK;
+  const int64_t n = CA.n;
   AMGB_TRY(P->dense.alloc_zero(ctx, n * n));
   // the coarsest level has no C/F splitting: its permutation is the identity
-  AMGB_LAUNCH(ctx, F_COARSE, 12.0 * C.A.nnz, csr_to_dense_kernel, (unsigned)div_up(n, 128), 128, 0, n,
-              C.A.rp.p, C.A.col.p, C.A.val.p, P->dense.p);
+  AMGB_LAUNCH(ctx, F_COARSE, 12.0 * CA.nnz, csr_to_dense_kernel, (unsigned)div_up(n, 128), 128, 0, n,
+              CA.rp.p, CA.col.p, CA.val.p, P->dense.p);
   if (n <= 96) {
     AMGB_LAUNCH(ctx, F_COARSE, 8.0 * n * n, dense_factor_kernel, 1, kBlock, 0, (int)n, P->dense.p);
   } else {
@@ -552,6 +553,8 @@ static int setup_dense(amgb_precond* P) {
   P->dense_ok = true;
   return AMGB_OK;
 }
+
+static int setup_dense(amgb_precond* P) { return setup_dense_from(P, P->lv.back().A); }
 
 int finish_solve_setup(amgb_precond* P) {
   amgb_ctx* ctx = P->ctx;
@@ -585,6 +588,7 @@ int finish_solve_setup(amgb_precond* P) {
         L.P.val.release();
       }
     }
+    L.n_solve = L.n_vec = n;
     AMGB_TRY(L.inv_relax.alloc(ctx, n));
     AMGB_DISPATCH_T(L.As.T, AMGB_LAUNCH(ctx, F_AUX, L.As.csr_bytes() + 8.0 * n, sell_aux_kernel<TT>,
                                         (unsigned)div_up(L.As.nslices * 32, kBlock), kBlock, 0,
@@ -606,25 +610,39 @@ int finish_solve_setup(amgb_precond* P) {
 // V-cycle (hypre_BoomerAMGCycle): pre-smooth, residual, restrict, recurse,
 // prolong-correct, post-smooth; C/F ordering per hypre_BoomerAMGRelaxIF.
 // ---------------------------------------------------------------------------
-// One hypre_BoomerAMGRelaxIF call.  Reads `u`, leaves the relaxed vector in `out`.
-static int relax_if(amgb_precond* P, int l, const double* f, const double* u, double* out, int cycle_param) {
+// Row-partitioned path: refresh the halo part of dst with the owners' values, an owner's
+// value of point p being (p < split ? lo[p] : hi[p]).  No-op on a single device.
+static int halo(amgb_precond* P, int l, const double* lo, const double* hi, int split, double* dst) {
+  if (!P->dist) return AMGB_OK;
+  P->ctx->cur_level = l;
+  return plan_sync_split(P->ctx, P->dist->comm, P->dist->dl[l].vplan, lo, hi, split, dst);
+}
+
+// One hypre_BoomerAMGRelaxIF call.  Reads `u` (halo fresh), leaves the relaxed vector in
+// `out` (halo stale).  On the row-partitioned path the halo of `u` is overwritten between
+// the two half sweeps.
+static int relax_if(amgb_precond* P, int l, const double* f, double* u, double* out, int cycle_param) {
   Level& L = P->lv[l];
   amgb_ctx* ctx = P->ctx;
   ctx->cur_level = l;
-  const int n = (int)L.A.n, nC = (int)L.n_coarse;
+  const int n = (int)L.n_solve, nC = (int)L.n_coarse;
   const double w = P->data.relax_weight;
   const int fam = l == 0 ? F_SMOOTH_L0 : F_SMOOTH;
   const double mat = L.As.csr_bytes();
   EpiJacobi epi{f, u, L.inv_relax.p, out, w};
-  if (P->data.relax_order == 1 && cycle_param < 3 && nC > 0 && nC < n) {
-    const double share_c = double(nC) / double(n);
+  // C/F ordering needs a splitting on this level (any rank may own no C or no F points)
+  const bool cf_order = P->data.relax_order == 1 && cycle_param < 3 && (P->dist ? L.cf.p != nullptr : (nC > 0 && nC < n));
+  if (cf_order) {
+    const double share_c = n > 0 ? double(nC) / double(n) : 0.0;
     // half sweep = the rows touched + 4 vectors on those rows
     const double bytes_c = share_c * mat + 32.0 * nC, bytes_f = (1.0 - share_c) * mat + 32.0 * (n - nC);
     if (cycle_param < 2) {  // down: C then F
       AMGB_TRY(launch_sell(ctx, L.As, 0, nC, u, u, 0, epi, fam, bytes_c));
+      AMGB_TRY(halo(P, l, out, u, nC, u));  // halo C points: fresh; halo F points: old
       AMGB_TRY(launch_sell(ctx, L.As, nC, n, out, u, nC, epi, fam, bytes_f));
     } else {  // up: F then C
       AMGB_TRY(launch_sell(ctx, L.As, nC, n, u, u, 0, epi, fam, bytes_f));
+      AMGB_TRY(halo(P, l, u, out, nC, out));  // halo F points: fresh; halo C points: old
       AMGB_TRY(launch_sell(ctx, L.As, 0, nC, u, out, nC, epi, fam, bytes_c));
     }
   } else {
@@ -633,21 +651,36 @@ static int relax_if(amgb_precond* P, int l, const double* f, const double* u, do
   return AMGB_OK;
 }
 
-// On entry `u` holds the initial guess, `alt` is scratch of the same size; on
-// exit the result is in `u` (the two pointers are swapped as needed).
-static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double* f) {
+// On entry `u` holds the initial guess (u_is_zero: it is identically zero, halo included),
+// `alt` is scratch of the same size; on exit the result is in `u` (the two pointers are
+// swapped as needed) and, on the row-partitioned path, its halo is stale.
+static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double* f, bool u_is_zero) {
   amgb_ctx* ctx = P->ctx;
   Level& L = P->lv[l];
   const int nl = (int)P->lv.size();
-  const int n = (int)L.A.n;
+  const int n = (int)L.n_solve;
   if (l == nl - 1) {
     if (P->relax_coarse == 9 && P->dense_ok) {
+      if (P->dist) {
+        // replicated dense solve: gather the right-hand side, solve, keep the owned block
+        amgb_dist_state* ds = P->dist;
+        const int nfull = (int)ds->coarse_n;
+        AMGB_TRY(allgather_f64(ctx, ds->comm, ds->coarse_starts, f, ds->coarse_f.p));
+        AMGB_LAUNCH(ctx, F_COARSE, 8.0 * nfull * nfull, dense_solve_kernel, 1, kDenseThreads,
+                    (size_t)nfull * sizeof(double), nfull, P->dense.p, ds->coarse_f.p, ds->coarse_x.p);
+        AMGB_CHECK_LAUNCH(ctx);
+        if (n > 0)
+          AMGB_CUDA(ctx, cudaMemcpyAsync(u, ds->coarse_x.p + ds->coarse_starts[ds->comm->rank], (size_t)n * sizeof(double),
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+        return AMGB_OK;
+      }
       AMGB_LAUNCH(ctx, F_COARSE, 8.0 * n * n, dense_solve_kernel, 1, kDenseThreads, (size_t)n * sizeof(double), n,
                   P->dense.p, f, u);
       AMGB_CHECK_LAUNCH(ctx);
     } else {
       const unsigned sweeps = P->data.n_sweeps_coarse ? P->data.n_sweeps_coarse : 1u;
       for (unsigned s = 0; s < sweeps; ++s) {
+        if (!(u_is_zero && s == 0)) AMGB_TRY(halo(P, l, u, u, 0, u));
         AMGB_TRY(relax_if(P, l, f, u, alt, 3));
         std::swap(u, alt);
       }
@@ -655,26 +688,31 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
     return AMGB_OK;
   }
   for (unsigned s = 0; s < P->data.n_sweeps; ++s) {
+    if (!(u_is_zero && s == 0)) AMGB_TRY(halo(P, l, u, u, 0, u));
     AMGB_TRY(relax_if(P, l, f, u, alt, 1));
     std::swap(u, alt);
   }
   // residual into the scratch buffer, restriction into the coarse rhs
   ctx->cur_level = l;
+  AMGB_TRY(halo(P, l, u, u, 0, u));
   AMGB_TRY(launch_sell(ctx, L.As, 0, n, u, u, 0, EpiResidual{f, alt}, l == 0 ? F_RESIDUAL_L0 : F_RESIDUAL,
                        L.As.csr_bytes() + 24.0 * n));
   Level& C = P->lv[l + 1];
-  const int ncrs = (int)C.A.n;
+  const int ncrs = (int)C.n_solve;
+  AMGB_TRY(halo(P, l, alt, alt, 0, alt));
   AMGB_TRY(launch_sell(ctx, L.Rs, 0, ncrs, alt, alt, 0, EpiStore{C.f.p}, l == 0 ? F_RESTRICT_L0 : F_RESTRICT,
                        L.Rs.csr_bytes() + 8.0 * n + 8.0 * ncrs));
-  AMGB_CUDA(ctx, cudaMemsetAsync(C.u.p, 0, (size_t)ncrs * sizeof(double), ctx->stream));
+  if (C.n_vec > 0) AMGB_CUDA(ctx, cudaMemsetAsync(C.u.p, 0, (size_t)C.n_vec * sizeof(double), ctx->stream));
   double* cu = C.u.p;
   double* calt = C.tmp.p;
-  AMGB_TRY(cycle(P, l + 1, cu, calt, C.f.p));
-  if (P->data.w_cycle && l + 1 < nl - 1) AMGB_TRY(cycle(P, l + 1, cu, calt, C.f.p));
+  AMGB_TRY(cycle(P, l + 1, cu, calt, C.f.p, true));
+  if (P->data.w_cycle && l + 1 < nl - 1) AMGB_TRY(cycle(P, l + 1, cu, calt, C.f.p, false));
   ctx->cur_level = l;
+  AMGB_TRY(halo(P, l + 1, cu, cu, 0, cu));
   AMGB_TRY(launch_sell(ctx, L.Ps, 0, n, cu, cu, 0, EpiAdd{u}, l == 0 ? F_PROLONG_L0 : F_PROLONG,
                        L.Ps.csr_bytes() + 8.0 * ncrs + 16.0 * n));
   for (unsigned s = 0; s < P->data.n_sweeps; ++s) {
+    AMGB_TRY(halo(P, l, u, u, 0, u));
     AMGB_TRY(relax_if(P, l, f, u, alt, 2));
     std::swap(u, alt);
   }
@@ -683,13 +721,13 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
 
 static int vcycle_launches(amgb_precond* P, double* z, const double* r) {
   amgb_ctx* ctx = P->ctx;
-  const size_t n = (size_t)P->lv[0].A.n;
-  AMGB_CUDA(ctx, cudaMemsetAsync(z, 0, n * sizeof(double), ctx->stream));
+  const size_t n = (size_t)P->lv[0].n_vec;
+  if (n) AMGB_CUDA(ctx, cudaMemsetAsync(z, 0, n * sizeof(double), ctx->stream));
   double* u = z;
   double* alt = P->lv[0].tmp.p;
   const unsigned iters = P->data.max_iter ? P->data.max_iter : 1u;
-  for (unsigned it = 0; it < iters; ++it) AMGB_TRY(cycle(P, 0, u, alt, r));
-  if (u != z) AMGB_CUDA(ctx, cudaMemcpyAsync(z, u, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  for (unsigned it = 0; it < iters; ++it) AMGB_TRY(cycle(P, 0, u, alt, r, it == 0));
+  if (u != z && n) AMGB_CUDA(ctx, cudaMemcpyAsync(z, u, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   ctx->cur_level = 0;
   return AMGB_OK;
 }
@@ -852,6 +890,49 @@ finalize_beta_kernel(const double* __restrict__ pzz, const double* __restrict__ 
   }
 }
 
+// Row-partitioned path: the block partials are summed locally (same fixed tree), the 1-2
+// local sums are all-reduced over the ranks, and the scalar updates read the global sums.
+__global__ void __launch_bounds__(kBlock)
+local_sums_kernel(const double* __restrict__ p1, const double* __restrict__ p2, int64_t m, double* __restrict__ red) {
+  __shared__ double ws[kWarps];
+  const double a = ordered_sum(p1, m, ws);
+  const double b = p2 ? ordered_sum(p2, m, ws) : 0.0;
+  if (threadIdx.x == 0) {
+    red[0] = a;
+    red[1] = b;
+  }
+}
+
+__global__ void finalize_alpha_red_kernel(const double* __restrict__ red, double* sc, int* fl) {
+  const double pw = red[0];
+  sc[2] = pw;
+  if (pw == 0.0 || pw != pw) {
+    fl[0] = 1;
+    fl[2] = AMGB_ERR_BREAKDOWN;
+    sc[3] = 0.0;
+  } else {
+    sc[3] = sc[0] / pw;
+  }
+}
+
+__global__ void finalize_beta_red_kernel(const double* __restrict__ red, double* sc, int* fl, double* hist,
+                                         int64_t hist_cap, double abs_tol, int first) {
+  const double zz = red[0], zr = red[1];
+  const double dp = sqrt(zz);
+  sc[4] = dp;
+  sc[1] = sc[0];
+  sc[0] = zr;
+  const int it = first ? 0 : fl[1] + 1;
+  fl[1] = it;
+  if (it < hist_cap) hist[it] = dp;
+  if (dp != dp) {
+    fl[0] = 1;
+    fl[2] = AMGB_ERR_BREAKDOWN;
+  } else if (dp <= abs_tol) {
+    fl[0] = 1;
+  }
+}
+
 __global__ void __launch_bounds__(kBlock)
 update_p_kernel(int64_t n, const double* __restrict__ z, double* __restrict__ p,
                 const double* __restrict__ sc, int first) {
@@ -894,23 +975,26 @@ struct PcgFlags {
   int done, iters, status, pad;
 };
 
-// x, b in the USER numbering (device); everything inside runs in the permuted one.
+// x, b in the USER numbering (device; on the row-partitioned path: the owned slab);
+// everything inside runs in the permuted one.
 static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const double* b_user,
                      amgb_precond* P, int64_t max_steps, double abs_tol, double* res_hist, int64_t hist_cap,
                      int64_t* n_iters) {
-  const int64_t n = A->A.n;
-  if (P->lv.empty() || P->lv[0].A.n != n || P->mat != A)
+  if (P->lv.empty()) return set_error(ctx, AMGB_ERR_BAD_ARG, "preconditioner is not initialised");
+  amgb_dist_state* ds = P->dist;
+  if (!ds && (!A || P->lv[0].A.n != A->A.n || P->mat != A))
     return set_error(ctx, AMGB_ERR_BAD_ARG, "preconditioner was initialised for another matrix");
   Level& L0 = P->lv[0];
+  const int64_t n = L0.n_solve, nv = L0.n_vec;  // rows here, vector length (rows + halo)
   const Sell& As = L0.As;
   DevBuf<double> x, b, r, z, p, w, sc, hist, pa, pb;
   DevBuf<int> fl;
-  AMGB_TRY(x.alloc(ctx, n));
-  AMGB_TRY(b.alloc(ctx, n));
-  AMGB_TRY(r.alloc(ctx, n));
-  AMGB_TRY(z.alloc(ctx, n));
-  AMGB_TRY(p.alloc(ctx, n));
-  AMGB_TRY(w.alloc(ctx, n));
+  AMGB_TRY(x.alloc(ctx, nv));
+  AMGB_TRY(b.alloc(ctx, nv));
+  AMGB_TRY(r.alloc(ctx, nv));
+  AMGB_TRY(z.alloc(ctx, nv));
+  AMGB_TRY(p.alloc(ctx, nv));
+  AMGB_TRY(w.alloc(ctx, nv));
   AMGB_TRY(sc.alloc_zero(ctx, 8));
   AMGB_TRY(fl.alloc_zero(ctx, 4));
   int64_t cap = hist_cap > 0 && res_hist ? hist_cap : 1;
@@ -919,20 +1003,35 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
   AMGB_TRY(hist.alloc_zero(ctx, cap));
   const int64_t dot_blocks = div_up(n, kDotChunk);
   const int64_t spmv_blocks = div_up(As.nslices * 32, kBlock);
-  AMGB_TRY(pa.alloc(ctx, spmv_blocks > dot_blocks ? spmv_blocks : dot_blocks));
-  AMGB_TRY(pb.alloc(ctx, dot_blocks));
+  AMGB_TRY(pa.alloc(ctx, (spmv_blocks > dot_blocks ? spmv_blocks : dot_blocks) + 1));
+  AMGB_TRY(pb.alloc(ctx, dot_blocks + 1));
   const unsigned vgrid = (unsigned)div_up(n, kBlock);
+  double* red = ds ? ds->red.p : nullptr;
+  auto finalize_beta = [&](int first) -> int {
+    if (ds) {
+      AMGB_LAUNCH(ctx, F_VEC, 16.0 * dot_blocks, local_sums_kernel, 1, kBlock, 0, (const double*)pa.p,
+                  (const double*)pb.p, dot_blocks, red);
+      AMGB_CHECK_LAUNCH(ctx);
+      AMGB_TRY(ds->comm->allreduce_sum_f64(ctx, red, 2));
+      AMGB_LAUNCH(ctx, F_VEC, 16.0, finalize_beta_red_kernel, 1, 1, 0, (const double*)red, sc.p, fl.p, hist.p, cap,
+                  abs_tol, first);
+    } else {
+      AMGB_LAUNCH(ctx, F_VEC, 16.0 * dot_blocks, finalize_beta_kernel, 1, kBlock, 0, pa.p, pb.p, dot_blocks, sc.p,
+                  fl.p, hist.p, cap, abs_tol, first);
+    }
+    AMGB_CHECK_LAUNCH(ctx);
+    return AMGB_OK;
+  };
 
   AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, gather_kernel, vgrid, kBlock, 0, n, L0.perm.p, x_user, x.p);
   AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, gather_kernel, vgrid, kBlock, 0, n, L0.perm.p, b_user, b.p);
   // r = b - A x ; z = M^{-1} r ; dp = ||z|| ; beta = (z, r)
+  AMGB_TRY(halo(P, 0, x.p, x.p, 0, x.p));
   AMGB_TRY(launch_sell(ctx, As, 0, (int)n, x.p, x.p, 0, EpiResidual{b.p, r.p}, F_RESIDUAL_L0,
                        As.csr_bytes() + 24.0 * n));
   AMGB_TRY(vcycle_apply(P, z.p, r.p));
   AMGB_LAUNCH(ctx, F_VEC, 16.0 * n, dot2_kernel, (unsigned)dot_blocks, kBlock, 0, n, z.p, r.p, pa.p, pb.p);
-  AMGB_LAUNCH(ctx, F_VEC, 16.0 * dot_blocks, finalize_beta_kernel, 1, kBlock, 0, pa.p, pb.p, dot_blocks,
-              sc.p, fl.p, hist.p, cap, abs_tol, 1);
-  AMGB_CHECK_LAUNCH(ctx);
+  AMGB_TRY(finalize_beta(1));
   PcgFlags* hf = (PcgFlags*)ctx->pinned;
   auto read_flags = [&]() -> int {
     AMGB_CUDA(ctx, cudaMemcpyAsync(hf, fl.p, sizeof(PcgFlags), cudaMemcpyDeviceToHost, ctx->stream));
@@ -943,18 +1042,25 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
   int64_t it = 0;
   while (!hf->done && it < max_steps) {
     AMGB_LAUNCH(ctx, F_VEC, 24.0 * n, update_p_kernel, vgrid, kBlock, 0, n, z.p, p.p, sc.p, it == 0 ? 1 : 0);
+    AMGB_TRY(halo(P, 0, p.p, p.p, 0, p.p));
     AMGB_DISPATCH_T(As.T, AMGB_LAUNCH(ctx, F_SPMV, As.csr_bytes() + 16.0 * n, sell_spmv_dot_kernel<TT>,
                                       (unsigned)spmv_blocks, kBlock, 0, (int)As.nslices, (int)n,
                                       As.slice_ptr.p, As.col.p, As.val.p, p.p, w.p, pa.p));
-    AMGB_LAUNCH(ctx, F_VEC, 8.0 * spmv_blocks, finalize_alpha_kernel, 1, kBlock, 0, pa.p, spmv_blocks, sc.p,
-                fl.p);
+    if (ds) {
+      AMGB_LAUNCH(ctx, F_VEC, 8.0 * spmv_blocks, local_sums_kernel, 1, kBlock, 0, (const double*)pa.p,
+                  (const double*)nullptr, spmv_blocks, red);
+      AMGB_CHECK_LAUNCH(ctx);
+      AMGB_TRY(ds->comm->allreduce_sum_f64(ctx, red, 1));
+      AMGB_LAUNCH(ctx, F_VEC, 8.0, finalize_alpha_red_kernel, 1, 1, 0, (const double*)red, sc.p, fl.p);
+    } else {
+      AMGB_LAUNCH(ctx, F_VEC, 8.0 * spmv_blocks, finalize_alpha_kernel, 1, kBlock, 0, pa.p, spmv_blocks, sc.p,
+                  fl.p);
+    }
     AMGB_LAUNCH(ctx, F_VEC, 48.0 * n, axpy2_kernel, vgrid, kBlock, 0, n, p.p, w.p, x.p, r.p, sc.p);
     AMGB_CHECK_LAUNCH(ctx);
     AMGB_TRY(vcycle_apply(P, z.p, r.p));
     AMGB_LAUNCH(ctx, F_VEC, 16.0 * n, dot2_kernel, (unsigned)dot_blocks, kBlock, 0, n, z.p, r.p, pa.p, pb.p);
-    AMGB_LAUNCH(ctx, F_VEC, 16.0 * dot_blocks, finalize_beta_kernel, 1, kBlock, 0, pa.p, pb.p, dot_blocks,
-                sc.p, fl.p, hist.p, cap, abs_tol, 0);
-    AMGB_CHECK_LAUNCH(ctx);
+    AMGB_TRY(finalize_beta(0));
     AMGB_TRY(read_flags());
     ++it;
   }
@@ -983,11 +1089,11 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
 static int vmult_user(amgb_precond* P, double* dst, const double* src) {
   amgb_ctx* ctx = P->ctx;
   Level& L0 = P->lv[0];
-  const int64_t n = L0.A.n;
+  const int64_t n = L0.n_solve;
   const unsigned vgrid = (unsigned)div_up(n, kBlock);
   DevBuf<double> r, z;
-  AMGB_TRY(r.alloc(ctx, n));
-  AMGB_TRY(z.alloc(ctx, n));
+  AMGB_TRY(r.alloc(ctx, L0.n_vec));
+  AMGB_TRY(z.alloc(ctx, L0.n_vec));
   AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, gather_kernel, vgrid, kBlock, 0, n, L0.perm.p, src, r.p);
   AMGB_CHECK_LAUNCH(ctx);
   const bool g = P->use_graph;
@@ -998,6 +1104,211 @@ static int vmult_user(amgb_precond* P, double* dst, const double* src) {
   AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, scatter_kernel, vgrid, kBlock, 0, n, L0.perm.p, z.p, dst);
   AMGB_CHECK_LAUNCH(ctx);
   AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMGB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Row-partitioned solve-phase setup.  Solve numbering of a rank on a level:
+//   [owned C points | owned F points | halo points referenced by owned rows, by global id]
+// The operators hold the owned rows only; the halo part of a vector is refreshed from the
+// owners (HaloPlan vplan) before every kernel that gathers from it.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+dist_perm_kernel(int64_t nloc, const int32_t* __restrict__ cf_own, const int32_t* __restrict__ f2c_own, int nC,
+                 int32_t* __restrict__ perm, int32_t* __restrict__ inv_perm) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= nloc) return;
+  const int rank = f2c_own[i] - f2c_own[0];  // owned C points before i
+  const int ni = cf_own[i] > 0 ? rank : nC + ((int)i - rank);
+  inv_perm[i] = ni;
+  perm[ni] = (int)i;
+}
+
+__global__ void __launch_bounds__(kBlock)
+mark_cols_kernel(int64_t nnz, const int32_t* __restrict__ col, int32_t* __restrict__ need) {
+  const int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (k < nnz) need[col[k]] = 1;
+}
+
+__device__ __forceinline__ int64_t lower_bound_i32(const int32_t* __restrict__ a, int64_t n, int32_t v) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kBlock)
+mark_gids_kernel(int64_t n, const int32_t* __restrict__ ids, const int32_t* __restrict__ gid, int64_t next,
+                 int32_t* __restrict__ need) {
+  const int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (k >= n) return;
+  const int64_t e = lower_bound_i32(gid, next, ids[k]);
+  if (e < next && gid[e] == ids[k]) need[e] = 1;
+}
+
+__global__ void __launch_bounds__(kBlock)
+colmap_kernel(int64_t next, int64_t o0, int64_t nloc, const int32_t* __restrict__ need,
+              const int32_t* __restrict__ pos, const int32_t* __restrict__ inv_perm,
+              const int32_t* __restrict__ gid, int32_t* __restrict__ colmap, int32_t* __restrict__ halo_gid) {
+  const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (e >= next) return;
+  int c = -1;
+  if (e >= o0 && e < o0 + nloc) {
+    c = inv_perm[e - o0];
+  } else if (need[e]) {
+    c = (int)nloc + pos[e];
+    halo_gid[pos[e]] = gid[e];
+  }
+  colmap[e] = c;
+}
+
+// compact coarse column t of Phat -> solve index on the next level
+__global__ void __launch_bounds__(kBlock)
+tcmap_kernel(int64_t nct, const int32_t* __restrict__ tc_gid, const int32_t* __restrict__ gid_next, int64_t next_n,
+             const int32_t* __restrict__ colmap_next, int32_t* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (t >= nct) return;
+  const int64_t e = lower_bound_i32(gid_next, next_n, tc_gid[t]);
+  out[t] = (e < next_n && gid_next[e] == tc_gid[t]) ? colmap_next[e] : -1;
+}
+
+static void csr_view(amgb_ctx* ctx, const DeviceCsr& M, int64_t row0, int64_t rows, int64_t nnz, int64_t ncols,
+                     DeviceCsr& V) {
+  V.n = rows;
+  V.ncols = ncols;
+  V.nnz = nnz;
+  V.rp.wrap(ctx, M.rp.p + row0, rows + 1);
+  V.col.wrap(ctx, M.col.p, M.col.n);
+  V.val.wrap(ctx, M.val.p, M.val.n);
+}
+
+int finish_solve_setup_dist(amgb_precond* P) {
+  amgb_ctx* ctx = P->ctx;
+  amgb_dist_state* ds = P->dist;
+  amgb_comm* comm = ds->comm;
+  const int nl = (int)P->lv.size();
+  // 1. numbering, halo lists, vector plans
+  for (int l = 0; l < nl; ++l) {
+    Level& L = P->lv[l];
+    DistLevel& D = ds->dl[l];
+    const int64_t nloc = D.nloc, o0 = D.o0, next = D.next;
+    ctx->cur_level = l;
+    AMGB_TRY(L.perm.alloc(ctx, nloc));
+    AMGB_TRY(L.inv_perm.alloc(ctx, nloc));
+    if (L.cf.p) {
+      AMGB_LAUNCH(ctx, F_AUX, 16.0 * nloc, dist_perm_kernel, (unsigned)div_up(nloc, kBlock), kBlock, 0, nloc,
+                  (const int32_t*)(L.cf.p + o0), (const int32_t*)(L.f2c.p + o0), (int)L.n_coarse, L.perm.p,
+                  L.inv_perm.p);
+    } else {
+      L.n_coarse = 0;
+      AMGB_LAUNCH(ctx, F_AUX, 16.0 * nloc, build_perm_kernel, (unsigned)div_up(nloc, kBlock), kBlock, 0, nloc,
+                  (const int32_t*)nullptr, (const int32_t*)nullptr, 0, L.perm.p, L.inv_perm.p);
+    }
+    AMGB_CHECK_LAUNCH(ctx);
+    DevBuf<int32_t> need, pos, halo_gid;
+    AMGB_TRY(need.alloc_zero(ctx, next));
+    AMGB_TRY(pos.alloc(ctx, next + 1));
+    // owned rows of Ahat are the entry range [rp[o0], rp[o0 + nloc])
+    int32_t eb = 0, ee = 0;
+    AMGB_TRY(read_i32(ctx, L.A.rp.p + o0, &eb));
+    AMGB_TRY(read_i32(ctx, L.A.rp.p + o0 + nloc, &ee));
+    AMGB_LAUNCH(ctx, F_AUX, 8.0 * (ee - eb), mark_cols_kernel, (unsigned)div_up(ee - eb, kBlock), kBlock, 0,
+                (int64_t)(ee - eb), (const int32_t*)(L.A.col.p + eb), need.p);
+    if (l > 0) {  // coarse points my fine rows interpolate from
+      const DeviceCsr& Pp = ds->dl[l - 1].Pown;
+      AMGB_LAUNCH(ctx, F_AUX, 8.0 * Pp.nnz, mark_gids_kernel, (unsigned)div_up(Pp.nnz, kBlock), kBlock, 0, Pp.nnz,
+                  (const int32_t*)Pp.col.p, (const int32_t*)D.gid.p, next, need.p);
+    }
+    AMGB_CHECK_LAUNCH(ctx);
+    if (nloc) AMGB_CUDA(ctx, cudaMemsetAsync(need.p + o0, 0, nloc * sizeof(int32_t), ctx->stream));
+    AMGB_TRY(exclusive_scan_i32(ctx, need.p, pos.p, next));
+    int32_t nh = 0;
+    AMGB_TRY(read_i32(ctx, pos.p + next, &nh));
+    D.nhalo = nh;
+    AMGB_TRY(halo_gid.alloc(ctx, nh));
+    AMGB_TRY(D.colmap.alloc(ctx, next));
+    AMGB_LAUNCH(ctx, F_AUX, 20.0 * next, colmap_kernel, (unsigned)div_up(next, kBlock), kBlock, 0, next, o0, nloc,
+                (const int32_t*)need.p, (const int32_t*)pos.p, (const int32_t*)L.inv_perm.p,
+                (const int32_t*)D.gid.p, D.colmap.p, halo_gid.p);
+    AMGB_CHECK_LAUNCH(ctx);
+    L.n_solve = nloc;
+    L.n_vec = nloc + nh;
+    AMGB_TRY(build_vector_plan(ctx, comm, halo_gid.p, nh, nloc, D.own.starts, L.inv_perm.p, D.vplan));
+  }
+  // 2. operators (owned rows) in SELL, smoother diagonals, work vectors
+  for (int l = 0; l < nl; ++l) {
+    Level& L = P->lv[l];
+    DistLevel& D = ds->dl[l];
+    const int64_t nloc = D.nloc, o0 = D.o0;
+    ctx->cur_level = l;
+    DeviceCsr Av;
+    csr_view(ctx, L.A, o0, nloc, D.own.M.nnz, L.n_vec, Av);
+    AMGB_TRY(csr_to_sell(ctx, Av, L.perm.p, D.colmap.p, L.As));
+    if (l + 1 < nl) {
+      Level& C = P->lv[l + 1];
+      DistLevel& Dn = ds->dl[l + 1];
+      DevBuf<int32_t> tcmap;
+      AMGB_TRY(tcmap.alloc(ctx, D.nct));
+      AMGB_LAUNCH(ctx, F_AUX, 12.0 * D.nct, tcmap_kernel, (unsigned)div_up(D.nct, kBlock), kBlock, 0, D.nct,
+                  (const int32_t*)D.tc_gid.p, (const int32_t*)Dn.gid.p, Dn.next, (const int32_t*)Dn.colmap.p, tcmap.p);
+      AMGB_CHECK_LAUNCH(ctx);
+      DeviceCsr Pv;
+      csr_view(ctx, L.P, o0, nloc, D.Pown.nnz, C.n_vec, Pv);
+      AMGB_TRY(csr_to_sell(ctx, Pv, L.perm.p, tcmap.p, L.Ps));
+      L.R.ncols = L.n_vec;
+      AMGB_TRY(csr_to_sell(ctx, L.R, C.perm.p, D.colmap.p, L.Rs));
+      AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // tcmap goes out of scope
+      L.R.rp.release();
+      L.R.col.release();
+      L.R.val.release();
+      L.P.rp.release();
+      L.P.col.release();
+      L.P.val.release();
+      if (!P->data.keep_setup_intermediates) {
+        D.Pown.rp.release();
+        D.Pown.col.release();
+        D.Pown.val.release();
+        D.Pown.nnz = 0;
+      }
+    }
+    AMGB_TRY(L.inv_relax.alloc(ctx, nloc));
+    AMGB_DISPATCH_T(L.As.T, AMGB_LAUNCH(ctx, F_AUX, L.As.csr_bytes() + 8.0 * nloc, sell_aux_kernel<TT>,
+                                        (unsigned)div_up(L.As.nslices * 32, kBlock), kBlock, 0,
+                                        (int)L.As.nslices, (int)nloc, L.As.slice_ptr.p, L.As.col.p, L.As.val.p,
+                                        P->relax_down, L.inv_relax.p));
+    AMGB_CHECK_LAUNCH(ctx);
+    AMGB_TRY(L.tmp.alloc(ctx, L.n_vec));
+    if (l > 0) {
+      AMGB_TRY(L.u.alloc(ctx, L.n_vec));
+      AMGB_TRY(L.f.alloc(ctx, L.n_vec));
+    }
+    // the extended matrix is only needed by the setup; the solve runs on the SELL copy
+    if (!P->data.keep_setup_intermediates) {
+      L.A.rp.release();
+      L.A.col.release();
+      L.A.val.release();
+    }
+    L.f2c.release();
+  }
+  ctx->cur_level = 0;
+  // 3. coarsest level: replicated dense factorisation
+  {
+    const OwnedCsr& own = ds->dl[nl - 1].own;
+    ds->coarse_n = own.n_global;
+    ds->coarse_starts = own.starts;
+    P->dense_ok = false;
+    if (P->relax_coarse == 9 && own.n_global <= kMaxDenseCoarse) {
+      DeviceCsr full;
+      AMGB_TRY(allgather_rows(ctx, comm, own, full));
+      AMGB_TRY(setup_dense_from(P, full));
+      AMGB_TRY(ds->coarse_f.alloc(ctx, own.n_global));
+      AMGB_TRY(ds->coarse_x.alloc(ctx, own.n_global));
+      AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  AMGB_TRY(ds->red.alloc_zero(ctx, 8));
   return AMGB_OK;
 }
 
@@ -1017,7 +1328,7 @@ int amgb_precond_vmult(amgb_precond* P, double* dst, const double* src) {
   if (!P || !dst || !src) return AMGB_ERR_BAD_ARG;
   amgb_ctx* ctx = P->ctx;
   cudaSetDevice(ctx->device);
-  const int64_t n = P->lv[0].A.n;
+  const int64_t n = P->lv[0].n_solve;  // row-partitioned path: the owned slab
   DevBuf<double> d, s;
   AMGB_TRY(d.alloc(ctx, n));
   AMGB_TRY(s.alloc(ctx, n));
@@ -1034,6 +1345,35 @@ int amgb_cg_solve_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_device, 
   if (!ctx || !A || !x_device || !b_device || !P || !n_iters || max_steps < 0) return AMGB_ERR_BAD_ARG;
   cudaSetDevice(ctx->device);
   return cg_device(ctx, A, x_device, b_device, P, max_steps, abs_tol, res_hist, hist_cap, n_iters);
+}
+
+// Row-partitioned PCG: x, b are this rank's owned slabs.  Collective over the communicator.
+int amgb_dist_cg_solve_device(amgb_ctx* ctx, double* x_local_device, const double* b_local_device, amgb_precond* P,
+                              int64_t max_steps, double abs_tol, double* res_hist, int64_t hist_cap,
+                              int64_t* n_iters) {
+  if (!ctx || !P || !P->dist || !n_iters || max_steps < 0) return AMGB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  return cg_device(ctx, nullptr, x_local_device, b_local_device, P, max_steps, abs_tol, res_hist, hist_cap, n_iters);
+}
+
+int amgb_dist_cg_solve(amgb_ctx* ctx, double* x_local, const double* b_local, amgb_precond* P, int64_t max_steps,
+                       double abs_tol, double* res_hist, int64_t hist_cap, int64_t* n_iters) {
+  if (!ctx || !P || !P->dist || !n_iters || max_steps < 0) return AMGB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  const int64_t n = P->lv[0].n_solve;
+  DevBuf<double> dx, db;
+  AMGB_TRY(dx.alloc(ctx, n));
+  AMGB_TRY(db.alloc(ctx, n));
+  if (n) {
+    AMGB_CUDA(ctx, cudaMemcpyAsync(dx.p, x_local, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    AMGB_CUDA(ctx, cudaMemcpyAsync(db.p, b_local, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const int rc = cg_device(ctx, nullptr, dx.p, db.p, P, max_steps, abs_tol, res_hist, hist_cap, n_iters);
+  if ((rc == AMGB_OK || rc == AMGB_ERR_NO_CONVERGENCE) && n) {
+    AMGB_CUDA(ctx, cudaMemcpyAsync(x_local, dx.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return rc;
 }
 
 int amgb_cg_solve(amgb_ctx* ctx, const amgb_matrix* A, double* x, const double* b, amgb_precond* P,

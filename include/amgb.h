@@ -210,6 +210,62 @@ int amgb_cg_solve_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_device,
 int amgb_make_view(amgb_ctx* ctx, const amgb_matrix* A, int32_t view_size, double* sum,
                    int64_t* count, double* max_pp, double* max_np, double* t_us);
 
+/* ---- row-partitioned (multi-GPU) path ------------------------------------- */
+/* For systems that do not fit one device (BASELINE config 5: >= 100 M DoFs, nnz > 2^31) the
+ * matrix is partitioned by contiguous global row ranges, one rank per GPU, like a PETSc
+ * MPIAIJ matrix (the reference itself runs on one rank only: t2 main.cpp:221-224,525).
+ * Every function below is COLLECTIVE: all ranks of the communicator call it in the same
+ * order.  Integer outputs (strength masks, C/F markers, patterns) and the operator values
+ * are identical to the single-device ones for any number of ranks; residual histories
+ * agree to rounding (the order of the dot-product reduction changes).
+ *
+ * Communicators: NCCL (one process per GPU; the 128-byte unique id is created on rank 0
+ * with amgb_nccl_unique_id and distributed by the caller, e.g. through torch.distributed
+ * or MPI_Bcast), or an in-process group whose ranks are host threads (one amgb_ctx each, on
+ * the same or on different devices). */
+typedef struct amgb_comm amgb_comm;
+typedef struct amgb_local_group amgb_local_group;
+typedef struct amgb_dist_matrix amgb_dist_matrix;
+#define AMGB_NCCL_UNIQUE_ID_BYTES 128
+int amgb_nccl_unique_id(void* out, int capacity);
+int amgb_comm_create_nccl(amgb_ctx* ctx, int nranks, int rank, const void* unique_id, amgb_comm** out);
+int amgb_local_group_create(int nranks, amgb_local_group** out);
+int amgb_local_group_destroy(amgb_local_group* g);
+int amgb_comm_create_local(amgb_local_group* g, int rank, amgb_comm** out);
+int amgb_comm_destroy(amgb_comm* c);
+int amgb_comm_rank(const amgb_comm* c);
+int amgb_comm_size(const amgb_comm* c);
+
+/* Owned rows [row_begin,row_end) of the global n_global x n_global matrix: rowptr_local has
+ * row_end-row_begin+1 entries starting at 0, col_global holds GLOBAL column ids (ascending
+ * per row, diagonal stored).  Ranges must ascend with the rank and tile [0,n_global).
+ * Host pointers.  n_global < 2^31; the local nnz must be < 2^31 (the global nnz need not). */
+int amgb_dist_matrix_create(amgb_ctx* ctx, amgb_comm* comm, int64_t n_global, int64_t row_begin,
+                            int64_t row_end, const int64_t* rowptr_local, const int32_t* col_global,
+                            const double* val, amgb_dist_matrix** out);
+int amgb_dist_matrix_destroy(amgb_dist_matrix* A);
+/* initialize() on the partitioned matrix; the result is used with the amgb_precond_*
+ * queries (level statistics are global) and destroyed with amgb_precond_destroy. */
+int amgb_dist_precond_initialize(amgb_ctx* ctx, const amgb_dist_matrix* A,
+                                 const amgb_boomeramg_data* data, amgb_precond** out);
+/* cg.solve() on the partitioned system: x and b are the owned slabs.  SpMV halo exchange
+ * and the dot-product all-reduce run on the communicator. */
+int amgb_dist_cg_solve(amgb_ctx* ctx, double* x_local, const double* b_local, amgb_precond* P,
+                       int64_t max_steps, double abs_tol, double* res_hist, int64_t hist_cap,
+                       int64_t* n_iters);
+int amgb_dist_cg_solve_device(amgb_ctx* ctx, double* x_local_device, const double* b_local_device,
+                              amgb_precond* P, int64_t max_steps, double abs_tol, double* res_hist,
+                              int64_t hist_cap, int64_t* n_iters);
+/* Parity accessors: the OWNED part of a level with global ids (not collective). */
+int amgb_dist_precond_level_dims(const amgb_precond* P, int32_t level, int64_t* n_global,
+                                 int64_t* row_begin, int64_t* n_local, int64_t* nnz_local,
+                                 int64_t* n_coarse_global, int64_t* coarse_begin, int64_t* nnz_P_local);
+int amgb_dist_precond_get_cf_marker(const amgb_precond* P, int32_t level, int32_t* cf_local);
+int amgb_dist_precond_get_A_rows(const amgb_precond* P, int32_t level, int32_t* rowptr_local,
+                                 int32_t* col_global, double* val);
+int amgb_dist_precond_get_P_rows(const amgb_precond* P, int32_t level, int32_t* rowptr_local,
+                                 int32_t* col_global, double* val);
+
 /* ---- measurement hooks (bench.py) ---------------------------------------- */
 /* Per-kernel-family device time accumulated with CUDA events on the context's
  * stream while profiling is enabled.  Families: see amgb_timer_name. */

@@ -1,0 +1,113 @@
+"""GPU (-m gpu): the row-partitioned path against the single-device path.  The ranks are
+host threads of one process on one GPU (in-process communicator); the NCCL back end runs
+the same code with one process per GPU (bench.py --partitioned, tests/test_dist_host.py for
+the host logic).  Integer outputs and operator values must be IDENTICAL for any number of
+ranks (SURVEY.md 8e "Determinism"); residual histories agree to 1e-10."""
+import numpy as np
+import pytest
+
+import amg_ann_b200 as ab
+from amg_ann_b200 import dist
+from helpers import device_data, poisson
+
+pytestmark = pytest.mark.gpu
+
+
+def _single(gpu_ctx, s, data):
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    P = ab.PreconditionBoomerAMG()
+    P.initialize(A, data)
+    ctl = ab.SolverControl(s.n, 1e-8)
+    x = s.x0.copy()
+    ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+    return A, P, ctl, x
+
+
+def _run_partitioned(m, contrast, starts, data, solve=True):
+    nranks = len(starts) - 1
+
+    def fn(rank, comm):
+        b, e = starts[rank], starts[rank + 1]
+        epsv = ab.gen.checkerboard_epsv(2, 3, contrast) if contrast else None
+        sl = ab.gen.poisson_q1(m, 2, 3, epsv, row_begin=b, row_end=e) if contrast else \
+            ab.gen.poisson_q1(m, row_begin=b, row_end=e)
+        A = dist.DistSparseMatrix(comm, sl.n, b, e, sl.rowptr, sl.col, sl.val)
+        P = dist.DistPreconditionBoomerAMG()
+        P.initialize(A, data)
+        out = dict(stats=P.level_stats(), levels=[])
+        for l in range(P.num_levels):
+            d = P.level_dims(l)
+            lev = dict(dims=d, A=P.A_rows(l))
+            if l + 1 < P.num_levels:
+                lev["cf"] = P.cf_marker(l)
+                lev["P"] = P.P_rows(l)
+            out["levels"].append(lev)
+        if solve:
+            ctl = ab.SolverControl(sl.n, 1e-8)
+            x = sl.x0.copy()
+            dist.DistSolverCG(ctl).solve(A, x, sl.rhs, P)
+            out.update(x=x, hist=ctl.history, niters=ctl.last_step())
+        P.close()
+        A.close()
+        return out
+
+    return dist.run_local_group(nranks, fn)
+
+
+def _assert_same_hierarchy(parts, P1):
+    nl = P1.num_levels
+    assert all(len(p["levels"]) == nl for p in parts)
+    for l in range(nl):
+        rp, cl, vl = P1.A(l)
+        n = len(rp) - 1
+        assert sum(p["levels"][l]["dims"]["n_local"] for p in parts) == n
+        for p in parts:
+            d = p["levels"][l]["dims"]
+            b, k = d["row_begin"], d["n_local"]
+            prp, pcl, pvl = p["levels"][l]["A"]
+            assert np.array_equal(prp, rp[b:b + k + 1] - rp[b]), f"A rowptr level {l}"
+            assert np.array_equal(pcl, cl[rp[b]:rp[b + k]]), f"A pattern level {l}"
+            assert np.array_equal(pvl, vl[rp[b]:rp[b + k]]), f"A values level {l}"
+        if l + 1 < nl:
+            cf = P1.cf_marker(l)
+            prp1, pcl1, pvl1, nc = P1.P(l)
+            for p in parts:
+                d = p["levels"][l]["dims"]
+                b, k = d["row_begin"], d["n_local"]
+                assert np.array_equal(p["levels"][l]["cf"], cf[b:b + k]), f"cf level {l}"
+                assert d["n_coarse_global"] == nc
+                qrp, qcl, qvl = p["levels"][l]["P"]
+                assert np.array_equal(qrp, prp1[b:b + k + 1] - prp1[b]), f"P rowptr level {l}"
+                assert np.array_equal(qcl, pcl1[prp1[b]:prp1[b + k]]), f"P pattern level {l}"
+                assert np.array_equal(qvl, pvl1[prp1[b]:prp1[b + k]]), f"P values level {l}"
+
+
+@pytest.mark.parametrize("m,nranks,theta,contrast", [(8, 2, 0.25, 0.0), (12, 3, 0.5, 3.0), (10, 4, 0.25, 6.0),
+                                                     (12, 2, 0.7, 6.0)])
+def test_partitioned_equals_single_device(gpu_ctx, m, nranks, theta, contrast):
+    s = poisson(m, contrast=contrast)
+    data = device_data(theta)
+    A1, P1, ctl1, x1 = _single(gpu_ctx, s, data)
+    parts = _run_partitioned(m, contrast, dist.slab_partition(m, nranks), data)
+    _assert_same_hierarchy(parts, P1)
+    st1 = P1.level_stats()
+    for p in parts:
+        assert np.array_equal(p["stats"]["rows"], st1["rows"]) and np.array_equal(p["stats"]["nnz"], st1["nnz"])
+        assert p["stats"]["memory"] == st1["memory"]
+        assert abs(p["niters"] - ctl1.last_step()) <= 1
+        k = min(len(p["hist"]), len(ctl1.history))
+        assert (np.abs(p["hist"][:k] - ctl1.history[:k]) <= 1e-10 * ctl1.history[:k]).all()
+        assert np.array_equal(p["hist"], parts[0]["hist"])  # every rank sees the same scalars
+    x = np.concatenate([p["x"] for p in parts])
+    assert np.abs(x - x1).max() <= 1e-9 * np.abs(x1).max()
+
+
+def test_partition_not_aligned_with_planes_and_single_rank(gpu_ctx):
+    m, theta = 9, 0.25
+    s = poisson(m, contrast=2.0)
+    data = device_data(theta)
+    A1, P1, ctl1, x1 = _single(gpu_ctx, s, data)
+    for starts in ([0, 137, 600, s.n], [0, s.n]):  # ragged ranges cutting through planes; one rank
+        parts = _run_partitioned(m, 2.0, starts, data)
+        _assert_same_hierarchy(parts, P1)
+        assert all(abs(p["niters"] - ctl1.last_step()) <= 1 for p in parts)

@@ -484,12 +484,21 @@ int transpose_csr(amgb_ctx* ctx, const DeviceCsr& P, DeviceCsr& R) {
 }
 
 // ---------------------------------------------------------------------------
-// SpGEMM C = A*B: two-phase hash (count, then fill), G lanes per output row,
-// hash tables in shared memory with a global-memory path for oversized rows.
-// Numeric phase: k (entries of A's row) is walked sequentially and the lanes of
-// the group spread over B's row k, whose columns are distinct, so every C(i,c)
-// accumulates a_ik*b_kc in ascending k exactly like the oracle's Gustavson loop.
-// Rows are finally sorted by column with a bitonic network over the table.
+// SpGEMM C = A*B: two-phase hash (count, then fill).  G lanes cooperate on one output
+// row (G = 8 for short B rows such as A*P, 32 otherwise), so a warp works on 32/G rows
+// at once; hash tables live in shared memory and are sized per row, with two fall-back
+// stages for the few rows that do not fit (a big shared-memory table, then a table in
+// global memory).
+//
+// Numeric phase, bit-exactness: the entries k of A's row are walked in order; for one k
+// the lanes of the group spread over B's row k, whose columns are distinct, so no two
+// lanes touch the same accumulator within a step and every C(i,c) accumulates a_ik*b_kc
+// in ascending k exactly like the oracle's Gustavson loop (a group barrier orders the
+// steps).  The A-row entries (column, value, B-row extent) are loaded G at a time by the
+// lanes and broadcast with shuffles, so the only dependent global load inside a step is
+// B's row itself.  Rows are finally ordered by column with a rank sort over the
+// (compacted) table; `sorted = false` skips that: the result is then only usable as the
+// inner operand T of R*(A*P), whose value does not depend on T's column order.
 // ---------------------------------------------------------------------------
 constexpr int kSpThreads = 128;
 constexpr unsigned kEmpty = 0xffffffffu;
@@ -525,7 +534,7 @@ __device__ __forceinline__ int group_sum(int v, unsigned gm) {
   return v;
 }
 
-// upper bound on the number of entries of row i of A*B
+// upper bound on the number of entries of row i of A*B (= number of products)
 template <int G>
 __device__ __forceinline__ int row_upper_bound(int b, int e, int gl, unsigned gm,
                                                const int32_t* __restrict__ acol,
@@ -547,13 +556,21 @@ __device__ __forceinline__ int symbolic_row(unsigned* keys, int H, int lgH, int 
   for (int t = gl; t < H; t += G) keys[t] = kEmpty;
   __syncwarp(gm);
   int cnt = 0, fail = 0;
-  for (int k = b; k < e; ++k) {
-    const int kk = acol[k];
-    const int bb = brp[kk], be = brp[kk + 1];
-    for (int m = bb + gl; m < be; m += G) {
-      const int r = hash_insert(keys, H, lgH, (unsigned)bcol[m]);
-      if (r < 0) { fail = 1; break; }
-      cnt += r;
+  for (int kb = b; kb < e; kb += G) {
+    const int k = kb + gl;
+    int my_bb = 0, my_len = 0;
+    if (k < e) {
+      const int kk = acol[k];
+      my_bb = brp[kk];
+      my_len = brp[kk + 1] - my_bb;
+    }
+    const int steps = min(G, e - kb);
+    for (int t = 0; t < steps; ++t) {
+      const int bb = __shfl_sync(gm, my_bb, t, G), len = __shfl_sync(gm, my_len, t, G);
+      for (int m = gl; m < len; m += G) {
+        const int r = hash_insert(keys, H, lgH, (unsigned)bcol[bb + m]);
+        if (r < 0) fail = 1; else cnt += r;
+      }
     }
     if (__any_sync(gm, fail)) {  // group-uniform: the table is full
       fail = 1;
@@ -565,37 +582,36 @@ __device__ __forceinline__ int symbolic_row(unsigned* keys, int H, int lgH, int 
   return fail ? -1 : cnt;
 }
 
-// CAP: shared-memory table capacity per row group (power of two).
+// rows: list of row ids (nullptr: identity).  Rows whose table would not fit CAP try the
+// full CAP table (ub overestimates the distinct count several times in a Galerkin product);
+// a full table is detected by the probe limit and the row goes to the overflow list.
 template <int G, int CAP>
 __global__ void __launch_bounds__(kSpThreads)
-spgemm_symbolic_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
-                       const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
-                       int32_t* __restrict__ count, int32_t* __restrict__ ovf_rows,
-                       int32_t* __restrict__ ovf_info /* [0]=count [1]=max ub */, int min_ub) {
+spgemm_symbolic_kernel(int64_t nrows, const int32_t* __restrict__ rows, const int32_t* __restrict__ arp,
+                       const int32_t* __restrict__ acol, const int32_t* __restrict__ brp,
+                       const int32_t* __restrict__ bcol, int32_t* __restrict__ count,
+                       int32_t* __restrict__ ovf_rows, int32_t* __restrict__ ovf_info /* [0]=count [1]=max ub */) {
   extern __shared__ unsigned smem_keys[];
   const int g = threadIdx.x / G, gl = threadIdx.x % G;
   const unsigned gm = group_mask(G);
-  const int64_t i = (int64_t)blockIdx.x * (kSpThreads / G) + g;
-  if (i >= n) return;
+  const int64_t idx = (int64_t)blockIdx.x * (kSpThreads / G) + g;
+  if (idx >= nrows) return;
+  const int i = rows ? rows[idx] : (int)idx;
   unsigned* keys = smem_keys + (size_t)g * CAP;
   const int b = arp[i], e = arp[i + 1];
   const int ub = row_upper_bound<G>(b, e, gl, gm, acol, brp);
-  if (ub <= min_ub) return;  // counted by the product-list kernel
   if (ub == 0) {
     if (gl == 0) count[i] = 0;
     return;
   }
-  // ub overestimates the distinct count a lot in a Galerkin product, so rows
-  // whose bound does not fit still try the full shared-memory table; a full
-  // table is detected by the probe limit and the row takes the global path.
   int lgH = ceil_log2(2 * ub);
-  if (lgH < 5) lgH = 5;
+  if (lgH < 3) lgH = 3;
   if ((1 << lgH) > CAP) lgH = ceil_log2(CAP);
   const int cnt = symbolic_row<G>(keys, 1 << lgH, lgH, b, e, gl, gm, acol, brp, bcol);
   if (gl == 0) {
     if (cnt < 0) {
       const int w = atomicAdd(&ovf_info[0], 1);
-      ovf_rows[w] = (int)i;
+      ovf_rows[w] = i;
       atomicMax(&ovf_info[1], ub);
       count[i] = 0;
     } else {
@@ -622,43 +638,138 @@ spgemm_symbolic_global_kernel(const int32_t* __restrict__ ovf_rows, int novf, in
   }
 }
 
+// accumulate row i of A*B into the (keys, vals) table, ascending k
 template <int G>
-__device__ __forceinline__ void numeric_row(unsigned* keys, double* vals, int H, int lgH, int b, int e,
-                                            int gl, unsigned gm, const int32_t* __restrict__ acol,
-                                            const double* __restrict__ aval,
-                                            const int32_t* __restrict__ brp,
-                                            const int32_t* __restrict__ bcol,
-                                            const double* __restrict__ bval, int out_b, int out_n,
-                                            int32_t* __restrict__ ccol, double* __restrict__ cval) {
+__device__ __forceinline__ void accumulate_row(unsigned* keys, double* vals, int H, int lgH, int b, int e, int gl,
+                                               unsigned gm, const int32_t* __restrict__ acol,
+                                               const double* __restrict__ aval, const int32_t* __restrict__ brp,
+                                               const int32_t* __restrict__ bcol, const double* __restrict__ bval) {
   for (int t = gl; t < H; t += G) keys[t] = kEmpty;
   __syncwarp(gm);
-  for (int k = b; k < e; ++k) {
-    const int kk = acol[k];
-    const double a = aval[k];
-    const int bb = brp[kk], be = brp[kk + 1];
-    for (int m = bb + gl; m < be; m += G) {
-      const unsigned key = (unsigned)bcol[m];
-      const double prod = __dmul_rn(a, bval[m]);
-      int h = hash_slot(key, lgH);
-      for (;;) {
-        const unsigned old = atomicCAS(&keys[h], kEmpty, key);
-        if (old == kEmpty) {
-          vals[h] = __dadd_rn(0.0, prod);
-          break;
-        }
-        if (old == key) {
-          vals[h] = __dadd_rn(vals[h], prod);
-          break;
-        }
-        h = (h + 1) & (H - 1);
-      }
+  for (int kb = b; kb < e; kb += G) {
+    const int k = kb + gl;
+    int my_bb = 0, my_len = 0;
+    double my_a = 0.0;
+    if (k < e) {
+      const int kk = acol[k];
+      my_a = aval[k];
+      my_bb = brp[kk];
+      my_len = brp[kk + 1] - my_bb;
     }
-    __syncwarp(gm);  // orders the accumulation over k
+    const int steps = min(G, e - kb);
+    for (int t = 0; t < steps; ++t) {
+      const int bb = __shfl_sync(gm, my_bb, t, G), len = __shfl_sync(gm, my_len, t, G);
+      const double a = __shfl_sync(gm, my_a, t, G);
+      for (int m = gl; m < len; m += G) {
+        const unsigned key = (unsigned)bcol[bb + m];
+        const double prod = __dmul_rn(a, bval[bb + m]);
+        int h = hash_slot(key, lgH);
+        for (;;) {
+          const unsigned old = atomicCAS(&keys[h], kEmpty, key);
+          if (old == kEmpty) {
+            vals[h] = __dadd_rn(0.0, prod);
+            break;
+          }
+          if (old == key) {
+            vals[h] = __dadd_rn(vals[h], prod);
+            break;
+          }
+          h = (h + 1) & (H - 1);
+        }
+      }
+      __syncwarp(gm);  // orders the accumulation over k
+    }
   }
-  // bitonic sort of the whole table by key (empty = 0xffffffff sorts last)
+}
+
+// in-place compaction of the occupied slots to the front (slot order); G slots at a time:
+// a chunk is read into registers before anything of it is overwritten, and the write
+// positions never run ahead of the chunk being read
+template <int G>
+__device__ __forceinline__ void compact_table(unsigned* keys, double* vals, int H, int gl, unsigned gm) {
+  int out = 0;
+  const int sh = (threadIdx.x & 31) / G * G;  // first lane of my group inside the warp
+  for (int tb = 0; tb < H; tb += G) {
+    const unsigned key = keys[tb + gl];
+    const double v = vals[tb + gl];
+    const bool occ = key != kEmpty;
+    const unsigned om = (__ballot_sync(gm, occ) >> sh) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+    __syncwarp(gm);
+    if (occ) {
+      const int w = out + __popc(om & ((1u << gl) - 1u));
+      keys[w] = key;
+      vals[w] = v;
+    }
+    out += __popc(om);
+    __syncwarp(gm);
+  }
+}
+
+// SORT: ascending columns through a rank sort of the compacted table (out_n is small here:
+// rows with big tables go to the second stage, which uses a bitonic network)
+template <int G, bool SORT>
+__device__ __forceinline__ void emit_row(unsigned* keys, double* vals, int H, int gl, unsigned gm, int out_b,
+                                         int out_n, int32_t* __restrict__ ccol, double* __restrict__ cval) {
+  compact_table<G>(keys, vals, H, gl, gm);
+  for (int t = gl; t < out_n; t += G) {
+    const unsigned key = keys[t];
+    int pos = t;
+    if (SORT) {
+      pos = 0;
+      for (int u = 0; u < out_n; ++u) pos += keys[u] < key ? 1 : 0;
+    }
+    ccol[out_b + pos] = (int)key;
+    cval[out_b + pos] = vals[t];
+  }
+}
+
+template <int G, int CAP, bool SORT>
+__global__ void __launch_bounds__(kSpThreads)
+spgemm_numeric_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
+                      const double* __restrict__ aval, const int32_t* __restrict__ brp,
+                      const int32_t* __restrict__ bcol, const double* __restrict__ bval,
+                      const int32_t* __restrict__ crp, int32_t* __restrict__ ccol,
+                      double* __restrict__ cval, int32_t* __restrict__ ovf_rows,
+                      int32_t* __restrict__ ovf_info) {
+  extern __shared__ unsigned char smem_raw[];
+  const int g = threadIdx.x / G, gl = threadIdx.x % G;
+  const unsigned gm = group_mask(G);
+  const int64_t i = (int64_t)blockIdx.x * (kSpThreads / G) + g;
+  if (i >= n) return;
+  const int out_b = crp[i], out_n = crp[i + 1] - out_b;
+  if (out_n == 0) return;
+  int lgH = ceil_log2(2 * out_n);
+  if ((1 << lgH) < G) lgH = ceil_log2(G);  // the compaction reads the table G slots at a time
+  if ((1 << lgH) > CAP) {
+    if (gl == 0) {
+      const int w = atomicAdd(&ovf_info[0], 1);
+      ovf_rows[w] = (int)i;
+      atomicMax(&ovf_info[1], out_n);
+    }
+    return;
+  }
+  constexpr int kGroups = kSpThreads / G;
+  double* vals = reinterpret_cast<double*>(smem_raw) + (size_t)g * CAP;
+  unsigned* keys = reinterpret_cast<unsigned*>(smem_raw + sizeof(double) * (size_t)kGroups * CAP) + (size_t)g * CAP;
+  const int H = 1 << lgH;
+  accumulate_row<G>(keys, vals, H, lgH, arp[i], arp[i + 1], gl, gm, acol, aval, brp, bcol, bval);
+  emit_row<G, SORT>(keys, vals, H, gl, gm, out_b, out_n, ccol, cval);
+}
+
+// second stage: one warp per listed row; bitonic sort of the whole table by key
+// (empty = 0xffffffff sorts last)
+__device__ __forceinline__ void big_row(unsigned* keys, double* vals, int H, int lgH, int i,
+                                        const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
+                                        const double* __restrict__ aval, const int32_t* __restrict__ brp,
+                                        const int32_t* __restrict__ bcol, const double* __restrict__ bval,
+                                        const int32_t* __restrict__ crp, int32_t* __restrict__ ccol,
+                                        double* __restrict__ cval) {
+  const int lane = threadIdx.x & 31;
+  const unsigned gm = 0xffffffffu;
+  accumulate_row<32>(keys, vals, H, lgH, arp[i], arp[i + 1], lane, gm, acol, aval, brp, bcol, bval);
   for (int kk = 2; kk <= H; kk <<= 1) {
     for (int j = kk >> 1; j > 0; j >>= 1) {
-      for (int t = gl; t < H; t += G) {
+      for (int t = lane; t < H; t += 32) {
         const int x = t ^ j;
         if (x > t) {
           const unsigned kt = keys[t], kx = keys[x];
@@ -675,44 +786,42 @@ __device__ __forceinline__ void numeric_row(unsigned* keys, double* vals, int H,
       __syncwarp(gm);
     }
   }
-  for (int t = gl; t < out_n; t += G) {
+  const int out_b = crp[i], out_n = crp[i + 1] - out_b;
+  for (int t = lane; t < out_n; t += 32) {
     ccol[out_b + t] = (int)keys[t];
     cval[out_b + t] = vals[t];
   }
   __syncwarp(gm);
 }
 
-template <int G, int CAP>
+template <int CAP>
 __global__ void __launch_bounds__(kSpThreads)
-spgemm_numeric_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
-                      const double* __restrict__ aval, const int32_t* __restrict__ brp,
-                      const int32_t* __restrict__ bcol, const double* __restrict__ bval,
-                      const int32_t* __restrict__ crp, int32_t* __restrict__ ccol,
-                      double* __restrict__ cval, int32_t* __restrict__ ovf_rows,
-                      int32_t* __restrict__ ovf_info, int min_ub) {
+spgemm_numeric_big_kernel(const int32_t* __restrict__ rows, int nrows, const int32_t* __restrict__ arp,
+                          const int32_t* __restrict__ acol, const double* __restrict__ aval,
+                          const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
+                          const double* __restrict__ bval, const int32_t* __restrict__ crp,
+                          int32_t* __restrict__ ccol, double* __restrict__ cval, int32_t* __restrict__ ovf_rows,
+                          int32_t* __restrict__ ovf_info) {
   extern __shared__ unsigned char smem_raw[];
-  const int g = threadIdx.x / G, gl = threadIdx.x % G;
-  const unsigned gm = group_mask(G);
-  const int64_t i = (int64_t)blockIdx.x * (kSpThreads / G) + g;
-  if (i >= n) return;
-  if (min_ub >= 0 && row_upper_bound<G>(arp[i], arp[i + 1], gl, gm, acol, brp) <= min_ub) return;
-  const int out_b = crp[i], out_n = crp[i + 1] - out_b;
-  if (out_n == 0) return;
+  constexpr int kWarpsPerBlock = kSpThreads / 32;
+  const int w = threadIdx.x >> 5;
+  const int idx = blockIdx.x * kWarpsPerBlock + w;
+  if (idx >= nrows) return;
+  const int i = rows[idx];
+  const int out_n = crp[i + 1] - crp[i];
   int lgH = ceil_log2(2 * out_n);
   if (lgH < 5) lgH = 5;
   if ((1 << lgH) > CAP) {
-    if (gl == 0) {
-      const int w = atomicAdd(&ovf_info[0], 1);
-      ovf_rows[w] = (int)i;
+    if ((threadIdx.x & 31) == 0) {
+      const int p = atomicAdd(&ovf_info[0], 1);
+      ovf_rows[p] = i;
       atomicMax(&ovf_info[1], out_n);
     }
     return;
   }
-  constexpr int kGroups = kSpThreads / G;
-  double* vals = reinterpret_cast<double*>(smem_raw) + (size_t)g * CAP;
-  unsigned* keys = reinterpret_cast<unsigned*>(smem_raw + sizeof(double) * (size_t)kGroups * CAP) + (size_t)g * CAP;
-  numeric_row<G>(keys, vals, 1 << lgH, lgH, arp[i], arp[i + 1], gl, gm, acol, aval, brp, bcol, bval, out_b,
-                 out_n, ccol, cval);
+  double* vals = reinterpret_cast<double*>(smem_raw) + (size_t)w * CAP;
+  unsigned* keys = reinterpret_cast<unsigned*>(smem_raw + sizeof(double) * (size_t)kWarpsPerBlock * CAP) + (size_t)w * CAP;
+  big_row(keys, vals, 1 << lgH, lgH, i, arp, acol, aval, brp, bcol, bval, crp, ccol, cval);
 }
 
 __global__ void __launch_bounds__(kSpThreads)
@@ -723,241 +832,69 @@ spgemm_numeric_global_kernel(const int32_t* __restrict__ ovf_rows, int novf, int
                              const int32_t* __restrict__ bcol, const double* __restrict__ bval,
                              const int32_t* __restrict__ crp, int32_t* __restrict__ ccol,
                              double* __restrict__ cval) {
-  const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * kSpThreads + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * kSpThreads) >> 5;
   unsigned* keys = key_tables + (size_t)warp * H;
   double* vals = val_tables + (size_t)warp * H;
-  for (int idx = warp; idx < novf; idx += nwarps) {
-    const int i = ovf_rows[idx];
-    const int out_b = crp[i], out_n = crp[i + 1] - out_b;
-    numeric_row<32>(keys, vals, H, lgH, arp[i], arp[i + 1], lane, 0xffffffffu, acol, aval, brp, bcol, bval,
-                    out_b, out_n, ccol, cval);
-  }
+  for (int idx = warp; idx < novf; idx += nwarps)
+    big_row(keys, vals, H, lgH, ovf_rows[idx], arp, acol, aval, brp, bcol, bval, crp, ccol, cval);
 }
 
-// ---------------------------------------------------------------------------
-// Product-list path for C = A*B with short B rows (A*P).  One warp per row:
-//  * the lanes take one entry k of A's row each and append their products
-//    (column, a_ik*b_kc) to a shared-memory list at offsets given by a warp
-//    prefix sum of the B-row lengths, so the list is in ascending k;
-//  * the distinct columns are found by inserting the list into a small hash
-//    table (parallel, order-free) and every product remembers its slot;
-//  * the list is then scanned once, lane L accumulating the products whose slot
-//    is congruent to L mod 32: no two lanes share a slot and every C(i,c) sums in
-//    ascending k -- bit-identical to the oracle -- without a barrier per k;
-//  * occupied slots are compacted to the output in slot order.  The result row
-//    is NOT sorted by column: it is only used as the inner operand T of
-//    R*(A*P), whose value does not depend on T's column order.
-// Rows with more than LCAP products are left to the generic hash kernels.
-// ---------------------------------------------------------------------------
-constexpr int kListWarps = 4;
-
-template <int LCAP>
-struct ListSmem {
-  unsigned keys[2 * LCAP];
-  double acc[2 * LCAP];
-  double lv[LCAP];
-  int lc[LCAP];
-};
-
-// builds the product list of row i; returns ub (total products), or -1 if > LCAP
-template <int LCAP, bool NUMERIC>
-__device__ __forceinline__ int list_build(ListSmem<LCAP>& sm, int b, int e, int lane,
-                                          const int32_t* __restrict__ acol, const double* __restrict__ aval,
-                                          const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
-                                          const double* __restrict__ bval) {
-  const unsigned full = 0xffffffffu;
-  int ub = 0;
-  for (int kb = b; kb < e; kb += 32) {
-    const int k = kb + lane;
-    int l = 0;
-    if (k < e) {
-      const int kk = acol[k];
-      l = brp[kk + 1] - brp[kk];
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) l += __shfl_xor_sync(full, l, d);
-    ub += l;
-  }
-  if (ub > LCAP) return -1;
-  int base = 0;
-  for (int kb = b; kb < e; kb += 32) {
-    const int k = kb + lane;
-    int bb = 0, l = 0;
-    double a = 0.0;
-    if (k < e) {
-      const int kk = acol[k];
-      bb = brp[kk];
-      l = brp[kk + 1] - bb;
-      if (NUMERIC) a = aval[k];
-    }
-    int incl = l;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(full, incl, d);
-      if (lane >= d) incl += t;
-    }
-    const int off = base + incl - l;
-    for (int m = 0; m < l; ++m) {
-      sm.lc[off + m] = bcol[bb + m];
-      if (NUMERIC) sm.lv[off + m] = __dmul_rn(a, bval[bb + m]);
-    }
-    base += __shfl_sync(full, incl, 31);
-  }
-  return ub;
+static int read_ovf(amgb_ctx* ctx, const int32_t* ovf_info, int* novf, int* maxv) {
+  int32_t* info = (int32_t*)ctx->pinned;
+  AMGB_CUDA(ctx, cudaMemcpyAsync(info, ovf_info, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *novf = info[0];
+  *maxv = info[1];
+  return AMGB_OK;
 }
 
-template <int LCAP>
-__global__ void __launch_bounds__(kListWarps * 32)
-spgemm_list_symbolic_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
-                            const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
-                            int32_t* __restrict__ count, int32_t* __restrict__ big_rows) {
-  extern __shared__ __align__(16) unsigned char list_raw[];
-  ListSmem<LCAP>& sm = reinterpret_cast<ListSmem<LCAP>*>(list_raw)[threadIdx.x >> 5];
-  const int lane = threadIdx.x & 31;
-  const int64_t i = (int64_t)blockIdx.x * kListWarps + (threadIdx.x >> 5);
-  if (i >= n) return;
-  const int ub = list_build<LCAP, false>(sm, arp[i], arp[i + 1], lane, acol, nullptr, brp, bcol, nullptr);
-  if (ub < 0) {
-    if (lane == 0) {
-      count[i] = 0;
-      atomicAdd(big_rows, 1);
-    }
-    return;
-  }
-  int lgH = ceil_log2(2 * ub);
-  if (lgH < 5) lgH = 5;
-  const int H = 1 << lgH;
-  for (int t = lane; t < H; t += 32) sm.keys[t] = kEmpty;
-  __syncwarp();
-  int cnt = 0;
-  for (int t = lane; t < ub; t += 32) cnt += hash_insert(sm.keys, H, lgH, (unsigned)sm.lc[t]) > 0 ? 1 : 0;
-  cnt = group_sum<32>(cnt, 0xffffffffu);
-  if (lane == 0) count[i] = cnt;
-}
-
-template <int LCAP>
-__global__ void __launch_bounds__(kListWarps * 32)
-spgemm_list_numeric_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
-                           const double* __restrict__ aval, const int32_t* __restrict__ brp,
-                           const int32_t* __restrict__ bcol, const double* __restrict__ bval,
-                           const int32_t* __restrict__ crp, int32_t* __restrict__ ccol,
-                           double* __restrict__ cval) {
-  extern __shared__ __align__(16) unsigned char list_raw[];
-  ListSmem<LCAP>& sm = reinterpret_cast<ListSmem<LCAP>*>(list_raw)[threadIdx.x >> 5];
-  const int lane = threadIdx.x & 31;
-  const unsigned full = 0xffffffffu;
-  const int64_t i = (int64_t)blockIdx.x * kListWarps + (threadIdx.x >> 5);
-  if (i >= n) return;
-  const int ub = list_build<LCAP, true>(sm, arp[i], arp[i + 1], lane, acol, aval, brp, bcol, bval);
-  if (ub <= 0) return;  // empty, or left to the generic kernels
-  int lgH = ceil_log2(2 * ub);
-  if (lgH < 5) lgH = 5;
-  const int H = 1 << lgH;
-  for (int t = lane; t < H; t += 32) {
-    sm.keys[t] = kEmpty;
-    sm.acc[t] = 0.0;
-  }
-  __syncwarp();
-  // slot of every product (parallel, order-free)
-  for (int t = lane; t < ub; t += 32) {
-    const unsigned key = (unsigned)sm.lc[t];
-    int h = hash_slot(key, lgH);
-    for (;;) {
-      const unsigned old = atomicCAS(&sm.keys[h], kEmpty, key);
-      if (old == kEmpty || old == key) break;
-      h = (h + 1) & (H - 1);
-    }
-    sm.lc[t] = h;
-  }
-  __syncwarp();
-  // ordered accumulation: lane owns the slots congruent to it mod 32
-  for (int t = 0; t < ub; ++t) {
-    const int h = sm.lc[t];
-    if ((h & 31) == lane) sm.acc[h] = __dadd_rn(sm.acc[h], sm.lv[t]);
-  }
-  __syncwarp();
-  // compaction in slot order
-  int out = crp[i];
-  for (int tb = 0; tb < H; tb += 32) {
-    const unsigned key = sm.keys[tb + lane];
-    const bool occ = key != kEmpty;
-    const unsigned om = __ballot_sync(full, occ);
-    if (occ) {
-      const int w = out + __popc(om & ((1u << lane) - 1u));
-      ccol[w] = (int)key;
-      cval[w] = sm.acc[tb + lane];
-    }
-    out += __popc(om);
-  }
-}
-
+// G: lanes per row; CAP_SYM / CAP_NUM: first-stage table capacities per row group
 template <int G, int CAP_SYM, int CAP_NUM>
-static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, int list_cap = 0) {
+static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, bool sorted) {
+  constexpr int kBigSym = 8192, kBigNum = 2048;  // second-stage capacities (one warp per row)
   const int64_t n = A.n;
   C.n = n;
   C.ncols = B.ncols;
-  DevBuf<int32_t> count, ovf_rows, ovf_info;
+  DevBuf<int32_t> count, ovf1, ovf2, info;
   AMGB_TRY(count.alloc(ctx, n));
-  AMGB_TRY(ovf_rows.alloc(ctx, n));
-  AMGB_TRY(ovf_info.alloc_zero(ctx, 2));
+  AMGB_TRY(ovf1.alloc(ctx, n));
+  AMGB_TRY(ovf2.alloc(ctx, n));
+  AMGB_TRY(info.alloc_zero(ctx, 4));
   AMGB_TRY(C.rp.alloc(ctx, n + 1));
   constexpr int kGroups = kSpThreads / G;
   const unsigned grid = (unsigned)div_up(n, kGroups);
   const double in_bytes = 12.0 * A.nnz + 4.0 * A.n + 12.0 * B.nnz + 4.0 * B.n;
   const int fb_blocks = ctx->sm_count * 2;
   const int fb_warps = fb_blocks * kSpThreads / 32;
-  const int min_ub = list_cap > 0 ? list_cap : -1;
-  bool run_generic = true;
-  const unsigned lgrid = (unsigned)div_up(n, kListWarps);
-  if (list_cap > 0) {
-    DevBuf<int32_t> big;
-    AMGB_TRY(big.alloc_zero(ctx, 1));
-    if (list_cap == 128) {
-      auto k = spgemm_list_symbolic_kernel<128>;
-      const size_t sm = sizeof(ListSmem<128>) * kListWarps;
-      AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, k, lgrid, kListWarps * 32, sm, n, A.rp.p, A.col.p, B.rp.p, B.col.p,
-                  count.p, big.p);
-    } else if (list_cap == 256) {
-      auto k = spgemm_list_symbolic_kernel<256>;
-      const size_t sm = sizeof(ListSmem<256>) * kListWarps;
-      AMGB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, k, lgrid, kListWarps * 32, sm, n, A.rp.p, A.col.p, B.rp.p, B.col.p,
-                  count.p, big.p);
-    } else {
-      auto k = spgemm_list_symbolic_kernel<512>;
-      const size_t sm = sizeof(ListSmem<512>) * kListWarps;
-      AMGB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, k, lgrid, kListWarps * 32, sm, n, A.rp.p, A.col.p, B.rp.p, B.col.p,
-                  count.p, big.p);
-    }
-    AMGB_CHECK_LAUNCH(ctx);
-    int32_t nbig = 0;
-    AMGB_TRY(read_i32(ctx, big.p, &nbig));
-    run_generic = nbig > 0;
-  }
-  if (run_generic) {
+  int novf = 0, maxv = 0;
+  // ---- symbolic
+  {
     auto kern = spgemm_symbolic_kernel<G, CAP_SYM>;
     const size_t smem = sizeof(unsigned) * (size_t)kGroups * CAP_SYM;
-    AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, kern, grid, kSpThreads, smem, n, A.rp.p, A.col.p, B.rp.p, B.col.p,
-                count.p, ovf_rows.p, ovf_info.p, min_ub);
+    AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, kern, grid, kSpThreads, smem, n, (const int32_t*)nullptr, A.rp.p, A.col.p,
+                B.rp.p, B.col.p, count.p, ovf1.p, info.p);
     AMGB_CHECK_LAUNCH(ctx);
-    int32_t* info = (int32_t*)ctx->pinned;
-    AMGB_CUDA(ctx, cudaMemcpyAsync(info, ovf_info.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int novf = info[0], max_ub = info[1];
+    AMGB_TRY(read_ovf(ctx, info.p, &novf, &maxv));
     if (novf > 0) {
-      int lgH = 5;
-      const long long want = std::min<long long>(2ll * max_ub, 2ll * B.ncols);
-      while ((1ll << lgH) < want) ++lgH;
-      const int H = 1 << lgH;
-      DevBuf<unsigned> tables;
-      AMGB_TRY(tables.alloc(ctx, (size_t)fb_warps * H));
-      AMGB_LAUNCH(ctx, F_SPGEMM, 0.0, spgemm_symbolic_global_kernel, fb_blocks, kSpThreads, 0, ovf_rows.p, novf,
-                  H, lgH, tables.p, A.rp.p, A.col.p, B.rp.p, B.col.p, count.p);
+      auto big = spgemm_symbolic_kernel<32, kBigSym>;
+      const size_t bsmem = sizeof(unsigned) * (size_t)(kSpThreads / 32) * kBigSym;
+      AMGB_CUDA(ctx, cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+      AMGB_LAUNCH(ctx, F_SPGEMM, 0.0, big, (unsigned)div_up(novf, kSpThreads / 32), kSpThreads, bsmem, (int64_t)novf,
+                  (const int32_t*)ovf1.p, A.rp.p, A.col.p, B.rp.p, B.col.p, count.p, ovf2.p, info.p + 2);
       AMGB_CHECK_LAUNCH(ctx);
+      AMGB_TRY(read_ovf(ctx, info.p + 2, &novf, &maxv));
+      if (novf > 0) {
+        int lgH = 5;
+        const long long want = std::min<long long>(2ll * maxv, 2ll * B.ncols);
+        while ((1ll << lgH) < want) ++lgH;
+        const int H = 1 << lgH;
+        DevBuf<unsigned> tables;
+        AMGB_TRY(tables.alloc(ctx, (size_t)fb_warps * H));
+        AMGB_LAUNCH(ctx, F_SPGEMM, 0.0, spgemm_symbolic_global_kernel, fb_blocks, kSpThreads, 0, ovf2.p, novf, H, lgH,
+                    tables.p, A.rp.p, A.col.p, B.rp.p, B.col.p, count.p);
+        AMGB_CHECK_LAUNCH(ctx);
+      }
     }
   }
   AMGB_TRY(exclusive_scan_i32(ctx, count.p, C.rp.p, n));
@@ -966,51 +903,43 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
   C.nnz = nnz;
   AMGB_TRY(C.col.alloc(ctx, nnz));
   AMGB_TRY(C.val.alloc(ctx, nnz));
-  AMGB_CUDA(ctx, cudaMemsetAsync(ovf_info.p, 0, 2 * sizeof(int32_t), ctx->stream));
-  if (list_cap > 0) {
+  AMGB_CUDA(ctx, cudaMemsetAsync(info.p, 0, 4 * sizeof(int32_t), ctx->stream));
+  // ---- numeric
+  {
+    const size_t smem = (sizeof(unsigned) + sizeof(double)) * (size_t)kGroups * CAP_NUM;
     const double bytes = in_bytes + 12.0 * nnz + 4.0 * n;
-    if (list_cap == 128) {
-      auto k = spgemm_list_numeric_kernel<128>;
-      const size_t sm = sizeof(ListSmem<128>) * kListWarps;
-      AMGB_LAUNCH(ctx, F_SPGEMM, bytes, k, lgrid, kListWarps * 32, sm, n, A.rp.p, A.col.p, A.val.p, B.rp.p,
-                  B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p);
-    } else if (list_cap == 256) {
-      auto k = spgemm_list_numeric_kernel<256>;
-      const size_t sm = sizeof(ListSmem<256>) * kListWarps;
-      AMGB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      AMGB_LAUNCH(ctx, F_SPGEMM, bytes, k, lgrid, kListWarps * 32, sm, n, A.rp.p, A.col.p, A.val.p, B.rp.p,
-                  B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p);
+    if (sorted) {
+      auto kern = spgemm_numeric_kernel<G, CAP_NUM, true>;
+      AMGB_LAUNCH(ctx, F_SPGEMM, bytes, kern, grid, kSpThreads, smem, n, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p,
+                  B.val.p, C.rp.p, C.col.p, C.val.p, ovf1.p, info.p);
     } else {
-      auto k = spgemm_list_numeric_kernel<512>;
-      const size_t sm = sizeof(ListSmem<512>) * kListWarps;
-      AMGB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      AMGB_LAUNCH(ctx, F_SPGEMM, bytes, k, lgrid, kListWarps * 32, sm, n, A.rp.p, A.col.p, A.val.p, B.rp.p,
-                  B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p);
+      auto kern = spgemm_numeric_kernel<G, CAP_NUM, false>;
+      AMGB_LAUNCH(ctx, F_SPGEMM, bytes, kern, grid, kSpThreads, smem, n, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p,
+                  B.val.p, C.rp.p, C.col.p, C.val.p, ovf1.p, info.p);
     }
     AMGB_CHECK_LAUNCH(ctx);
-  }
-  if (run_generic) {
-    auto kern = spgemm_numeric_kernel<G, CAP_NUM>;
-    const size_t smem = (sizeof(unsigned) + sizeof(double)) * (size_t)kGroups * CAP_NUM;
-    AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes + 12.0 * nnz + 4.0 * n, kern, grid, kSpThreads, smem, n, A.rp.p, A.col.p,
-                A.val.p, B.rp.p, B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p, ovf_rows.p, ovf_info.p, min_ub);
-    AMGB_CHECK_LAUNCH(ctx);
-    int32_t* info = (int32_t*)ctx->pinned;
-    AMGB_CUDA(ctx, cudaMemcpyAsync(info, ovf_info.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int novf = info[0], max_n = info[1];
+    AMGB_TRY(read_ovf(ctx, info.p, &novf, &maxv));
     if (novf > 0) {
-      int lgH = 5;
-      while ((1ll << lgH) < 2ll * max_n) ++lgH;
-      const int H = 1 << lgH;
-      DevBuf<unsigned> kt;
-      DevBuf<double> vt;
-      AMGB_TRY(kt.alloc(ctx, (size_t)fb_warps * H));
-      AMGB_TRY(vt.alloc(ctx, (size_t)fb_warps * H));
-      AMGB_LAUNCH(ctx, F_SPGEMM, 0.0, spgemm_numeric_global_kernel, fb_blocks, kSpThreads, 0, ovf_rows.p, novf, H,
-                  lgH, kt.p, vt.p, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p);
+      auto big = spgemm_numeric_big_kernel<kBigNum>;
+      const size_t bsmem = (sizeof(unsigned) + sizeof(double)) * (size_t)(kSpThreads / 32) * kBigNum;
+      AMGB_CUDA(ctx, cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+      AMGB_LAUNCH(ctx, F_SPGEMM, 0.0, big, (unsigned)div_up(novf, kSpThreads / 32), kSpThreads, bsmem,
+                  (const int32_t*)ovf1.p, novf, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p, B.val.p, C.rp.p, C.col.p,
+                  C.val.p, ovf2.p, info.p + 2);
       AMGB_CHECK_LAUNCH(ctx);
+      AMGB_TRY(read_ovf(ctx, info.p + 2, &novf, &maxv));
+      if (novf > 0) {
+        int lgH = 5;
+        while ((1ll << lgH) < 2ll * maxv) ++lgH;
+        const int H = 1 << lgH;
+        DevBuf<unsigned> kt;
+        DevBuf<double> vt;
+        AMGB_TRY(kt.alloc(ctx, (size_t)fb_warps * H));
+        AMGB_TRY(vt.alloc(ctx, (size_t)fb_warps * H));
+        AMGB_LAUNCH(ctx, F_SPGEMM, 0.0, spgemm_numeric_global_kernel, fb_blocks, kSpThreads, 0, ovf2.p, novf, H, lgH,
+                    kt.p, vt.p, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p);
+        AMGB_CHECK_LAUNCH(ctx);
+      }
     }
   }
   return AMGB_OK;
@@ -1018,15 +947,9 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
 
 // sorted = false: the caller does not need ascending columns (inner operand of R*(A*P))
 int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, bool sorted) {
-  const double avg_a = A.n > 0 ? double(A.nnz) / double(A.n) : 0.0;
   const double avg_b = B.n > 0 ? double(B.nnz) / double(B.n) : 0.0;
-  int list_cap = 0;
-  if (!sorted && avg_b <= 8.0) {
-    const double est = 2.5 * avg_a * avg_b;
-    list_cap = est <= 128.0 ? 128 : (est <= 256.0 ? 256 : 512);
-  }
-  if (avg_b <= 8.0) return spgemm_impl<8, 1024, 512>(ctx, A, B, C, list_cap);
-  return spgemm_impl<32, 4096, 2048>(ctx, A, B, C, list_cap);
+  if (avg_b <= 8.0) return spgemm_impl<8, 256, 128>(ctx, A, B, C, sorted);
+  return spgemm_impl<32, 1024, 512>(ctx, A, B, C, sorted);
 }
 
 // ---- setup stages as host functions (shared with the row-partitioned driver) ----

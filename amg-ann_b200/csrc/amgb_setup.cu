@@ -254,6 +254,8 @@ interp_count_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __
   count[i] = c;
 }
 
+constexpr int kInterpStage = 48;  // P-row entries staged in shared memory per warp
+
 // position of coarse column cc in the sorted slice pcol[0..len), or -1
 __device__ __forceinline__ int find_sorted(const int32_t* pcol, int len, int cc) {
   int lo = 0, hi = len;
@@ -290,8 +292,13 @@ interp_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __r
     return;
   }
   const int b = rp[i], e = rp[i + 1];
-  int32_t* myc = pcol + jb;
-  double* myv = pval + jb;
+  // the row of P under construction lives in shared memory when it is short (the usual
+  // case): it is searched and updated once per strong F neighbour
+  __shared__ int32_t s_c[kBlock / 32][kInterpStage];
+  __shared__ double s_v[kBlock / 32][kInterpStage];
+  const bool staged = len <= kInterpStage;
+  int32_t* myc = staged ? s_c[threadIdx.x >> 5] : pcol + jb;
+  double* myv = staged ? s_v[threadIdx.x >> 5] : pval + jb;
   // phase 0: diagonal, and the strong C neighbours (fine ids) in row order
   double diagonal = 0.0;
   {
@@ -412,8 +419,8 @@ interp_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __r
   // phase 2: scale, renumber to coarse ids
   const double nd = -diagonal;
   for (int t = lane; t < len; t += 32) {
-    myv[t] = diagonal == 0.0 ? 0.0 : myv[t] / nd;
-    myc[t] = f2c[myc[t]];
+    pval[jb + t] = diagonal == 0.0 ? 0.0 : myv[t] / nd;
+    pcol[jb + t] = f2c[myc[t]];
   }
 }
 

@@ -257,13 +257,28 @@ __device__ __forceinline__ double sell_lane_dot(int w, int64_t base, const int32
       s1 += v[u + 1] * x[u + 1];
     }
   }
-  for (; j < w; ++j) {
+  if (j < w) {
+    // tail: the same batch, predicated, so that its loads are in flight together too
+    // (27-entry stencil rows leave 3 entries here; short coarse-level rows live here entirely)
     const int64_t p = base + (int64_t)j * 32;
-    const int c = ld_mat<STREAM>(col + p);
-    const double v = ld_mat<STREAM>(val + p);
-    const double* src = x_hi;
-    if (SPLIT) src = c < split ? x_lo : x_hi;
-    s0 += v * src[c];
+    const int rem = w - j;
+    int c[U];
+    double v[U], x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = u < rem ? ld_mat<STREAM>(col + p + u * 32) : -1;
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = u < rem ? ld_mat<STREAM>(val + p + u * 32) : 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double* src = x_hi;
+      if (SPLIT) src = c[u] < split ? x_lo : x_hi;
+      x[u] = u < rem ? src[c[u]] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u += 2) {
+      s0 += v[u] * x[u];
+      s1 += v[u + 1] * x[u + 1];
+    }
   }
   return s0 + s1;
 }

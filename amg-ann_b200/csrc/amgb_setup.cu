@@ -325,95 +325,122 @@ interp_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __r
     }
   }
   __syncwarp();
-  // phase 1: entries of row i in order
+  // phase 1: entries of row i in order.  Each accumulator keeps the sequential order of
+  // its own terms: P(i,p) receives the C entry p and the distributions of the strong F
+  // neighbours in entry order; the diagonal receives the weak entries and the strong F
+  // neighbours that share no C point with i, in entry order, at the end of the chunk.
+  // The row of the NEXT strong F neighbour (values, columns, C/F markers of the columns)
+  // is fetched while the current one is reduced, so its latency is off the critical path.
   int seen_c = 0;
   for (int kb = b; kb < e; kb += 32) {
     const int k = kb + lane;
-    int my_i1 = -1, my_c1 = -3, my_strong = 0;
-    double my_a = 0.0;
+    int my_i1 = -1, my_c1 = -3, my_strong = 0, my_b1 = 0, my_len1 = 0;
+    double my_a = 0.0, my_sgn = 1.0;
     if (k < e) {
       my_i1 = col[k];
       my_a = val[k];
       my_strong = mask[k];
       my_c1 = cf[my_i1];
     }
-    const int cnt = min(32, e - kb);
-    for (int t = 0; t < cnt; ++t) {
-      const int i1 = __shfl_sync(full, my_i1, t);
+    const bool offd = k < e && my_i1 != (int)i;
+    const bool is_c = offd && my_strong && my_c1 > 0;
+    const bool is_sf = offd && my_strong && my_c1 <= 0 && my_c1 != -3;
+    const bool is_weak = offd && !my_strong && my_c1 != -3;
+    if (is_sf) {
+      my_b1 = rp[my_i1];
+      my_len1 = rp[my_i1 + 1] - my_b1;
+      my_sgn = diagv[my_i1] < 0 ? -1.0 : 1.0;
+    }
+    const unsigned sfm = __ballot_sync(full, is_sf), cm = __ballot_sync(full, is_c);
+    const unsigned wm = __ballot_sync(full, is_weak);
+    unsigned zero_sum = 0, rest = sfm;
+    double nv = 0.0;  // prefetched row of the lowest strong F neighbour in `rest`
+    int ncol = -1, ncf = 0;
+    auto prefetch = [&](unsigned m) {
+      nv = 0.0;
+      ncol = -1;
+      ncf = 0;
+      if (!m) return;
+      const int nt = __ffs(m) - 1;
+      const int pb = __shfl_sync(full, my_b1, nt), pl = __shfl_sync(full, my_len1, nt);
+      if (pl <= 32 && lane < pl) {
+        nv = val[pb + lane];
+        ncol = col[pb + lane];
+        ncf = cf[ncol];
+      }
+    };
+    prefetch(rest);
+    for (unsigned both = sfm | cm; both; both &= both - 1) {
+      const int t = __ffs(both) - 1;
       const double a = __shfl_sync(full, my_a, t);
-      const int strong = __shfl_sync(full, my_strong, t);
-      const int c1 = __shfl_sync(full, my_c1, t);
-      if (i1 == (int)i) continue;
-      if (strong && c1 > 0) {
+      if ((cm >> t) & 1u) {
         if (lane == 0) myv[seen_c] = __dadd_rn(myv[seen_c], a);
         ++seen_c;
         __syncwarp();
-      } else if (strong && c1 != -3) {
-        // strong F neighbour: distribute a_ik over the C points i and k share
-        const int b1 = rp[i1], e1 = rp[i1 + 1];
-        const double sgn = diagv[i1] < 0 ? -1.0 : 1.0;
-        double sum = 0.0;
-        if (e1 - b1 <= 32) {
-          // the usual case: row k fits one warp-wide read, the qualifying
-          // entries stay in registers between the sum and the distribution
-          const int k1 = b1 + lane;
+        continue;
+      }
+      // strong F neighbour: distribute a_ik over the C points i and k share
+      const int b1 = __shfl_sync(full, my_b1, t), len1 = __shfl_sync(full, my_len1, t);
+      const double sgn = __shfl_sync(full, my_sgn, t);
+      const int e1 = b1 + len1;
+      double sum = 0.0;
+      if (len1 <= 32) {
+        // the usual case: row k fits one warp-wide read (already in registers)
+        const double v = nv;
+        const int i2 = ncol, f2 = ncf;
+        rest &= rest - 1;
+        prefetch(rest);
+        int pos = -1;
+        if (i2 >= 0 && sgn * v < 0 && f2 > 0) pos = find_sorted(myc, len, i2);
+        for (unsigned m = __ballot_sync(full, pos >= 0); m; m &= m - 1)
+          sum = __dadd_rn(sum, __shfl_sync(full, v, __ffs(m) - 1));
+        if (sum != 0) {
+          const double distribute = a / sum;
+          if (pos >= 0) myv[pos] = __dadd_rn(myv[pos], __dmul_rn(distribute, v));
+          __syncwarp();
+        } else {
+          zero_sum |= 1u << t;
+        }
+      } else {
+        for (int k1b = b1; k1b < e1; k1b += 32) {
+          const int k1 = k1b + lane;
           double v = 0.0;
-          int pos = -1;
+          bool q = false;
           if (k1 < e1) {
             v = val[k1];
             if (sgn * v < 0) {
               const int i2 = col[k1];
-              if (cf[i2] > 0) pos = find_sorted(myc, len, i2);
+              q = cf[i2] > 0 && find_sorted(myc, len, i2) >= 0;
             }
           }
-          for (unsigned m = __ballot_sync(full, pos >= 0); m; m &= m - 1)
+          for (unsigned m = __ballot_sync(full, q); m; m &= m - 1)
             sum = __dadd_rn(sum, __shfl_sync(full, v, __ffs(m) - 1));
-          if (sum != 0) {
-            const double distribute = a / sum;
-            if (pos >= 0) myv[pos] = __dadd_rn(myv[pos], __dmul_rn(distribute, v));
-            __syncwarp();
-          } else {
-            diagonal = __dadd_rn(diagonal, a);
-          }
-        } else {
+        }
+        if (sum != 0) {
+          const double distribute = a / sum;
           for (int k1b = b1; k1b < e1; k1b += 32) {
             const int k1 = k1b + lane;
-            double v = 0.0;
-            bool q = false;
             if (k1 < e1) {
-              v = val[k1];
+              const double v = val[k1];
               if (sgn * v < 0) {
                 const int i2 = col[k1];
-                q = cf[i2] > 0 && find_sorted(myc, len, i2) >= 0;
-              }
-            }
-            for (unsigned m = __ballot_sync(full, q); m; m &= m - 1)
-              sum = __dadd_rn(sum, __shfl_sync(full, v, __ffs(m) - 1));
-          }
-          if (sum != 0) {
-            const double distribute = a / sum;
-            for (int k1b = b1; k1b < e1; k1b += 32) {
-              const int k1 = k1b + lane;
-              if (k1 < e1) {
-                const double v = val[k1];
-                if (sgn * v < 0) {
-                  const int i2 = col[k1];
-                  if (cf[i2] > 0) {
-                    const int pos = find_sorted(myc, len, i2);
-                    if (pos >= 0) myv[pos] = __dadd_rn(myv[pos], __dmul_rn(distribute, v));
-                  }
+                if (cf[i2] > 0) {
+                  const int pos = find_sorted(myc, len, i2);
+                  if (pos >= 0) myv[pos] = __dadd_rn(myv[pos], __dmul_rn(distribute, v));
                 }
               }
             }
-            __syncwarp();
-          } else {
-            diagonal = __dadd_rn(diagonal, a);
           }
+          __syncwarp();
+        } else {
+          zero_sum |= 1u << t;
         }
-      } else if (c1 != -3) {
-        diagonal = __dadd_rn(diagonal, a);  // weak connection
+        rest &= rest - 1;
+        prefetch(rest);
       }
     }
+    for (unsigned m = wm | zero_sum; m; m &= m - 1)
+      diagonal = __dadd_rn(diagonal, __shfl_sync(full, my_a, __ffs(m) - 1));
   }
   __syncwarp();
   // phase 2: scale, renumber to coarse ids

@@ -19,10 +19,16 @@ ap.add_argument("--mode", default="full")
 ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--max-steps", type=int, default=0)
 ap.add_argument("--timers", action="store_true", help="per-family CUDA-event timers (disables the V-cycle graph)")
+ap.add_argument("--kind", default="poisson", choices=["poisson", "elasticity"])
 args = ap.parse_args()
 
 epsv = ab.gen.checkerboard_epsv(4, 3, args.contrast)
-s = ab.gen.poisson_q1(args.m, 4, 3, epsv)
+t_gen = time.perf_counter()
+if args.kind == "elasticity":   # BASELINE config 3: Q1 vector elasticity, 3 DoF/node, scalar AMG
+    s = ab.gen.elasticity_q1(args.m, 4, 3, 10.0 ** epsv)
+else:
+    s = ab.gen.poisson_q1(args.m, 4, 3, epsv)
+print(f"{args.kind} m={args.m}: n={s.n} nnz={s.nnz} generated in {time.perf_counter() - t_gen:.1f} s", flush=True)
 R = ab.RelaxationType
 data = ab.AdditionalData(True, args.theta, 0.9, 0, True, relaxation_type_up=R.l1scaledJacobi,
                          relaxation_type_down=R.l1scaledJacobi)

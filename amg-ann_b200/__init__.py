@@ -419,6 +419,22 @@ class ViewMaker:
         _chk(A.ctx._h, rc, "amgb_make_view")
         return self
 
+    NORM_MODES = {"nothing": 0, "pure": 1, "resc": 2, "pure_log": 3, "resc_log": 4, "mean": 5}
+
+    def make_model_input(self, A, normalization_mode="pure_log", count_channel_as_reference=True):
+        """ANN-ready [V, V, 4] tensor (sum, max_pp, max_np, count channel), pooled and
+        normalised on the device: ref data-modeling/train_ann.py:133-172 (norm_view) and
+        :247-256 ("sum+max+c" stacking)."""
+        V = self.view_size
+        out = np.empty((V, V, 4))
+        t = C.c_double()
+        rc = amgb_lib().amgb_make_view_normalized(A.ctx._h, A._h, V, self.NORM_MODES[normalization_mode],
+                                                  int(bool(count_channel_as_reference)), _p(out, c_f64p),
+                                                  C.byref(t))
+        self.t_device_us = t.value
+        _chk(A.ctx._h, rc, "amgb_make_view_normalized")
+        return out
+
 
 from . import dist  # noqa: E402  (row-partitioned front end; needs the names above)
 

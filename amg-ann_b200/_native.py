@@ -87,7 +87,7 @@ AMGB_SYMBOLS = [
     "amgb_precond_num_levels", "amgb_precond_level_stats", "amgb_precond_effective_relax",
     "amgb_precond_level_dims", "amgb_precond_get_strength_mask", "amgb_precond_get_cf_marker",
     "amgb_precond_get_A_csr", "amgb_precond_get_P_csr", "amgb_cg_solve",
-    "amgb_cg_solve_device", "amgb_make_view", "amgb_ctx_enable_timers",
+    "amgb_cg_solve_device", "amgb_make_view", "amgb_make_view_normalized", "amgb_ctx_enable_timers",
     "amgb_ctx_reset_timers", "amgb_timer_count", "amgb_timer_name", "amgb_ctx_get_timer",
     "amgb_ctx_get_timer_level",
     # row-partitioned path
@@ -153,6 +153,7 @@ def amgb_lib():
              c_f64p, C.c_int64, c_i64p)
         _sig(L.amgb_make_view, C.c_int, vp, vp, C.c_int32, c_f64p, c_i64p, c_f64p, c_f64p,
              c_f64p)
+        _sig(L.amgb_make_view_normalized, C.c_int, vp, vp, C.c_int32, C.c_int32, C.c_int32, c_f64p, c_f64p)
         _sig(L.amgb_ctx_enable_timers, C.c_int, vp, C.c_int)
         _sig(L.amgb_ctx_reset_timers, C.c_int, vp)
         _sig(L.amgb_timer_count, C.c_int)

@@ -149,13 +149,9 @@ pool_finalize_kernel(int V, int tiles, const double* __restrict__ part_sum,
 
 using namespace amgb;
 
-extern "C" int amgb_make_view(amgb_ctx* ctx, const amgb_matrix* A, int32_t view_size, double* sum,
-                              int64_t* count, double* max_pp, double* max_np, double* t_us) {
-  if (!ctx || !A || !sum || !count || !max_pp || !max_np || view_size < 1) return AMGB_ERR_BAD_ARG;
-  if (view_size > kMaxView)
-    return set_error(ctx, AMGB_ERR_UNSUPPORTED, "view_size %d > %d", view_size, kMaxView);
-  cudaSetDevice(ctx->device);
-  const int V = view_size;
+// Pooling into device buffers (vv = V*V entries each); ms: device time of the pass.
+static int pool_to_device(amgb_ctx* ctx, const amgb_matrix* A, int V, double* d_sum, long long* d_cnt, double* d_pp,
+                          double* d_np, float* ms_out) {
   const int n = (int)A->A.n;
   BinMap bm;
   bm.V = V;
@@ -170,16 +166,12 @@ extern "C" int amgb_make_view(amgb_ctx* ctx, const amgb_matrix* A, int32_t view_
   if (tiles < 1) tiles = 1;
   const size_t vv = (size_t)V * V;
   const size_t np = (size_t)V * tiles * V;
-  DevBuf<double> p_sum, p_pp, p_np, d_sum, d_pp, d_np;
-  DevBuf<long long> p_cnt, d_cnt;
+  DevBuf<double> p_sum, p_pp, p_np;
+  DevBuf<long long> p_cnt;
   AMGB_TRY(p_sum.alloc(ctx, np));
   AMGB_TRY(p_pp.alloc(ctx, np));
   AMGB_TRY(p_np.alloc(ctx, np));
   AMGB_TRY(p_cnt.alloc(ctx, np));
-  AMGB_TRY(d_sum.alloc(ctx, vv));
-  AMGB_TRY(d_pp.alloc(ctx, vv));
-  AMGB_TRY(d_np.alloc(ctx, vv));
-  AMGB_TRY(d_cnt.alloc(ctx, vv));
   const size_t smem = (size_t)kPoolWarps * V * (3 * sizeof(double) + sizeof(int));
   AMGB_CUDA(ctx, cudaFuncSetAttribute(pool_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0, e1;
@@ -191,23 +183,117 @@ extern "C" int amgb_make_view(amgb_ctx* ctx, const amgb_matrix* A, int32_t view_
   AMGB_LAUNCH(ctx, F_POOL, bytes, pool_tiles_kernel, (unsigned)(V * tiles), kPoolBlock, smem, bm, tiles,
               A->A.rp.p, A->A.col.p, A->A.val.p, p_sum.p, p_cnt.p, p_pp.p, p_np.p);
   AMGB_LAUNCH(ctx, F_POOL, 28.0 * np + 28.0 * vv, pool_finalize_kernel, (unsigned)div_up(vv, kPoolBlock),
-              kPoolBlock, 0, V, tiles, p_sum.p, p_cnt.p, p_pp.p, p_np.p, d_sum.p, d_cnt.p, d_pp.p, d_np.p);
+              kPoolBlock, 0, V, tiles, p_sum.p, p_cnt.p, p_pp.p, p_np.p, d_sum, d_cnt, d_pp, d_np);
   cudaError_t le = cudaGetLastError();
-  AMGB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
-  if (le != cudaSuccess) {
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    return cuda_fail(ctx, le, "pooling launch", __FILE__, __LINE__);
-  }
+  if (le == cudaSuccess) le = cudaEventRecord(e1, ctx->stream);
+  if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
+  float ms = 0.f;
+  if (le == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (le != cudaSuccess) return cuda_fail(ctx, le, "pooling", __FILE__, __LINE__);
+  if (ms_out) *ms_out = ms;
+  return AMGB_OK;
+}
+
+extern "C" int amgb_make_view(amgb_ctx* ctx, const amgb_matrix* A, int32_t view_size, double* sum,
+                              int64_t* count, double* max_pp, double* max_np, double* t_us) {
+  if (!ctx || !A || !sum || !count || !max_pp || !max_np || view_size < 1) return AMGB_ERR_BAD_ARG;
+  if (view_size > kMaxView)
+    return set_error(ctx, AMGB_ERR_UNSUPPORTED, "view_size %d > %d", view_size, kMaxView);
+  cudaSetDevice(ctx->device);
+  const size_t vv = (size_t)view_size * view_size;
+  DevBuf<double> d_sum, d_pp, d_np;
+  DevBuf<long long> d_cnt;
+  AMGB_TRY(d_sum.alloc(ctx, vv));
+  AMGB_TRY(d_pp.alloc(ctx, vv));
+  AMGB_TRY(d_np.alloc(ctx, vv));
+  AMGB_TRY(d_cnt.alloc(ctx, vv));
+  float ms = 0.f;
+  AMGB_TRY(pool_to_device(ctx, A, view_size, d_sum.p, d_cnt.p, d_pp.p, d_np.p, &ms));
   AMGB_CUDA(ctx, cudaMemcpyAsync(sum, d_sum.p, vv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   AMGB_CUDA(ctx, cudaMemcpyAsync(count, d_cnt.p, vv * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   AMGB_CUDA(ctx, cudaMemcpyAsync(max_pp, d_pp.p, vv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   AMGB_CUDA(ctx, cudaMemcpyAsync(max_np, d_np.p, vv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (t_us) *t_us = (double)ms * 1000.0;
+  return AMGB_OK;
+}
+
+namespace amgb {
+
+// ref data-modeling/train_ann.py:133-172 (norm_view) applied per channel, and the
+// channels-last stacking of "sum+max+c" (:247-256).  One block per channel: transform,
+// max |.| over the image (order-independent), scale.
+__device__ __forceinline__ double view_transform(int mode, double x, double cnt) {
+  const double resc = cnt > 0 ? x / cnt : 0.0;
+  switch (mode) {
+    case AMGB_NORM_RESC:
+    case AMGB_NORM_MEAN: return resc;
+    case AMGB_NORM_PURE_LOG: return log(fabs(x) + 1.0) * ((x > 0) - (x < 0));
+    case AMGB_NORM_RESC_LOG: return log(fabs(resc) + 1.0) * ((resc > 0) - (resc < 0));
+    default: return x;  // pure, nothing
+  }
+}
+
+__global__ void __launch_bounds__(kPoolBlock)
+view_normalize_kernel(int vv, int mode, int count_as_reference, const double* __restrict__ sum,
+                      const long long* __restrict__ cnt, const double* __restrict__ pp,
+                      const double* __restrict__ np, double* __restrict__ out) {
+  __shared__ double red[kPoolWarps];
+  __shared__ double vmax;
+  const int c = blockIdx.x;
+  const double* src = c == 0 ? sum : (c == 1 ? pp : np);
+  const bool from_count = c == 3 && !count_as_reference;
+  double m = 0.0;
+  for (int i = threadIdx.x; i < vv; i += kPoolBlock) {
+    const double x = from_count ? (double)cnt[i] : src[i];
+    m = fmax(m, fabs(view_transform(mode, x, (double)cnt[i])));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kPoolWarps; ++w) t = fmax(t, red[w]);
+    vmax = t;
+  }
+  __syncthreads();
+  const bool scaled = mode == AMGB_NORM_PURE || mode == AMGB_NORM_RESC || mode == AMGB_NORM_PURE_LOG ||
+                      mode == AMGB_NORM_RESC_LOG;
+  const double den = vmax;
+  for (int i = threadIdx.x; i < vv; i += kPoolBlock) {
+    const double x = from_count ? (double)cnt[i] : src[i];
+    const double t = view_transform(mode, x, (double)cnt[i]);
+    out[(size_t)i * 4 + c] = scaled ? t / den : t;  // 0/0 -> NaN like numpy (the reference then rejects the image)
+  }
+}
+
+}  // namespace amgb
+
+extern "C" int amgb_make_view_normalized(amgb_ctx* ctx, const amgb_matrix* A, int32_t view_size, int32_t mode,
+                                         int32_t count_channel_as_reference, double* out, double* t_us) {
+  if (!ctx || !A || !out || view_size < 1) return AMGB_ERR_BAD_ARG;
+  if (mode < AMGB_NORM_NOTHING || mode > AMGB_NORM_MEAN) return AMGB_ERR_BAD_ARG;
+  if (view_size > kMaxView)
+    return set_error(ctx, AMGB_ERR_UNSUPPORTED, "view_size %d > %d", view_size, kMaxView);
+  cudaSetDevice(ctx->device);
+  const size_t vv = (size_t)view_size * view_size;
+  DevBuf<double> d_sum, d_pp, d_np, d_out;
+  DevBuf<long long> d_cnt;
+  AMGB_TRY(d_sum.alloc(ctx, vv));
+  AMGB_TRY(d_pp.alloc(ctx, vv));
+  AMGB_TRY(d_np.alloc(ctx, vv));
+  AMGB_TRY(d_cnt.alloc(ctx, vv));
+  AMGB_TRY(d_out.alloc(ctx, vv * 4));
   float ms = 0.f;
-  cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  AMGB_TRY(pool_to_device(ctx, A, view_size, d_sum.p, d_cnt.p, d_pp.p, d_np.p, &ms));
+  AMGB_LAUNCH(ctx, F_POOL, 60.0 * vv, view_normalize_kernel, 4, kPoolBlock, 0, (int)vv, mode,
+              count_channel_as_reference, d_sum.p, d_cnt.p, d_pp.p, d_np.p, d_out.p);
+  AMGB_CHECK_LAUNCH(ctx);
+  AMGB_CUDA(ctx, cudaMemcpyAsync(out, d_out.p, vv * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (t_us) *t_us = (double)ms * 1000.0;
   return AMGB_OK;
 }

@@ -109,6 +109,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(family, m):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
+    (profiles/traffic.json); only valid for the mesh it was captured on."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if m != 200 or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f).get(family)
+    return t["traffic_bytes_per_launch"] if t else None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -326,10 +337,10 @@ def run_gpu(args):
     dom = "smooth_l0" if "smooth_l0" in kern else max(kern, key=lambda k: kern[k]["ms"])
     d = fam[dom]
     ach = d["bytes"] / d["ms"] / 1e6
-    roofline = {"bound": "hbm", "kernel": f"{dom} (csr_rows_kernel<LANES,EpiJacobi>, level 0)",
+    roofline = {"bound": "hbm", "kernel": f"{dom} (sell_rows_kernel<1,SPLIT,EpiJacobi>, level-0 C/F half sweeps)",
                 "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                 "peak_source": peak_src, "frac_of_nominal_8TBps": round(ach / 8000.0, 4),
-                "traffic": None,
+                "traffic": measured_traffic(dom, args.m),
                 "avg_launch_ms": round(d["ms"] / d["launches"], 4),
                 "algorithmic_bytes_per_launch": round(d["bytes"] / d["launches"]),
                 "families": kern}

@@ -210,6 +210,25 @@ int amgb_cg_solve_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_device,
 int amgb_make_view(amgb_ctx* ctx, const amgb_matrix* A, int32_t view_size, double* sum,
                    int64_t* count, double* max_pp, double* max_np, double* t_us);
 
+/* ANN-ready image: pooling followed, still on the device, by the per-channel normalisation
+ * of ref code/data-modeling/train_ann.py:133-172 (norm_view) and the channels-last stacking
+ * of its "sum+max+c" view type (:247-256).  out: V*V*4 doubles, [bin][channel] with channels
+ * (sum, max_pp, max_np, count).  count_channel_as_reference != 0 reproduces the reference's
+ * own count channel, which normalize_view_df (:189-193) computes from the max_np view (its
+ * loop variable is left at the last view type); 0 normalises the true counts.
+ * An all-zero channel gives NaN under the scaled modes, as numpy does (the reference then
+ * rejects the image, :200-209). */
+enum {
+  AMGB_NORM_NOTHING = 0,  /* "nothing"  */
+  AMGB_NORM_PURE = 1,     /* "pure":     x / max|x|                        */
+  AMGB_NORM_RESC = 2,     /* "resc":     (x / count) / max|.|              */
+  AMGB_NORM_PURE_LOG = 3, /* "pure_log": sign(x) log(|x|+1) / max|.|      */
+  AMGB_NORM_RESC_LOG = 4, /* "resc_log"                                    */
+  AMGB_NORM_MEAN = 5      /* "mean":     x / count                         */
+};
+int amgb_make_view_normalized(amgb_ctx* ctx, const amgb_matrix* A, int32_t view_size, int32_t mode,
+                              int32_t count_channel_as_reference, double* out, double* t_us);
+
 /* ---- row-partitioned (multi-GPU) path ------------------------------------- */
 /* For systems that do not fit one device (BASELINE config 5: >= 100 M DoFs, nnz > 2^31) the
  * matrix is partitioned by contiguous global row ranges, one rank per GPU, like a PETSc

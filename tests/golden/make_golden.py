@@ -70,6 +70,39 @@ def run_ref_view(rowptr, col, val, V):
     return view, count, mpp, mnp
 
 
+def reference_norm_view():
+    """The reference's own norm_view (ref code/data-modeling/train_ann.py:133-172), taken from
+    where it lies: the function's source is cut out of the file with ast and executed with
+    numpy only (the module itself imports tensorflow, which is not installed)."""
+    import ast
+    path = "/root/reference/code/data-modeling/train_ann.py"
+    src = open(path).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "norm_view")
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns["norm_view"]
+
+
+NORM_CASE = ("poisson", dict(m=10, contrast=2.0), 12)   # the image every mode is applied to
+NORM_MODES = ["nothing", "pure", "resc", "pure_log", "resc_log", "mean"]
+
+
+def make_norm_golden():
+    norm_view = reference_norm_view()
+    kind, kw, V = NORM_CASE
+    rp, col, val = build_case(kind, kw)
+    view, count, mpp, mnp = run_ref_view(rp, col, val, V)
+    row = {"view": view, "view_count": count, "view_max_pp": mpp, "view_max_np": mnp}
+    out = {}
+    for mode in NORM_MODES:
+        ch = [norm_view(row, mode, None, vt) for vt in ("", "_max_pp", "_max_np")]
+        # normalize_view_df (:189-193) fills view_count_<mode> from the LAST view type (max_np)
+        ch.append(norm_view(row, mode, None, "_max_np"))
+        out[mode] = np.stack(ch, axis=-1)          # "sum+max+c" stacking, :247-256
+    np.savez_compressed(os.path.join(HERE, "view_norm_poisson_m10_c2_V12.npz"), **out)
+    print("norm golden:", {k: v.shape for k, v in out.items()})
+
+
 def run_tool(name, args, text):
     return subprocess.run([os.path.join(REFDIR, name)] + args, input=text, capture_output=True, text=True,
                           check=True).stdout
@@ -90,6 +123,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"view_{name}.npz"), view=view, count=count, max_pp=mpp,
                             max_np=mnp, view_size=V, input_sha256=digest)
         print(name, "nnz", len(col), "count sum", count.sum())
+    make_norm_golden()
     lv = "".join(f"{r} {z}\n" for r, z in SCRAPE_LEVELS)
     text = run_tool("format_probe", ["boomeramg", "0.25", "0.9", "25"], lv)
     parsed = run_tool("ref_parse", ["boomeramg"], text).split("\n")

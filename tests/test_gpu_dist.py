@@ -111,3 +111,19 @@ def test_partition_not_aligned_with_planes_and_single_rank(gpu_ctx):
         parts = _run_partitioned(m, 2.0, starts, data)
         _assert_same_hierarchy(parts, P1)
         assert all(abs(p["niters"] - ctl1.last_step()) <= 1 for p in parts)
+
+
+@pytest.mark.parametrize("kw", [dict(w_cycle=True), dict(n_sweeps=2, max_iter=2),
+                                dict(relaxation_type_coarse=ab.RelaxationType.l1scaledJacobi, n_sweeps_coarse=2),
+                                dict(max_levels=3)])
+def test_partitioned_cycle_options(gpu_ctx, kw):
+    m = 10
+    s = poisson(m, contrast=3.0)
+    data = device_data(0.25, **kw)
+    A1, P1, ctl1, x1 = _single(gpu_ctx, s, data)
+    parts = _run_partitioned(m, 3.0, dist.slab_partition(m, 3), data)
+    _assert_same_hierarchy(parts, P1)
+    for p in parts:
+        assert abs(p["niters"] - ctl1.last_step()) <= 1
+        k = min(len(p["hist"]), len(ctl1.history))
+        assert (np.abs(p["hist"][:k] - ctl1.history[:k]) <= 1e-10 * ctl1.history[:k]).all()

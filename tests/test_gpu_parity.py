@@ -233,3 +233,51 @@ def test_truncated_hierarchy_dense_or_relaxed_coarsest(gpu_ctx, m, max_levels):
     assert abs(ctl.last_step() - nit) <= 1
     k = min(len(hist), len(ctl.history), 60)
     assert (np.abs(ctl.history[:k] - hist[:k]) <= 1e-9 * hist[:k]).all()
+
+
+@pytest.mark.parametrize("kw", [dict(w_cycle=True), dict(n_sweeps=2), dict(max_iter=2),
+                                dict(relaxation_type_coarse=ab.RelaxationType.l1scaledJacobi, n_sweeps_coarse=3),
+                                dict(max_coarse_size=60), dict(max_row_sum=1.0)])
+def test_cycle_options_of_additional_data(gpu_ctx, kw):
+    """The remaining deal.II AdditionalData / PCHYPRE knobs: W-cycle,
+    several sweeps, several cycles per application, relaxed coarsest grid, larger coarsest
+    grid, no dependency weakening."""
+    s = poisson(12, contrast=3.0)
+    mrs = kw.pop("max_row_sum", 0.9)
+    data = device_data(0.25, **kw)
+    data.max_row_sum = mrs
+    A, P, H = _both(gpu_ctx, s, data)
+    _assert_hierarchy_identical(P, H)
+    r = np.random.default_rng(7).standard_normal(s.n)
+    z = np.empty(s.n)
+    P.vmult(z, r)
+    zo = H.vmult(r)
+    assert np.abs(z - zo).max() <= 1e-11 * np.abs(zo).max()
+    ctl = ab.SolverControl(s.n, 1e-8)
+    x = s.x0.copy()
+    ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+    rc, xo, nit, hist = H.cg_solve(s.rhs, s.x0, abs_tol=1e-8)
+    assert rc == 0 and abs(ctl.last_step() - nit) <= 1
+    k = min(len(hist), len(ctl.history))
+    assert (np.abs(ctl.history[:k] - hist[:k]) <= RES_RTOL * hist[:k]).all()
+
+
+def test_bad_arguments_are_reported_not_crashed(gpu_ctx):
+    s = poisson(6)
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    P = ab.PreconditionBoomerAMG()
+    with pytest.raises(ab.AmgbError) as e:
+        P.initialize(A, device_data(0.25, coarsen_type=ab.COARSEN_FALGOUT))   # serial algorithm: not on device
+    assert e.value.status == -5
+    with pytest.raises(ab.AmgbError):
+        P.initialize(A, device_data(0.25, interp_type=6))
+    with pytest.raises(ab.AmgbError):
+        P.initialize(A, device_data(0.25, max_levels=0))
+    with pytest.raises(ab.AmgbError):
+        ab.ViewMaker(100000).make_view(A)
+    # a preconditioner built for another matrix is refused by cg.solve
+    s2 = poisson(5)
+    A2 = ab.SparseMatrix(gpu_ctx, s2.rowptr32(), s2.col, s2.val)
+    P.initialize(A2, device_data(0.25))
+    with pytest.raises(ab.AmgbError):
+        ab.SolverCG(ab.SolverControl(10, 1e-8)).solve(A, s.x0.copy(), s.rhs, P)

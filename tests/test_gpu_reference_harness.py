@@ -107,3 +107,26 @@ def test_cpp_datagen_driver_writes_the_reference_csv_schema(gpu_ctx, tmp_path):
     for row in rows[1:]:
         cnt = np.array([int(float(v)) for v in row[13].split(",")])
         assert cnt.sum() == (3 * 8 + 1) ** 3 and int(row[11]) == 10
+
+
+@pytest.mark.parametrize("mode", make_golden.NORM_MODES)
+def test_device_view_normalisation_equals_reference_norm_view_golden(gpu_ctx, mode):
+    """f3: pooled image normalised + stacked on the device vs the reference's own norm_view
+    (golden generated from ref data-modeling/train_ann.py:133-172 by tests/golden/make_golden.py)."""
+    kind, kw, V = make_golden.NORM_CASE
+    rp, col, val = make_golden.build_case(kind, kw)
+    A = ab.SparseMatrix(gpu_ctx, rp.astype(np.int32), col, val)
+    g = np.load(os.path.join(GOLD, "view_norm_poisson_m10_c2_V12.npz"))[mode].reshape(V, V, 4)
+    out = ab.ViewMaker(V).make_model_input(A, mode, count_channel_as_reference=True)
+    assert out.shape == (V, V, 4)
+    # fp64: the pooled sum differs from the serial sum in the last bits, log() by <= 1 ulp
+    assert np.allclose(out, g, rtol=1e-12, atol=1e-13)
+    if mode in ("pure", "pure_log", "resc", "resc_log"):
+        assert np.abs(out).max() <= 1.0 and np.isclose(np.abs(out[..., 0]).max(), 1.0)
+    # the true-count channel (library extension): counts normalised under the same mode
+    own = ab.ViewMaker(V).make_model_input(A, mode, count_channel_as_reference=False)
+    cnt = ab.ViewMaker(V).make_view(A).count.reshape(V, V).astype(float)
+    expect = {"nothing": cnt, "pure": cnt / cnt.max(), "mean": (cnt > 0).astype(float)}.get(mode)
+    if expect is not None:
+        assert np.allclose(own[..., 3], expect, rtol=1e-15, atol=0)
+    assert np.array_equal(own[..., :3], out[..., :3])

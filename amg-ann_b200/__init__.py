@@ -233,6 +233,31 @@ class SparseMatrix:
         _chk(ctx._h, rc, "amgb_matrix_wrap_device_csr")
         return self
 
+    @classmethod
+    def assemble_poisson_q1(cls, ctx, m, pattern_size=1, mode=1, epsv=None, rhs_ptr=0, x0_ptr=0):
+        """On-device assembly (ref t2 main.cpp:255-320), bit-identical to gen.poisson_q1.
+        rhs_ptr / x0_ptr: device pointers to (m+1)^3 doubles (e.g. torch data_ptr()), or 0."""
+        if epsv is None:
+            epsv = np.zeros(pattern_size ** mode)
+        epsv = np.ascontiguousarray(epsv, dtype=np.float64)
+        self = cls.__new__(cls)
+        self.ctx, self.n = ctx, (m + 1) ** 3
+        self._h = C.c_void_p()
+        rc = amgb_lib().amgb_matrix_assemble_poisson_q1(ctx._h, m, pattern_size, mode, _p(epsv, c_f64p), len(epsv),
+                                                        C.byref(self._h), C.c_void_p(rhs_ptr), C.c_void_p(x0_ptr))
+        _chk(ctx._h, rc, "amgb_matrix_assemble_poisson_q1")
+        return self
+
+    def download(self):
+        n, nnz = C.c_int64(), C.c_int64()
+        amgb_lib().amgb_matrix_dims(self._h, C.byref(n), C.byref(nnz))
+        rp = np.empty(n.value + 1, dtype=np.int32)
+        cl = np.empty(nnz.value, dtype=np.int32)
+        vl = np.empty(nnz.value)
+        _chk(self.ctx._h, amgb_lib().amgb_matrix_download_csr(self._h, _p(rp, c_i32p), _p(cl, c_i32p),
+                                                              _p(vl, c_f64p)), "amgb_matrix_download_csr")
+        return rp, cl, vl
+
     def m(self):
         return self.n
 

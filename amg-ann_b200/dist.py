@@ -124,6 +124,24 @@ class DistSparseMatrix:
                                                 _p(v, c_f64p), C.byref(self._h))
         _chk(self.ctx._h, rc, "amgb_dist_matrix_create")
 
+    @classmethod
+    def assemble_poisson_q1(cls, comm, m, row_begin, row_end, pattern_size=1, mode=1, epsv=None, rhs_ptr=0,
+                            x0_ptr=0):
+        """This rank's slab assembled on its device (bit-identical to gen.poisson_q1 with the
+        same row range).  rhs_ptr / x0_ptr: device pointers to row_end-row_begin doubles, or 0."""
+        if epsv is None:
+            epsv = np.zeros(pattern_size ** mode)
+        epsv = np.ascontiguousarray(epsv, dtype=np.float64)
+        self = cls.__new__(cls)
+        self.comm, self.ctx = comm, comm.ctx
+        self.n_global, self.row_begin, self.row_end = (m + 1) ** 3, int(row_begin), int(row_end)
+        self._h = C.c_void_p()
+        rc = amgb_lib().amgb_dist_matrix_assemble_poisson_q1(
+            self.ctx._h, comm._h, m, pattern_size, mode, _p(epsv, c_f64p), len(epsv), self.row_begin, self.row_end,
+            C.byref(self._h), C.c_void_p(rhs_ptr), C.c_void_p(x0_ptr))
+        _chk(self.ctx._h, rc, "amgb_dist_matrix_assemble_poisson_q1")
+        return self
+
     @property
     def n_local(self):
         return self.row_end - self.row_begin

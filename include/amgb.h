@@ -148,6 +148,17 @@ int amgb_matrix_upload_csr64(amgb_ctx* ctx, int64_t n, const int64_t* rowptr,
 int amgb_matrix_wrap_device_csr(amgb_ctx* ctx, int64_t n, int64_t nnz,
                                 const int32_t* rowptr_device, const int32_t* col_device,
                                 const double* val_device, amgb_matrix** out);
+/* On-device assembly of the Q1 diffusion system of the reference's structured test case
+ * (ref testcase2-diffusion-structured/src/main.cpp:255-320; mu = 10^epsv on a
+ * pattern_size^mode pattern, :101-113; Dirichlet rows as :312-318; lexicographic node
+ * numbering; m cells per direction on [-1,1]^3).  Bit-identical to the host generator
+ * amgb_gen_poisson_q1 (include/amgb_gen.h), but the matrix is born in HBM.  rhs_device /
+ * x0_device: device arrays of n = (m+1)^3 doubles, or NULL. */
+int amgb_matrix_assemble_poisson_q1(amgb_ctx* ctx, int32_t m, int32_t pattern_size, int32_t mode,
+                                    const double* epsv, int64_t n_epsv, amgb_matrix** out,
+                                    double* rhs_device, double* x0_device);
+/* CSR of a resident matrix back to host arrays (any pointer may be NULL). */
+int amgb_matrix_download_csr(const amgb_matrix* A, int32_t* rowptr, int32_t* col, double* val);
 int amgb_matrix_destroy(amgb_matrix* A);
 int amgb_matrix_dims(const amgb_matrix* A, int64_t* n, int64_t* nnz);
 /* y = A x (host vectors); the plain SpMV, exposed for parity tests. */
@@ -262,6 +273,12 @@ int amgb_comm_size(const amgb_comm* c);
 int amgb_dist_matrix_create(amgb_ctx* ctx, amgb_comm* comm, int64_t n_global, int64_t row_begin,
                             int64_t row_end, const int64_t* rowptr_local, const int32_t* col_global,
                             const double* val, amgb_dist_matrix** out);
+/* The slab [row_begin,row_end) of the same system assembled on this rank's device
+ * (rhs_device / x0_device: row_end-row_begin doubles, or NULL).  Collective. */
+int amgb_dist_matrix_assemble_poisson_q1(amgb_ctx* ctx, amgb_comm* comm, int32_t m, int32_t pattern_size,
+                                         int32_t mode, const double* epsv, int64_t n_epsv,
+                                         int64_t row_begin, int64_t row_end, amgb_dist_matrix** out,
+                                         double* rhs_device, double* x0_device);
 int amgb_dist_matrix_destroy(amgb_dist_matrix* A);
 /* initialize() on the partitioned matrix; the result is used with the amgb_precond_*
  * queries (level statistics are global) and destroyed with amgb_precond_destroy. */

@@ -82,7 +82,7 @@ AMGB_SYMBOLS = [
     "amgb_status_string", "amgb_version", "amgb_ctx_kernel_launches",
     "amgb_ctx_reset_kernel_launches", "amgb_matrix_upload_csr", "amgb_matrix_upload_csr64",
     "amgb_matrix_wrap_device_csr", "amgb_matrix_destroy", "amgb_matrix_dims",
-    "amgb_matrix_assemble_poisson_q1", "amgb_matrix_download_csr", "amgb_dist_matrix_assemble_poisson_q1",
+    "amgb_matrix_assemble_poisson_q1", "amgb_matrix_assemble_poisson_q1_hostvec", "amgb_matrix_download_csr", "amgb_dist_matrix_assemble_poisson_q1",
     "amgb_matrix_vmult", "amgb_boomeramg_data_default", "amgb_precond_initialize",
     "amgb_precond_destroy", "amgb_precond_vmult", "amgb_precond_vmult_device",
     "amgb_precond_num_levels", "amgb_precond_level_stats", "amgb_precond_effective_relax",
@@ -132,6 +132,8 @@ def amgb_lib():
              C.POINTER(vp))
         _sig(L.amgb_matrix_assemble_poisson_q1, C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, c_f64p, C.c_int64,
              C.POINTER(vp), vp, vp)
+        _sig(L.amgb_matrix_assemble_poisson_q1_hostvec, C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, c_f64p,
+             C.c_int64, C.POINTER(vp), c_f64p, c_f64p)
         _sig(L.amgb_matrix_download_csr, C.c_int, vp, c_i32p, c_i32p, c_f64p)
         _sig(L.amgb_dist_matrix_assemble_poisson_q1, C.c_int, vp, vp, C.c_int32, C.c_int32, C.c_int32, c_f64p,
              C.c_int64, C.c_int64, C.c_int64, C.POINTER(vp), vp, vp)

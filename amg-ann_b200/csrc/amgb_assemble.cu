@@ -331,6 +331,24 @@ int amgb_dist_matrix_assemble_poisson_q1(amgb_ctx* ctx, amgb_comm* comm, int32_t
   return AMGB_OK;
 }
 
+/* Same, with the right-hand side and the initial guess returned in HOST arrays (n doubles
+ * each, or NULL): for host code that keeps its vectors on the host (dealii_compat). */
+int amgb_matrix_assemble_poisson_q1_hostvec(amgb_ctx* ctx, int32_t m, int32_t pattern_size, int32_t mode,
+                                            const double* epsv, int64_t n_epsv, amgb_matrix** out, double* rhs_host,
+                                            double* x0_host) {
+  if (!ctx || !out || m < 1) return AMGB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  const int64_t N = (int64_t)m + 1, n = N * N * N;
+  DevBuf<double> drhs, dx0;
+  if (rhs_host) AMGB_TRY(drhs.alloc(ctx, n));
+  if (x0_host) AMGB_TRY(dx0.alloc(ctx, n));
+  AMGB_TRY(amgb_matrix_assemble_poisson_q1(ctx, m, pattern_size, mode, epsv, n_epsv, out, drhs.p, dx0.p));
+  if (rhs_host) AMGB_CUDA(ctx, cudaMemcpyAsync(rhs_host, drhs.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (x0_host) AMGB_CUDA(ctx, cudaMemcpyAsync(x0_host, dx0.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMGB_OK;
+}
+
 /* CSR of a resident matrix back to the host (tests; rowptr may be NULL etc.). */
 int amgb_matrix_download_csr(const amgb_matrix* A, int32_t* rowptr, int32_t* col, double* val) {
   if (!A) return AMGB_ERR_BAD_ARG;

@@ -64,6 +64,16 @@ class Matrix {
       : ctx_(&ctx) {
     ctx.check(amgb_matrix_upload_csr(ctx.get(), n, rowptr, col, val, &h_), "amgb_matrix_upload_csr");
   }
+  // on-device assembly of the Q1 diffusion system (ref t2 main.cpp:255-320); rhs / x0 on the host
+  static Matrix assemble_poisson_q1(const Context& ctx, int m, int pattern_size, int mode, const double* epsv,
+                                    int64_t n_epsv, double* rhs_host, double* x0_host) {
+    Matrix M;
+    M.ctx_ = &ctx;
+    ctx.check(amgb_matrix_assemble_poisson_q1_hostvec(ctx.get(), m, pattern_size, mode, epsv, n_epsv, &M.h_,
+                                                      rhs_host, x0_host),
+              "amgb_matrix_assemble_poisson_q1_hostvec");
+    return M;
+  }
   ~Matrix() { reset(); }
   Matrix(Matrix&& o) noexcept : ctx_(o.ctx_), h_(o.h_) { o.h_ = nullptr; }
   Matrix& operator=(Matrix&& o) noexcept {

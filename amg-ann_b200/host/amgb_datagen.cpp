@@ -5,7 +5,7 @@
 //   amgb_datagen [--m 100] [--pattern-size 4] [--mode 3] [--contrast 6 | --seed S --eps-max 6]
 //                [--theta 0.05,0.96,0.05] [--max-row-sum 0.9] [--tol 1e-8] [--details 1]
 //                [--make-view 0|1] [--view-size 75] [--systems 1] [--threads 1]
-//                [--setting NAME] --out stats.csv
+//                [--device-assembly 0|1] [--setting NAME] --out stats.csv
 //
 // --systems N --threads T: N independent systems (seeds S..S+N-1, ref 00_data-generation.py
 // :105-116 fans them out over processes) are processed by T host threads, each with its own
@@ -26,6 +26,7 @@ namespace {
 
 struct Args {
   int m = 100, ps = 4, mode = 3, details = 1, make_view = 0, view_size = 75, systems = 1, threads = 1;
+  int device_assembly = 0;
   double contrast = 6.0, eps_max = 6.0, t0 = 0.05, t1 = 0.96, dt = 0.05, mrs = 0.9, tol = 1e-8;
   long seed = -1;
   std::string out, setting = "synthetic";
@@ -49,6 +50,7 @@ bool parse(int argc, char** argv, Args& a) {
     else if (k == "--view-size") a.view_size = std::atoi(val());
     else if (k == "--systems") a.systems = std::atoi(val());
     else if (k == "--threads") a.threads = std::atoi(val());
+    else if (k == "--device-assembly") a.device_assembly = std::atoi(val());
     else if (k == "--setting") a.setting = val();
     else if (k == "--out") a.out = val();
     else return false;
@@ -70,19 +72,23 @@ void run_system(const Args& a, long seed, std::ostream& out, Totals& tot) {
   std::vector<double> epsv(ne);
   if (seed >= 0) amgb_gen_random_vec(seed, ne, a.eps_max, epsv.data());  // ref myutils.h:47-54
   else amgb_gen_checkerboard_epsv(a.ps, a.mode, a.contrast, epsv.data());
-  std::vector<int64_t> rp(n + 1);
-  std::vector<int32_t> col(nnz);
-  std::vector<double> val(nnz), rhs(n), x0(n);
-  if (amgb_gen_poisson_q1(a.m, a.ps, a.mode, epsv.data(), ne, 0, n, rp.data(), col.data(), val.data(), rhs.data(),
-                          x0.data()))
-    throw std::runtime_error("amgb_gen_poisson_q1");
   using namespace dealii;
   PETScWrappers::MPI::SparseMatrix system_matrix;
-  system_matrix.reinit_csr(n, rp.data(), col.data(), val.data());
   PETScWrappers::MPI::Vector system_rhs(n), solution(n), zero_solution(n);
-  for (int64_t i = 0; i < n; ++i) {
-    system_rhs[i] = rhs[i];
-    zero_solution[i] = x0[i];
+  if (a.device_assembly) {  // the matrix is born in HBM (amgb_matrix_assemble_poisson_q1)
+    system_matrix.reinit_device_poisson_q1(a.m, a.ps, a.mode, epsv.data(), ne, system_rhs, zero_solution);
+  } else {
+    std::vector<int64_t> rp(n + 1);
+    std::vector<int32_t> col(nnz);
+    std::vector<double> val(nnz), rhs(n), x0(n);
+    if (amgb_gen_poisson_q1(a.m, a.ps, a.mode, epsv.data(), ne, 0, n, rp.data(), col.data(), val.data(), rhs.data(),
+                            x0.data()))
+      throw std::runtime_error("amgb_gen_poisson_q1");
+    system_matrix.reinit_csr(n, rp.data(), col.data(), val.data());
+    for (int64_t i = 0; i < n; ++i) {
+      system_rhs[i] = rhs[i];
+      zero_solution[i] = x0[i];
+    }
   }
   auto print_stats = [&]() {  // ref t2 main.cpp:498-512
     out << std::scientific << std::setprecision(17);

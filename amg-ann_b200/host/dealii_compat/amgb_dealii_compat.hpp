@@ -139,7 +139,7 @@ typedef const amgb::compat::CsrHost* Mat;
 
 inline PetscErrorCode MatGetRow(Mat A, PetscInt row, PetscInt* ncols, const PetscInt** cols,
                                 const PetscScalar** vals) {
-  if (!A || row < 0 || row >= A->n) return 63;  // PETSC_ERR_ARG_OUTOFRANGE
+  if (!A || row < 0 || row >= A->n || (int64_t)A->rowptr.size() != A->n + 1) return 63;  // PETSC_ERR_ARG_OUTOFRANGE
   const int64_t b = A->rowptr[row];
   if (ncols) *ncols = (PetscInt)(A->rowptr[row + 1] - b);
   if (cols) *cols = A->col.data() + b;
@@ -260,9 +260,22 @@ class SparseMatrix {
     host_.val.assign(val, val + nnz);
     dev_.reset();
   }
+  // The system assembled directly in device memory (no host CSR: MatGetRow is not served;
+  // pooling and the solve run on the device copy).  rhs / x0: n = (m+1)^3 doubles.
+  void reinit_device_poisson_q1(int m, int pattern_size, int mode, const double* epsv, int64_t n_epsv, Vector& rhs,
+                                Vector& x0) {
+    const int64_t N = (int64_t)m + 1, n = N * N * N;
+    host_ = amgb::compat::CsrHost();
+    host_.n = n;
+    host_.rowptr.assign(1, 0);  // no host entries
+    rhs.reinit((size_t)n);
+    x0.reinit((size_t)n);
+    dev_ = amgb::Matrix::assemble_poisson_q1(amgb::compat::default_context(), m, pattern_size, mode, epsv, n_epsv,
+                                             rhs.data(), x0.data());
+  }
   PetscInt m() const { return (PetscInt)host_.n; }
   PetscInt n() const { return (PetscInt)host_.n; }
-  int64_t n_nonzero_elements() const { return host_.n ? host_.rowptr[host_.n] : 0; }
+  int64_t n_nonzero_elements() const { return host_.rowptr.size() > 1 ? host_.rowptr.back() : 0; }
   Mat petsc_matrix() const { return &host_; }
   operator Mat() const { return &host_; }
   const amgb::Matrix& device() const {

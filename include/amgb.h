@@ -157,6 +157,10 @@ int amgb_matrix_wrap_device_csr(amgb_ctx* ctx, int64_t n, int64_t nnz,
 int amgb_matrix_assemble_poisson_q1(amgb_ctx* ctx, int32_t m, int32_t pattern_size, int32_t mode,
                                     const double* epsv, int64_t n_epsv, amgb_matrix** out,
                                     double* rhs_device, double* x0_device);
+/* Same, returning the right-hand side and the initial guess in HOST arrays (n doubles, or NULL). */
+int amgb_matrix_assemble_poisson_q1_hostvec(amgb_ctx* ctx, int32_t m, int32_t pattern_size, int32_t mode,
+                                            const double* epsv, int64_t n_epsv, amgb_matrix** out,
+                                            double* rhs_host, double* x0_host);
 /* CSR of a resident matrix back to host arrays (any pointer may be NULL). */
 int amgb_matrix_download_csr(const amgb_matrix* A, int32_t* rowptr, int32_t* col, double* val);
 int amgb_matrix_destroy(amgb_matrix* A);

@@ -130,3 +130,19 @@ def test_device_view_normalisation_equals_reference_norm_view_golden(gpu_ctx, mo
     if expect is not None:
         assert np.allclose(own[..., 3], expect, rtol=1e-15, atol=0)
     assert np.array_equal(own[..., :3], out[..., :3])
+
+
+def test_cpp_driver_with_device_assembly_gives_identical_rows(tmp_path):
+    exe = os.path.join(os.path.dirname(HERE), "amg-ann_b200", "host", "amgb_datagen")
+    outs = []
+    for dev in ("0", "1"):
+        out = tmp_path / f"stats{dev}.csv"
+        r = subprocess.run([exe, "--m", "10", "--pattern-size", "2", "--mode", "3", "--seed", "7", "--theta",
+                            "0.25,0.6,0.25", "--device-assembly", dev, "--out", str(out)], capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(list(csv.reader(open(out))))
+    assert len(outs[0]) == len(outs[1]) == 3
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        # everything but the timestamp / timing columns is identical (the matrices are bit-identical)
+        assert a[:9] == b[:9] and a[10:15] == b[10:15] and a[17:] == b[17:]

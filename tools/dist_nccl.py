@@ -30,6 +30,7 @@ ap.add_argument("--contrast", type=float, default=0.0)
 ap.add_argument("--repeat", type=int, default=2)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--timers", action="store_true")
+ap.add_argument("--device-assembly", action="store_true", help="assemble the slab on the GPU instead of the host")
 args = ap.parse_args()
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
@@ -53,9 +54,18 @@ epsv = ab.gen.checkerboard_epsv(4, 3, args.contrast)
 starts = dist.slab_partition(args.m, world)
 b, e = starts[rank], starts[rank + 1]
 t0 = time.perf_counter()
-sl = ab.gen.poisson_q1(args.m, 4, 3, epsv, row_begin=b, row_end=e)
-t_gen = time.perf_counter() - t0
-A = dist.DistSparseMatrix(comm, sl.n, b, e, sl.rowptr, sl.col, sl.val)
+if args.device_assembly:
+    from types import SimpleNamespace
+    d_rhs = torch.empty(e - b, dtype=torch.float64, device="cuda")
+    d_x0 = torch.empty(e - b, dtype=torch.float64, device="cuda")
+    A = dist.DistSparseMatrix.assemble_poisson_q1(comm, args.m, b, e, 4, 3, epsv, d_rhs.data_ptr(), d_x0.data_ptr())
+    ctx.synchronize()
+    sl = SimpleNamespace(n=(args.m + 1) ** 3, rhs=d_rhs.cpu().numpy(), x0=d_x0.cpu().numpy())
+    t_gen = time.perf_counter() - t0
+else:
+    sl = ab.gen.poisson_q1(args.m, 4, 3, epsv, row_begin=b, row_end=e)
+    t_gen = time.perf_counter() - t0
+    A = dist.DistSparseMatrix(comm, sl.n, b, e, sl.rowptr, sl.col, sl.val)
 
 
 def tmax(v):

@@ -1027,6 +1027,315 @@ int build_interp(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const i
   return AMGB_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Aggressive coarsening (levels < aggressive_coarsening_num_levels; ref t3 main.cpp:456):
+// second PMIS on the distance-two strength graph S2 of the first-stage C points
+// (hypre_BoomerAMGCreate2ndS, num_paths = 1) and multipass interpolation
+// (hypre_BoomerAMGBuildMultipass).  Operation for operation the oracle's
+// aggressive_second_pass / interp_multipass.  S2 is the pattern product A1*B
+// (A1: strong rows of the C points; B: unit rows for C points, strong C neighbours for
+// F points) computed with the SpGEMM above; the passes of the interpolation are sparse
+// products W_k * P_(<k) whose ordered accumulation is again the SpGEMM's.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+agg_rowlen_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                  const uint8_t* __restrict__ mask, const int32_t* __restrict__ cf, const int32_t* __restrict__ f2c,
+                  int32_t* __restrict__ len_a1, int32_t* __restrict__ len_b) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  int s = 0, sc = 0;
+  for (int k = rp[i]; k < rp[i + 1]; ++k)
+    if (mask[k]) {
+      ++s;
+      sc += cf[col[k]] > 0;
+    }
+  if (cf[i] > 0) {
+    len_a1[f2c[i]] = s;
+    len_b[i] = 1;
+  } else {
+    len_b[i] = sc;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+agg_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                const uint8_t* __restrict__ mask, const int32_t* __restrict__ cf, const int32_t* __restrict__ f2c,
+                const int32_t* __restrict__ a1_rp, int32_t* __restrict__ a1_col, double* __restrict__ a1_val,
+                const int32_t* __restrict__ b_rp, int32_t* __restrict__ b_col, double* __restrict__ b_val) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  int w = b_rp[i];
+  if (cf[i] > 0) {
+    b_col[w] = f2c[i];
+    b_val[w] = 1.0;
+    int a = a1_rp[f2c[i]];
+    for (int k = rp[i]; k < rp[i + 1]; ++k)
+      if (mask[k]) {
+        a1_col[a] = col[k];
+        a1_val[a] = 1.0;
+        ++a;
+      }
+  } else {
+    for (int k = rp[i]; k < rp[i + 1]; ++k)
+      if (mask[k] && cf[col[k]] > 0) {
+        b_col[w] = f2c[col[k]];
+        b_val[w] = 1.0;
+        ++w;
+      }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+offdiag_mask_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                    uint8_t* __restrict__ mask, int32_t* __restrict__ has_strong) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  int any = 0;
+  for (int k = rp[i]; k < rp[i + 1]; ++k) {
+    const uint8_t m = col[k] != (int)i;
+    mask[k] = m;
+    any |= m;
+  }
+  has_strong[i] = any;
+}
+
+__global__ void __launch_bounds__(kBlock)
+correct_cf_kernel(int64_t n, int32_t* __restrict__ cf, const int32_t* __restrict__ f2c,
+                  const int32_t* __restrict__ cf2) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i < n && cf[i] > 0) cf[i] = cf2[f2c[i]];
+}
+
+// cf (in: first-stage splitting with its numbering f2c; out: corrected splitting)
+static int aggressive_second_pass(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, int32_t* cf,
+                                  const int32_t* f2c, int32_t nc1) {
+  const int64_t n = A.n;
+  const unsigned grid = (unsigned)div_up(n, kBlock);
+  DeviceCsr A1, B, M;
+  DevBuf<int32_t> len_a1, len_b;
+  AMGB_TRY(len_a1.alloc(ctx, nc1));
+  AMGB_TRY(len_b.alloc(ctx, n));
+  AMGB_LAUNCH(ctx, F_COARSEN, 5.0 * A.nnz + 12.0 * n, agg_rowlen_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p, mask,
+              (const int32_t*)cf, f2c, len_a1.p, len_b.p);
+  A1.n = nc1;
+  A1.ncols = n;
+  B.n = n;
+  B.ncols = nc1;
+  AMGB_TRY(A1.rp.alloc(ctx, nc1 + 1));
+  AMGB_TRY(B.rp.alloc(ctx, n + 1));
+  AMGB_TRY(exclusive_scan_i32(ctx, len_a1.p, A1.rp.p, nc1));
+  AMGB_TRY(exclusive_scan_i32(ctx, len_b.p, B.rp.p, n));
+  int32_t nnz_a1 = 0, nnz_b = 0;
+  AMGB_TRY(read_i32(ctx, A1.rp.p + nc1, &nnz_a1));
+  AMGB_TRY(read_i32(ctx, B.rp.p + n, &nnz_b));
+  A1.nnz = nnz_a1;
+  B.nnz = nnz_b;
+  AMGB_TRY(A1.col.alloc(ctx, nnz_a1));
+  AMGB_TRY(A1.val.alloc(ctx, nnz_a1));
+  AMGB_TRY(B.col.alloc(ctx, nnz_b));
+  AMGB_TRY(B.val.alloc(ctx, nnz_b));
+  AMGB_LAUNCH(ctx, F_COARSEN, 5.0 * A.nnz + 12.0 * (nnz_a1 + nnz_b), agg_fill_kernel, grid, kBlock, 0, n, A.rp.p,
+              A.col.p, mask, (const int32_t*)cf, f2c, (const int32_t*)A1.rp.p, A1.col.p, A1.val.p,
+              (const int32_t*)B.rp.p, B.col.p, B.val.p);
+  AMGB_CHECK_LAUNCH(ctx);
+  AMGB_TRY(spgemm(ctx, A1, B, M, true));
+  DevBuf<uint8_t> mask2;
+  DevBuf<int32_t> has2, cf2;
+  AMGB_TRY(mask2.alloc(ctx, M.nnz));
+  AMGB_TRY(has2.alloc(ctx, nc1));
+  AMGB_TRY(cf2.alloc(ctx, nc1));
+  AMGB_LAUNCH(ctx, F_COARSEN, 5.0 * M.nnz + 8.0 * nc1, offdiag_mask_kernel, (unsigned)div_up(nc1, kBlock), kBlock, 0,
+              (int64_t)nc1, M.rp.p, M.col.p, mask2.p, has2.p);
+  AMGB_CHECK_LAUNCH(ctx);
+  AMGB_TRY(coarsen_pmis(ctx, M, mask2.p, has2.p, cf2.p, nullptr));
+  AMGB_LAUNCH(ctx, F_COARSEN, 12.0 * n, correct_cf_kernel, grid, kBlock, 0, n, cf, f2c, (const int32_t*)cf2.p);
+  AMGB_CHECK_LAUNCH(ctx);
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMGB_OK;
+}
+
+// ---- multipass interpolation ----
+__global__ void __launch_bounds__(kBlock)
+mp_init_kernel(int64_t n, const int32_t* __restrict__ cf, int32_t* __restrict__ pass, int32_t* __restrict__ len) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const int c = cf[i] > 0;
+  pass[i] = c ? 0 : -1;
+  len[i] = c;
+}
+
+__global__ void __launch_bounds__(kBlock)
+mp_assign_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                 const uint8_t* __restrict__ mask, int32_t* __restrict__ pass, int k, int32_t* __restrict__ newly) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  int hit = 0;
+  if (i < n && pass[i] < 0) {
+    // neighbours of pass k-1 are final; points assigned in this sweep get k != k-1
+    for (int e = rp[i]; e < rp[i + 1]; ++e)
+      if (mask[e] && pass[col[e]] == k - 1) {
+        hit = 1;
+        break;
+      }
+    if (hit) pass[i] = k;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(newly, __popc(b));
+}
+
+__global__ void __launch_bounds__(kBlock)
+mp_count_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                const uint8_t* __restrict__ mask, const int32_t* __restrict__ pass, int k,
+                int32_t* __restrict__ len) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  int c = 0;
+  if (pass[i] == k)
+    for (int e = rp[i]; e < rp[i + 1]; ++e) c += (col[e] != (int)i && mask[e] && pass[col[e]] == k - 1);
+  len[i] = c;
+}
+
+// one thread per row: the four sign sums in entry order, then the weights (oracle order)
+__global__ void __launch_bounds__(kBlock)
+mp_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+               const double* __restrict__ val, const uint8_t* __restrict__ mask, const int32_t* __restrict__ pass,
+               int k, const int32_t* __restrict__ colmap, const int32_t* __restrict__ wrp, int32_t* __restrict__ wcol,
+               double* __restrict__ wval) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n || pass[i] != k) return;
+  double diag = 0.0, nneg = 0.0, npos = 0.0, cneg = 0.0, cpos = 0.0;
+  for (int e = rp[i]; e < rp[i + 1]; ++e) {
+    const int j = col[e];
+    const double v = val[e];
+    if (j == (int)i) {
+      diag = v;
+      continue;
+    }
+    const bool in = mask[e] && pass[j] == k - 1;
+    if (v < 0) {
+      nneg = __dadd_rn(nneg, v);
+      if (in) cneg = __dadd_rn(cneg, v);
+    } else if (v > 0) {
+      npos = __dadd_rn(npos, v);
+      if (in) cpos = __dadd_rn(cpos, v);
+    }
+  }
+  if (cpos == 0) diag = __dadd_rn(diag, npos);
+  if (cneg == 0) diag = __dadd_rn(diag, nneg);
+  const double alfa = (cneg != 0 && diag != 0) ? (nneg / cneg) / diag : 0.0;
+  const double beta = (cpos != 0 && diag != 0) ? (npos / cpos) / diag : 0.0;
+  int w = wrp[i];
+  for (int e = rp[i]; e < rp[i + 1]; ++e) {
+    const int j = col[e];
+    if (j == (int)i || !(mask[e] && pass[j] == k - 1)) continue;
+    const double v = val[e];
+    wcol[w] = colmap ? colmap[j] : j;
+    wval[w] = v < 0 ? __dmul_rn(-alfa, v) : __dmul_rn(-beta, v);
+    ++w;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+unit_rows_kernel(int64_t n, const int32_t* __restrict__ cf, const int32_t* __restrict__ f2c,
+                 const int32_t* __restrict__ prp, int32_t* __restrict__ pcol, double* __restrict__ pval) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i < n && cf[i] > 0) {
+    pcol[prp[i]] = f2c[i];
+    pval[prp[i]] = 1.0;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+merge_len_kernel(int64_t n, const int32_t* __restrict__ xrp, const int32_t* __restrict__ yrp,
+                 int32_t* __restrict__ len) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i < n) len[i] = (xrp[i + 1] - xrp[i]) + (yrp[i + 1] - yrp[i]);
+}
+
+__global__ void __launch_bounds__(kBlock)
+merge_fill_kernel(int64_t n, const int32_t* __restrict__ xrp, const int32_t* __restrict__ xcol,
+                  const double* __restrict__ xval, const int32_t* __restrict__ yrp, const int32_t* __restrict__ ycol,
+                  const double* __restrict__ yval, const int32_t* __restrict__ crp, int32_t* __restrict__ ccol,
+                  double* __restrict__ cval) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  int w = crp[i];
+  for (int k = xrp[i]; k < xrp[i + 1]; ++k, ++w) {
+    ccol[w] = xcol[k];
+    cval[w] = xval[k];
+  }
+  for (int k = yrp[i]; k < yrp[i + 1]; ++k, ++w) {
+    ccol[w] = ycol[k];
+    cval[w] = yval[k];
+  }
+}
+
+static int csr_from_lengths(amgb_ctx* ctx, int64_t n, int64_t ncols, const int32_t* len, DeviceCsr& M) {
+  M.n = n;
+  M.ncols = ncols;
+  AMGB_TRY(M.rp.alloc(ctx, n + 1));
+  AMGB_TRY(exclusive_scan_i32(ctx, len, M.rp.p, n));
+  int32_t nnz = 0;
+  AMGB_TRY(read_i32(ctx, M.rp.p + n, &nnz));
+  M.nnz = nnz;
+  AMGB_TRY(M.col.alloc(ctx, nnz));
+  AMGB_TRY(M.val.alloc(ctx, nnz));
+  return AMGB_OK;
+}
+
+static int build_interp_multipass(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const int32_t* cf,
+                                  const int32_t* f2c, int64_t nc, DeviceCsr& P) {
+  const int64_t n = A.n;
+  const unsigned grid = (unsigned)div_up(n, kBlock);
+  DevBuf<int32_t> pass, len, newly;
+  AMGB_TRY(pass.alloc(ctx, n));
+  AMGB_TRY(len.alloc(ctx, n));
+  AMGB_TRY(newly.alloc(ctx, 1));
+  AMGB_LAUNCH(ctx, F_INTERP, 12.0 * n, mp_init_kernel, grid, kBlock, 0, n, cf, pass.p, len.p);
+  DeviceCsr cur;
+  AMGB_TRY(csr_from_lengths(ctx, n, nc, len.p, cur));
+  AMGB_LAUNCH(ctx, F_INTERP, 24.0 * nc, unit_rows_kernel, grid, kBlock, 0, n, cf, f2c, (const int32_t*)cur.rp.p,
+              cur.col.p, cur.val.p);
+  AMGB_CHECK_LAUNCH(ctx);
+  int npass = 0;
+  for (int k = 1; k < 1000; ++k) {
+    AMGB_CUDA(ctx, cudaMemsetAsync(newly.p, 0, sizeof(int32_t), ctx->stream));
+    AMGB_LAUNCH(ctx, F_INTERP, 5.0 * A.nnz + 8.0 * n, mp_assign_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p, mask,
+                pass.p, k, newly.p);
+    AMGB_CHECK_LAUNCH(ctx);
+    int32_t nn = 0;
+    AMGB_TRY(read_i32(ctx, newly.p, &nn));
+    if (nn == 0) break;
+    npass = k;
+  }
+  for (int k = 1; k <= npass; ++k) {
+    AMGB_LAUNCH(ctx, F_INTERP, 5.0 * A.nnz + 8.0 * n, mp_count_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p, mask,
+                (const int32_t*)pass.p, k, len.p);
+    DeviceCsr W, Pk, merged;
+    AMGB_TRY(csr_from_lengths(ctx, n, k == 1 ? nc : n, len.p, W));
+    AMGB_LAUNCH(ctx, F_INTERP, 13.0 * A.nnz + 12.0 * W.nnz, mp_fill_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p,
+                A.val.p, mask, (const int32_t*)pass.p, k, k == 1 ? f2c : (const int32_t*)nullptr,
+                (const int32_t*)W.rp.p, W.col.p, W.val.p);
+    AMGB_CHECK_LAUNCH(ctx);
+    const DeviceCsr* add = &W;
+    if (k > 1) {
+      AMGB_TRY(spgemm(ctx, W, cur, Pk, true));
+      add = &Pk;
+    }
+    AMGB_LAUNCH(ctx, F_INTERP, 16.0 * n, merge_len_kernel, grid, kBlock, 0, n, (const int32_t*)cur.rp.p,
+                (const int32_t*)add->rp.p, len.p);
+    AMGB_TRY(csr_from_lengths(ctx, n, nc, len.p, merged));
+    AMGB_LAUNCH(ctx, F_INTERP, 24.0 * merged.nnz, merge_fill_kernel, grid, kBlock, 0, n, (const int32_t*)cur.rp.p,
+                (const int32_t*)cur.col.p, (const double*)cur.val.p, (const int32_t*)add->rp.p,
+                (const int32_t*)add->col.p, (const double*)add->val.p, (const int32_t*)merged.rp.p, merged.col.p,
+                merged.val.p);
+    AMGB_CHECK_LAUNCH(ctx);
+    AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cur = std::move(merged);
+  }
+  P = std::move(cur);
+  return AMGB_OK;
+}
+
 // deal.II forwards theta / max_row_sum to PETSc through std::to_string (6 decimals)
 static double option_roundtrip(double v) { return std::strtod(std::to_string(v).c_str(), nullptr); }
 
@@ -1053,8 +1362,8 @@ static int hypre_relax_type(int dealii_type, bool symmetric_operator) {
 int resolve_options(amgb_precond* P) {
   amgb_ctx* ctx = P->ctx;
   const amgb_boomeramg_data& d = P->data;
-  if (d.aggressive_coarsening_num_levels != 0)
-    return set_error(ctx, AMGB_ERR_UNSUPPORTED, "aggressive coarsening is not available on the device yet");
+  if (d.aggressive_coarsening_num_levels != 0 && P->dist)
+    return set_error(ctx, AMGB_ERR_UNSUPPORTED, "aggressive coarsening is not available on the row-partitioned path");
   if (d.coarsen_type != AMGB_COARSEN_PMIS)
     return set_error(ctx, AMGB_ERR_UNSUPPORTED,
                      "coarsen_type %d: only PMIS (8) runs on the device (Falgout/RS is sequential)",
@@ -1122,6 +1431,11 @@ int build_hierarchy(amgb_precond* P) {
     AMGB_TRY(L.f2c.alloc(ctx, n + 1));
     int32_t nc = 0;
     AMGB_TRY(number_coarse_points(ctx, n, L.cf.p, L.f2c.p, &nc));
+    const bool aggressive = (unsigned)level < d.aggressive_coarsening_num_levels;
+    if (aggressive && nc > 0 && nc < n) {
+      AMGB_TRY(aggressive_second_pass(ctx, L.A, L.mask.p, L.cf.p, L.f2c.p, nc));
+      AMGB_TRY(number_coarse_points(ctx, n, L.cf.p, L.f2c.p, &nc));
+    }
     if (nc == 0 || nc == n) {
       // coarsening stalled: this level is the coarsest
       L.mask.release();
@@ -1130,7 +1444,8 @@ int build_hierarchy(amgb_precond* P) {
       break;
     }
     L.n_coarse = nc;
-    AMGB_TRY(build_interp(ctx, L.A, L.mask.p, L.cf.p, L.f2c.p, diagv.p, 0, n, nc, L.P));
+    if (aggressive) AMGB_TRY(build_interp_multipass(ctx, L.A, L.mask.p, L.cf.p, L.f2c.p, nc, L.P));
+    else AMGB_TRY(build_interp(ctx, L.A, L.mask.p, L.cf.p, L.f2c.p, diagv.p, 0, n, nc, L.P));
     AMGB_TRY(transpose_csr(ctx, L.P, L.R));
     // Galerkin product A_c = R (A P)
     DeviceCsr T;

@@ -93,7 +93,7 @@ typedef struct amgb_boomeramg_data {
   int32_t symmetric_operator;               /* default 0 (reference always passes 1) */
   double strong_threshold;                  /* theta, default 0.25 */
   double max_row_sum;                       /* default 0.9 */
-  uint32_t aggressive_coarsening_num_levels;/* default 0; >0 is AMGB_ERR_UNSUPPORTED for now */
+  uint32_t aggressive_coarsening_num_levels;/* default 0; >0: second PMIS on S2 + multipass interp. */
   int32_t output_details;                   /* collect level statistics */
   int32_t relaxation_type_up;               /* amgb_relaxation_type, default SORJacobi */
   int32_t relaxation_type_down;
@@ -151,8 +151,8 @@ int amgb_matrix_wrap_device_csr(amgb_ctx* ctx, int64_t n, int64_t nnz,
 /* On-device assembly of the Q1 diffusion system of the reference's structured test case
  * (ref testcase2-diffusion-structured/src/main.cpp:255-320; mu = 10^epsv on a
  * pattern_size^mode pattern, :101-113; Dirichlet rows as :312-318; lexicographic node
- * numbering; m cells per direction on [-1,1]^3).  Bit-identical to the host generator
- * amgb_gen_poisson_q1 (include/amgb_gen.h), but the matrix is born in HBM.  rhs_device /
+ * numbering; m cells per direction on [-1,1]^3).  Bit-identical to the host generator of
+ * include/amgb_gen.h, but the matrix is born in HBM.  rhs_device /
  * x0_device: device arrays of n = (m+1)^3 doubles, or NULL. */
 int amgb_matrix_assemble_poisson_q1(amgb_ctx* ctx, int32_t m, int32_t pattern_size, int32_t mode,
                                     const double* epsv, int64_t n_epsv, amgb_matrix** out,

@@ -389,6 +389,173 @@ void coarsen_falgout(int64_t n, const int32_t* rp, const int32_t* col, const uin
 }
 
 // ---------------------------------------------------------------------------
+// A.3 aggressive coarsening (levels < agg_nl), restated from memory like the rest of the
+// AMG part (PARITY UNPINNED):
+//  * hypre_BoomerAMGCreate2ndS with num_paths = 1 (PCHYPRE default agg_num_paths): for a
+//    C point i, S2_i = { C points k != i : k in S_i, or k in S_j for some F point j in S_i }
+//    (paths of length <= 2), built as the pattern product A1*B below, in coarse numbering;
+//  * a second PMIS on S2 (random part restarted: coarse point c gets hypre_Rand #c);
+//  * hypre_BoomerAMGCorrectCFMarker: first-stage C points take the second marker.
+// ---------------------------------------------------------------------------
+void spgemm(const Csr& A, const Csr& B, Csr& C);
+
+void aggressive_second_pass(const Csr& A, const std::vector<uint8_t>& mask, std::vector<int32_t>& cf) {
+  const int64_t n = A.n;
+  std::vector<int32_t> f2c(n, -1);
+  int32_t nc1 = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (cf[i] > 0) f2c[i] = nc1++;
+  Csr A1, B, M;
+  A1.n = nc1;
+  A1.ncols = n;
+  A1.rp.assign(1, 0);
+  B.n = n;
+  B.ncols = nc1;
+  B.rp.assign(1, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    if (cf[i] > 0) {
+      for (int32_t k = A.rp[i]; k < A.rp[i + 1]; ++k)
+        if (mask[k]) {
+          A1.col.push_back(A.col[k]);
+          A1.val.push_back(1.0);
+        }
+      A1.rp.push_back((int32_t)A1.col.size());
+      B.col.push_back(f2c[i]);
+      B.val.push_back(1.0);
+    } else {
+      for (int32_t k = A.rp[i]; k < A.rp[i + 1]; ++k)
+        if (mask[k] && cf[A.col[k]] > 0) {
+          B.col.push_back(f2c[A.col[k]]);
+          B.val.push_back(1.0);
+        }
+    }
+    B.rp.push_back((int32_t)B.col.size());
+  }
+  spgemm(A1, B, M);
+  std::vector<uint8_t> mask2(M.nnz());
+  for (int64_t c = 0; c < nc1; ++c)
+    for (int32_t k = M.rp[c]; k < M.rp[c + 1]; ++k) mask2[k] = M.col[k] != c;
+  std::vector<int32_t> cf2;
+  coarsen_pmis(nc1, M.rp.data(), M.col.data(), mask2.data(), cf2);
+  int32_t cnt = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (cf[i] > 0) cf[i] = cf2[cnt++];
+}
+
+// C <- rows of X and Y (same shape; for every row at most one of them is non-empty)
+void merge_disjoint_rows(const Csr& X, const Csr& Y, Csr& C) {
+  C.n = X.n;
+  C.ncols = X.ncols;
+  C.rp.assign(1, 0);
+  C.col.clear();
+  C.val.clear();
+  for (int64_t i = 0; i < X.n; ++i) {
+    const Csr& S = X.rp[i + 1] > X.rp[i] ? X : Y;
+    for (int32_t k = S.rp[i]; k < S.rp[i + 1]; ++k) {
+      C.col.push_back(S.col[k]);
+      C.val.push_back(S.val[k]);
+    }
+    C.rp.push_back((int32_t)C.col.size());
+  }
+}
+
+// ---------------------------------------------------------------------------
+// A.3 multipass interpolation (agg_interp_type 4, hypre_BoomerAMGBuildMultipass), restated
+// from memory (PARITY UNPINNED).  pass(i) = 0 for C points; an F point joins pass k >= 1 if
+// it has a strong neighbour of pass k-1.  For a point i of pass k, with interpolatory set
+// I_i = { j in S_i : pass(j) = k-1 } and the sums over the negative / positive off-diagonal
+// entries of row i (N: all, C: those in I_i):
+//     positive (negative) entries are lumped into the diagonal if I_i has none of that sign;
+//     alfa = (sum_N_neg / sum_C_neg) / diag,  beta = (sum_N_pos / sum_C_pos) / diag;
+//     w_ij = -alfa a_ij (a_ij < 0) or -beta a_ij (a_ij > 0),  j in I_i;
+//     P(i,:) = sum_j w_ij P(j,:)   (pass 1: P(j,:) is the unit row of the C point j),
+// accumulated over ascending j.  Points no pass reaches keep an empty row.
+// ---------------------------------------------------------------------------
+void interp_multipass(const Csr& A, const std::vector<uint8_t>& mask, const std::vector<int32_t>& cf, Csr& P,
+                      int64_t* n_coarse) {
+  const int64_t n = A.n;
+  std::vector<int32_t> f2c(n, -1), pass(n, -1);
+  int32_t nc = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (cf[i] > 0) {
+      f2c[i] = nc++;
+      pass[i] = 0;
+    }
+  *n_coarse = nc;
+  int npass = 0;
+  for (int k = 1;; ++k) {
+    int64_t newly = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      if (pass[i] >= 0) continue;
+      for (int32_t e = A.rp[i]; e < A.rp[i + 1]; ++e)
+        if (mask[e] && pass[A.col[e]] == k - 1) {
+          pass[i] = k;
+          ++newly;
+          break;
+        }
+    }
+    if (newly == 0) break;
+    npass = k;
+  }
+  Csr cur;
+  cur.n = n;
+  cur.ncols = nc;
+  cur.rp.assign(1, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    if (cf[i] > 0) {
+      cur.col.push_back(f2c[i]);
+      cur.val.push_back(1.0);
+    }
+    cur.rp.push_back((int32_t)cur.col.size());
+  }
+  for (int k = 1; k <= npass; ++k) {
+    Csr W;
+    W.n = n;
+    W.ncols = k == 1 ? nc : n;
+    W.rp.assign(1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+      if (pass[i] == k) {
+        double diag = 0.0, nneg = 0.0, npos = 0.0, cneg = 0.0, cpos = 0.0;
+        for (int32_t e = A.rp[i]; e < A.rp[i + 1]; ++e) {
+          const int32_t j = A.col[e];
+          const double v = A.val[e];
+          if (j == i) {
+            diag = v;
+            continue;
+          }
+          const bool in = mask[e] && pass[j] == k - 1;
+          if (v < 0) {
+            nneg += v;
+            if (in) cneg += v;
+          } else if (v > 0) {
+            npos += v;
+            if (in) cpos += v;
+          }
+        }
+        if (cpos == 0) diag += npos;
+        if (cneg == 0) diag += nneg;
+        const double alfa = (cneg != 0 && diag != 0) ? (nneg / cneg) / diag : 0.0;
+        const double beta = (cpos != 0 && diag != 0) ? (npos / cpos) / diag : 0.0;
+        for (int32_t e = A.rp[i]; e < A.rp[i + 1]; ++e) {
+          const int32_t j = A.col[e];
+          if (j == i || !(mask[e] && pass[j] == k - 1)) continue;
+          const double v = A.val[e];
+          W.col.push_back(k == 1 ? f2c[j] : j);
+          W.val.push_back(v < 0 ? -alfa * v : -beta * v);
+        }
+      }
+      W.rp.push_back((int32_t)W.col.size());
+    }
+    Csr Pk, merged;
+    if (k == 1) Pk = W;
+    else spgemm(W, cur, Pk);
+    merge_disjoint_rows(cur, Pk, merged);
+    cur = merged;
+  }
+  P = cur;
+}
+
+// ---------------------------------------------------------------------------
 // A.3 Interpolation type 0, "modified classical": hypre_BoomerAMGBuildInterp.
 // Off-diagonal entries are visited in ascending column order.
 // ---------------------------------------------------------------------------
@@ -774,7 +941,9 @@ int orc_coarsen_falgout(int64_t n, const int32_t* rowptr, const int32_t* col,
 int orc_setup(int64_t n, const int32_t* rowptr, const int32_t* col, const double* val,
               const amgb_boomeramg_data* data, orc_hier** out) {
   if (!rowptr || !col || !val || !data || !out || n < 1) return AMGB_ERR_BAD_ARG;
-  if (data->aggressive_coarsening_num_levels != 0) return AMGB_ERR_UNSUPPORTED;
+  // aggressive levels: restated for PMIS only (second PMIS on S2 + multipass interpolation)
+  if (data->aggressive_coarsening_num_levels != 0 && data->coarsen_type != AMGB_COARSEN_PMIS)
+    return AMGB_ERR_UNSUPPORTED;
   if (data->interp_type != AMGB_INTERP_CLASSICAL) return AMGB_ERR_UNSUPPORTED;
   orc_hier* h = new orc_hier;
   h->data = *data;
@@ -813,15 +982,22 @@ int orc_setup(int64_t n, const int32_t* rowptr, const int32_t* col, const double
       delete h;
       return AMGB_ERR_UNSUPPORTED;
     }
+    const bool aggressive = (unsigned)level < data->aggressive_coarsening_num_levels;
     int64_t nc = 0;
     for (int32_t c : L.cf) nc += c > 0;
+    if (aggressive && nc > 0 && nc < L.A.n) {
+      aggressive_second_pass(L.A, L.mask, L.cf);
+      nc = 0;
+      for (int32_t c : L.cf) nc += c > 0;
+    }
     if (nc == 0 || nc == L.A.n) {
       // coarsening stalled: this level is the coarsest
       L.mask.clear();
       L.cf.clear();
       break;
     }
-    interp_classical(L.A, L.mask, L.cf, L.P, &nc);
+    if (aggressive) interp_multipass(L.A, L.mask, L.cf, L.P, &nc);
+    else interp_classical(L.A, L.mask, L.cf, L.P, &nc);
     transpose(L.P, L.R);
     Csr T;
     spgemm(L.A, L.P, T);

@@ -351,3 +351,33 @@ def test_product_does_not_reference_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle/" not in txt.replace("oracle/amg_oracle.cpp", "") or f.endswith((".cu", ".cuh")), f
                 assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_aggressive_coarsening_oracle_properties():
+    """Second-stage PMIS + multipass interpolation (oracle): far fewer coarse points, rows of
+    P reproduce constants where the operator has zero row sum, PCG still converges."""
+    import amg_ann_b200 as ab
+    from oracle import binding as orc
+    from helpers import device_data, poisson
+    s = poisson(14, contrast=2.0)
+    d0, d2 = device_data(0.25), device_data(0.25)
+    d2.aggressive_coarsening_num_levels = 2
+    H0 = orc.Hierarchy(s.rowptr32(), s.col, s.val, d0.to_struct())
+    H2 = orc.Hierarchy(s.rowptr32(), s.col, s.val, d2.to_struct())
+    r0, r2 = H0.stats()["rows"], H2.stats()["rows"]
+    assert r2[1] * 4 < r0[1] and H2.stats()["operator"] < H0.stats()["operator"]
+    cf0, cf2 = H0.cf_marker(0), H2.cf_marker(0)
+    assert set(np.flatnonzero(cf2 > 0)) <= set(np.flatnonzero(cf0 > 0))   # second stage only removes C points
+    rp, cl, vl, nc = H2.P(0)
+    rows = np.flatnonzero(np.diff(rp) > 0)
+    sums = np.add.reduceat(vl, rp[rows])
+    A = s.to_scipy()
+    zero_sum = np.abs(np.asarray(A.sum(axis=1)).ravel()[rows]) < 1e-9 * np.abs(A.diagonal()[rows])
+    assert zero_sum.any() and np.allclose(sums[zero_sum], 1.0, atol=1e-12)
+    rc, x, nit, hist = H2.cg_solve(s.rhs, s.x0, abs_tol=1e-8)
+    assert rc == 0 and hist[-1] <= 1e-8
+    # Falgout + aggressive levels is not restated
+    d = device_data(0.25, coarsen_type=ab.COARSEN_FALGOUT)
+    d.aggressive_coarsening_num_levels = 1
+    with pytest.raises(Exception):
+        orc.Hierarchy(s.rowptr32(), s.col, s.val, d.to_struct())

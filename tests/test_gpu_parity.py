@@ -136,8 +136,9 @@ def test_reference_default_smoother_is_substituted_or_rejected(gpu_ctx):
     with pytest.raises(ab.AmgbError) as e:
         P.initialize(A, ab.AdditionalData(True, 0.25, 0.9, 0, True, smoother_policy=ab.SMOOTHER_STRICT))
     assert e.value.status == -5
+    # aggressive levels need the parallel coarsening; with the reference's serial Falgout they are refused
     with pytest.raises(ab.AmgbError):
-        P.initialize(A, ab.AdditionalData(True, 0.25, 0.9, 2, True))  # aggressive levels
+        P.initialize(A, ab.AdditionalData(True, 0.25, 0.9, 2, True, coarsen_type=ab.COARSEN_FALGOUT))
 
 
 def test_no_convergence_is_reported(gpu_ctx):
@@ -281,3 +282,35 @@ def test_bad_arguments_are_reported_not_crashed(gpu_ctx):
     P.initialize(A2, device_data(0.25))
     with pytest.raises(ab.AmgbError):
         ab.SolverCG(ab.SolverControl(10, 1e-8)).solve(A, s.x0.copy(), s.rhs, P)
+
+
+@pytest.mark.parametrize("m,theta,contrast,agg", [(12, 0.25, 0.0, 1), (16, 0.25, 3.0, 2), (14, 0.5, 6.0, 2),
+                                                  (20, 0.25, 0.0, 2), (10, 0.7, 0.0, 3)])
+def test_aggressive_coarsening_and_multipass_interpolation(gpu_ctx, m, theta, contrast, agg):
+    """aggressive_coarsening_num_levels > 0 (ref t3 main.cpp:456 passes 2): second PMIS on
+    the distance-two strength graph + multipass interpolation, bit-exact vs the oracle."""
+    s = poisson(m, contrast=contrast)
+    data = device_data(theta)
+    data.aggressive_coarsening_num_levels = agg
+    A, P, H = _both(gpu_ctx, s, data)
+    _assert_hierarchy_identical(P, H)
+    std = ab.PreconditionBoomerAMG()
+    std.initialize(A, device_data(theta))
+    assert P.level_stats()["operator"] < std.level_stats()["operator"]   # that is the point of it
+    ctl = ab.SolverControl(s.n, 1e-8)
+    x = s.x0.copy()
+    ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+    rc, xo, nit, hist = H.cg_solve(s.rhs, s.x0, abs_tol=1e-8)
+    assert rc == 0 and abs(ctl.last_step() - nit) <= 1
+    k = min(len(hist), len(ctl.history))
+    assert (np.abs(ctl.history[:k] - hist[:k]) <= RES_RTOL * hist[:k]).all()
+
+
+def test_aggressive_coarsening_elasticity_like_the_reference_case(gpu_ctx):
+    # testcase 3: vector elasticity, scalar AMG, agg_nl = 2 (ref t3 main.cpp:454-464)
+    young = 10.0 ** ab.gen.checkerboard_epsv(2, 3, 2.0)
+    s = ab.gen.elasticity_q1(6, 2, 3, young)
+    data = device_data(0.5)
+    data.aggressive_coarsening_num_levels = 2
+    A, P, H = _both(gpu_ctx, s, data)
+    _assert_hierarchy_identical(P, H)

@@ -42,7 +42,8 @@ class BoomerAMGDataStruct(C.Structure):
         ("smoother_policy", C.c_int32),
         ("options_via_string", C.c_int32),
         ("keep_setup_intermediates", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("dist_replicate_below", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -96,7 +97,7 @@ AMGB_SYMBOLS = [
     "amgb_local_group_destroy", "amgb_comm_create_local", "amgb_comm_destroy", "amgb_comm_rank",
     "amgb_comm_size", "amgb_dist_matrix_create", "amgb_dist_matrix_destroy",
     "amgb_dist_precond_initialize", "amgb_dist_cg_solve", "amgb_dist_cg_solve_device",
-    "amgb_dist_precond_level_dims", "amgb_dist_precond_get_cf_marker",
+    "amgb_dist_precond_level_dims", "amgb_dist_precond_replicated_from", "amgb_dist_precond_get_cf_marker",
     "amgb_dist_precond_get_A_rows", "amgb_dist_precond_get_P_rows",
 ]
 
@@ -187,6 +188,7 @@ def amgb_lib():
              C.c_int64, c_i64p)
         _sig(L.amgb_dist_precond_level_dims, C.c_int, vp, C.c_int32, c_i64p, c_i64p, c_i64p, c_i64p,
              c_i64p, c_i64p, c_i64p)
+        _sig(L.amgb_dist_precond_replicated_from, C.c_int, vp, c_i32p)
         _sig(L.amgb_dist_precond_get_cf_marker, C.c_int, vp, C.c_int32, c_i32p)
         _sig(L.amgb_dist_precond_get_A_rows, C.c_int, vp, C.c_int32, c_i32p, c_i32p, c_f64p)
         _sig(L.amgb_dist_precond_get_P_rows, C.c_int, vp, C.c_int32, c_i32p, c_i32p, c_f64p)

@@ -112,6 +112,7 @@ struct NcclComm : amgb_comm {
     AMGB_NCCL(ctx, nccl_api().AllReduce(buf, buf, (size_t)count, kNcclFloat64, kNcclSum, comm, ctx->stream));
     return AMGB_OK;
   }
+  bool capturable() const override { return true; }
 };
 
 // ---------------------------------------------------------------------------

@@ -29,6 +29,9 @@ struct amgb_comm {
   virtual int allgather_host(amgb_ctx* ctx, const void* mine, size_t bytes, void* all) = 0;
   // In place, on ctx->stream: buf[i] <- sum over ranks (rank order, same bits on every rank).
   virtual int allreduce_sum_f64(amgb_ctx* ctx, double* buf_device, int count) = 0;
+  // true if alltoallv / allreduce_sum_f64 only enqueue stream work (no host synchronisation),
+  // so a sequence of kernels and exchanges can be captured in a CUDA graph
+  virtual bool capturable() const { return false; }
 };
 
 namespace amgb {

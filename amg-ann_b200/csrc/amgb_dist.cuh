@@ -69,6 +69,10 @@ struct amgb_dist_state {
   amgb_comm* comm = nullptr;
   const amgb_dist_matrix* mat = nullptr;
   std::vector<amgb::DistLevel> dl;
+  // levels >= replicated_from hold the WHOLE operator on every rank and run the
+  // single-device code without exchanges (coarse-level replication)
+  int replicated_from = 1 << 30;
+  amgb::DevBuf<double> repl_own, repl_full;  // restriction onto the first replicated level
   // coarsest level, replicated
   int64_t coarse_n = 0;
   std::vector<int64_t> coarse_starts;

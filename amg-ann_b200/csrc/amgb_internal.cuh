@@ -278,9 +278,12 @@ int build_interp(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const i
 int transpose_csr(amgb_ctx* ctx, const DeviceCsr& P, DeviceCsr& R);
 int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, bool sorted);
 int resolve_options(amgb_precond* P);
+int build_levels_from(amgb_precond* P, int level0);
 int build_hierarchy(amgb_precond* P);
 // amgb_solve.cu
 int finish_solve_setup(amgb_precond* P);
+// the same for levels [l0, nl) only (replicated coarse levels of the row-partitioned path)
+int finish_solve_setup_range(amgb_precond* P, int l0);
 // z = M^{-1} r with z, r in the level-0 permuted numbering
 int vcycle_apply(amgb_precond* P, double* z_dev, const double* r_dev);
 int spmv(amgb_ctx* ctx, const DeviceCsr& A, const double* x, double* y, int family);

@@ -1397,24 +1397,12 @@ int resolve_options(amgb_precond* P) {
   return AMGB_OK;
 }
 
-int build_hierarchy(amgb_precond* P) {
+// The level loop of the single-device setup, starting from P->lv[level0].A (which must be
+// set).  Also used by the row-partitioned driver for the replicated coarse levels.
+int build_levels_from(amgb_precond* P, int level0) {
   amgb_ctx* ctx = P->ctx;
-  AMGB_TRY(resolve_options(P));
   const amgb_boomeramg_data& d = P->data;
-  const DeviceCsr& A0 = P->mat->A;
-  P->lv.clear();
-  P->lv.emplace_back();
-  {
-    Level& L = P->lv[0];
-    L.A.n = A0.n;
-    L.A.ncols = A0.ncols;
-    L.A.nnz = A0.nnz;
-    L.A.rp.wrap(ctx, A0.rp.p, A0.rp.n);
-    L.A.col.wrap(ctx, A0.col.p, A0.col.n);
-    L.A.val.wrap(ctx, A0.val.p, A0.val.n);
-  }
-  P->lv.reserve(d.max_levels + 1);
-  for (int level = 0;; ++level) {
+  for (int level = level0;; ++level) {
     Level& L = P->lv[level];
     const int64_t n = L.A.n;
     ctx->cur_level = level;
@@ -1455,6 +1443,27 @@ int build_hierarchy(amgb_precond* P) {
     AMGB_TRY(spgemm(ctx, P->lv[level].R, T, Lc.A, true));
     if (!d.keep_setup_intermediates) P->lv[level].mask.release();
   }
+  return AMGB_OK;
+}
+
+int build_hierarchy(amgb_precond* P) {
+  amgb_ctx* ctx = P->ctx;
+  AMGB_TRY(resolve_options(P));
+  const amgb_boomeramg_data& d = P->data;
+  const DeviceCsr& A0 = P->mat->A;
+  P->lv.clear();
+  P->lv.reserve(d.max_levels + 1);
+  P->lv.emplace_back();
+  {
+    Level& L = P->lv[0];
+    L.A.n = A0.n;
+    L.A.ncols = A0.ncols;
+    L.A.nnz = A0.nnz;
+    L.A.rp.wrap(ctx, A0.rp.p, A0.rp.n);
+    L.A.col.wrap(ctx, A0.col.p, A0.col.n);
+    L.A.val.wrap(ctx, A0.val.p, A0.val.n);
+  }
+  AMGB_TRY(build_levels_from(P, 0));
   P->st_rows.clear();
   P->st_nnz.clear();
   P->st_nnzP.clear();

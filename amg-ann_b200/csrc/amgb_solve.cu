@@ -19,6 +19,7 @@
 // split-source gather (col < n_C ? x_lo : x_hi), which removes all full-vector
 // copies.  All kernels are HBM-bound; algorithmic bytes per launch follow
 // SURVEY.md 8(d) (defined on plain CSR) and go to the roofline report.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -576,11 +577,13 @@ static int setup_dense_from(amgb_precond* P, const DeviceCsr& CA) {
 
 static int setup_dense(amgb_precond* P) { return setup_dense_from(P, P->lv.back().A); }
 
-int finish_solve_setup(amgb_precond* P) {
+int finish_solve_setup(amgb_precond* P) { return finish_solve_setup_range(P, 0); }
+
+int finish_solve_setup_range(amgb_precond* P, int l0) {
   amgb_ctx* ctx = P->ctx;
   const int nl = (int)P->lv.size();
   // 1. permutations (C points first) on every level
-  for (int l = 0; l < nl; ++l) {
+  for (int l = l0; l < nl; ++l) {
     Level& L = P->lv[l];
     const int64_t n = L.A.n;
     AMGB_TRY(L.perm.alloc(ctx, n));
@@ -590,7 +593,7 @@ int finish_solve_setup(amgb_precond* P) {
     AMGB_CHECK_LAUNCH(ctx);
   }
   // 2. operators: A (rows, cols permuted), P (fine rows, coarse cols), R = P^T
-  for (int l = 0; l < nl; ++l) {
+  for (int l = l0; l < nl; ++l) {
     Level& L = P->lv[l];
     const int64_t n = L.A.n;
     ctx->cur_level = l;
@@ -632,8 +635,15 @@ int finish_solve_setup(amgb_precond* P) {
 // ---------------------------------------------------------------------------
 // Row-partitioned path: refresh the halo part of dst with the owners' values, an owner's
 // value of point p being (p < split ? lo[p] : hi[p]).  No-op on a single device.
+__global__ void gather_kernel(int64_t n, const int32_t* __restrict__ perm, const double* __restrict__ in,
+                              double* __restrict__ out);
+
+static inline bool partitioned_level(const amgb_precond* P, int l) {
+  return P->dist && l < P->dist->replicated_from;
+}
+
 static int halo(amgb_precond* P, int l, const double* lo, const double* hi, int split, double* dst) {
-  if (!P->dist) return AMGB_OK;
+  if (!partitioned_level(P, l)) return AMGB_OK;
   P->ctx->cur_level = l;
   return plan_sync_split(P->ctx, P->dist->comm, P->dist->dl[l].vplan, lo, hi, split, dst);
 }
@@ -651,7 +661,8 @@ static int relax_if(amgb_precond* P, int l, const double* f, double* u, double* 
   const double mat = L.As.csr_bytes();
   EpiJacobi epi{f, u, L.inv_relax.p, out, w};
   // C/F ordering needs a splitting on this level (any rank may own no C or no F points)
-  const bool cf_order = P->data.relax_order == 1 && cycle_param < 3 && (P->dist ? L.cf.p != nullptr : (nC > 0 && nC < n));
+  const bool cf_order = P->data.relax_order == 1 && cycle_param < 3 &&
+                       (partitioned_level(P, l) ? L.cf.p != nullptr : (nC > 0 && nC < n));
   if (cf_order) {
     const double share_c = n > 0 ? double(nC) / double(n) : 0.0;
     // half sweep = the rows touched + 4 vectors on those rows
@@ -681,7 +692,7 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
   const int n = (int)L.n_solve;
   if (l == nl - 1) {
     if (P->relax_coarse == 9 && P->dense_ok) {
-      if (P->dist) {
+      if (partitioned_level(P, l)) {
         // replicated dense solve: gather the right-hand side, solve, keep the owned block
         amgb_dist_state* ds = P->dist;
         const int nfull = (int)ds->coarse_n;
@@ -720,8 +731,21 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
   Level& C = P->lv[l + 1];
   const int ncrs = (int)C.n_solve;
   AMGB_TRY(halo(P, l, alt, alt, 0, alt));
-  AMGB_TRY(launch_sell(ctx, L.Rs, 0, ncrs, alt, alt, 0, EpiStore{C.f.p}, l == 0 ? F_RESTRICT_L0 : F_RESTRICT,
-                       L.Rs.csr_bytes() + 8.0 * n + 8.0 * ncrs));
+  if (partitioned_level(P, l) && !partitioned_level(P, l + 1)) {
+    // onto the first replicated level: restrict to my coarse points (natural order), gather the
+    // whole right-hand side on every rank, then into that level's C/F numbering
+    amgb_dist_state* ds = P->dist;
+    const DistLevel& D = ds->dl[l];
+    AMGB_TRY(launch_sell(ctx, L.Rs, 0, (int)D.nc_own, alt, alt, 0, EpiStore{ds->repl_own.p},
+                         l == 0 ? F_RESTRICT_L0 : F_RESTRICT, L.Rs.csr_bytes() + 8.0 * n + 8.0 * D.nc_own));
+    AMGB_TRY(allgather_f64(ctx, ds->comm, D.cstarts, ds->repl_own.p, ds->repl_full.p));
+    AMGB_LAUNCH(ctx, F_VEC, 20.0 * ncrs, gather_kernel, (unsigned)div_up(ncrs, kBlock), kBlock, 0, (int64_t)ncrs,
+                (const int32_t*)C.perm.p, (const double*)ds->repl_full.p, C.f.p);
+    AMGB_CHECK_LAUNCH(ctx);
+  } else {
+    AMGB_TRY(launch_sell(ctx, L.Rs, 0, ncrs, alt, alt, 0, EpiStore{C.f.p}, l == 0 ? F_RESTRICT_L0 : F_RESTRICT,
+                         L.Rs.csr_bytes() + 8.0 * n + 8.0 * ncrs));
+  }
   if (C.n_vec > 0) AMGB_CUDA(ctx, cudaMemsetAsync(C.u.p, 0, (size_t)C.n_vec * sizeof(double), ctx->stream));
   double* cu = C.u.p;
   double* calt = C.tmp.p;
@@ -1204,13 +1228,24 @@ static void csr_view(amgb_ctx* ctx, const DeviceCsr& M, int64_t row0, int64_t ro
   V.val.wrap(ctx, M.val.p, M.val.n);
 }
 
+// natural (ascending global id) position -> C/F-permuted index of a replicated level
+__global__ void __launch_bounds__(kBlock)
+tcmap_replicated_kernel(int64_t nct, const int32_t* __restrict__ tc_gid, const int32_t* __restrict__ inv_perm_next,
+                        int32_t* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (t < nct) out[t] = inv_perm_next[tc_gid[t]];
+}
+
 int finish_solve_setup_dist(amgb_precond* P) {
   amgb_ctx* ctx = P->ctx;
   amgb_dist_state* ds = P->dist;
   amgb_comm* comm = ds->comm;
   const int nl = (int)P->lv.size();
+  const int nd = std::min(nl, ds->replicated_from);  // partitioned levels are [0, nd)
+  // replicated tail first: its numbering is needed by the last partitioned level
+  if (nd < nl) AMGB_TRY(finish_solve_setup_range(P, nd));
   // 1. numbering, halo lists, vector plans
-  for (int l = 0; l < nl; ++l) {
+  for (int l = 0; l < nd; ++l) {
     Level& L = P->lv[l];
     DistLevel& D = ds->dl[l];
     const int64_t nloc = D.nloc, o0 = D.o0, next = D.next;
@@ -1258,7 +1293,7 @@ int finish_solve_setup_dist(amgb_precond* P) {
     AMGB_TRY(build_vector_plan(ctx, comm, halo_gid.p, nh, nloc, D.own.starts, L.inv_perm.p, D.vplan));
   }
   // 2. operators (owned rows) in SELL, smoother diagonals, work vectors
-  for (int l = 0; l < nl; ++l) {
+  for (int l = 0; l < nd; ++l) {
     Level& L = P->lv[l];
     DistLevel& D = ds->dl[l];
     const int64_t nloc = D.nloc, o0 = D.o0;
@@ -1268,17 +1303,30 @@ int finish_solve_setup_dist(amgb_precond* P) {
     AMGB_TRY(csr_to_sell(ctx, Av, L.perm.p, D.colmap.p, L.As));
     if (l + 1 < nl) {
       Level& C = P->lv[l + 1];
-      DistLevel& Dn = ds->dl[l + 1];
-      DevBuf<int32_t> tcmap;
+      const bool to_replicated = l + 1 >= nd;
+      DevBuf<int32_t> tcmap, natural, natural_inv;
       AMGB_TRY(tcmap.alloc(ctx, D.nct));
-      AMGB_LAUNCH(ctx, F_AUX, 12.0 * D.nct, tcmap_kernel, (unsigned)div_up(D.nct, kBlock), kBlock, 0, D.nct,
-                  (const int32_t*)D.tc_gid.p, (const int32_t*)Dn.gid.p, Dn.next, (const int32_t*)Dn.colmap.p, tcmap.p);
+      if (to_replicated) {
+        // the next level lives whole on every rank: columns of P address its C/F numbering
+        // directly; the restriction writes my coarse points in natural order (gathered in cycle())
+        AMGB_LAUNCH(ctx, F_AUX, 12.0 * D.nct, tcmap_replicated_kernel, (unsigned)div_up(D.nct, kBlock), kBlock, 0,
+                    D.nct, (const int32_t*)D.tc_gid.p, (const int32_t*)C.inv_perm.p, tcmap.p);
+        AMGB_TRY(natural.alloc(ctx, D.nc_own));
+        AMGB_TRY(natural_inv.alloc(ctx, D.nc_own));
+        AMGB_LAUNCH(ctx, F_AUX, 8.0 * D.nc_own, build_perm_kernel, (unsigned)div_up(D.nc_own, kBlock), kBlock, 0,
+                    D.nc_own, (const int32_t*)nullptr, (const int32_t*)nullptr, 0, natural.p, natural_inv.p);
+      } else {
+        DistLevel& Dn = ds->dl[l + 1];
+        AMGB_LAUNCH(ctx, F_AUX, 12.0 * D.nct, tcmap_kernel, (unsigned)div_up(D.nct, kBlock), kBlock, 0, D.nct,
+                    (const int32_t*)D.tc_gid.p, (const int32_t*)Dn.gid.p, Dn.next, (const int32_t*)Dn.colmap.p,
+                    tcmap.p);
+      }
       AMGB_CHECK_LAUNCH(ctx);
       DeviceCsr Pv;
       csr_view(ctx, L.P, o0, nloc, D.Pown.nnz, C.n_vec, Pv);
       AMGB_TRY(csr_to_sell(ctx, Pv, L.perm.p, tcmap.p, L.Ps));
       L.R.ncols = L.n_vec;
-      AMGB_TRY(csr_to_sell(ctx, L.R, C.perm.p, D.colmap.p, L.Rs));
+      AMGB_TRY(csr_to_sell(ctx, L.R, to_replicated ? natural.p : C.perm.p, D.colmap.p, L.Rs));
       AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // tcmap goes out of scope
       L.R.rp.release();
       L.R.col.release();
@@ -1291,6 +1339,10 @@ int finish_solve_setup_dist(amgb_precond* P) {
         D.Pown.col.release();
         D.Pown.val.release();
         D.Pown.nnz = 0;
+      }
+      if (to_replicated) {
+        AMGB_TRY(ds->repl_own.alloc(ctx, D.nc_own));
+        AMGB_TRY(ds->repl_full.alloc(ctx, D.nc_global));
       }
     }
     AMGB_TRY(L.inv_relax.alloc(ctx, nloc));
@@ -1313,8 +1365,8 @@ int finish_solve_setup_dist(amgb_precond* P) {
     L.f2c.release();
   }
   ctx->cur_level = 0;
-  // 3. coarsest level: replicated dense factorisation
-  {
+  // 3. coarsest level still partitioned: replicated dense factorisation
+  if (nd == nl) {
     const OwnedCsr& own = ds->dl[nl - 1].own;
     ds->coarse_n = own.n_global;
     ds->coarse_starts = own.starts;

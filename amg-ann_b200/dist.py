@@ -189,6 +189,33 @@ class DistPreconditionBoomerAMG:
         return dict(rows=rows[:k].copy(), nnz=nnz[:k].copy(), sparsity=sp[:k].copy(), grid=g.value,
                     operator=o.value, memory=m.value)
 
+    @property
+    def replicated_from(self):
+        """First level held whole on every rank (= num_levels if none)."""
+        v = C.c_int32()
+        _chk(self.ctx._h, amgb_lib().amgb_dist_precond_replicated_from(self._h, C.byref(v)), "replicated_from")
+        return v.value
+
+    def full_level(self, level):
+        """(A, cf, P) of a replicated level through the single-device accessors."""
+        L = amgb_lib()
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _chk(self.ctx._h, L.amgb_precond_level_dims(self._h, level, C.byref(a), C.byref(b), C.byref(c), C.byref(d)),
+             "level_dims")
+        n, nnz, nc, nnzp = a.value, b.value, c.value, d.value
+        rp, cl, vl = np.empty(n + 1, dtype=np.int32), np.empty(nnz, dtype=np.int32), np.empty(nnz)
+        _chk(self.ctx._h, L.amgb_precond_get_A_csr(self._h, level, _p(rp, c_i32p), _p(cl, c_i32p), _p(vl, c_f64p)),
+             "get_A_csr")
+        out = dict(A=(rp, cl, vl))
+        if level + 1 < self.num_levels:
+            cf = np.empty(n, dtype=np.int32)
+            _chk(self.ctx._h, L.amgb_precond_get_cf_marker(self._h, level, _p(cf, c_i32p)), "get_cf_marker")
+            prp, pcl, pvl = np.empty(n + 1, dtype=np.int32), np.empty(nnzp, dtype=np.int32), np.empty(nnzp)
+            _chk(self.ctx._h, L.amgb_precond_get_P_csr(self._h, level, _p(prp, c_i32p), _p(pcl, c_i32p),
+                                                       _p(pvl, c_f64p)), "get_P_csr")
+            out.update(cf=cf, P=(prp, pcl, pvl, nc))
+        return out
+
     def level_dims(self, level):
         v = [C.c_int64() for _ in range(7)]
         _chk(self.ctx._h, amgb_lib().amgb_dist_precond_level_dims(self._h, level, *[C.byref(x) for x in v]),

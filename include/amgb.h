@@ -115,7 +115,10 @@ typedef struct amgb_boomeramg_data {
                                  std::to_string (6 decimals) as deal.II forwards
                                  them to PETSc (Appendix A.1, hard part H4) */
   int32_t keep_setup_intermediates; /* 1: keep strength masks etc. for the parity accessors */
-  int32_t reserved[7];
+  int32_t dist_replicate_below;     /* row-partitioned path: levels (other than the finest) with at
+                                       most this many rows are gathered and handled redundantly on
+                                       every rank, without further exchanges (default 32768; 0: never) */
+  int32_t reserved[6];
 } amgb_boomeramg_data;
 
 typedef struct amgb_ctx amgb_ctx;
@@ -300,6 +303,9 @@ int amgb_dist_cg_solve_device(amgb_ctx* ctx, double* x_local_device, const doubl
 int amgb_dist_precond_level_dims(const amgb_precond* P, int32_t level, int64_t* n_global,
                                  int64_t* row_begin, int64_t* n_local, int64_t* nnz_local,
                                  int64_t* n_coarse_global, int64_t* coarse_begin, int64_t* nnz_P_local);
+/* First level that is replicated on every rank (= number of levels if none): from there on
+ * the single-device accessors (amgb_precond_get_cf_marker, _get_A_csr, _get_P_csr) apply. */
+int amgb_dist_precond_replicated_from(const amgb_precond* P, int32_t* level);
 int amgb_dist_precond_get_cf_marker(const amgb_precond* P, int32_t level, int32_t* cf_local);
 int amgb_dist_precond_get_A_rows(const amgb_precond* P, int32_t level, int32_t* rowptr_local,
                                  int32_t* col_global, double* val);

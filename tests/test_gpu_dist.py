@@ -34,8 +34,11 @@ def _run_partitioned(m, contrast, starts, data, solve=True):
         A = dist.DistSparseMatrix(comm, sl.n, b, e, sl.rowptr, sl.col, sl.val)
         P = dist.DistPreconditionBoomerAMG()
         P.initialize(A, data)
-        out = dict(stats=P.level_stats(), levels=[])
+        out = dict(stats=P.level_stats(), levels=[], replicated_from=P.replicated_from)
         for l in range(P.num_levels):
+            if l >= P.replicated_from:      # held whole on every rank
+                out["levels"].append(dict(full=P.full_level(l)))
+                continue
             d = P.level_dims(l)
             lev = dict(dims=d, A=P.A_rows(l))
             if l + 1 < P.num_levels:
@@ -60,6 +63,15 @@ def _assert_same_hierarchy(parts, P1):
     for l in range(nl):
         rp, cl, vl = P1.A(l)
         n = len(rp) - 1
+        if "full" in parts[0]["levels"][l]:     # replicated level: every rank holds the single-device level
+            for p in parts:
+                f = p["levels"][l]["full"]
+                assert all(np.array_equal(a, b) for a, b in zip(f["A"], (rp, cl, vl))), f"replicated A level {l}"
+                if l + 1 < nl:
+                    assert np.array_equal(f["cf"], P1.cf_marker(l)), f"replicated cf level {l}"
+                    prp1, pcl1, pvl1, nc = P1.P(l)
+                    assert f["P"][3] == nc and all(np.array_equal(a, b) for a, b in zip(f["P"][:3], (prp1, pcl1, pvl1)))
+            continue
         assert sum(p["levels"][l]["dims"]["n_local"] for p in parts) == n
         for p in parts:
             d = p["levels"][l]["dims"]
@@ -82,11 +94,14 @@ def _assert_same_hierarchy(parts, P1):
                 assert np.array_equal(qvl, pvl1[prp1[b]:prp1[b + k]]), f"P values level {l}"
 
 
+@pytest.mark.parametrize("replicate_below", [0, 300, 1 << 20])
 @pytest.mark.parametrize("m,nranks,theta,contrast", [(8, 2, 0.25, 0.0), (12, 3, 0.5, 3.0), (10, 4, 0.25, 6.0),
                                                      (12, 2, 0.7, 6.0)])
-def test_partitioned_equals_single_device(gpu_ctx, m, nranks, theta, contrast):
+def test_partitioned_equals_single_device(gpu_ctx, m, nranks, theta, contrast, replicate_below):
+    """replicate_below: 0 = every level partitioned; 300 = the small levels gathered on every
+    rank; 2^20 = everything below the finest level replicated."""
     s = poisson(m, contrast=contrast)
-    data = device_data(theta)
+    data = device_data(theta, dist_replicate_below=replicate_below)
     A1, P1, ctl1, x1 = _single(gpu_ctx, s, data)
     parts = _run_partitioned(m, contrast, dist.slab_partition(m, nranks), data)
     _assert_same_hierarchy(parts, P1)
@@ -105,7 +120,7 @@ def test_partitioned_equals_single_device(gpu_ctx, m, nranks, theta, contrast):
 def test_partition_not_aligned_with_planes_and_single_rank(gpu_ctx):
     m, theta = 9, 0.25
     s = poisson(m, contrast=2.0)
-    data = device_data(theta)
+    data = device_data(theta, dist_replicate_below=0)
     A1, P1, ctl1, x1 = _single(gpu_ctx, s, data)
     for starts in ([0, 137, 600, s.n], [0, s.n]):  # ragged ranges cutting through planes; one rank
         parts = _run_partitioned(m, 2.0, starts, data)
@@ -119,7 +134,7 @@ def test_partition_not_aligned_with_planes_and_single_rank(gpu_ctx):
 def test_partitioned_cycle_options(gpu_ctx, kw):
     m = 10
     s = poisson(m, contrast=3.0)
-    data = device_data(0.25, **kw)
+    data = device_data(0.25, dist_replicate_below=100, **kw)
     A1, P1, ctl1, x1 = _single(gpu_ctx, s, data)
     parts = _run_partitioned(m, 3.0, dist.slab_partition(m, 3), data)
     _assert_same_hierarchy(parts, P1)

@@ -83,7 +83,7 @@ class AdditionalData:
                  coarsen_type=COARSEN_PMIS, interp_type=INTERP_CLASSICAL, relax_order=1,
                  n_sweeps=1, max_levels=25, max_coarse_size=9, relax_weight=1.0,
                  smoother_policy=SMOOTHER_SUBSTITUTE, options_via_string=True,
-                 keep_setup_intermediates=False, dist_replicate_below=32768):
+                 keep_setup_intermediates=False, dist_replicate_below=262144):
         self.symmetric_operator = bool(symmetric_operator)
         self.strong_threshold = float(strong_threshold)
         self.max_row_sum = float(max_row_sum)

@@ -495,7 +495,7 @@ int amgb_boomeramg_data_default(amgb_boomeramg_data* d) {
   d->smoother_policy = AMGB_SMOOTHER_SUBSTITUTE;
   d->options_via_string = 1;
   d->keep_setup_intermediates = 0;
-  d->dist_replicate_below = 32768;
+  d->dist_replicate_below = 262144;
   return AMGB_OK;
 }
 

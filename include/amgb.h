@@ -117,7 +117,7 @@ typedef struct amgb_boomeramg_data {
   int32_t keep_setup_intermediates; /* 1: keep strength masks etc. for the parity accessors */
   int32_t dist_replicate_below;     /* row-partitioned path: levels (other than the finest) with at
                                        most this many rows are gathered and handled redundantly on
-                                       every rank, without further exchanges (default 32768; 0: never) */
+                                       every rank, without further exchanges (default 262144; 0: never) */
   int32_t reserved[6];
 } amgb_boomeramg_data;
 

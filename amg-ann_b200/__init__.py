@@ -334,6 +334,14 @@ class PreconditionBoomerAMG:
         return dict(rows=rows[:k].copy(), nnz=nnz[:k].copy(), sparsity=sp[:k].copy(),
                     grid=g.value, operator=o.value, memory=m.value)
 
+    def level_row_stats(self, level):
+        """(min, max entries per row, min, max row sum) of a level: hypre's stats table."""
+        a, b = C.c_int32(), C.c_int32()
+        c, d = C.c_double(), C.c_double()
+        _chk(self.ctx._h, amgb_lib().amgb_precond_level_row_stats(self._h, level, C.byref(a), C.byref(b),
+                                                                  C.byref(c), C.byref(d)), "level_row_stats")
+        return a.value, b.value, c.value, d.value
+
     def effective_relax(self):
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
         _chk(self.ctx._h, amgb_lib().amgb_precond_effective_relax(self._h, C.byref(a), C.byref(b),

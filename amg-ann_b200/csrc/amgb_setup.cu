@@ -1563,6 +1563,24 @@ int amgb_precond_level_dims(const amgb_precond* P, int32_t level, int64_t* n, in
   return AMGB_OK;
 }
 
+// per-level row statistics of hypre's setup printout (par_stats.c): entries per row and row sums
+__global__ void __launch_bounds__(256)
+row_stats_kernel(int64_t n, const int32_t* __restrict__ rp, const double* __restrict__ val, int32_t* __restrict__ imm,
+                 unsigned long long* __restrict__ dmm) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int b = rp[i], e = rp[i + 1];
+  double s = 0.0;
+  for (int k = b; k < e; ++k) s += val[k];
+  atomicMin(&imm[0], e - b);
+  atomicMax(&imm[1], e - b);
+  // order-preserving map of doubles to unsigned integers, so min / max are integer atomics
+  unsigned long long u = (unsigned long long)__double_as_longlong(s);
+  u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+  atomicMin(&dmm[0], u);
+  atomicMax(&dmm[1], u);
+}
+
 static int d2h(amgb_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (bytes == 0) return AMGB_OK;
   AMGB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1594,6 +1612,42 @@ static int get_csr(amgb_ctx* ctx, const DeviceCsr& M, int32_t* rowptr, int32_t* 
   if (rowptr) AMGB_TRY(d2h(ctx, rowptr, M.rp.p, (M.n + 1) * sizeof(int32_t)));
   if (col) AMGB_TRY(d2h(ctx, col, M.col.p, M.nnz * sizeof(int32_t)));
   if (val) AMGB_TRY(d2h(ctx, val, M.val.p, M.nnz * sizeof(double)));
+  return AMGB_OK;
+}
+
+int amgb_precond_level_row_stats(const amgb_precond* P, int32_t level, int32_t* min_entries, int32_t* max_entries,
+                                 double* min_row_sum, double* max_row_sum) {
+  if (!P) return AMGB_ERR_BAD_ARG;
+  if (level < 0 || level >= (int)P->lv.size()) return AMGB_ERR_RANGE;
+  const DeviceCsr& A = P->lv[level].A;
+  amgb_ctx* ctx = P->ctx;
+  if (!A.rp.p || P->dist) return set_error(ctx, AMGB_ERR_RANGE, "level %d: operator not held in CSR form", level);
+  cudaSetDevice(ctx->device);
+  DevBuf<int32_t> imm;
+  DevBuf<unsigned long long> dmm;
+  AMGB_TRY(imm.alloc(ctx, 2));
+  AMGB_TRY(dmm.alloc(ctx, 2));
+  const int32_t i0[2] = {INT32_MAX, INT32_MIN};
+  const unsigned long long d0[2] = {~0ull, 0ull};
+  AMGB_CUDA(ctx, cudaMemcpyAsync(imm.p, i0, sizeof i0, cudaMemcpyHostToDevice, ctx->stream));
+  AMGB_CUDA(ctx, cudaMemcpyAsync(dmm.p, d0, sizeof d0, cudaMemcpyHostToDevice, ctx->stream));
+  AMGB_LAUNCH(ctx, F_AUX, 8.0 * A.nnz + 4.0 * A.n, row_stats_kernel, (unsigned)div_up(A.n, 256), 256, 0, A.n,
+              (const int32_t*)A.rp.p, (const double*)A.val.p, imm.p, dmm.p);
+  AMGB_CHECK_LAUNCH(ctx);
+  int32_t ih[2];
+  unsigned long long dh[2];
+  AMGB_TRY(d2h(ctx, ih, imm.p, sizeof ih));
+  AMGB_TRY(d2h(ctx, dh, dmm.p, sizeof dh));
+  auto back = [](unsigned long long u) {
+    u = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    double d;
+    std::memcpy(&d, &u, sizeof d);
+    return d;
+  };
+  if (min_entries) *min_entries = ih[0];
+  if (max_entries) *max_entries = ih[1];
+  if (min_row_sum) *min_row_sum = back(dh[0]);
+  if (max_row_sum) *max_row_sum = back(dh[1]);
   return AMGB_OK;
 }
 

@@ -82,9 +82,15 @@ struct CsrHost {
 // hypre_BoomerAMGSetupStats (par_stats.c) layout, as the reference's regex expects it
 // (ref common/parser.h:185-225).  Columns the parser does not read (entries per row,
 // row sums, interpolation table) carry the values the library reports.
+struct RowStats {
+  int32_t min_entries = 0, max_entries = 0;
+  double min_row_sum = 0.0, max_row_sum = 0.0;
+};
+
 inline std::string format_hypre_setup_stats(const LevelStats& st, double theta, double max_row_sum,
                                             int max_levels, const char* coarsening, const char* interpolation,
-                                            const std::vector<int64_t>* nnz_P = nullptr) {
+                                            const std::vector<int64_t>* nnz_P = nullptr,
+                                            const std::vector<RowStats>* rows = nullptr) {
   std::string out;
   char buf[512];
   auto add = [&](const char* fmt, auto... a) {
@@ -106,8 +112,10 @@ inline std::string format_hypre_setup_stats(const LevelStats& st, double theta, 
   out += "======================================================================\n";
   for (int l = 0; l < nl; ++l) {
     const double avg = st.rows[l] ? double(st.nnz[l]) / double(st.rows[l]) : 0.0;
+    const RowStats rs = rows ? (*rows)[l] : RowStats();
     add("%2d %7lld %8lld  %0.3f  %4d %4d  %6.1f  %10.3e  %10.3e\n", l, (long long)st.rows[l],
-        (long long)st.nnz[l], st.sparsity[l], 0, 0, avg, 0.0, 0.0);
+        (long long)st.nnz[l], st.sparsity[l], (int)rs.min_entries, (int)rs.max_entries, avg, rs.min_row_sum,
+        rs.max_row_sum);
   }
   out += "\n\nInterpolation Matrix Information:\n";
   out += "                    entries/row        min        max            row sums\n";
@@ -395,9 +403,13 @@ class PreconditionBoomerAMG {
       }
       const double theta = std::strtod(std::to_string(data.strong_threshold).c_str(), nullptr);
       const double mrs = std::strtod(std::to_string(data.max_row_sum).c_str(), nullptr);
+      std::vector<amgb::compat::RowStats> rows(st.rows.size());
+      for (int l = 0; l < (int)st.rows.size(); ++l)
+        amgb_precond_level_row_stats(prec_.get(), l, &rows[l].min_entries, &rows[l].max_entries,
+                                     &rows[l].min_row_sum, &rows[l].max_row_sum);
       const std::string text = amgb::compat::format_hypre_setup_stats(
           st, theta, mrs, d.max_levels, d.coarsen_type == AMGB_COARSEN_PMIS ? "PMIS" : "Falgout-CLJP",
-          "modified classical interpolation", &nnzP);
+          "modified classical interpolation", &nnzP, &rows);
       std::fputs(text.c_str(), stdout);  // C stdio: the reference redirects fd 1 (redirector.h:101)
     }
   }

@@ -188,6 +188,10 @@ int amgb_precond_level_stats(const amgb_precond* P, int32_t capacity, int32_t* n
                              int64_t* rows, int64_t* nnz, double* sparsity,
                              double* grid_complexity, double* operator_complexity,
                              double* memory_complexity);
+/* The remaining columns of hypre's "Operator Matrix Information" table (par_stats.c): entries
+ * per row and row sums of one level (computed on request; single-device hierarchies). */
+int amgb_precond_level_row_stats(const amgb_precond* P, int32_t level, int32_t* min_entries,
+                                 int32_t* max_entries, double* min_row_sum, double* max_row_sum);
 /* hypre relax type actually run on the device for down/up/coarse (after the
  * smoother policy was applied). */
 int amgb_precond_effective_relax(const amgb_precond* P, int32_t* down, int32_t* up,

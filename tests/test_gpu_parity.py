@@ -314,3 +314,16 @@ def test_aggressive_coarsening_elasticity_like_the_reference_case(gpu_ctx):
     data.aggressive_coarsening_num_levels = 2
     A, P, H = _both(gpu_ctx, s, data)
     _assert_hierarchy_identical(P, H)
+
+
+def test_level_row_stats_match_the_level_operators(gpu_ctx):
+    s = poisson(10, contrast=2.0)
+    A, P, H = _both(gpu_ctx, s, device_data(0.25))
+    for l in range(P.num_levels):
+        rp, cl, vl = P.A(l)
+        lens = np.diff(rp)
+        sums = np.add.reduceat(vl, rp[:-1])
+        mn, mx, smin, smax = P.level_row_stats(l)
+        assert (mn, mx) == (lens.min(), lens.max())
+        assert smin == pytest.approx(sums.min(), abs=1e-12 * np.abs(vl).max())
+        assert smax == pytest.approx(sums.max(), abs=1e-12 * np.abs(vl).max())

@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -113,6 +114,22 @@ struct NcclComm : amgb_comm {
     return AMGB_OK;
   }
   bool capturable() const override { return true; }
+  // one process per GPU: CUDA IPC handles; the mapping enables peer access over NVLink
+  bool peer_capable() const override { return true; }
+  int export_mem(amgb_ctx* ctx, void* base, char* handle) override {
+    static_assert(sizeof(cudaIpcMemHandle_t) <= kPeerHandleBytes, "handle size");
+    cudaIpcMemHandle_t h;
+    AMGB_CUDA(ctx, cudaIpcGetMemHandle(&h, base));
+    std::memcpy(handle, &h, sizeof h);
+    return AMGB_OK;
+  }
+  int import_mem(amgb_ctx* ctx, int, int, const char* handle, void** out) override {
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    AMGB_CUDA(ctx, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return AMGB_OK;
+  }
+  void close_mem(void* p) override { cudaIpcCloseMemHandle(p); }
 };
 
 // ---------------------------------------------------------------------------
@@ -202,7 +219,134 @@ struct LocalComm : amgb_comm {
     AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `sum` goes out of scope
     return AMGB_OK;
   }
+  int launch_fence() override {
+    g->barrier.wait();
+    return AMGB_OK;
+  }
+  // ranks share one address space: the "handle" is the pointer itself
+  bool peer_capable() const override { return true; }
+  int export_mem(amgb_ctx*, void* base, char* handle) override {
+    std::memset(handle, 0, kPeerHandleBytes);
+    std::memcpy(handle, &base, sizeof base);
+    return AMGB_OK;
+  }
+  int import_mem(amgb_ctx* ctx, int, int owner_device, const char* handle, void** out) override {
+    std::memcpy(out, handle, sizeof(void*));
+    if (owner_device != ctx->device) {
+      int can = 0;
+      AMGB_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, owner_device));
+      if (!can) return set_error(ctx, AMGB_ERR_COMM, "device %d cannot access device %d", ctx->device, owner_device);
+      const cudaError_t e = cudaDeviceEnablePeerAccess(owner_device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(ctx, e, "enable peer access", __FILE__, __LINE__);
+      (void)cudaGetLastError();
+    }
+    return AMGB_OK;
+  }
 };
+
+}  // namespace amgb
+
+// ---------------------------------------------------------------------------
+// Peer windows (see amgb_comm.cuh).  Grow-only per slot, kept for the life of the
+// communicator so that a theta sweep re-uses the same allocation and mappings.
+// ---------------------------------------------------------------------------
+int amgb_comm::window_acquire(amgb_ctx* ctx, size_t bytes, const void* mine, size_t extra_bytes, void* all,
+                              int* slot_out) {
+  using namespace amgb;
+  *slot_out = -1;
+  window_device = ctx->device;
+  const char* env = std::getenv("AMGB_PEER");
+  const bool want = peer_capable() && size > 1 && !(env && env[0] == '0');
+  int slot = 0;
+  while (slot < (int)windows.size() && windows[slot].in_use) ++slot;
+  if (slot == (int)windows.size()) windows.emplace_back();
+  PeerWindow& w = windows[slot];
+  w.peer_base.resize(size, nullptr);
+  w.peer_gen.resize(size, 0);
+  int ok = want ? 1 : 0;
+  if (ok && w.cap < bytes) {
+    if (w.base) retired.push_back(w.base);
+    w.base = nullptr;
+    w.cap = 0;
+    size_t cap = bytes + bytes / 4;
+    if (cap < (size_t(1) << 20)) cap = size_t(1) << 20;
+    if (cudaMalloc((void**)&w.base, cap) != cudaSuccess) {
+      (void)cudaGetLastError();
+      w.base = nullptr;
+      ok = 0;
+    } else {
+      w.cap = cap;
+      ++w.gen;
+    }
+  }
+  // payload: [ok, device, generation][handle][caller's table]
+  const size_t head = 3 * sizeof(int64_t) + kPeerHandleBytes, per = head + extra_bytes;
+  std::vector<char> snd(per, 0), rcv(per * (size_t)size);
+  if (ok) {
+    if (cudaMemsetAsync(w.base, 0, bytes, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+        export_mem(ctx, w.base, snd.data() + 3 * sizeof(int64_t)) != AMGB_OK) {
+      (void)cudaGetLastError();
+      ok = 0;
+    }
+  }
+  const int64_t hd[3] = {ok, ctx->device, (int64_t)w.gen};
+  std::memcpy(snd.data(), hd, sizeof hd);
+  if (extra_bytes) std::memcpy(snd.data() + head, mine, extra_bytes);
+  AMGB_TRY(allgather_host(ctx, snd.data(), per, rcv.data()));
+  bool all_ok = true, any_new = false;
+  for (int q = 0; q < size; ++q) {
+    int64_t h[3];
+    std::memcpy(h, rcv.data() + per * q, sizeof h);
+    if (!h[0]) all_ok = false;
+    if (q != rank && (uint64_t)h[2] != w.peer_gen[q]) any_new = true;
+    if (extra_bytes) std::memcpy((char*)all + extra_bytes * q, rcv.data() + per * q + head, extra_bytes);
+  }
+  if (!all_ok) return AMGB_OK;  // the same verdict on every rank
+  if (any_new) {
+    int64_t good = 1;
+    for (int q = 0; q < size; ++q) {
+      if (q == rank) continue;
+      int64_t h[3];
+      std::memcpy(h, rcv.data() + per * q, sizeof h);
+      if ((uint64_t)h[2] == w.peer_gen[q]) continue;
+      if (w.peer_base[q]) close_mem(w.peer_base[q]);
+      w.peer_base[q] = nullptr;
+      w.peer_gen[q] = 0;
+      void* mapped = nullptr;
+      if (import_mem(ctx, q, (int)h[1], rcv.data() + per * q + 3 * sizeof(int64_t), &mapped) != AMGB_OK) {
+        (void)cudaGetLastError();
+        good = 0;
+        continue;
+      }
+      w.peer_base[q] = (char*)mapped;
+      w.peer_gen[q] = (uint64_t)h[2];
+    }
+    AMGB_TRY(allreduce_min_i64_host(ctx, this, &good));  // every rank maps every window, or nobody uses them
+    if (!good) return AMGB_OK;
+  }
+  w.in_use = true;
+  *slot_out = slot;
+  return AMGB_OK;
+}
+
+void amgb_comm::window_release(int slot) {
+  if (slot >= 0 && slot < (int)windows.size()) windows[slot].in_use = false;
+}
+
+void amgb_comm::windows_destroy() {
+  if (window_device >= 0) cudaSetDevice(window_device);
+  for (amgb::PeerWindow& w : windows) {
+    for (char* p : w.peer_base)
+      if (p) close_mem(p);
+    if (w.base) cudaFree(w.base);
+  }
+  windows.clear();
+  for (void* p : retired) cudaFree(p);
+  retired.clear();
+}
+
+namespace amgb {
 
 static int gather_i64(amgb_ctx* ctx, amgb_comm* comm, int64_t v, std::vector<int64_t>& all) {
   all.resize(comm->size);
@@ -299,6 +443,7 @@ int amgb_comm_create_local(amgb_local_group* g, int rank, amgb_comm** out) {
 }
 
 int amgb_comm_destroy(amgb_comm* c) {
+  if (c) c->windows_destroy();
   delete c;
   return AMGB_OK;
 }

@@ -17,9 +17,52 @@
 
 #include "amgb_internal.cuh"
 
+namespace amgb {
+
+// A window of this rank's device memory that every other rank of the communicator can
+// store into directly (NVLink peer memory).  The kernels of the solve phase put halo
+// values and reduction partials straight into the consumer's window and signal with a
+// flag; no library call sits on that path (DESIGN.md "Peer windows").
+struct PeerWindow {
+  char* base = nullptr;            // my allocation (cudaMalloc: exportable)
+  size_t cap = 0;
+  uint64_t gen = 0;                // bumped on every re-allocation
+  bool in_use = false;
+  std::vector<char*> peer_base;    // my mapping of rank q's window (null for myself)
+  std::vector<uint64_t> peer_gen;  // generation of that mapping
+};
+
+constexpr int kPeerHandleBytes = 64;
+
+}  // namespace amgb
+
 struct amgb_comm {
   int rank = 0, size = 1;
   virtual ~amgb_comm() {}
+  // ---- peer windows -------------------------------------------------------------------
+  // COLLECTIVE.  A zeroed window of at least `bytes` on every rank (sizes may differ per
+  // rank) with the peers' windows mapped; `mine` (extra_bytes, the same size on every rank)
+  // is gathered into `all` (size * extra_bytes) on the way, after every rank's window has
+  // been zeroed.  *slot < 0 on return means that peer memory is not available on some rank
+  // and every rank must use the library exchanges instead.
+  int window_acquire(amgb_ctx* ctx, size_t bytes, const void* mine, size_t extra_bytes, void* all, int* slot);
+  void window_release(int slot);
+  void windows_destroy();
+  std::vector<amgb::PeerWindow> windows;
+  int window_device = -1;
+  std::vector<void*> retired;  // outgrown windows; peers may still hold a mapping until they re-import
+  // back-end primitives of the above
+  // Called before a kernel that spins on the peers' flags is launched.  Ranks that share a
+  // device (threads of one process) meet here on the host, so that every rank has LAUNCHED
+  // its puts before anyone spins: a launch may have to load its kernel first (lazy module
+  // loading), and that waits for the kernels already running in the context.
+  virtual int launch_fence() { return AMGB_OK; }
+  virtual bool peer_capable() const { return false; }
+  virtual int export_mem(amgb_ctx*, void*, char*) { return AMGB_ERR_UNSUPPORTED; }
+  virtual int import_mem(amgb_ctx*, int /*owner*/, int /*owner_device*/, const char*, void**) {
+    return AMGB_ERR_UNSUPPORTED;
+  }
+  virtual void close_mem(void*) {}
   // recv[rdispl[q] .. +rcount[q]) <- rank q's send[sdispl_q[me] .. +scount_q[me]).
   // Device buffers; ordered on ctx->stream; the call returns after the data has landed
   // (LocalComm) or has been enqueued (NcclComm).

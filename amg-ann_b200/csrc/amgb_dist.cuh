@@ -56,6 +56,46 @@ struct DistLevel {
   DevBuf<int32_t> colmap;    // extended -> solve index (-1: not referenced)
 };
 
+// ---- peer-memory exchanges of the solve phase (amgb_peer.cu) ----
+// One PeerPlan = one recurring exchange among a fixed set of peers: every time, each rank
+// PUTS its values straight into the peers' windows (NVLink stores from the pack kernel),
+// signals a per-peer flag with the exchange's epoch, and later WAITS for the peers' flags
+// and unpacks its own window.  Two staging slots alternate by epoch; a sender cannot be two
+// exchanges ahead of a receiver because it has to wait for that receiver's flag of the
+// exchange in between (peer sets are symmetric).  Everything is stream work on ctx->stream:
+// no host synchronisation, no library call, capturable in a CUDA graph.
+constexpr int kMaxPeers = 7;
+
+struct PeerTab {  // kernel parameter
+  int npeers, me_pos;                        // me_pos: peers with a smaller rank than mine
+  int send_end[kMaxPeers];                   // prefix ends of the peers' segments in my send list
+  int recv_end[kMaxPeers];                   // prefix ends of the peers' runs in my staging slot
+  long long dst_off[kMaxPeers];              // where peer j's run goes in the destination vector
+  double* r_stage[kMaxPeers];                // my run in peer j's staging, slot 0
+  long long r_stride[kMaxPeers];             // peer j's slot stride (elements)
+  unsigned long long* r_flag[kMaxPeers];     // my flag at peer j
+  const unsigned long long* l_flag[kMaxPeers];  // peer j's flag here
+  double* staging;                           // my two slots
+  long long stride;
+  unsigned long long* ctr;                   // completed exchanges of this plan (device)
+  unsigned* ticket;
+  int* err;                                  // set when a wait timed out
+};
+
+struct PeerPlan {
+  bool on = false;
+  amgb_comm* comm = nullptr;
+  PeerTab tab;
+  int64_t send_total = 0, recv_total = 0;
+  const int32_t* send_idx = nullptr;  // source index of every send-list entry; null: position within the peer's segment
+};
+
+// host description of a plan while the windows are laid out (all per rank, in elements)
+struct PeerSpec {
+  std::vector<int64_t> send_cnt, recv_cnt, dst_off;
+  const int32_t* send_idx = nullptr;
+};
+
 }  // namespace amgb
 
 struct amgb_dist_matrix {
@@ -78,6 +118,15 @@ struct amgb_dist_state {
   std::vector<int64_t> coarse_starts;
   amgb::DevBuf<double> coarse_f, coarse_x;  // full-length staging
   amgb::DevBuf<double> red;                 // PCG reduction staging (device)
+  // peer-memory exchanges (window_slot < 0: library exchanges through `comm`)
+  int window_slot = -1;
+  std::vector<amgb::PeerPlan> vpeer;  // halo plans of the partitioned levels
+  amgb::PeerPlan gather_peer;         // all-gather at the replication cut / of the coarsest right-hand side
+  amgb::PeerPlan red_peer;            // PCG scalars
+  int* peer_err = nullptr;            // device word in my window
+  ~amgb_dist_state() {
+    if (comm && window_slot >= 0) comm->window_release(window_slot);
+  }
 };
 
 namespace amgb {
@@ -99,5 +148,17 @@ int build_vector_plan(amgb_ctx* ctx, amgb_comm* comm, const int32_t* halo_gid, i
 int allgather_rows(amgb_ctx* ctx, amgb_comm* comm, const OwnedCsr& own, DeviceCsr& full);
 int allgather_f64(amgb_ctx* ctx, amgb_comm* comm, const std::vector<int64_t>& starts, const double* mine,
                   double* full);
+// amgb_peer.cu
+// COLLECTIVE: lays the plans out in a peer window and fills their device tables; leaves
+// every plan off (and returns OK) when peer memory is not available on some rank
+int build_peer_plans(amgb_ctx* ctx, amgb_comm* comm, const std::vector<PeerSpec>& specs, std::vector<PeerPlan>& plans,
+                     int* window_slot, int** err_word);
+// put my values (source index p -> p < split ? lo[p] : hi[p]) into the peers' windows and signal
+int peer_put(amgb_ctx* ctx, const PeerPlan& pl, const double* lo, const double* hi, int split);
+// wait for the peers' puts of the same exchange and unpack them into dst
+int peer_get(amgb_ctx* ctx, const PeerPlan& pl, double* dst);
+// red[0..count) <- sum over ranks, in rank order (the same bits on every rank); count <= 8
+int peer_allreduce(amgb_ctx* ctx, const PeerPlan& pl, double* red, int count);
+int peer_check(amgb_ctx* ctx, const int* err_word);
 
 }  // namespace amgb

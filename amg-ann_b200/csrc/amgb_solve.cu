@@ -645,13 +645,58 @@ static inline bool partitioned_level(const amgb_precond* P, int l) {
 static int halo(amgb_precond* P, int l, const double* lo, const double* hi, int split, double* dst) {
   if (!partitioned_level(P, l)) return AMGB_OK;
   P->ctx->cur_level = l;
-  return plan_sync_split(P->ctx, P->dist->comm, P->dist->dl[l].vplan, lo, hi, split, dst);
+  amgb_dist_state* ds = P->dist;
+  if (ds->window_slot >= 0) {
+    AMGB_TRY(peer_put(P->ctx, ds->vpeer[l], lo, hi, split));
+    return peer_get(P->ctx, ds->vpeer[l], dst);
+  }
+  return plan_sync_split(P->ctx, ds->comm, ds->dl[l].vplan, lo, hi, split, dst);
+}
+
+// every rank's block of a vector partitioned by `starts`, on every rank: mine is full + starts[rank]
+static int gather_blocks(amgb_precond* P, const std::vector<int64_t>& starts, const double* mine, double* full) {
+  amgb_dist_state* ds = P->dist;
+  amgb_ctx* ctx = P->ctx;
+  if (ds->window_slot >= 0) {
+    const int me = ds->comm->rank;
+    AMGB_TRY(peer_put(ctx, ds->gather_peer, mine, mine, 0));
+    double* own = full + starts[me];
+    const size_t bytes = (size_t)(starts[me + 1] - starts[me]) * sizeof(double);
+    if (own != mine && bytes)
+      AMGB_CUDA(ctx, cudaMemcpyAsync(own, mine, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return peer_get(ctx, ds->gather_peer, full);
+  }
+  return allgather_f64(ctx, ds->comm, starts, mine, full);
+}
+
+static int reduce_scalars(amgb_precond* P, double* red, int count) {
+  amgb_dist_state* ds = P->dist;
+  if (ds->window_slot >= 0) return peer_allreduce(P->ctx, ds->red_peer, red, count);
+  return ds->comm->allreduce_sum_f64(P->ctx, red, count);
 }
 
 // One hypre_BoomerAMGRelaxIF call.  Reads `u` (halo fresh), leaves the relaxed vector in
 // `out` (halo stale).  On the row-partitioned path the halo of `u` is overwritten between
 // the two half sweeps.
-static int relax_if(amgb_precond* P, int l, const double* f, double* u, double* out, int cycle_param) {
+// Jacobi-type sweep from a zero guess on rows [lo, hi): A u = 0, so the matrix is not read.
+// "0.0 +" keeps the sign of zero that the general formula produces.
+__global__ void __launch_bounds__(kBlock)
+jacobi_zero_kernel(int lo, int hi, const double* __restrict__ f, const double* __restrict__ inv_relax, double w,
+                   double* __restrict__ out) {
+  const int row = lo + (int)((int64_t)blockIdx.x * kBlock + threadIdx.x);
+  if (row < hi) out[row] = 0.0 + w * (f[row] - 0.0) * inv_relax[row];
+}
+
+static int relax_zero(amgb_ctx* ctx, const Level& L, int lo, int hi, const double* f, double w, double* out) {
+  if (hi <= lo) return AMGB_OK;
+  AMGB_LAUNCH(ctx, F_VEC, 24.0 * (hi - lo), jacobi_zero_kernel, (unsigned)div_up(hi - lo, kBlock), kBlock, 0, lo, hi,
+              f, (const double*)L.inv_relax.p, w, out);
+  AMGB_CHECK_LAUNCH(ctx);
+  return AMGB_OK;
+}
+
+static int relax_if(amgb_precond* P, int l, const double* f, double* u, double* out, int cycle_param,
+                    bool u_is_zero = false) {
   Level& L = P->lv[l];
   amgb_ctx* ctx = P->ctx;
   ctx->cur_level = l;
@@ -668,14 +713,18 @@ static int relax_if(amgb_precond* P, int l, const double* f, double* u, double* 
     // half sweep = the rows touched + 4 vectors on those rows
     const double bytes_c = share_c * mat + 32.0 * nC, bytes_f = (1.0 - share_c) * mat + 32.0 * (n - nC);
     if (cycle_param < 2) {  // down: C then F
-      AMGB_TRY(launch_sell(ctx, L.As, 0, nC, u, u, 0, epi, fam, bytes_c));
+      if (u_is_zero) AMGB_TRY(relax_zero(ctx, L, 0, nC, f, w, out));
+      else AMGB_TRY(launch_sell(ctx, L.As, 0, nC, u, u, 0, epi, fam, bytes_c));
       AMGB_TRY(halo(P, l, out, u, nC, u));  // halo C points: fresh; halo F points: old
       AMGB_TRY(launch_sell(ctx, L.As, nC, n, out, u, nC, epi, fam, bytes_f));
     } else {  // up: F then C
-      AMGB_TRY(launch_sell(ctx, L.As, nC, n, u, u, 0, epi, fam, bytes_f));
+      if (u_is_zero) AMGB_TRY(relax_zero(ctx, L, nC, n, f, w, out));
+      else AMGB_TRY(launch_sell(ctx, L.As, nC, n, u, u, 0, epi, fam, bytes_f));
       AMGB_TRY(halo(P, l, u, out, nC, out));  // halo F points: fresh; halo C points: old
       AMGB_TRY(launch_sell(ctx, L.As, 0, nC, u, out, nC, epi, fam, bytes_c));
     }
+  } else if (u_is_zero) {
+    AMGB_TRY(relax_zero(ctx, L, 0, n, f, w, out));
   } else {
     AMGB_TRY(launch_sell(ctx, L.As, 0, n, u, u, 0, epi, fam, mat + 32.0 * n));
   }
@@ -696,7 +745,7 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
         // replicated dense solve: gather the right-hand side, solve, keep the owned block
         amgb_dist_state* ds = P->dist;
         const int nfull = (int)ds->coarse_n;
-        AMGB_TRY(allgather_f64(ctx, ds->comm, ds->coarse_starts, f, ds->coarse_f.p));
+        AMGB_TRY(gather_blocks(P, ds->coarse_starts, f, ds->coarse_f.p));
         AMGB_LAUNCH(ctx, F_COARSE, 8.0 * nfull * nfull, dense_solve_kernel, 1, kDenseThreads,
                     (size_t)nfull * sizeof(double), nfull, P->dense.p, ds->coarse_f.p, ds->coarse_x.p);
         AMGB_CHECK_LAUNCH(ctx);
@@ -712,7 +761,7 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
       const unsigned sweeps = P->data.n_sweeps_coarse ? P->data.n_sweeps_coarse : 1u;
       for (unsigned s = 0; s < sweeps; ++s) {
         if (!(u_is_zero && s == 0)) AMGB_TRY(halo(P, l, u, u, 0, u));
-        AMGB_TRY(relax_if(P, l, f, u, alt, 3));
+        AMGB_TRY(relax_if(P, l, f, u, alt, 3, u_is_zero && s == 0));
         std::swap(u, alt);
       }
     }
@@ -720,7 +769,7 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
   }
   for (unsigned s = 0; s < P->data.n_sweeps; ++s) {
     if (!(u_is_zero && s == 0)) AMGB_TRY(halo(P, l, u, u, 0, u));
-    AMGB_TRY(relax_if(P, l, f, u, alt, 1));
+    AMGB_TRY(relax_if(P, l, f, u, alt, 1, u_is_zero && s == 0));
     std::swap(u, alt);
   }
   // residual into the scratch buffer, restriction into the coarse rhs
@@ -736,9 +785,11 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
     // whole right-hand side on every rank, then into that level's C/F numbering
     amgb_dist_state* ds = P->dist;
     const DistLevel& D = ds->dl[l];
-    AMGB_TRY(launch_sell(ctx, L.Rs, 0, (int)D.nc_own, alt, alt, 0, EpiStore{ds->repl_own.p},
+    // (with peer windows the owned block is produced in place inside the full vector)
+    double* own = ds->window_slot >= 0 ? ds->repl_full.p + D.cstarts[ds->comm->rank] : ds->repl_own.p;
+    AMGB_TRY(launch_sell(ctx, L.Rs, 0, (int)D.nc_own, alt, alt, 0, EpiStore{own},
                          l == 0 ? F_RESTRICT_L0 : F_RESTRICT, L.Rs.csr_bytes() + 8.0 * n + 8.0 * D.nc_own));
-    AMGB_TRY(allgather_f64(ctx, ds->comm, D.cstarts, ds->repl_own.p, ds->repl_full.p));
+    AMGB_TRY(gather_blocks(P, D.cstarts, own, ds->repl_full.p));
     AMGB_LAUNCH(ctx, F_VEC, 20.0 * ncrs, gather_kernel, (unsigned)div_up(ncrs, kBlock), kBlock, 0, (int64_t)ncrs,
                 (const int32_t*)C.perm.p, (const double*)ds->repl_full.p, C.f.p);
     AMGB_CHECK_LAUNCH(ctx);
@@ -1056,7 +1107,7 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
       AMGB_LAUNCH(ctx, F_VEC, 16.0 * dot_blocks, local_sums_kernel, 1, kBlock, 0, (const double*)pa.p,
                   (const double*)pb.p, dot_blocks, red);
       AMGB_CHECK_LAUNCH(ctx);
-      AMGB_TRY(ds->comm->allreduce_sum_f64(ctx, red, 2));
+      AMGB_TRY(reduce_scalars(P, red, 2));
       AMGB_LAUNCH(ctx, F_VEC, 16.0, finalize_beta_red_kernel, 1, 1, 0, (const double*)red, sc.p, fl.p, hist.p, cap,
                   abs_tol, first);
     } else {
@@ -1094,7 +1145,7 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
       AMGB_LAUNCH(ctx, F_VEC, 8.0 * spmv_blocks, local_sums_kernel, 1, kBlock, 0, (const double*)pa.p,
                   (const double*)nullptr, spmv_blocks, red);
       AMGB_CHECK_LAUNCH(ctx);
-      AMGB_TRY(ds->comm->allreduce_sum_f64(ctx, red, 1));
+      AMGB_TRY(reduce_scalars(P, red, 1));
       AMGB_LAUNCH(ctx, F_VEC, 8.0, finalize_alpha_red_kernel, 1, 1, 0, (const double*)red, sc.p, fl.p);
     } else {
       AMGB_LAUNCH(ctx, F_VEC, 8.0 * spmv_blocks, finalize_alpha_kernel, 1, kBlock, 0, pa.p, spmv_blocks, sc.p,
@@ -1122,6 +1173,7 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
   AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   // the graph was captured for this call's (z, r): drop it before they are freed
   destroy_solve_state(P);
+  if (ds) AMGB_TRY(peer_check(ctx, ds->peer_err));
   if (status != 0) return set_error(ctx, status, "PCG breakdown at iteration %d", iters);
   if (!done)
     return set_error(ctx, AMGB_ERR_NO_CONVERGENCE, "PCG did not reach %g in %lld steps", abs_tol,
@@ -1148,6 +1200,7 @@ static int vmult_user(amgb_precond* P, double* dst, const double* src) {
   AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, scatter_kernel, vgrid, kBlock, 0, n, L0.perm.p, z.p, dst);
   AMGB_CHECK_LAUNCH(ctx);
   AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (P->dist) AMGB_TRY(peer_check(ctx, P->dist->peer_err));
   return AMGB_OK;
 }
 
@@ -1381,6 +1434,44 @@ int finish_solve_setup_dist(amgb_precond* P) {
     }
   }
   AMGB_TRY(ds->red.alloc_zero(ctx, 8));
+  // 4. peer-memory plans: halo of every partitioned level, the all-gather below the last
+  //    partitioned level (replication cut or coarsest right-hand side), the PCG scalars
+  {
+    const int S = comm->size, me = comm->rank;
+    std::vector<PeerSpec> specs(nd + 2);
+    for (int l = 0; l < nd; ++l) {
+      const HaloPlan& pl = ds->dl[l].vplan;
+      specs[l].send_cnt = pl.send_cnt;
+      specs[l].recv_cnt = pl.recv_cnt;
+      specs[l].dst_off = pl.recv_off;
+      specs[l].send_idx = pl.send_idx.p;
+    }
+    const std::vector<int64_t>& gs = nd < nl ? ds->dl[nd - 1].cstarts : ds->coarse_starts;
+    PeerSpec& g = specs[nd];
+    PeerSpec& r = specs[nd + 1];
+    g.send_cnt.assign(S, 0);
+    g.recv_cnt.assign(S, 0);
+    g.dst_off.assign(S, 0);
+    r.send_cnt.assign(S, 8);
+    r.recv_cnt.assign(S, 8);
+    r.dst_off.assign(S, 0);
+    r.send_cnt[me] = r.recv_cnt[me] = 0;
+    if ((int)gs.size() == S + 1) {
+      for (int q = 0; q < S; ++q) {
+        if (q == me) continue;
+        g.send_cnt[q] = gs[me + 1] - gs[me];
+        g.recv_cnt[q] = gs[q + 1] - gs[q];
+        g.dst_off[q] = gs[q];
+      }
+    }
+    std::vector<PeerPlan> plans;
+    AMGB_TRY(build_peer_plans(ctx, comm, specs, plans, &ds->window_slot, &ds->peer_err));
+    if (ds->window_slot >= 0) {
+      ds->vpeer.assign(plans.begin(), plans.begin() + nd);
+      ds->gather_peer = plans[nd];
+      ds->red_peer = plans[nd + 1];
+    }
+  }
   return AMGB_OK;
 }
 

@@ -95,7 +95,7 @@ AMGB_SYMBOLS = [
     "amgb_ctx_get_timer_level",
     # row-partitioned path
     "amgb_nccl_unique_id", "amgb_comm_create_nccl", "amgb_local_group_create",
-    "amgb_local_group_destroy", "amgb_comm_create_local", "amgb_comm_destroy", "amgb_comm_rank",
+    "amgb_local_group_destroy", "amgb_local_group_abort", "amgb_comm_create_local", "amgb_comm_destroy", "amgb_comm_rank",
     "amgb_comm_size", "amgb_dist_matrix_create", "amgb_dist_matrix_destroy",
     "amgb_dist_precond_initialize", "amgb_dist_cg_solve", "amgb_dist_cg_solve_device",
     "amgb_dist_precond_level_dims", "amgb_dist_precond_replicated_from", "amgb_dist_precond_get_cf_marker",
@@ -175,6 +175,7 @@ def amgb_lib():
         _sig(L.amgb_comm_create_nccl, C.c_int, vp, C.c_int, C.c_int, vp, C.POINTER(vp))
         _sig(L.amgb_local_group_create, C.c_int, C.c_int, C.POINTER(vp))
         _sig(L.amgb_local_group_destroy, C.c_int, vp)
+        _sig(L.amgb_local_group_abort, C.c_int, vp)
         _sig(L.amgb_comm_create_local, C.c_int, vp, C.c_int, C.POINTER(vp))
         _sig(L.amgb_comm_destroy, C.c_int, vp)
         _sig(L.amgb_comm_rank, C.c_int, vp)

@@ -3,6 +3,7 @@
 // Interface and semantics: amgb_comm.cuh.
 #include <dlfcn.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -135,22 +136,40 @@ struct NcclComm : amgb_comm {
 // ---------------------------------------------------------------------------
 // In-process group: ranks are host threads.
 // ---------------------------------------------------------------------------
+// A rank that left with an error never arrives: the others give up after kBarrierSeconds and
+// the group stays broken (every later wait fails at once) instead of hanging the process.
+constexpr int kBarrierSeconds = 120;
+
 struct Barrier {
   std::mutex m;
   std::condition_variable cv;
   int count = 0, generation = 0, parties = 1;
-  void wait() {
+  bool broken = false;
+  bool wait() {
     std::unique_lock<std::mutex> lk(m);
+    if (broken) return false;
     const int gen = generation;
     if (++count == parties) {
       count = 0;
       ++generation;
       cv.notify_all();
-    } else {
-      cv.wait(lk, [&] { return gen != generation; });
+      return true;
     }
+    if (!cv.wait_for(lk, std::chrono::seconds(kBarrierSeconds), [&] { return gen != generation || broken; }) ||
+        broken) {
+      broken = true;
+      cv.notify_all();
+      return false;
+    }
+    return true;
   }
 };
+
+#define AMGB_BARRIER(ctx, g)                                                                              \
+  do {                                                                                                    \
+    if (!(g)->barrier.wait())                                                                             \
+      return set_error((ctx), AMGB_ERR_COMM, "in-process group: a rank did not arrive (it failed earlier)"); \
+  } while (0)
 
 struct Slot {
   const void* send = nullptr;
@@ -179,7 +198,7 @@ struct LocalComm : amgb_comm {
     me.send = send;
     me.scount = scount;
     me.sdispl = sdispl;
-    g->barrier.wait();
+    AMGB_BARRIER(ctx, g);
     int rc = AMGB_OK;
     for (int q = 0; q < size && rc == AMGB_OK; ++q) {
       const Slot& s = g->slots[q];
@@ -195,14 +214,15 @@ struct LocalComm : amgb_comm {
     }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == AMGB_OK)
       rc = set_error(ctx, AMGB_ERR_CUDA, "alltoallv sync failed");
-    g->barrier.wait();  // everyone has read my send buffer
+    if (!g->barrier.wait() && rc == AMGB_OK)  // everyone has read my send buffer
+      rc = set_error(ctx, AMGB_ERR_COMM, "in-process group: a rank did not arrive (it failed earlier)");
     return rc;
   }
-  int allgather_host(amgb_ctx*, const void* mine, size_t bytes, void* all) override {
+  int allgather_host(amgb_ctx* ctx, const void* mine, size_t bytes, void* all) override {
     g->slots[rank].host = mine;
-    g->barrier.wait();
+    AMGB_BARRIER(ctx, g);
     for (int q = 0; q < size; ++q) std::memcpy((char*)all + (size_t)q * bytes, g->slots[q].host, bytes);
-    g->barrier.wait();
+    AMGB_BARRIER(ctx, g);
     return AMGB_OK;
   }
   int allreduce_sum_f64(amgb_ctx* ctx, double* buf, int count) override {
@@ -210,19 +230,16 @@ struct LocalComm : amgb_comm {
     me.red.resize(count);
     AMGB_CUDA(ctx, cudaMemcpyAsync(me.red.data(), buf, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    g->barrier.wait();
+    AMGB_BARRIER(ctx, g);
     std::vector<double> sum(count, 0.0);
     for (int q = 0; q < size; ++q)
       for (int i = 0; i < count; ++i) sum[i] += g->slots[q].red[i];
-    g->barrier.wait();  // everyone has read every slot
+    AMGB_BARRIER(ctx, g);  // everyone has read every slot
     AMGB_CUDA(ctx, cudaMemcpyAsync(buf, sum.data(), count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `sum` goes out of scope
     return AMGB_OK;
   }
-  int launch_fence() override {
-    g->barrier.wait();
-    return AMGB_OK;
-  }
+  int launch_fence() override { return g->barrier.wait() ? AMGB_OK : AMGB_ERR_COMM; }
   // ranks share one address space: the "handle" is the pointer itself
   bool peer_capable() const override { return true; }
   int export_mem(amgb_ctx*, void* base, char* handle) override {
@@ -424,6 +441,14 @@ int amgb_local_group_create(int nranks, amgb_local_group** out) {
   g->barrier.parties = nranks;
   g->slots.resize(nranks);
   *out = g;
+  return AMGB_OK;
+}
+
+int amgb_local_group_abort(amgb_local_group* g) {
+  if (!g) return AMGB_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(g->barrier.m);
+  g->barrier.broken = true;
+  g->barrier.cv.notify_all();
   return AMGB_OK;
 }
 

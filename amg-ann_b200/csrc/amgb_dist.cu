@@ -1064,7 +1064,9 @@ int amgb_dist_precond_get_cf_marker(const amgb_precond* P, int32_t level, int32_
   if (level < 0 || level >= (int)P->dist->dl.size() || level >= P->dist->replicated_from) return AMGB_ERR_RANGE;
   const DistLevel& D = P->dist->dl[level];
   const Level& L = P->lv[level];
-  if (!L.cf.p) return set_error(P->ctx, AMGB_ERR_RANGE, "level %d is the coarsest: no C/F splitting", level);
+  if (level + 1 >= (int)P->lv.size())
+    return set_error(P->ctx, AMGB_ERR_RANGE, "level %d is the coarsest: no C/F splitting", level);
+  if (D.nloc == 0) return AMGB_OK;  // this rank owns nothing on the level
   cudaSetDevice(P->ctx->device);
   return d2h_sync(P->ctx, cf_local, L.cf.p + D.o0, D.nloc * sizeof(int32_t));
 }

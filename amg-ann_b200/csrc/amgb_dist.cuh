@@ -124,6 +124,9 @@ struct amgb_dist_state {
   amgb::PeerPlan gather_peer;         // all-gather at the replication cut / of the coarsest right-hand side
   amgb::PeerPlan red_peer;            // PCG scalars
   int* peer_err = nullptr;            // device word in my window
+  // operators with at least this many rows overlap their halo exchange with the rows that
+  // do not need it (amgb_solve.cu launch_sell_halo); smaller ones exchange first
+  int64_t overlap_min_rows = 65536;
   ~amgb_dist_state() {
     if (comm && window_slot >= 0) comm->window_release(window_slot);
   }

@@ -158,6 +158,10 @@ struct Sell {
   DevBuf<int32_t> slice_ptr;  // nslices+1, in units of 32 elements
   DevBuf<int32_t> col;
   DevBuf<double> val;
+  // row-partitioned path: rows [ilo[b], ihi[b]) of block b (0: rows below bsplit, 1: the
+  // rest) reference no halo column, so they can run while the halo is still in flight
+  bool has_interior = false;
+  int bsplit = 0, ilo[2] = {0, 0}, ihi[2] = {0, 0};
   double csr_bytes() const { return 12.0 * nnz + 4.0 * (n + 1); }
 };
 

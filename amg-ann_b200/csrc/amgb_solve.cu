@@ -313,13 +313,13 @@ sell_rows_kernel(int s_begin, int s_end, int row_lo, int row_hi, const int32_t* 
 // w = A p fused with the partial dot (p, w): one partial per block, fixed tree.
 template <int T>
 __global__ void __launch_bounds__(kBlock)
-sell_spmv_dot_kernel(int nslices, int n, const int32_t* __restrict__ slice_ptr,
+sell_spmv_dot_kernel(int s_begin, int s_end, int row_lo, int row_hi, const int32_t* __restrict__ slice_ptr,
                      const int32_t* __restrict__ col, const double* __restrict__ val,
                      const double* __restrict__ x, double* __restrict__ y, double* __restrict__ partial) {
-  const int s = (int)(((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5);
+  const int s = s_begin + (int)(((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   const int row = s * (32 / T) + lane / T;
-  const bool act = s < nslices && row < n;
+  const bool act = s < s_end && row >= row_lo && row < row_hi;
   double sum = 0.0;
   if (act) {
     const int sp = slice_ptr[s];
@@ -344,6 +344,20 @@ sell_spmv_dot_kernel(int nslices, int n, const int32_t* __restrict__ slice_ptr,
     for (int i = 0; i < kWarps; ++i) t += ws[i];
     partial[blockIdx.x] = t;
   }
+}
+
+// w = A p on rows [row_lo, row_hi) with one partial of (p, w) per block, written from partial[*count] on
+static int launch_spmv_dot(amgb_ctx* ctx, const Sell& S, int row_lo, int row_hi, const double* x, double* y,
+                           double* partial, int64_t* count, double bytes) {
+  if (row_hi <= row_lo) return AMGB_OK;
+  const int rps = 32 / S.T;
+  const int s_begin = row_lo / rps, s_end = (int)div_up(row_hi, rps);
+  const unsigned grid = (unsigned)div_up((int64_t)(s_end - s_begin) * 32, kBlock);
+  AMGB_DISPATCH_T(S.T, AMGB_LAUNCH(ctx, F_SPMV, bytes, sell_spmv_dot_kernel<TT>, grid, kBlock, 0, s_begin, s_end,
+                                   row_lo, row_hi, S.slice_ptr.p, S.col.p, S.val.p, x, y, partial + *count));
+  AMGB_CHECK_LAUNCH(ctx);
+  *count += grid;
+  return AMGB_OK;
 }
 
 template <class Epi>
@@ -398,6 +412,58 @@ sell_aux_kernel(int nslices, int n, const int32_t* __restrict__ slice_ptr, const
     if (diag != 0.0) inv = relax_type == 18 ? 1.0 / l1 : 1.0 / diag;
     inv_relax[row] = inv;
   }
+}
+
+// ---------------------------------------------------------------------------
+// Row-partitioned path: which rows gather from the halo part of the vector (columns >=
+// halo_begin)?  With a contiguous row partition they sit at the two ends of the C block and
+// of the F block; the rows in between form the interior ranges of Sell::ilo/ihi.
+//   out[0] = end of the leading halo rows of block 0, out[1] = start of its trailing ones,
+//   out[2], out[3] the same for block 1 (initialised to {0, bsplit, bsplit, n}).
+// ---------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(kBlock)
+sell_halo_rows_kernel(int nslices, int n, const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ col,
+                      int halo_begin, int bsplit, int* __restrict__ out) {
+  const int s = (int)(((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (s >= nslices) return;
+  const int row = s * (32 / T) + lane / T;
+  bool touches = false;
+  if (row < n) {
+    const int sp = slice_ptr[s];
+    const int w = slice_ptr[s + 1] - sp;
+    const int64_t base = (int64_t)sp * 32 + lane;
+    for (int j = 0; j < w; ++j) touches |= col[base + (int64_t)j * 32] >= halo_begin;
+  }
+  if (!touches) return;
+  if (row < bsplit) {
+    if (row < bsplit / 2) atomicMax(&out[0], row + 1); else atomicMin(&out[1], row);
+  } else {
+    if (row < bsplit + (n - bsplit) / 2) atomicMax(&out[2], row + 1); else atomicMin(&out[3], row);
+  }
+}
+
+static int find_interior_rows(amgb_ctx* ctx, Sell& S, int halo_begin, int bsplit) {
+  const int n = (int)S.n;
+  DevBuf<int> out;
+  AMGB_TRY(out.alloc(ctx, 4));
+  const int init[4] = {0, bsplit, bsplit, n};
+  AMGB_CUDA(ctx, cudaMemcpyAsync(out.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+  AMGB_DISPATCH_T(S.T, AMGB_LAUNCH(ctx, F_AUX, 4.0 * S.nnz, sell_halo_rows_kernel<TT>,
+                                   (unsigned)div_up(S.nslices * 32, kBlock), kBlock, 0, (int)S.nslices, n,
+                                   S.slice_ptr.p, S.col.p, halo_begin, bsplit, out.p));
+  AMGB_CHECK_LAUNCH(ctx);
+  int h[4];
+  AMGB_CUDA(ctx, cudaMemcpyAsync(h, out.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  S.bsplit = bsplit;
+  S.ilo[0] = h[0];
+  S.ihi[0] = std::max(h[0], h[1]);
+  S.ilo[1] = h[2];
+  S.ihi[1] = std::max(h[2], h[3]);
+  S.has_interior = true;
+  return AMGB_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -678,6 +744,41 @@ static int reduce_scalars(amgb_precond* P, double* red, int count) {
 // One hypre_BoomerAMGRelaxIF call.  Reads `u` (halo fresh), leaves the relaxed vector in
 // `out` (halo stale).  On the row-partitioned path the halo of `u` is overwritten between
 // the two half sweeps.
+// One SELL product on rows [row_lo, row_hi) whose gather source needs its halo refreshed
+// first (halo of h_dst <- the owners' p < h_split ? h_lo[p] : h_hi[p], on level `lp`).
+// With peer windows on a large level the exchange is overlapped: put, rows that reference
+// no halo column, wait + unpack, the remaining (boundary) rows.
+template <class Epi>
+static int launch_sell_halo(amgb_precond* P, int lp, const Sell& S, int row_lo, int row_hi, const double* x_lo,
+                            const double* x_hi, int split, Epi epi, int family, double bytes, const double* h_lo,
+                            const double* h_hi, int h_split, double* h_dst) {
+  amgb_ctx* ctx = P->ctx;
+  amgb_dist_state* ds = P->dist;
+  const int lvl = ctx->cur_level;
+  const bool overlap = partitioned_level(P, lp) && ds->window_slot >= 0 && S.has_interior &&
+                       S.n >= ds->overlap_min_rows && row_hi > row_lo;
+  if (!overlap) {
+    AMGB_TRY(halo(P, lp, h_lo, h_hi, h_split, h_dst));
+    ctx->cur_level = lvl;
+    return launch_sell(ctx, S, row_lo, row_hi, x_lo, x_hi, split, epi, family, bytes);
+  }
+  const double per_row = bytes / double(row_hi - row_lo);
+  AMGB_TRY(peer_put(ctx, ds->vpeer[lp], h_lo, h_hi, h_split));
+  for (int b = 0; b < 2; ++b) {
+    const int a = std::max(row_lo, S.ilo[b]), e = std::min(row_hi, S.ihi[b]);
+    if (a < e) AMGB_TRY(launch_sell(ctx, S, a, e, x_lo, x_hi, split, epi, family, per_row * (e - a)));
+  }
+  AMGB_TRY(peer_get(ctx, ds->vpeer[lp], h_dst));
+  const int cut[4] = {S.ilo[0], S.ihi[0], S.ilo[1], S.ihi[1]};
+  int from = row_lo;
+  for (int b = 0; b < 3; ++b) {  // the three gaps around the two interior ranges
+    const int to = b < 2 ? std::min(row_hi, std::max(from, cut[2 * b])) : row_hi;
+    if (from < to) AMGB_TRY(launch_sell(ctx, S, from, to, x_lo, x_hi, split, epi, family, per_row * (to - from)));
+    if (b < 2) from = std::max(from, std::min(row_hi, std::max(cut[2 * b + 1], cut[2 * b])));
+  }
+  return AMGB_OK;
+}
+
 // Jacobi-type sweep from a zero guess on rows [lo, hi): A u = 0, so the matrix is not read.
 // "0.0 +" keeps the sign of zero that the general formula produces.
 __global__ void __launch_bounds__(kBlock)
@@ -697,6 +798,7 @@ static int relax_zero(amgb_ctx* ctx, const Level& L, int lo, int hi, const doubl
 
 static int relax_if(amgb_precond* P, int l, const double* f, double* u, double* out, int cycle_param,
                     bool u_is_zero = false) {
+  // on the row-partitioned path the halo of `u` is refreshed here, overlapped with the rows that do not need it
   Level& L = P->lv[l];
   amgb_ctx* ctx = P->ctx;
   ctx->cur_level = l;
@@ -707,26 +809,26 @@ static int relax_if(amgb_precond* P, int l, const double* f, double* u, double* 
   EpiJacobi epi{f, u, L.inv_relax.p, out, w};
   // C/F ordering needs a splitting on this level (any rank may own no C or no F points)
   const bool cf_order = P->data.relax_order == 1 && cycle_param < 3 &&
-                       (partitioned_level(P, l) ? L.cf.p != nullptr : (nC > 0 && nC < n));
+                       (partitioned_level(P, l) ? l + 1 < (int)P->lv.size() : (nC > 0 && nC < n));
   if (cf_order) {
     const double share_c = n > 0 ? double(nC) / double(n) : 0.0;
     // half sweep = the rows touched + 4 vectors on those rows
     const double bytes_c = share_c * mat + 32.0 * nC, bytes_f = (1.0 - share_c) * mat + 32.0 * (n - nC);
     if (cycle_param < 2) {  // down: C then F
       if (u_is_zero) AMGB_TRY(relax_zero(ctx, L, 0, nC, f, w, out));
-      else AMGB_TRY(launch_sell(ctx, L.As, 0, nC, u, u, 0, epi, fam, bytes_c));
-      AMGB_TRY(halo(P, l, out, u, nC, u));  // halo C points: fresh; halo F points: old
-      AMGB_TRY(launch_sell(ctx, L.As, nC, n, out, u, nC, epi, fam, bytes_f));
+      else AMGB_TRY(launch_sell_halo(P, l, L.As, 0, nC, u, u, 0, epi, fam, bytes_c, u, u, 0, u));
+      // halo C points: fresh; halo F points: old
+      AMGB_TRY(launch_sell_halo(P, l, L.As, nC, n, out, u, nC, epi, fam, bytes_f, out, u, nC, u));
     } else {  // up: F then C
       if (u_is_zero) AMGB_TRY(relax_zero(ctx, L, nC, n, f, w, out));
-      else AMGB_TRY(launch_sell(ctx, L.As, nC, n, u, u, 0, epi, fam, bytes_f));
-      AMGB_TRY(halo(P, l, u, out, nC, out));  // halo F points: fresh; halo C points: old
-      AMGB_TRY(launch_sell(ctx, L.As, 0, nC, u, out, nC, epi, fam, bytes_c));
+      else AMGB_TRY(launch_sell_halo(P, l, L.As, nC, n, u, u, 0, epi, fam, bytes_f, u, u, 0, u));
+      // halo F points: fresh; halo C points: old
+      AMGB_TRY(launch_sell_halo(P, l, L.As, 0, nC, u, out, nC, epi, fam, bytes_c, u, out, nC, out));
     }
   } else if (u_is_zero) {
     AMGB_TRY(relax_zero(ctx, L, 0, n, f, w, out));
   } else {
-    AMGB_TRY(launch_sell(ctx, L.As, 0, n, u, u, 0, epi, fam, mat + 32.0 * n));
+    AMGB_TRY(launch_sell_halo(P, l, L.As, 0, n, u, u, 0, epi, fam, mat + 32.0 * n, u, u, 0, u));
   }
   return AMGB_OK;
 }
@@ -760,7 +862,6 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
     } else {
       const unsigned sweeps = P->data.n_sweeps_coarse ? P->data.n_sweeps_coarse : 1u;
       for (unsigned s = 0; s < sweeps; ++s) {
-        if (!(u_is_zero && s == 0)) AMGB_TRY(halo(P, l, u, u, 0, u));
         AMGB_TRY(relax_if(P, l, f, u, alt, 3, u_is_zero && s == 0));
         std::swap(u, alt);
       }
@@ -768,18 +869,15 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
     return AMGB_OK;
   }
   for (unsigned s = 0; s < P->data.n_sweeps; ++s) {
-    if (!(u_is_zero && s == 0)) AMGB_TRY(halo(P, l, u, u, 0, u));
     AMGB_TRY(relax_if(P, l, f, u, alt, 1, u_is_zero && s == 0));
     std::swap(u, alt);
   }
   // residual into the scratch buffer, restriction into the coarse rhs
   ctx->cur_level = l;
-  AMGB_TRY(halo(P, l, u, u, 0, u));
-  AMGB_TRY(launch_sell(ctx, L.As, 0, n, u, u, 0, EpiResidual{f, alt}, l == 0 ? F_RESIDUAL_L0 : F_RESIDUAL,
-                       L.As.csr_bytes() + 24.0 * n));
+  AMGB_TRY(launch_sell_halo(P, l, L.As, 0, n, u, u, 0, EpiResidual{f, alt}, l == 0 ? F_RESIDUAL_L0 : F_RESIDUAL,
+                            L.As.csr_bytes() + 24.0 * n, u, u, 0, u));
   Level& C = P->lv[l + 1];
   const int ncrs = (int)C.n_solve;
-  AMGB_TRY(halo(P, l, alt, alt, 0, alt));
   if (partitioned_level(P, l) && !partitioned_level(P, l + 1)) {
     // onto the first replicated level: restrict to my coarse points (natural order), gather the
     // whole right-hand side on every rank, then into that level's C/F numbering
@@ -787,15 +885,16 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
     const DistLevel& D = ds->dl[l];
     // (with peer windows the owned block is produced in place inside the full vector)
     double* own = ds->window_slot >= 0 ? ds->repl_full.p + D.cstarts[ds->comm->rank] : ds->repl_own.p;
-    AMGB_TRY(launch_sell(ctx, L.Rs, 0, (int)D.nc_own, alt, alt, 0, EpiStore{own},
-                         l == 0 ? F_RESTRICT_L0 : F_RESTRICT, L.Rs.csr_bytes() + 8.0 * n + 8.0 * D.nc_own));
+    AMGB_TRY(launch_sell_halo(P, l, L.Rs, 0, (int)D.nc_own, alt, alt, 0, EpiStore{own},
+                              l == 0 ? F_RESTRICT_L0 : F_RESTRICT, L.Rs.csr_bytes() + 8.0 * n + 8.0 * D.nc_own, alt,
+                              alt, 0, alt));
     AMGB_TRY(gather_blocks(P, D.cstarts, own, ds->repl_full.p));
     AMGB_LAUNCH(ctx, F_VEC, 20.0 * ncrs, gather_kernel, (unsigned)div_up(ncrs, kBlock), kBlock, 0, (int64_t)ncrs,
                 (const int32_t*)C.perm.p, (const double*)ds->repl_full.p, C.f.p);
     AMGB_CHECK_LAUNCH(ctx);
   } else {
-    AMGB_TRY(launch_sell(ctx, L.Rs, 0, ncrs, alt, alt, 0, EpiStore{C.f.p}, l == 0 ? F_RESTRICT_L0 : F_RESTRICT,
-                         L.Rs.csr_bytes() + 8.0 * n + 8.0 * ncrs));
+    AMGB_TRY(launch_sell_halo(P, l, L.Rs, 0, ncrs, alt, alt, 0, EpiStore{C.f.p}, l == 0 ? F_RESTRICT_L0 : F_RESTRICT,
+                              L.Rs.csr_bytes() + 8.0 * n + 8.0 * ncrs, alt, alt, 0, alt));
   }
   if (C.n_vec > 0) AMGB_CUDA(ctx, cudaMemsetAsync(C.u.p, 0, (size_t)C.n_vec * sizeof(double), ctx->stream));
   double* cu = C.u.p;
@@ -803,11 +902,9 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
   AMGB_TRY(cycle(P, l + 1, cu, calt, C.f.p, true));
   if (P->data.w_cycle && l + 1 < nl - 1) AMGB_TRY(cycle(P, l + 1, cu, calt, C.f.p, false));
   ctx->cur_level = l;
-  AMGB_TRY(halo(P, l + 1, cu, cu, 0, cu));
-  AMGB_TRY(launch_sell(ctx, L.Ps, 0, n, cu, cu, 0, EpiAdd{u}, l == 0 ? F_PROLONG_L0 : F_PROLONG,
-                       L.Ps.csr_bytes() + 8.0 * ncrs + 16.0 * n));
+  AMGB_TRY(launch_sell_halo(P, l + 1, L.Ps, 0, n, cu, cu, 0, EpiAdd{u}, l == 0 ? F_PROLONG_L0 : F_PROLONG,
+                            L.Ps.csr_bytes() + 8.0 * ncrs + 16.0 * n, cu, cu, 0, cu));
   for (unsigned s = 0; s < P->data.n_sweeps; ++s) {
-    AMGB_TRY(halo(P, l, u, u, 0, u));
     AMGB_TRY(relax_if(P, l, f, u, alt, 2));
     std::swap(u, alt);
   }
@@ -1098,7 +1195,8 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
   AMGB_TRY(hist.alloc_zero(ctx, cap));
   const int64_t dot_blocks = div_up(n, kDotChunk);
   const int64_t spmv_blocks = div_up(As.nslices * 32, kBlock);
-  AMGB_TRY(pa.alloc(ctx, (spmv_blocks > dot_blocks ? spmv_blocks : dot_blocks) + 1));
+  // (+16: the overlapped product is launched in up to five row ranges, each rounding up to whole blocks)
+  AMGB_TRY(pa.alloc(ctx, (spmv_blocks > dot_blocks ? spmv_blocks : dot_blocks) + 16));
   AMGB_TRY(pb.alloc(ctx, dot_blocks + 1));
   const unsigned vgrid = (unsigned)div_up(n, kBlock);
   double* red = ds ? ds->red.p : nullptr;
@@ -1121,9 +1219,8 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
   AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, gather_kernel, vgrid, kBlock, 0, n, L0.perm.p, x_user, x.p);
   AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, gather_kernel, vgrid, kBlock, 0, n, L0.perm.p, b_user, b.p);
   // r = b - A x ; z = M^{-1} r ; dp = ||z|| ; beta = (z, r)
-  AMGB_TRY(halo(P, 0, x.p, x.p, 0, x.p));
-  AMGB_TRY(launch_sell(ctx, As, 0, (int)n, x.p, x.p, 0, EpiResidual{b.p, r.p}, F_RESIDUAL_L0,
-                       As.csr_bytes() + 24.0 * n));
+  AMGB_TRY(launch_sell_halo(P, 0, As, 0, (int)n, x.p, x.p, 0, EpiResidual{b.p, r.p}, F_RESIDUAL_L0,
+                            As.csr_bytes() + 24.0 * n, x.p, x.p, 0, x.p));
   AMGB_TRY(vcycle_apply(P, z.p, r.p));
   AMGB_LAUNCH(ctx, F_VEC, 16.0 * n, dot2_kernel, (unsigned)dot_blocks, kBlock, 0, n, z.p, r.p, pa.p, pb.p);
   AMGB_TRY(finalize_beta(1));
@@ -1137,19 +1234,31 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
   int64_t it = 0;
   while (!hf->done && it < max_steps) {
     AMGB_LAUNCH(ctx, F_VEC, 24.0 * n, update_p_kernel, vgrid, kBlock, 0, n, z.p, p.p, sc.p, it == 0 ? 1 : 0);
-    AMGB_TRY(halo(P, 0, p.p, p.p, 0, p.p));
-    AMGB_DISPATCH_T(As.T, AMGB_LAUNCH(ctx, F_SPMV, As.csr_bytes() + 16.0 * n, sell_spmv_dot_kernel<TT>,
-                                      (unsigned)spmv_blocks, kBlock, 0, (int)As.nslices, (int)n,
-                                      As.slice_ptr.p, As.col.p, As.val.p, p.p, w.p, pa.p));
+    int64_t np = 0;  // partials of (p, w)
+    const double spmv_bytes = As.csr_bytes() + 16.0 * n;
+    if (ds && ds->window_slot >= 0 && As.has_interior && As.n >= ds->overlap_min_rows && n > 0) {
+      // halo of p in flight while the rows that do not gather from it are multiplied
+      const double per_row = spmv_bytes / double(n);
+      AMGB_TRY(peer_put(ctx, ds->vpeer[0], p.p, p.p, 0));
+      int edge[6] = {0, As.ilo[0], As.ihi[0], As.ilo[1], As.ihi[1], (int)n};
+      for (int k = 1; k < 6; ++k) edge[k] = std::max(edge[k], edge[k - 1]);
+      for (int k = 1; k < 5; k += 2)
+        AMGB_TRY(launch_spmv_dot(ctx, As, edge[k], edge[k + 1], p.p, w.p, pa.p, &np, per_row * (edge[k + 1] - edge[k])));
+      AMGB_TRY(peer_get(ctx, ds->vpeer[0], p.p));
+      for (int k = 0; k < 6; k += 2)
+        AMGB_TRY(launch_spmv_dot(ctx, As, edge[k], edge[k + 1], p.p, w.p, pa.p, &np, per_row * (edge[k + 1] - edge[k])));
+    } else {
+      AMGB_TRY(halo(P, 0, p.p, p.p, 0, p.p));
+      AMGB_TRY(launch_spmv_dot(ctx, As, 0, (int)n, p.p, w.p, pa.p, &np, spmv_bytes));
+    }
     if (ds) {
-      AMGB_LAUNCH(ctx, F_VEC, 8.0 * spmv_blocks, local_sums_kernel, 1, kBlock, 0, (const double*)pa.p,
-                  (const double*)nullptr, spmv_blocks, red);
+      AMGB_LAUNCH(ctx, F_VEC, 8.0 * np, local_sums_kernel, 1, kBlock, 0, (const double*)pa.p,
+                  (const double*)nullptr, np, red);
       AMGB_CHECK_LAUNCH(ctx);
       AMGB_TRY(reduce_scalars(P, red, 1));
       AMGB_LAUNCH(ctx, F_VEC, 8.0, finalize_alpha_red_kernel, 1, 1, 0, (const double*)red, sc.p, fl.p);
     } else {
-      AMGB_LAUNCH(ctx, F_VEC, 8.0 * spmv_blocks, finalize_alpha_kernel, 1, kBlock, 0, pa.p, spmv_blocks, sc.p,
-                  fl.p);
+      AMGB_LAUNCH(ctx, F_VEC, 8.0 * np, finalize_alpha_kernel, 1, kBlock, 0, pa.p, np, sc.p, fl.p);
     }
     AMGB_LAUNCH(ctx, F_VEC, 48.0 * n, axpy2_kernel, vgrid, kBlock, 0, n, p.p, w.p, x.p, r.p, sc.p);
     AMGB_CHECK_LAUNCH(ctx);
@@ -1295,6 +1404,11 @@ int finish_solve_setup_dist(amgb_precond* P) {
   amgb_comm* comm = ds->comm;
   const int nl = (int)P->lv.size();
   const int nd = std::min(nl, ds->replicated_from);  // partitioned levels are [0, nd)
+  if (const char* e = std::getenv("AMGB_OVERLAP_MIN_ROWS")) ds->overlap_min_rows = std::atoll(e);
+  auto interior = [&](Sell& S, int64_t halo_begin, int64_t bsplit) -> int {
+    if (comm->size < 2 || S.n < ds->overlap_min_rows) return AMGB_OK;
+    return find_interior_rows(ctx, S, (int)halo_begin, (int)bsplit);
+  };
   // replicated tail first: its numbering is needed by the last partitioned level
   if (nd < nl) AMGB_TRY(finish_solve_setup_range(P, nd));
   // 1. numbering, halo lists, vector plans
@@ -1305,7 +1419,7 @@ int finish_solve_setup_dist(amgb_precond* P) {
     ctx->cur_level = l;
     AMGB_TRY(L.perm.alloc(ctx, nloc));
     AMGB_TRY(L.inv_perm.alloc(ctx, nloc));
-    if (L.cf.p) {
+    if (l + 1 < nl) {  // (a rank may own nothing here: cf is then an empty array)
       AMGB_LAUNCH(ctx, F_AUX, 16.0 * nloc, dist_perm_kernel, (unsigned)div_up(nloc, kBlock), kBlock, 0, nloc,
                   (const int32_t*)(L.cf.p + o0), (const int32_t*)(L.f2c.p + o0), (int)L.n_coarse, L.perm.p,
                   L.inv_perm.p);
@@ -1354,6 +1468,7 @@ int finish_solve_setup_dist(amgb_precond* P) {
     DeviceCsr Av;
     csr_view(ctx, L.A, o0, nloc, D.own.M.nnz, L.n_vec, Av);
     AMGB_TRY(csr_to_sell(ctx, Av, L.perm.p, D.colmap.p, L.As));
+    AMGB_TRY(interior(L.As, nloc, L.n_coarse));
     if (l + 1 < nl) {
       Level& C = P->lv[l + 1];
       const bool to_replicated = l + 1 >= nd;
@@ -1378,8 +1493,10 @@ int finish_solve_setup_dist(amgb_precond* P) {
       DeviceCsr Pv;
       csr_view(ctx, L.P, o0, nloc, D.Pown.nnz, C.n_vec, Pv);
       AMGB_TRY(csr_to_sell(ctx, Pv, L.perm.p, tcmap.p, L.Ps));
+      if (!to_replicated) AMGB_TRY(interior(L.Ps, C.n_solve, L.n_coarse));
       L.R.ncols = L.n_vec;
       AMGB_TRY(csr_to_sell(ctx, L.R, to_replicated ? natural.p : C.perm.p, D.colmap.p, L.Rs));
+      AMGB_TRY(interior(L.Rs, nloc, to_replicated ? 0 : C.n_coarse));
       AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // tcmap goes out of scope
       L.R.rp.release();
       L.R.col.release();

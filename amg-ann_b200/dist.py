@@ -60,6 +60,11 @@ class LocalGroup:
             raise AmgbError(rc, "amgb_local_group_create")
         self.size = int(nranks)
 
+    def abort(self):
+        """Called by a failing rank: the others' collectives return an error instead of waiting."""
+        if self._h:
+            amgb_lib().amgb_local_group_abort(self._h)
+
     def close(self):
         if self._h:
             amgb_lib().amgb_local_group_destroy(self._h)
@@ -283,6 +288,7 @@ def run_local_group(nranks, fn, device_ids=None):
             out[r] = fn(r, comm)
         except BaseException as e:  # noqa: BLE001 - reported to the caller below
             err[r] = e
+            group.abort()
         finally:
             if comm:
                 comm.close()

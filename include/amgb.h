@@ -272,6 +272,9 @@ int amgb_nccl_unique_id(void* out, int capacity);
 int amgb_comm_create_nccl(amgb_ctx* ctx, int nranks, int rank, const void* unique_id, amgb_comm** out);
 int amgb_local_group_create(int nranks, amgb_local_group** out);
 int amgb_local_group_destroy(amgb_local_group* g);
+/* A rank that fails calls this so that the other ranks' collectives return AMGB_ERR_COMM
+ * instead of waiting for it. */
+int amgb_local_group_abort(amgb_local_group* g);
 int amgb_comm_create_local(amgb_local_group* g, int rank, amgb_comm** out);
 int amgb_comm_destroy(amgb_comm* c);
 int amgb_comm_rank(const amgb_comm* c);

@@ -142,3 +142,41 @@ def test_partitioned_cycle_options(gpu_ctx, kw):
         assert abs(p["niters"] - ctl1.last_step()) <= 1
         k = min(len(p["hist"]), len(ctl1.history))
         assert (np.abs(p["hist"][:k] - ctl1.history[:k]) <= 1e-10 * ctl1.history[:k]).all()
+
+
+@pytest.mark.parametrize("starts_kind", ["slabs", "ragged"])
+@pytest.mark.parametrize("replicate_below", [0, 300])
+def test_overlapped_halo_exchange_equals_single_device(gpu_ctx, monkeypatch, starts_kind, replicate_below):
+    """AMGB_OVERLAP_MIN_ROWS=0 forces the interior/boundary row split (put, interior rows, wait,
+    boundary rows) on every partitioned level of a small system; ragged ranges give interior
+    ranges that do not line up with mesh planes, or none at all."""
+    monkeypatch.setenv("AMGB_OVERLAP_MIN_ROWS", "0")
+    m, contrast = 12, 3.0
+    s = poisson(m, contrast=contrast)
+    data = device_data(0.25, dist_replicate_below=replicate_below)
+    A1, P1, ctl1, x1 = _single(gpu_ctx, s, data)
+    starts = dist.slab_partition(m, 3) if starts_kind == "slabs" else [0, 5, 911, 1400, s.n]
+    parts = _run_partitioned(m, contrast, starts, data)
+    _assert_same_hierarchy(parts, P1)
+    for p in parts:
+        assert abs(p["niters"] - ctl1.last_step()) <= 1
+        k = min(len(p["hist"]), len(ctl1.history))
+        assert (np.abs(p["hist"][:k] - ctl1.history[:k]) <= 1e-10 * ctl1.history[:k]).all()
+        assert np.array_equal(p["hist"], parts[0]["hist"])
+    x = np.concatenate([p["x"] for p in parts])
+    assert np.abs(x - x1).max() <= 1e-9 * np.abs(x1).max()
+
+
+def test_library_exchanges_still_work_without_peer_windows(gpu_ctx, monkeypatch):
+    """AMGB_PEER=0: the communicator's alltoallv / allreduce carry the solve-phase exchanges
+    (the path taken when a rank cannot map its peers' memory)."""
+    monkeypatch.setenv("AMGB_PEER", "0")
+    m, contrast = 10, 3.0
+    s = poisson(m, contrast=contrast)
+    data = device_data(0.25, dist_replicate_below=100)
+    A1, P1, ctl1, x1 = _single(gpu_ctx, s, data)
+    parts = _run_partitioned(m, contrast, dist.slab_partition(m, 3), data)
+    for p in parts:
+        assert abs(p["niters"] - ctl1.last_step()) <= 1
+        k = min(len(p["hist"]), len(ctl1.history))
+        assert (np.abs(p["hist"][:k] - ctl1.history[:k]) <= 1e-10 * ctl1.history[:k]).all()

@@ -6,9 +6,9 @@
 //   put     every block stores its share of the send list into the peers' staging slot e&1;
 //           the block that finishes last publishes e in my flag word at every peer
 //           (bar.sync -> fence.sys -> ticket; last: fence.sys -> st.release.sys)
-//   wait    one warp polls the peers' flag words in MY window (ld.acquire.sys) until all
-//           hold >= e, then advances the plan's counter
-//   unpack  copies slot e&1 of my staging into the destination vector
+//   get     a few blocks poll the peers' flag words in MY window (ld.acquire.sys) until all
+//           hold >= e, copy slot e&1 of my staging into the destination vector, and the
+//           last one advances the plan's counter
 // A slot is re-used by exchange e+2; the sender can only get there after it has waited for
 // my flag of exchange e+1, which I publish after my unpack of e is complete (stream order).
 #include <cstring>
@@ -64,23 +64,33 @@ peer_put_kernel(int n, const int32_t* __restrict__ idx, const double* __restrict
   }
 }
 
-__global__ void peer_wait_kernel(PeerTab t) {
-  const unsigned long long e = *(volatile unsigned long long*)t.ctr + 1;
-  const int j = threadIdx.x;
-  if (j < t.npeers && !wait_flag(t.l_flag[j], e)) atomicExch(t.err, 1);
-  __syncwarp();
-  if (j == 0) *(volatile unsigned long long*)t.ctr = e;
-}
+// wait + unpack in one launch: a handful of blocks (never enough to fill the device, so the
+// peers' puts always find room when ranks share a GPU) poll the flags, then copy grid-stride;
+// the block that finishes last advances the plan's counter.
+constexpr int kGetBlocks = 48;
 
 __global__ void __launch_bounds__(kBlock)
-peer_unpack_kernel(int n, PeerTab t, double* __restrict__ dst) {
-  const long long slot = (long long)(*(volatile unsigned long long*)t.ctr & 1ull);
-  const int k = blockIdx.x * kBlock + threadIdx.x;
-  if (k >= n) return;
-  int j = 0;
-  while (k >= t.recv_end[j]) ++j;
-  const int i = k - (j ? t.recv_end[j - 1] : 0);
-  dst[t.dst_off[j] + i] = t.staging[slot * t.stride + k];
+peer_get_kernel(int n, PeerTab t, double* __restrict__ dst) {
+  const unsigned long long e = *(volatile unsigned long long*)t.ctr + 1;
+  const long long slot = (long long)(e & 1ull);
+  if (threadIdx.x < t.npeers && !wait_flag(t.l_flag[threadIdx.x], e)) atomicExch(t.err, 1);
+  __syncthreads();
+  const double* __restrict__ src = t.staging + slot * t.stride;
+  for (int k = blockIdx.x * kBlock + threadIdx.x; k < n; k += gridDim.x * kBlock) {
+    int j = 0;
+    while (k >= t.recv_end[j]) ++j;
+    dst[t.dst_off[j] + (k - (j ? t.recv_end[j - 1] : 0))] = src[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    // the put kernel's ticket is back at zero by now (its last block reset it before the flags went out)
+    const unsigned prev = atomicAdd(t.ticket + 1, 1u);
+    if (prev == gridDim.x - 1) {
+      t.ticket[1] = 0;
+      *(volatile unsigned long long*)t.ctr = e;
+    }
+  }
 }
 
 // put + wait + ordered sum in one block: every rank stores its partials into every other
@@ -132,10 +142,10 @@ int peer_put(amgb_ctx* ctx, const PeerPlan& pl, const double* lo, const double* 
 int peer_get(amgb_ctx* ctx, const PeerPlan& pl, double* dst) {
   AMGB_TRY(pl.comm->launch_fence());
   if (pl.tab.npeers == 0) return AMGB_OK;
-  AMGB_LAUNCH(ctx, F_VEC, 8.0 * pl.tab.npeers, peer_wait_kernel, 1, 32, 0, pl.tab);
-  if (pl.recv_total > 0)
-    AMGB_LAUNCH(ctx, F_VEC, 16.0 * pl.recv_total, peer_unpack_kernel, (unsigned)div_up(pl.recv_total, kBlock), kBlock,
-                0, (int)pl.recv_total, pl.tab, dst);
+  int64_t grid = div_up(pl.recv_total, kBlock);
+  grid = grid < 1 ? 1 : (grid > kGetBlocks ? kGetBlocks : grid);
+  AMGB_LAUNCH(ctx, F_VEC, 16.0 * pl.recv_total, peer_get_kernel, (unsigned)grid, kBlock, 0, (int)pl.recv_total, pl.tab,
+              dst);
   AMGB_CHECK_LAUNCH(ctx);
   return AMGB_OK;
 }
@@ -159,7 +169,7 @@ int peer_check(amgb_ctx* ctx, const int* err_word) {
 }
 
 // Window layout of one rank:  [256 B: error word] then per plan [256 B control: counter @0,
-// ticket @8, flag of source rank q @64+8q] [staging: 2 slots x recv_total doubles].
+// tickets @8 (put) and @12 (get), flag of source rank q @64+8q] [staging: 2 slots x recv_total doubles].
 constexpr size_t kCtrlBytes = 256;
 static size_t round256(size_t b) { return (b + 255) / 256 * 256; }
 
@@ -239,8 +249,7 @@ int build_peer_plans(amgb_ctx* ctx, amgb_comm* comm, const std::vector<PeerSpec>
   // the kernels of the protocol are loaded now, not at their first launch (see launch_fence)
   cudaFuncAttributes fa;
   AMGB_CUDA(ctx, cudaFuncGetAttributes(&fa, peer_put_kernel));
-  AMGB_CUDA(ctx, cudaFuncGetAttributes(&fa, peer_wait_kernel));
-  AMGB_CUDA(ctx, cudaFuncGetAttributes(&fa, peer_unpack_kernel));
+  AMGB_CUDA(ctx, cudaFuncGetAttributes(&fa, peer_get_kernel));
   AMGB_CUDA(ctx, cudaFuncGetAttributes(&fa, peer_allreduce_kernel));
   *window_slot = slot;
   *err_word = (int*)w.base;

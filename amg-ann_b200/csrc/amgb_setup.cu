@@ -14,6 +14,7 @@
 //    ascending column within a row, ascending k for C(i,c) = sum_k a_ik b_kc.
 #include <algorithm>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 #include <string>
 
@@ -255,6 +256,8 @@ interp_count_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __
 }
 
 constexpr int kInterpStage = 48;  // P-row entries staged in shared memory per warp
+constexpr int kInterpLaneMax = 16;     // longest P row of the lane-parallel route
+constexpr int kInterpLaneStride = 17;  // (odd stride: the lanes of phase A hit distinct banks)
 
 // position of coarse column cc in the sorted slice pcol[0..len), or -1
 __device__ __forceinline__ int find_sorted(const int32_t* pcol, int len, int cc) {
@@ -299,6 +302,16 @@ interp_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __r
   const bool staged = len <= kInterpStage;
   int32_t* myc = staged ? s_c[threadIdx.x >> 5] : pcol + jb;
   double* myv = staged ? s_v[threadIdx.x >> 5] : pval + jb;
+  // Short P rows (the usual case) take the lane-parallel route: every strong F neighbour of
+  // a 32-entry chunk is reduced by its own lane (phase A), the matched entries of its row
+  // parked in s_m, and lane p then accumulates P entry p over the chunk in entry order
+  // (phase B).  Same operands, same order as the one-neighbour-at-a-time route below.
+  __shared__ double s_m[kBlock / 32][32 * kInterpLaneStride];
+  __shared__ int s_lane[kBlock / 32][32], s_b1[kBlock / 32][32], s_e1[kBlock / 32][32];
+  __shared__ unsigned s_has[kBlock / 32][32];
+  const bool lane_parallel = len <= kInterpLaneMax;
+  double* mym = s_m[threadIdx.x >> 5];
+  double acc = 0.0;  // lane p's P entry (lane_parallel)
   // phase 0: diagonal, and the strong C neighbours (fine ids) in row order
   double diagonal = 0.0;
   {
@@ -353,6 +366,68 @@ interp_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __r
     }
     const unsigned sfm = __ballot_sync(full, is_sf), cm = __ballot_sync(full, is_c);
     const unsigned wm = __ballot_sync(full, is_weak);
+    if (lane_parallel) {
+      // phase A: one lane per (strong F neighbour k, C point p of the P row) pair looks a_kp up
+      // in row k by binary search (rows are sorted); the hits are parked in s_m and flagged
+      const int wi = threadIdx.x >> 5;
+      const int32_t* sc = s_c[wi];
+      const int nsf = __popc(sfm);
+      if (is_sf) {
+        const int t = __popc(sfm & ((1u << lane) - 1u));
+        s_lane[wi][t] = lane;
+        s_b1[wi][t] = my_b1;
+        s_e1[wi][t] = my_sgn < 0 ? -(my_b1 + my_len1) - 1 : my_b1 + my_len1;  // sign of a_kk rides along
+        s_has[wi][lane] = 0u;
+      }
+      __syncwarp();
+      for (int q = lane; q < nsf * len; q += 32) {
+        const int t = q / len, pos = q - t * len;
+        const int lt = s_lane[wi][t], want = sc[pos];
+        const int ee = s_e1[wi][t];
+        const int e1 = ee < 0 ? -(ee + 1) : ee;
+        int lo = s_b1[wi][t], hi = e1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (col[mid] < want) lo = mid + 1; else hi = mid;
+        }
+        if (lo < e1 && col[lo] == want) {
+          const double v = val[lo];
+          if (ee < 0 ? v > 0 : v < 0) {
+            mym[lt * kInterpLaneStride + pos] = v;
+            atomicOr(&s_has[wi][lt], 1u << pos);
+          }
+        }
+      }
+      __syncwarp();
+      // the sum of neighbour k over the shared C points, in column order
+      double my_sum = 0.0;
+      unsigned my_has = 0;
+      if (is_sf) {
+        my_has = s_has[wi][lane];
+        for (unsigned m = my_has; m; m &= m - 1)
+          my_sum = __dadd_rn(my_sum, mym[lane * kInterpLaneStride + __ffs(m) - 1]);
+      }
+      const double my_dist = (is_sf && my_sum != 0) ? my_a / my_sum : 0.0;
+      const unsigned zs = __ballot_sync(full, is_sf && my_sum == 0);
+      __syncwarp();
+      // phase B: P entry `lane` over the chunk, in entry order
+      for (unsigned both = sfm | cm; both; both &= both - 1) {
+        const int t = __ffs(both) - 1;
+        if ((cm >> t) & 1u) {
+          const double a = __shfl_sync(full, my_a, t);
+          if (lane == seen_c) acc = __dadd_rn(acc, a);
+          ++seen_c;
+        } else {
+          const double dist = __shfl_sync(full, my_dist, t);
+          const unsigned has = __shfl_sync(full, my_has, t);
+          if ((has >> lane) & 1u) acc = __dadd_rn(acc, __dmul_rn(dist, mym[t * kInterpLaneStride + lane]));
+        }
+      }
+      __syncwarp();  // s_m is rewritten by the next chunk
+      for (unsigned m = wm | zs; m; m &= m - 1)
+        diagonal = __dadd_rn(diagonal, __shfl_sync(full, my_a, __ffs(m) - 1));
+      continue;
+    }
     unsigned zero_sum = 0, rest = sfm;
     double nv = 0.0;  // prefetched row of the lowest strong F neighbour in `rest`
     int ncol = -1, ncf = 0;
@@ -442,6 +517,7 @@ interp_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __r
     for (unsigned m = wm | zero_sum; m; m &= m - 1)
       diagonal = __dadd_rn(diagonal, __shfl_sync(full, my_a, __ffs(m) - 1));
   }
+  if (lane_parallel && lane < len) myv[lane] = acc;
   __syncwarp();
   // phase 2: scale, renumber to coarse ids
   const double nd = -diagonal;

@@ -288,11 +288,14 @@ class PreconditionBoomerAMG:
         self._h = C.c_void_p()
         self.ctx = None
 
-    def initialize(self, matrix, data=None):
+    def initialize(self, matrix, data=None, ctx=None):
+        """ctx: build (and later apply) the hierarchy on another context of the same device
+        than the one that uploaded the matrix.  A matrix is read-only once uploaded, so the
+        independent systems of a theta sweep can be in flight on several streams at once."""
         self.close()
         data = data or AdditionalData()
         s = data.to_struct()
-        self.ctx = matrix.ctx
+        self.ctx = ctx or matrix.ctx
         rc = amgb_lib().amgb_precond_initialize(self.ctx._h, matrix._h, C.byref(s),
                                                 C.byref(self._h))
         _chk(self.ctx._h, rc, "amgb_precond_initialize")
@@ -419,14 +422,15 @@ class SolverCG:
         cap = min(self.control.max_steps, 1 << 20) + 1
         hist = np.zeros(cap)
         nit = C.c_int64()
-        rc = amgb_lib().amgb_cg_solve(A.ctx._h, A._h, _p(x, c_f64p), _p(b, c_f64p),
+        ctx = preconditioner.ctx or A.ctx
+        rc = amgb_lib().amgb_cg_solve(ctx._h, A._h, _p(x, c_f64p), _p(b, c_f64p),
                                       preconditioner._h, self.control.max_steps,
                                       self.control.tol, _p(hist, c_f64p), cap, C.byref(nit))
         k = min(cap, nit.value + 1)
         self.control._last_step = nit.value
         self.control.history = hist[:k].copy()
         self.control._last_value = float(hist[k - 1]) if k else float("nan")
-        _chk(A.ctx._h, rc, "amgb_cg_solve")
+        _chk(ctx._h, rc, "amgb_cg_solve")
 
 
 class ViewMaker:
@@ -473,15 +477,16 @@ class ViewMaker:
 from . import dist  # noqa: E402  (row-partitioned front end; needs the names above)
 
 
-def amg_solve(data, rtol, A, b, x):
+def amg_solve(data, rtol, A, b, x, ctx=None):
     """Python mirror of ref common/amg_solver.h:22-92: timed initialize + timed
-    cg.solve, returning the CSV fields as a dict instead of scraping stdout."""
+    cg.solve, returning the CSV fields as a dict instead of scraping stdout.
+    ctx: context (stream) to run on when several systems share one uploaded matrix."""
     control = SolverControl(A.m(), rtol)
     cg = SolverCG(control)
     prec = PreconditionBoomerAMG()
     t1 = time.perf_counter()
-    prec.initialize(A, data)
-    A.ctx.synchronize()
+    prec.initialize(A, data, ctx)
+    prec.ctx.synchronize()
     t2 = time.perf_counter()
     t3 = time.perf_counter()
     cg.solve(A, x, b, prec)

@@ -251,38 +251,85 @@ def run_gpu(args):
     nit = C.c_int64()
     results = {}
 
+    # The systems of a sweep are independent (the reference fans them out over processes,
+    # 00_data-generation.py:105-116): `lanes` host threads, one context + stream each, take
+    # them from a queue, so one system's latency-bound phases (coarse levels, PMIS rounds,
+    # host round trips of PCG) overlap another's bandwidth-bound ones on the same GPU.
+    lanes = max(1, args.streams)
+    lane_streams = [stream] + [torch.cuda.Stream() for _ in range(lanes - 1)]
+    lane_ctx = [ctx] + [ab.Context(local, st.cuda_stream) for st in lane_streams[1:]]
+    lane_x = [d_x] + [torch.empty_like(d_x0) for _ in range(lanes - 1)]
+
+    def solve_device(w, th):
+        c = lane_ctx[w]
+        h, k = np.zeros(4096), C.c_int64()
+        with torch.cuda.stream(lane_streams[w]):
+            lane_x[w].copy_(d_x0)                # solution = m_zero_solution (t2 main.cpp:446)
+        P = ab.PreconditionBoomerAMG()
+        P.initialize(A_dev, device_options(ab, th), c)
+        rc = L.amgb_cg_solve_device(c._h, A_dev._h, C.c_void_p(lane_x[w].data_ptr()),
+                                    C.c_void_p(d_b.data_ptr()), P._h, n, TOL,
+                                    h.ctypes.data_as(c_f64p), len(h), C.byref(k))
+        if rc != 0:
+            raise RuntimeError(f"amgb_cg_solve_device -> {rc}: {L.amgb_last_error(c._h).decode()}")
+        results[th] = (k.value, P.level_stats() if th == thetas[0] else None)
+        P.close()
+
+    def fan_out(solve):
+        """run solve(lane, theta) for the whole sweep; most expensive systems (large theta) first"""
+        if lanes == 1:
+            for th in thetas:
+                solve(0, th)
+            return
+        todo, lock, errs = list(thetas), threading.Lock(), []
+
+        def worker(w):
+            torch.cuda.set_device(local)
+            try:
+                while True:
+                    with lock:
+                        if not todo or errs:
+                            return
+                        th = todo.pop()
+                    solve(w, th)
+            except BaseException as e:  # noqa: BLE001 - re-raised below
+                errs.append(e)
+        ts = [threading.Thread(target=worker, args=(w,)) for w in range(lanes)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        if errs:
+            raise errs[0]
+
     def sweep_device():
+        fan_out(solve_device)
+
+    def sweep_device_one_lane():
         for th in thetas:
-            d_x.copy_(d_x0)                      # solution = m_zero_solution (t2 main.cpp:446)
-            P = ab.PreconditionBoomerAMG()
-            P.initialize(A_dev, device_options(ab, th))
-            rc = L.amgb_cg_solve_device(ctx._h, A_dev._h, C.c_void_p(d_x.data_ptr()),
-                                        C.c_void_p(d_b.data_ptr()), P._h, n, TOL,
-                                        hist.ctypes.data_as(c_f64p), len(hist), C.byref(nit))
-            if rc != 0:
-                raise RuntimeError(f"amgb_cg_solve_device -> {rc}: {L.amgb_last_error(ctx._h).decode()}")
-            results[th] = (nit.value, P.level_stats() if th == thetas[0] else None)
-            P.close()
+            solve_device(0, th)
 
     # ---- host buffers for `e2e` (pinned)
     def pinned(a):
         return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     h_rp, h_col, h_val = pinned(rp32), pinned(s.col), pinned(s.val)
     h_b, h_x0 = pinned(s.rhs), pinned(s.x0)
-    h_x = pinned(s.x0)
+    h_xs = [pinned(s.x0) for _ in range(lanes)]
     e2e_bytes = {"h2d": 0, "d2h": 0}
 
     def sweep_e2e():
         A = ab.SparseMatrix(ctx, h_rp, h_col, h_val)     # H2D of the CSR, once per sweep
-        h2d = h_rp.nbytes + h_col.nbytes + h_val.nbytes
-        d2h = 0
-        for th in thetas:
+        moved = {"h2d": h_rp.nbytes + h_col.nbytes + h_val.nbytes, "d2h": 0}
+        mlock = threading.Lock()
+
+        def solve_host(w, th):
+            h_x = h_xs[w]
             h_x[...] = h_x0
-            row = ab.amg_solve(device_options(ab, th), TOL, A, h_b, h_x)  # x,b H2D; x,hist D2H
-            h2d += h_b.nbytes + h_x.nbytes
-            d2h += h_x.nbytes + 8 * (row["niters"] + 1)
+            row = ab.amg_solve(device_options(ab, th), TOL, A, h_b, h_x, lane_ctx[w])  # x,b H2D; x,hist D2H
+            with mlock:
+                moved["h2d"] += h_b.nbytes + h_x.nbytes
+                moved["d2h"] += h_x.nbytes + 8 * (row["niters"] + 1)
+        fan_out(solve_host)
         A.close()
-        e2e_bytes["h2d"], e2e_bytes["d2h"] = h2d, d2h
+        e2e_bytes["h2d"], e2e_bytes["d2h"] = moved["h2d"], moved["d2h"]
 
     def barrier():
         if world > 1:
@@ -296,14 +343,17 @@ def run_gpu(args):
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
             sampler.start()
-        ctx.reset_kernel_launches()
+        for c in lane_ctx:
+            c.reset_kernel_launches()
+        # every lane's stream is idle here and again when fn() returns (each solve ends with a
+        # synchronised read of its result), so the two events bracket the device work of all lanes
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
             fn()
         e1.record(stream)
         barrier()
-        launches = ctx.kernel_launches()
+        launches = sum(c.kernel_launches() for c in lane_ctx)
         clocks = sampler.stop() if sampler else None
         ms = e0.elapsed_time(e1)
         if world > 1:
@@ -322,7 +372,7 @@ def run_gpu(args):
     # launching stream) over one more sweep: roofline of the dominant kernel
     ctx.enable_timers(True)
     ctx.reset_timers()
-    sweep_device()
+    sweep_device_one_lane()
     fam = ctx.timers()
     ctx.enable_timers(False)
     peak, peak_src = measured_peaks()
@@ -368,6 +418,7 @@ def run_gpu(args):
                 "data": "synthetic",
                 "config": {"workload": workload_name(args.m), "n": n, "nnz": nnz, "systems_per_step": nsys,
                            "per_gpu": "one matrix + full theta sweep per rank",
+                           "systems_in_flight": lanes,
                            "l2": "inputs (2.6 GB CSR) exceed the 126 MB L2; no flush needed",
                            "iters": {f"{th:.2f}": results[th][0] for th in thetas},
                            "levels_theta0.05": [int(r) for r in st["rows"]] if st else None,
@@ -530,6 +581,8 @@ def main():
     ap.add_argument("--m", "--cells", dest="m", type=int, default=200, help="cells per direction (default: config 2); use --cells under torchrun")
     ap.add_argument("--cpu-m", type=int, default=56, help="mesh of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--streams", type=int, default=3,
+                    help="independent systems of the sweep kept in flight per GPU (host threads, one stream each)")
     ap.add_argument("--workload", default="sweep", choices=["sweep", "partitioned"],
                     help="sweep: config 2 theta sweep, one system per GPU (default, the headline metric); "
                          "partitioned: config 5, one system row-partitioned over all GPUs (use --cells 464)")

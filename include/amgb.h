@@ -142,7 +142,10 @@ int amgb_ctx_reset_kernel_launches(amgb_ctx* ctx);
 /* ---- matrix (resident across the theta sweep) ---------------------------- */
 /* CSR with ascending column ids per row and a stored diagonal in every row
  * (PETSc AIJ as deal.II builds it).  rowptr has n+1 entries.  The 32-bit variant
- * matches PetscInt of a default PETSc build. */
+ * matches PetscInt of a default PETSc build.  The upload is complete when the call
+ * returns and the matrix is read-only afterwards: preconditioners and solves of SEVERAL
+ * contexts (streams, host threads) of the same device may use it at the same time, which
+ * is how the independent systems of a theta sweep are kept in flight together. */
 int amgb_matrix_upload_csr(amgb_ctx* ctx, int64_t n, const int32_t* rowptr,
                            const int32_t* col, const double* val, amgb_matrix** out);
 int amgb_matrix_upload_csr64(amgb_ctx* ctx, int64_t n, const int64_t* rowptr,

@@ -28,32 +28,29 @@ constexpr int kBlock = 256;
 // Strength (hypre_BoomerAMGCreateS).  One thread per row, sequential in the
 // oracle's order: diagonal first, then off-diagonals left to right.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock)
-strength_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
-                const double* __restrict__ val, double theta, double max_row_sum,
-                uint8_t* __restrict__ mask, int32_t* __restrict__ has_strong,
-                double* __restrict__ diagv) {
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
-  const int b = rp[i], e = rp[i + 1];
+// (c, v, mk are indexed by the global entry number k: either the arrays themselves or the
+// warp's shared-memory copy shifted by its first entry)
+__device__ __forceinline__ void strength_row(int i, int b, int e, const int32_t* c, const double* v, uint8_t* mk,
+                                             double theta, double max_row_sum, int32_t* __restrict__ has_strong,
+                                             double* __restrict__ diagv) {
   double diag = 0.0;
   for (int k = b; k < e; ++k)
-    if (col[k] == i) diag = val[k];
+    if (c[k] == i) diag = v[k];
   diagv[i] = diag;
   double row_scale = 0.0, row_sum = diag;
   if (diag < 0) {
     for (int k = b; k < e; ++k)
-      if (col[k] != i) {
-        const double v = val[k];
-        row_scale = row_scale < v ? v : row_scale;
-        row_sum = __dadd_rn(row_sum, v);
+      if (c[k] != i) {
+        const double a = v[k];
+        row_scale = row_scale < a ? a : row_scale;
+        row_sum = __dadd_rn(row_sum, a);
       }
   } else {
     for (int k = b; k < e; ++k)
-      if (col[k] != i) {
-        const double v = val[k];
-        row_scale = v < row_scale ? v : row_scale;
-        row_sum = __dadd_rn(row_sum, v);
+      if (c[k] != i) {
+        const double a = v[k];
+        row_scale = a < row_scale ? a : row_scale;
+        row_sum = __dadd_rn(row_sum, a);
       }
   }
   int any = 0;
@@ -61,14 +58,57 @@ strength_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __rest
   const double thr = __dmul_rn(theta, row_scale);
   for (int k = b; k < e; ++k) {
     uint8_t m = 0;
-    if (!all_weak && col[k] != i) {
-      const double v = val[k];
-      m = diag < 0 ? (v > thr) : (v < thr);
+    if (!all_weak && c[k] != i) {
+      const double a = v[k];
+      m = diag < 0 ? (a > thr) : (a < thr);
     }
-    mask[k] = m;
+    mk[k] = m;
     any |= m;
   }
   has_strong[i] = any;
+}
+
+// The 32 rows of a warp are one contiguous run of entries: it is copied to shared memory
+// with coalesced loads (a thread walking its own row straight from global memory touches a
+// new line at nearly every step), the rows are evaluated there, and the mask goes back the
+// same way.  Runs longer than the stage (sized by the host from the average row) are evaluated in place.
+constexpr int kStrengthBlock = 128;
+
+__global__ void __launch_bounds__(kStrengthBlock)
+strength_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                const double* __restrict__ val, double theta, double max_row_sum,
+                uint8_t* __restrict__ mask, int32_t* __restrict__ has_strong,
+                double* __restrict__ diagv, int stage) {
+  // per warp: `stage` values, column ids and mask bytes (stage is a multiple of 8)
+  extern __shared__ double strength_smem[];
+  constexpr int kW = kStrengthBlock / 32;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* my_val = strength_smem + (size_t)w * stage;
+  int32_t* my_col = reinterpret_cast<int32_t*>(strength_smem + (size_t)kW * stage) + (size_t)w * stage;
+  uint8_t* my_mask = reinterpret_cast<uint8_t*>(reinterpret_cast<int32_t*>(strength_smem + (size_t)kW * stage) +
+                                                (size_t)kW * stage) + (size_t)w * stage;
+  const int64_t r0 = ((int64_t)blockIdx.x * (kStrengthBlock / 32) + w) * 32;
+  if (r0 >= n) return;
+  const int64_t r1 = r0 + 32 < n ? r0 + 32 : n;
+  const int eb = rp[r0], cnt = rp[r1] - eb;
+  const int64_t i = r0 + lane;
+  const bool staged = cnt <= stage;
+  if (staged) {
+    for (int t = lane; t < cnt; t += 32) {
+      my_col[t] = col[eb + t];
+      my_val[t] = val[eb + t];
+    }
+    __syncwarp();
+  }
+  if (i < n) {
+    if (staged) strength_row((int)i, rp[i], rp[i + 1], my_col - eb, my_val - eb, my_mask - eb, theta, max_row_sum,
+                             has_strong, diagv);
+    else strength_row((int)i, rp[i], rp[i + 1], col, val, mask, theta, max_row_sum, has_strong, diagv);
+  }
+  if (staged) {
+    __syncwarp();
+    for (int t = lane; t < cnt; t += 32) mask[eb + t] = my_mask[t];
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -550,13 +590,58 @@ transpose_fill_kernel(int64_t n, const int32_t* __restrict__ prp, const int32_t*
   }
 }
 
-// the atomic fill leaves each row in arbitrary order: insertion sort per row
+// the atomic fill leaves each row in arbitrary order.  One warp per row: the row's column
+// ids go to shared memory, every lane ranks the entries it holds in registers against all
+// of them (ids are distinct) and writes them back at their rank.  Rows longer than
+// kSortStage fall back to an insertion sort by one lane.
+constexpr int kSortStage = 256;
+
+template <int PER>  // entries per lane: rows of up to 32 * PER entries
+__device__ __forceinline__ void rank_sort_row(int32_t* key, int lane, int b, int len, int32_t* __restrict__ col,
+                                              double* __restrict__ val) {
+  int c[PER], rank[PER];
+  double v[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int t = j * 32 + lane;
+    c[j] = t < len ? col[b + t] : INT_MAX;
+    v[j] = t < len ? val[b + t] : 0.0;
+    rank[j] = 0;
+    if (t < len) key[t] = c[j];
+  }
+  __syncwarp();  // the whole row is in registers / shared memory from here on
+  for (int u = 0; u < len; ++u) {
+    const int k = key[u];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) rank[j] += k < c[j] ? 1 : 0;
+  }
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    if (j * 32 + lane < len) {
+      col[b + rank[j]] = c[j];
+      val[b + rank[j]] = v[j];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kBlock)
 sort_rows_kernel(int64_t n, const int32_t* __restrict__ rp, int32_t* __restrict__ col,
                  double* __restrict__ val) {
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  __shared__ int32_t s_key[kBlock / 32][kSortStage];
+  const int64_t i = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (i >= n) return;
-  const int b = rp[i], e = rp[i + 1];
+  const int b = rp[i], e = rp[i + 1], len = e - b;
+  if (len <= 1) return;
+  if (len <= 64) {
+    rank_sort_row<2>(s_key[w], lane, b, len, col, val);
+    return;
+  }
+  if (len <= kSortStage) {
+    rank_sort_row<kSortStage / 32>(s_key[w], lane, b, len, col, val);
+    return;
+  }
+  if (lane != 0) return;
   for (int a = b + 1; a < e; ++a) {
     const int c = col[a];
     const double v = val[a];
@@ -587,7 +672,7 @@ int transpose_csr(amgb_ctx* ctx, const DeviceCsr& P, DeviceCsr& R) {
   AMGB_TRY(exclusive_scan_i32(ctx, count.p, R.rp.p, R.n));
   AMGB_LAUNCH(ctx, F_TRANSPOSE, 24.0 * P.nnz + 4.0 * P.n, transpose_fill_kernel, (unsigned)div_up(P.n, kBlock),
               kBlock, 0, P.n, P.rp.p, P.col.p, P.val.p, R.rp.p, cursor.p, R.col.p, R.val.p);
-  AMGB_LAUNCH(ctx, F_TRANSPOSE, 24.0 * R.nnz + 4.0 * R.n, sort_rows_kernel, (unsigned)div_up(R.n, kBlock),
+  AMGB_LAUNCH(ctx, F_TRANSPOSE, 24.0 * R.nnz + 4.0 * R.n, sort_rows_kernel, (unsigned)div_up(R.n * 32, kBlock),
               kBlock, 0, R.n, R.rp.p, R.col.p, R.val.p);
   AMGB_CHECK_LAUNCH(ctx);
   return AMGB_OK;
@@ -1065,8 +1150,15 @@ int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, 
 // ---- setup stages as host functions (shared with the row-partitioned driver) ----
 int run_strength(amgb_ctx* ctx, const DeviceCsr& A, double theta, double max_row_sum, uint8_t* mask,
                  int32_t* has_strong, double* diagv) {
-  AMGB_LAUNCH(ctx, F_STRENGTH, 13.0 * A.nnz + 8.0 * A.n, strength_kernel, (unsigned)div_up(A.n, kBlock), kBlock, 0,
-              A.n, A.rp.p, A.col.p, A.val.p, theta, max_row_sum, mask, has_strong, diagv);
+  // stage: 32 average rows plus a quarter, at most about 100 KB per block
+  const double avg = A.n > 0 ? double(A.nnz) / double(A.n) : 1.0;
+  int stage = (int)(40.0 * avg) / 128 * 128 + 128;
+  stage = std::min(std::max(stage, 256), 2048);
+  const size_t smem = (size_t)(kStrengthBlock / 32) * stage * 13;
+  if (smem > 48 * 1024)  // per device: set whenever it is needed
+    AMGB_CUDA(ctx, cudaFuncSetAttribute(strength_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2048 * 13));
+  AMGB_LAUNCH(ctx, F_STRENGTH, 13.0 * A.nnz + 8.0 * A.n, strength_kernel, (unsigned)div_up(A.n, kStrengthBlock),
+              kStrengthBlock, smem, A.n, A.rp.p, A.col.p, A.val.p, theta, max_row_sum, mask, has_strong, diagv, stage);
   AMGB_CHECK_LAUNCH(ctx);
   return AMGB_OK;
 }

@@ -438,7 +438,8 @@ def run_gpu(args):
 # --------------------------------------------------------------------------- config 5
 def run_partitioned(args):
     """--workload partitioned: BASELINE config 5, ONE system row-partitioned over the N GPUs
-    (z-slabs, NCCL halo exchange + all-reduced dots).  step = setup + PCG solve for theta in
+    (z-slabs; halo exchange and dot-product reductions as put/flag kernels over NVLink peer
+    windows, NCCL when AMGB_PEER=0).  step = setup + PCG solve for theta in
     {0.25, 0.5}; strong scaling (total work fixed)."""
     os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // max(1, int(os.environ.get("WORLD_SIZE", 1)))))
     import torch
@@ -463,6 +464,7 @@ def run_partitioned(args):
     L = amgb_lib()
     m = args.m
     thetas = [0.25, 0.5]
+    exch = "NCCL" if os.environ.get("AMGB_PEER", "1").startswith("0") else "NVLink peer-window (put/flag kernels)"
     starts = dist.slab_partition(m, world)
     b0, e0 = starts[rank], starts[rank + 1]
     sl = ab.gen.poisson_q1(m, row_begin=b0, row_end=e0)          # mu = 1: 3D Poisson
@@ -548,8 +550,8 @@ def run_partitioned(args):
                 "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"3D Poisson Q1, m={m} ({sl.n} DoFs, {int(st['nnz'][0])} nnz), ONE system "
-                                       f"row-partitioned in z-slabs over {world} GPUs (NCCL halo exchange, all-reduced "
-                                       f"dots), theta in {thetas}, PMIS + classical interp + C/F l1-Jacobi V(1,1), "
+                                       f"row-partitioned in z-slabs over {world} GPUs ({exch} halo exchange and "
+                                       f"dot-product reductions), theta in {thetas}, PMIS + classical interp + C/F l1-Jacobi V(1,1), "
                                        f"PCG tol 1e-8 abs",
                            "n": sl.n, "nnz": int(st["nnz"][0]), "systems_per_step": len(thetas),
                            "l2": "per-GPU slab exceeds the 126 MB L2; no flush needed",

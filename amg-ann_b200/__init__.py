@@ -345,6 +345,14 @@ class PreconditionBoomerAMG:
                                                                   C.byref(c), C.byref(d)), "level_row_stats")
         return a.value, b.value, c.value, d.value
 
+    def level_cheby(self, level):
+        """(max_eig, min_eig, coefficients) of the Chebyshev smoother of a level."""
+        mx, mn, k = C.c_double(), C.c_double(), C.c_int32()
+        co = np.zeros(5)
+        _chk(self.ctx._h, amgb_lib().amgb_precond_level_cheby(self._h, level, C.byref(mx), C.byref(mn),
+                                                              _p(co, c_f64p), C.byref(k)), "level_cheby")
+        return mx.value, mn.value, co[:k.value].copy()
+
     def effective_relax(self):
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
         _chk(self.ctx._h, amgb_lib().amgb_precond_effective_relax(self._h, C.byref(a), C.byref(b),

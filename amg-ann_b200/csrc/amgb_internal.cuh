@@ -179,6 +179,11 @@ struct Level {
   Sell As, Ps, Rs;
   DevBuf<double> inv_relax;  // new order: 1/l1 (type 18) or 1/diag (type 0); 0 = skip row
   DevBuf<double> u, f, tmp;  // new order
+  // Chebyshev smoother (relax type 16; amgb_cheby.cu): 1/sqrt(diag) in the solve numbering,
+  // spectrum estimates of D^-1/2 A D^-1/2, coefficients of p in u += p(A) r, work vectors
+  DevBuf<double> cheby_ds, cheby_r, cheby_t[2];
+  double cheby_max_eig = 0.0, cheby_min_eig = 0.0, cheby_coefs[5] = {0, 0, 0, 0, 0};
+  int cheby_degree = 0;
   // solve-phase sizes: rows relaxed here and vector length (= rows + halo in the
   // row-partitioned path; both equal A.n on a single device)
   int64_t n_solve = 0, n_vec = 0;
@@ -291,5 +296,7 @@ int finish_solve_setup_range(amgb_precond* P, int l0);
 // z = M^{-1} r with z, r in the level-0 permuted numbering
 int vcycle_apply(amgb_precond* P, double* z_dev, const double* r_dev);
 int spmv(amgb_ctx* ctx, const DeviceCsr& A, const double* x, double* y, int family);
+// amgb_cheby.cu: Chebyshev smoother data of level l (needs the level's CSR operator and perm)
+int cheby_setup_level(amgb_precond* P, int l);
 void destroy_solve_state(amgb_precond* P);
 }  // namespace amgb

@@ -225,6 +225,45 @@ struct EpiJacobi {  // out = u_old + w (f - A u) inv_relax  (hypre relax types 0
   }
 };
 
+// Chebyshev sweep (hypre_ParCSRRelax_Cheby_Solve with scaling), u += D^-1/2 p(D^-1/2 A D^-1/2) D^-1/2 (f - A u):
+// first pass r = ds (f - A u), t = ds (c_k r); middle passes q = c_i r + ds (A t), t' = ds q;
+// last pass u' = u + ds (c_0 r + ds (A t)).
+struct EpiChebyFirst {
+  const double* f;
+  const double* ds;
+  double* r;
+  double* t;
+  double ck;
+  __device__ __forceinline__ void store(int row, double s) const {
+    const double d = ds[row], rr = d * (f[row] - s);
+    r[row] = rr;
+    t[row] = d * (ck * rr);
+  }
+};
+
+struct EpiChebyMid {
+  const double* r;
+  const double* ds;
+  double* t;
+  double ci;
+  __device__ __forceinline__ void store(int row, double s) const {
+    const double d = ds[row];
+    t[row] = d * (ci * r[row] + d * s);
+  }
+};
+
+struct EpiChebyLast {
+  const double* u;
+  const double* r;
+  const double* ds;
+  double* out;
+  double c0;
+  __device__ __forceinline__ void store(int row, double s) const {
+    const double d = ds[row];
+    out[row] = u[row] + d * (c0 * r[row] + d * s);
+  }
+};
+
 // STREAM: evict-first loads for operators that are far larger than L2; small
 // levels use plain loads so that they stay L2-resident across V-cycles.
 template <bool STREAM, class V>
@@ -678,11 +717,14 @@ int finish_solve_setup_range(amgb_precond* P, int l0) {
       }
     }
     L.n_solve = L.n_vec = n;
+    if (P->relax_down == 16) AMGB_TRY(cheby_setup_level(P, l));
+    // (with Chebyshev on the way down and up, inv_relax only serves a Jacobi-type coarse relaxation)
+    const int aux_type = P->relax_down == 16 ? (P->relax_coarse == 9 ? 0 : P->relax_coarse) : P->relax_down;
     AMGB_TRY(L.inv_relax.alloc(ctx, n));
     AMGB_DISPATCH_T(L.As.T, AMGB_LAUNCH(ctx, F_AUX, L.As.csr_bytes() + 8.0 * n, sell_aux_kernel<TT>,
                                         (unsigned)div_up(L.As.nslices * 32, kBlock), kBlock, 0,
                                         (int)L.As.nslices, (int)n, L.As.slice_ptr.p, L.As.col.p, L.As.val.p,
-                                        P->relax_down, L.inv_relax.p));
+                                        aux_type, L.inv_relax.p));
     AMGB_CHECK_LAUNCH(ctx);
     AMGB_TRY(L.tmp.alloc(ctx, n));
     if (l > 0) {
@@ -796,8 +838,64 @@ static int relax_zero(amgb_ctx* ctx, const Level& L, int lo, int hi, const doubl
   return AMGB_OK;
 }
 
+// first pass of a Chebyshev sweep from the zero guess: r = ds f, t = ds (c_k r); no matrix pass
+__global__ void __launch_bounds__(kBlock)
+cheby_zero_kernel(int n, const double* __restrict__ f, const double* __restrict__ ds, double ck,
+                  double* __restrict__ r, double* __restrict__ t) {
+  const int row = (int)((int64_t)blockIdx.x * kBlock + threadIdx.x);
+  if (row >= n) return;
+  const double d = ds[row], rr = d * (f[row] - 0.0);
+  r[row] = rr;
+  t[row] = d * (ck * rr);
+}
+
+__global__ void __launch_bounds__(kBlock)
+add_kernel(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  const int row = (int)((int64_t)blockIdx.x * kBlock + threadIdx.x);
+  if (row < n) out[row] = a[row] + b[row];
+}
+
+// One Chebyshev sweep on all points of the level (par_cycle.c: no C/F ordering for type 16)
+static int relax_cheby(amgb_precond* P, int l, const double* f, double* u, double* out, bool u_is_zero) {
+  Level& L = P->lv[l];
+  amgb_ctx* ctx = P->ctx;
+  ctx->cur_level = l;
+  const int n = (int)L.n_solve;
+  if (n == 0) return AMGB_OK;
+  const int fam = l == 0 ? F_SMOOTH_L0 : F_SMOOTH;
+  const double mat = L.As.csr_bytes();
+  const int k = L.cheby_degree;
+  const double* ds = L.cheby_ds.p;
+  double* r = L.cheby_r.p;
+  double* cur = L.cheby_t[0].p;
+  double* nxt = L.cheby_t[1].p;
+  const unsigned vgrid = (unsigned)div_up(n, kBlock);
+  if (u_is_zero) {
+    AMGB_LAUNCH(ctx, F_VEC, 32.0 * n, cheby_zero_kernel, vgrid, kBlock, 0, n, f, ds, L.cheby_coefs[k], r, cur);
+    AMGB_CHECK_LAUNCH(ctx);
+  } else {
+    AMGB_TRY(launch_sell(ctx, L.As, 0, n, u, u, 0, EpiChebyFirst{f, ds, r, cur, L.cheby_coefs[k]}, fam,
+                         mat + 40.0 * n));
+  }
+  for (int i = k - 1; i >= 1; --i) {
+    AMGB_TRY(launch_sell(ctx, L.As, 0, n, cur, cur, 0, EpiChebyMid{r, ds, nxt, L.cheby_coefs[i]}, fam,
+                         mat + 32.0 * n));
+    std::swap(cur, nxt);
+  }
+  if (k == 0) {
+    AMGB_LAUNCH(ctx, F_VEC, 24.0 * n, add_kernel, vgrid, kBlock, 0, n, (const double*)u, (const double*)cur, out);
+    AMGB_CHECK_LAUNCH(ctx);
+  } else {
+    AMGB_TRY(launch_sell(ctx, L.As, 0, n, cur, cur, 0, EpiChebyLast{u, r, ds, out, L.cheby_coefs[0]}, fam,
+                         mat + 40.0 * n));
+  }
+  return AMGB_OK;
+}
+
 static int relax_if(amgb_precond* P, int l, const double* f, double* u, double* out, int cycle_param,
                     bool u_is_zero = false) {
+  if (P->relax_down == 16 && (cycle_param < 3 || P->relax_coarse == 9))
+    return relax_cheby(P, l, f, u, out, u_is_zero);
   // on the row-partitioned path the halo of `u` is refreshed here, overlapped with the rows that do not need it
   Level& L = P->lv[l];
   amgb_ctx* ctx = P->ctx;

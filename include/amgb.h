@@ -195,6 +195,11 @@ int amgb_precond_level_stats(const amgb_precond* P, int32_t capacity, int32_t* n
  * per row and row sums of one level (computed on request; single-device hierarchies). */
 int amgb_precond_level_row_stats(const amgb_precond* P, int32_t level, int32_t* min_entries,
                                  int32_t* max_entries, double* min_row_sum, double* max_row_sum);
+/* Chebyshev smoother (RelaxationType::Chebyshev, hypre relax type 16) of a level: the
+ * CG/Lanczos estimates of the extreme eigenvalues of D^-1/2 A D^-1/2 and the coefficients
+ * of the polynomial (coefs needs room for 4; n_coefs = hypre's cheby_order, default 2). */
+int amgb_precond_level_cheby(const amgb_precond* P, int32_t level, double* max_eig, double* min_eig,
+                             double* coefs, int32_t* n_coefs);
 /* hypre relax type actually run on the device for down/up/coarse (after the
  * smoother policy was applied). */
 int amgb_precond_effective_relax(const amgb_precond* P, int32_t* down, int32_t* up,

@@ -732,6 +732,10 @@ struct Level {
   std::vector<int32_t> cf_relax; // -3 folded into -1 (end of BuildInterp)
   std::vector<double> diag, l1;
   std::vector<double> u, f, tmp; // work vectors
+  // Chebyshev smoother (relax type 16): 1/sqrt(diag), spectrum estimates, polynomial
+  std::vector<double> cheby_ds;
+  double cheby_max_eig = 0.0, cheby_min_eig = 0.0, cheby_coefs[5] = {0, 0, 0, 0, 0};
+  int cheby_order = 0;  // degree of p in u += p(A) r (hypre's "order" minus one)
 };
 
 }  // namespace
@@ -764,6 +768,223 @@ void level_aux(Level& L) {
   L.u.assign(n, 0.0);
   L.f.assign(n, 0.0);
   L.tmp.assign(n, 0.0);
+}
+
+// ---------------------------------------------------------------------------
+// Chebyshev smoother, hypre relax type 16 (par_cheby.c; PCHYPRE defaults: order 2,
+// eigenvalue estimate by 10 CG iterations, fraction 0.3, variant 0, diagonal scaling).
+// ---------------------------------------------------------------------------
+// EISPACK tql1: eigenvalues of a symmetric tridiagonal matrix, ascending in d.  e holds the
+// sub-diagonal in e[1..n) (e[0] arbitrary), as hypre_LINPACKcgtql1 takes it.
+double pythag(double a, double b) {
+  const double p = std::max(std::fabs(a), std::fabs(b));
+  if (p == 0.0) return 0.0;
+  const double q = std::min(std::fabs(a), std::fabs(b)) / p;
+  double r = q * q;
+  double pp = p;
+  for (;;) {
+    const double t = 4.0 + r;
+    if (t == 4.0) break;
+    const double sq = r / t;
+    const double u = 1.0 + 2.0 * sq;
+    pp = u * pp;
+    r = (sq / u) * (sq / u) * r;
+  }
+  return pp;
+}
+
+int tql1(int n, double* d, double* e) {
+  if (n <= 1) return 0;
+  for (int i = 1; i < n; ++i) e[i - 1] = e[i];
+  double f = 0.0, tst1 = 0.0;
+  e[n - 1] = 0.0;
+  for (int l = 0; l < n; ++l) {
+    int j = 0;
+    const double h0 = std::fabs(d[l]) + std::fabs(e[l]);
+    if (tst1 < h0) tst1 = h0;
+    int m = l;
+    for (; m < n; ++m)
+      if (tst1 + std::fabs(e[m]) == tst1) break;  // e[n-1] = 0 ends the search
+    if (m != l) {
+      double tst2;
+      do {
+        if (j == 30) return l + 1;
+        ++j;
+        const int l1 = l + 1, l2 = l1 + 1;
+        double g = d[l];
+        double p = (d[l1] - g) / (2.0 * e[l]);
+        double r = pythag(p, 1.0);
+        const double sr = p >= 0.0 ? std::fabs(r) : -std::fabs(r);
+        d[l] = e[l] / (p + sr);
+        d[l1] = e[l] * (p + sr);
+        const double dl1 = d[l1];
+        double h = g - d[l];
+        for (int i = l2; i < n; ++i) d[i] -= h;
+        f += h;
+        p = d[m];
+        double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0;
+        const double el1 = e[l1];
+        for (int i = m - 1; i >= l; --i) {
+          c3 = c2;
+          c2 = c;
+          s2 = s;
+          g = c * e[i];
+          h = c * p;
+          r = pythag(p, e[i]);
+          e[i + 1] = s * r;
+          s = e[i] / r;
+          c = p / r;
+          p = c * d[i] - s * g;
+          d[i + 1] = h + s * (c * g + s * d[i]);
+        }
+        p = -s * s2 * c3 * el1 * e[l] / dl1;
+        e[l] = s * p;
+        d[l] = c * p;
+        tst2 = tst1 + std::fabs(e[l]);
+      } while (tst2 > tst1);
+    }
+    const double p = d[l] + f;
+    int i = l;
+    for (; i >= 1; --i) {
+      if (p >= d[i - 1]) break;
+      d[i] = d[i - 1];
+    }
+    d[i] = p;
+  }
+  return 0;
+}
+
+// Inner product in the order of the device kernel (so that the spectrum estimates are the
+// same bits on both sides): blocks of 256 products, each warp of 32 by the shuffle-down tree
+// (16, 8, 4, 2, 1), the 8 warp sums left to right, the block sums left to right.
+double tree_dot(const double* x, const double* y, int64_t n) {
+  double total = 0.0;
+  for (int64_t b0 = 0; b0 < n; b0 += 256) {
+    double block = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      double v[32];
+      for (int l = 0; l < 32; ++l) {
+        const int64_t i = b0 + 32 * w + l;
+        v[l] = i < n ? x[i] * y[i] : 0.0;
+      }
+      for (int off = 16; off > 0; off >>= 1)
+        for (int l = 0; l < off; ++l) v[l] = v[l] + v[l + off];
+      block = block + v[0];
+    }
+    total = total + block;
+  }
+  return total;
+}
+
+// hypre_ParCSRMaxEigEstimateCG with scale = 1: Lanczos through `max_iter` CG steps on
+// D^{-1/2} A D^{-1/2} from the random vector of hypre_ParVectorSetRandomValues(r, 1).
+void cheby_eig_estimate(const Csr& A, const std::vector<double>& ds, int max_iter, double* max_eig,
+                        double* min_eig) {
+  const int64_t n = A.n;
+  if (n < max_iter) max_iter = (int)n;
+  std::vector<double> r(n), p(n), s(n), u(n), tri(max_iter + 2, 0.0), off(max_iter + 2, 0.0);
+  int64_t seed = 1;
+  for (int64_t i = 0; i < n; ++i) {
+    seed = rand_next(seed);
+    r[i] = 2.0 * ((double)seed / (double)kRandM) - 1.0;
+  }
+  double gamma = 1.0;
+  int it = 0;
+  while (it < max_iter) {
+    const double gamma_old = gamma;
+    gamma = tree_dot(r.data(), r.data(), n);
+    if (!(gamma > 0.0)) break;
+    double beta = 1.0;
+    if (it == 0) {
+      p = r;
+    } else {
+      beta = gamma / gamma_old;
+      for (int64_t i = 0; i < n; ++i) p[i] = r[i] + beta * p[i];
+    }
+    for (int64_t i = 0; i < n; ++i) u[i] = ds[i] * p[i];
+    spmv(A, u.data(), s.data());
+    for (int64_t i = 0; i < n; ++i) s[i] = ds[i] * s[i];
+    const double sdotp = tree_dot(s.data(), p.data(), n);
+    if (!(sdotp > 0.0)) break;
+    const double alpha = gamma / sdotp;
+    const double alphainv = 1.0 / alpha;
+    tri[it + 1] = alphainv;
+    tri[it] *= beta;
+    tri[it] += alphainv;
+    off[it + 1] = alphainv;
+    off[it] *= std::sqrt(beta);
+    for (int64_t i = 0; i < n; ++i) r[i] = r[i] - alpha * s[i];
+    ++it;
+  }
+  if (it == 0) {
+    *max_eig = *min_eig = 1.0;
+    return;
+  }
+  tql1(it, tri.data(), off.data());
+  *max_eig = tri[it - 1];
+  *min_eig = tri[0];
+}
+
+// hypre_ParCSRRelax_Cheby_Setup, variant 0: coefficients of p in u += p(A) r.
+void cheby_coefficients(double max_eig, double min_eig, double fraction, int order, double* coefs,
+                        int* cheby_order) {
+  if (order > 4) order = 4;
+  if (order < 1) order = 1;
+  const int k = order - 1;
+  const double upper = max_eig * 1.1;
+  const double lower = (upper - min_eig) * fraction + min_eig;
+  const double theta = (upper + lower) / 2, delta = (upper - lower) / 2;
+  double den;
+  switch (k) {
+    case 0:
+      coefs[0] = 1.0 / theta;
+      break;
+    case 1:
+      den = 2 * theta * theta - delta * delta;
+      coefs[0] = 4 * theta / den;
+      coefs[1] = -2 / den;
+      break;
+    case 2:
+      den = 4 * (theta * theta * theta) - 3 * (delta * delta) * theta;
+      coefs[0] = (12 * (theta * theta) - 3 * (delta * delta)) / den;
+      coefs[1] = -12 * theta / den;
+      coefs[2] = 4 / den;
+      break;
+    default:
+      den = std::pow(delta, 4) - 8 * (delta * delta) * (theta * theta) + 8 * std::pow(theta, 4);
+      coefs[0] = (32 * std::pow(theta, 3) - 16 * (delta * delta) * theta) / den;
+      coefs[1] = (8 * (delta * delta) - 48 * (theta * theta)) / den;
+      coefs[2] = 32 * theta / den;
+      coefs[3] = -8 / den;
+      break;
+  }
+  *cheby_order = k;
+}
+
+void cheby_setup(Level& L, int order, int eig_est, double fraction) {
+  const int64_t n = L.A.n;
+  L.cheby_ds.assign(n, 0.0);
+  for (int64_t i = 0; i < n; ++i) L.cheby_ds[i] = 1.0 / std::sqrt(L.diag[i]);
+  cheby_eig_estimate(L.A, L.cheby_ds, eig_est, &L.cheby_max_eig, &L.cheby_min_eig);
+  cheby_coefficients(L.cheby_max_eig, L.cheby_min_eig, fraction, order, L.cheby_coefs, &L.cheby_order);
+}
+
+// hypre_ParCSRRelax_Cheby_Solve with scaling: u += D^{-1/2} p(D^{-1/2} A D^{-1/2}) D^{-1/2} (f - A u)
+void cheby_relax(const Level& L, const double* f, double* u, double* tmp) {
+  const Csr& A = L.A;
+  const int64_t n = A.n;
+  const double* ds = L.cheby_ds.data();
+  std::vector<double> r(n), q(n), t(n);
+  spmv(A, u, tmp);
+  for (int64_t i = 0; i < n; ++i) r[i] = ds[i] * (f[i] - tmp[i]);
+  const int k = L.cheby_order;
+  for (int64_t i = 0; i < n; ++i) q[i] = L.cheby_coefs[k] * r[i];
+  for (int c = k - 1; c >= 0; --c) {
+    for (int64_t i = 0; i < n; ++i) t[i] = ds[i] * q[i];
+    spmv(A, t.data(), tmp);
+    for (int64_t i = 0; i < n; ++i) q[i] = L.cheby_coefs[c] * r[i] + ds[i] * tmp[i];
+  }
+  for (int64_t i = 0; i < n; ++i) u[i] = u[i] + ds[i] * q[i];
 }
 
 // One hypre_BoomerAMGRelax call: relax_points 0 = all, else only cf == relax_points.
@@ -824,6 +1045,10 @@ void relax(const Level& L, int type, int relax_points, double w, const double* f
 void relax_if(const orc_hier& h, const Level& L, int type, int cycle_param, const double* f,
               double* u, double* tmp) {
   const double w = h.data.relax_weight;
+  if (type == 16) {  // par_cycle.c: the polynomial smoother runs on all points, no C/F ordering
+    cheby_relax(L, f, u, tmp);
+    return;
+  }
   if (h.data.relax_order == 1 && cycle_param < 3) {
     const int pts[2] = {cycle_param < 2 ? 1 : -1, cycle_param < 2 ? -1 : 1};
     relax(L, type, pts[0], w, f, u, tmp);
@@ -956,7 +1181,9 @@ int orc_setup(int64_t n, const int32_t* rowptr, const int32_t* col, const double
   h->relax_up = hypre_relax_type(data->relaxation_type_up, sym);
   h->relax_coarse = hypre_relax_type(data->relaxation_type_coarse, sym);
   auto supported = [](int t) { return t == 0 || t == 3 || t == 4 || t == 6 || t == 18; };
-  if (!supported(h->relax_down) || !supported(h->relax_up) ||
+  if (h->relax_down == 16 && h->relax_up == 16 && (supported(h->relax_coarse) || h->relax_coarse == 9)) {
+    // Chebyshev on the way down and up
+  } else if (!supported(h->relax_down) || !supported(h->relax_up) ||
       !(supported(h->relax_coarse) || h->relax_coarse == 9)) {
     delete h;
     return AMGB_ERR_UNSUPPORTED;
@@ -1011,6 +1238,8 @@ int orc_setup(int64_t n, const int32_t* rowptr, const int32_t* col, const double
     if (L.cf_relax.empty()) L.cf_relax.assign(L.A.n, 0);
     level_aux(L);
   }
+  if (h->relax_down == 16)  // PCHYPRE / hypre defaults: order 2, 10 CG steps, fraction 0.3
+    for (Level& L : h->lv) cheby_setup(L, 2, 10, 0.3);
   Level& C = h->lv.back();
   if (h->relax_coarse == 9 && C.A.n <= kMaxDenseCoarse) {
     const int64_t nc = C.A.n;
@@ -1101,6 +1330,21 @@ int orc_effective_relax(const orc_hier* h, int32_t* down, int32_t* up, int32_t* 
   if (coarse) *coarse = h->relax_coarse;
   return 0;
 }
+
+int orc_level_cheby(const orc_hier* h, int level, double* max_eig, double* min_eig, double* coefs,
+                    int32_t* n_coefs) {
+  if (!h || level < 0 || level >= (int)h->lv.size()) return AMGB_ERR_RANGE;
+  const Level& L = h->lv[level];
+  if (L.cheby_ds.empty()) return AMGB_ERR_RANGE;
+  if (max_eig) *max_eig = L.cheby_max_eig;
+  if (min_eig) *min_eig = L.cheby_min_eig;
+  if (coefs)
+    for (int i = 0; i <= L.cheby_order; ++i) coefs[i] = L.cheby_coefs[i];
+  if (n_coefs) *n_coefs = L.cheby_order + 1;
+  return AMGB_OK;
+}
+
+int orc_tql1(int32_t n, double* diag, double* offdiag) { return tql1(n, diag, offdiag); }
 
 int orc_vmult(orc_hier* h, double* z, const double* r) {
   if (!h || !z || !r) return AMGB_ERR_BAD_ARG;

@@ -64,6 +64,12 @@ int orc_level_stats(const orc_hier* h, int capacity, int32_t* n_levels, int64_t*
                     int64_t* nnz, double* sparsity, double* grid_cx, double* op_cx,
                     double* mem_cx);
 int orc_effective_relax(const orc_hier* h, int32_t* down, int32_t* up, int32_t* coarse);
+/* Chebyshev smoother (hypre relax type 16, par_cheby.c) of a level: CG/Lanczos spectrum
+ * estimates of D^-1/2 A D^-1/2 and the polynomial coefficients (n_coefs = order). */
+int orc_level_cheby(const orc_hier* h, int level, double* max_eig, double* min_eig, double* coefs,
+                    int32_t* n_coefs);
+/* EISPACK tql1 as hypre_LINPACKcgtql1 takes its arguments (offdiag[1..n) used). */
+int orc_tql1(int32_t n, double* diag, double* offdiag);
 
 /* z = one V-cycle applied to r from a zero initial guess (PCApply_HYPRE). */
 int orc_vmult(orc_hier* h, double* z, const double* r);

@@ -51,6 +51,8 @@ def lib():
         sig("orc_level_stats", C.c_int, vp, C.c_int, c_i32p, c_i64p, c_i64p, c_f64p, c_f64p,
             c_f64p, c_f64p)
         sig("orc_effective_relax", C.c_int, vp, c_i32p, c_i32p, c_i32p)
+        sig("orc_level_cheby", C.c_int, vp, C.c_int, c_f64p, c_f64p, c_f64p, c_i32p)
+        sig("orc_tql1", C.c_int, C.c_int32, c_f64p, c_f64p)
         sig("orc_vmult", C.c_int, vp, c_f64p, c_f64p)
         sig("orc_cg_solve", C.c_int, vp, C.c_int64, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p,
             C.c_int64, C.c_double, c_f64p, C.c_int64, c_i64p)
@@ -205,6 +207,15 @@ class Hierarchy:
         lib().orc_effective_relax(self._h, C.byref(a), C.byref(b), C.byref(c))
         return a.value, b.value, c.value
 
+    def level_cheby(self, level):
+        """(max_eig, min_eig, coefficients) of the Chebyshev smoother of a level"""
+        mx, mn, k = C.c_double(), C.c_double(), C.c_int32()
+        co = np.zeros(5)
+        rc = lib().orc_level_cheby(self._h, level, C.byref(mx), C.byref(mn), _p(co, c_f64p), C.byref(k))
+        if rc != 0:
+            raise RuntimeError(f"orc_level_cheby -> {rc}")
+        return mx.value, mn.value, co[:k.value].copy()
+
     def vmult(self, r):
         r = np.ascontiguousarray(r, dtype=np.float64)
         z = np.empty_like(r)
@@ -223,3 +234,14 @@ class Hierarchy:
                                 _p(self.vl, c_f64p), _p(x, c_f64p), _p(b, c_f64p), max_steps,
                                 abs_tol, _p(hist, c_f64p), cap, C.byref(nit))
         return rc, x, nit.value, hist[:min(cap, nit.value + 1)].copy()
+
+
+def tql1(diag, offdiag):
+    """Eigenvalues (ascending) of the symmetric tridiagonal matrix with diagonal `diag` and
+    sub-diagonal offdiag[1:] (EISPACK tql1 argument convention)."""
+    d = np.array(diag, dtype=np.float64, copy=True)
+    e = np.array(offdiag, dtype=np.float64, copy=True)
+    rc = lib().orc_tql1(len(d), _p(d, c_f64p), _p(e, c_f64p))
+    if rc != 0:
+        raise RuntimeError(f"tql1 did not converge at eigenvalue {rc}")
+    return d

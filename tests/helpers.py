@@ -34,3 +34,23 @@ def random_spd_csr(n, density, seed):
     A = (B + sp.diags(d)).tocsr()
     A.sort_indices()
     return A
+
+
+def spd_laplacian(m, seed=0, decades=2.0):
+    """Symmetric positive definite test system: 7-point Laplacian on an m^3 grid, symmetrically
+    scaled by 10^U(0, decades) per point.  (The Q1 generators keep deal.II's row-only
+    elimination of Dirichlet values for PETSc matrices, so their matrices are not symmetric;
+    smoothers that estimate a spectrum with CG need a symmetric operator.)"""
+    import scipy.sparse as sp
+    from types import SimpleNamespace
+    rng = np.random.default_rng(seed)
+    eye = sp.identity(m)
+    t = sp.diags([-np.ones(m - 1), 2 * np.ones(m), -np.ones(m - 1)], [-1, 0, 1])
+    A = sp.kron(sp.kron(t, eye), eye) + sp.kron(sp.kron(eye, t), eye) + sp.kron(sp.kron(eye, eye), t)
+    w = sp.diags(10.0 ** rng.uniform(0, decades, m ** 3))
+    A = (w @ A @ w).tocsr()
+    A.sort_indices()
+    n = A.shape[0]
+    return SimpleNamespace(n=n, nnz=A.nnz, rowptr=A.indptr.astype(np.int64), col=A.indices.astype(np.int32),
+                           val=A.data.astype(np.float64), rhs=rng.normal(size=n), x0=np.zeros(n), csr=A,
+                           rowptr32=lambda: A.indptr.astype(np.int32))

@@ -381,3 +381,47 @@ def test_aggressive_coarsening_oracle_properties():
     d.aggressive_coarsening_num_levels = 1
     with pytest.raises(Exception):
         orc.Hierarchy(s.rowptr32(), s.col, s.val, d.to_struct())
+
+
+# ---- Chebyshev smoother (hypre relax type 16) ----
+def test_tql1_matches_lapack_on_random_tridiagonals():
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 7, 10, 25):
+        d, e = rng.normal(size=n), rng.normal(size=n)
+        T = np.diag(d) + np.diag(e[1:], 1) + np.diag(e[1:], -1)
+        assert np.allclose(orc.tql1(d, e), np.linalg.eigvalsh(T), rtol=0, atol=1e-13 * max(1.0, abs(T).max()))
+
+
+def test_chebyshev_spectrum_estimates_bracket_like_lanczos():
+    """10 CG/Lanczos steps: Ritz values lie inside the spectrum of D^-1/2 A D^-1/2 and the
+    largest one is close to its top."""
+    from helpers import spd_laplacian
+    s = spd_laplacian(10, seed=1)
+    R = ab.RelaxationType
+    d = device_data(0.25, relaxation_type_up=R.Chebyshev, relaxation_type_down=R.Chebyshev)
+    H = orc.Hierarchy(s.rowptr32(), s.col, s.val, d.to_struct())
+    assert H.effective_relax()[:2] == (16, 16)
+    ds = 1.0 / np.sqrt(s.csr.diagonal())
+    ev = np.linalg.eigvalsh((sp.diags(ds) @ s.csr @ sp.diags(ds)).toarray())
+    mx, mn, coefs = H.level_cheby(0)
+    assert ev[0] - 1e-12 <= mn <= mx <= ev[-1] + 1e-12
+    assert mx > 0.9 * ev[-1]
+    # order 2: p(t) = c0 + c1 t with the residual polynomial 1 - t p(t) small on [lower, upper]
+    assert len(coefs) == 2 and coefs[0] > 0 > coefs[1]
+    upper = 1.1 * mx
+    lower = (upper - mn) * 0.3 + mn
+    t = np.linspace(lower, upper, 101)
+    assert np.abs(1 - t * (coefs[0] + coefs[1] * t)).max() < 0.5
+
+
+def test_chebyshev_smoothed_pcg_converges_to_the_direct_solution():
+    from helpers import spd_laplacian
+    s = spd_laplacian(12, seed=2)
+    R = ab.RelaxationType
+    for kw in (dict(), dict(w_cycle=True), dict(n_sweeps=2)):
+        d = device_data(0.25, relaxation_type_up=R.Chebyshev, relaxation_type_down=R.Chebyshev, **kw)
+        H = orc.Hierarchy(s.rowptr32(), s.col, s.val, d.to_struct())
+        rc, x, nit, hist = H.cg_solve(s.rhs, s.x0, abs_tol=1e-10)
+        assert rc == 0 and nit < 60
+        xd = spl.spsolve(s.csr.tocsc(), s.rhs)
+        assert np.abs(x - xd).max() <= 1e-6 * np.abs(xd).max()

@@ -327,3 +327,59 @@ def test_level_row_stats_match_the_level_operators(gpu_ctx):
         assert (mn, mx) == (lens.min(), lens.max())
         assert smin == pytest.approx(sums.min(), abs=1e-12 * np.abs(vl).max())
         assert smax == pytest.approx(sums.max(), abs=1e-12 * np.abs(vl).max())
+
+
+# ---- Chebyshev smoother (RelaxationType::Chebyshev, hypre relax type 16) ----
+def _cheby_data(**kw):
+    R = ab.RelaxationType
+    return device_data(0.25, relaxation_type_up=R.Chebyshev, relaxation_type_down=R.Chebyshev, **kw)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(w_cycle=True), dict(n_sweeps=2), dict(max_levels=2)])
+def test_chebyshev_smoother_matches_the_oracle(gpu_ctx, kw):
+    from helpers import spd_laplacian
+    s = spd_laplacian(14, seed=5, decades=1.0)
+    data = _cheby_data(**kw)
+    A, P, H = _both(gpu_ctx, s, data)
+    assert P.effective_relax()[:2] == (16, 16)
+    _assert_hierarchy_identical(P, H)
+    # the spectrum estimates are computed in a fixed arithmetic order: identical bits
+    for l in range(P.num_levels):
+        mx, mn, co = P.level_cheby(l)
+        omx, omn, oco = H.level_cheby(l)
+        assert (mx, mn) == (omx, omn), (l, mx - omx, mn - omn)
+        assert np.array_equal(co, oco)
+    ctl = ab.SolverControl(s.n, 1e-9)
+    x = s.x0.copy()
+    ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+    rc, xo, nit, hist = H.cg_solve(s.rhs, s.x0, abs_tol=1e-9)
+    assert rc == 0 and abs(ctl.last_step() - nit) <= 1
+    k = min(len(hist), len(ctl.history))
+    d = np.abs(ctl.history[:k] - hist[:k])
+    assert (d[:12] <= RES_RTOL * hist[:12]).all()   # north_star: 1e-10 relative
+    # rounding differences grow with the iteration count on this badly scaled system
+    assert (d <= RES_RTOL * hist[0]).all() and (d <= 1e-8 * hist[:k]).all()
+    assert np.abs(x - xo).max() <= 1e-8 * np.abs(xo).max()
+
+
+def test_chebyshev_on_symmetric_elasticity_and_vmult(gpu_ctx):
+    """testcase-3 style system (constraints eliminated symmetrically): one V-cycle applied to
+    a vector agrees with the oracle's."""
+    s = ab.gen.elasticity_q1(6, 2, 3, 10.0 ** ab.gen.checkerboard_epsv(2, 3, 1.0))
+    A, P, H = _both(gpu_ctx, s, _cheby_data())
+    for l in range(P.num_levels):
+        assert P.level_cheby(l)[:2] == H.level_cheby(l)[:2]
+    r = np.random.default_rng(0).normal(size=s.n)
+    z = np.empty_like(r)
+    P.vmult(z, r)
+    zo = H.vmult(r)
+    assert np.abs(z - zo).max() <= 1e-12 * np.abs(zo).max()
+
+
+def test_chebyshev_is_rejected_on_the_coarse_grid_and_when_partitioned(gpu_ctx):
+    from helpers import spd_laplacian
+    R = ab.RelaxationType
+    s = spd_laplacian(6)
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    with pytest.raises(ab.AmgbError):
+        ab.PreconditionBoomerAMG().initialize(A, _cheby_data(relaxation_type_coarse=R.Chebyshev))

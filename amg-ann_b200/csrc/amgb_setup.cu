@@ -14,6 +14,7 @@
 //    ascending column within a row, ascending k for C(i,c) = sum_k a_ik b_kc.
 #include <algorithm>
 #include <cstdlib>
+#include <chrono>
 #include <climits>
 #include <cstring>
 #include <string>
@@ -427,7 +428,7 @@ interp_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __r
         const int e1 = ee < 0 ? -(ee + 1) : ee;
         int lo = s_b1[wi][t], hi = e1;
         while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
+          const int mid = lo + ((hi - lo) >> 1);  // entry numbers reach past 2^30: lo + hi would overflow
           if (col[mid] < want) lo = mid + 1; else hi = mid;
         }
         if (lo < e1 && col[lo] == want) {
@@ -1572,9 +1573,33 @@ int resolve_options(amgb_precond* P) {
 
 // The level loop of the single-device setup, starting from P->lv[level0].A (which must be
 // set).  Also used by the row-partitioned driver for the replicated coarse levels.
+// AMGB_TRACE=1: host wall time of every setup stage (stream synchronised at the stage
+// boundaries), to stderr.  A diagnosis aid: allocation and host round trips show up here,
+// not in the per-kernel timers.
+struct StageTrace {
+  amgb_ctx* ctx;
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  explicit StageTrace(amgb_ctx* c) : ctx(c), on(std::getenv("AMGB_TRACE") != nullptr) {
+    if (on) {
+      cudaStreamSynchronize(ctx->stream);
+      t0 = std::chrono::steady_clock::now();
+    }
+  }
+  void mark(int level, const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[amgb trace] level %d %-12s %9.3f ms\n", level, what,
+                 std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 int build_levels_from(amgb_precond* P, int level0) {
   amgb_ctx* ctx = P->ctx;
   const amgb_boomeramg_data& d = P->data;
+  StageTrace trace(ctx);
   for (int level = level0;; ++level) {
     Level& L = P->lv[level];
     const int64_t n = L.A.n;
@@ -1586,8 +1611,11 @@ int build_levels_from(amgb_precond* P, int level0) {
     AMGB_TRY(has_strong.alloc(ctx, n));
     AMGB_TRY(diagv.alloc(ctx, n));
     AMGB_TRY(L.cf.alloc(ctx, n));
+    trace.mark(level, "alloc");
     AMGB_TRY(run_strength(ctx, L.A, P->theta_eff, P->mrs_eff, L.mask.p, has_strong.p, diagv.p));
+    trace.mark(level, "strength");
     AMGB_TRY(coarsen_pmis(ctx, L.A, L.mask.p, has_strong.p, L.cf.p, nullptr));
+    trace.mark(level, "pmis");
     // coarse numbering: ascending fine index of the C points
     AMGB_TRY(L.f2c.alloc(ctx, n + 1));
     int32_t nc = 0;
@@ -1607,13 +1635,17 @@ int build_levels_from(amgb_precond* P, int level0) {
     L.n_coarse = nc;
     if (aggressive) AMGB_TRY(build_interp_multipass(ctx, L.A, L.mask.p, L.cf.p, L.f2c.p, nc, L.P));
     else AMGB_TRY(build_interp(ctx, L.A, L.mask.p, L.cf.p, L.f2c.p, diagv.p, 0, n, nc, L.P));
+    trace.mark(level, "interp");
     AMGB_TRY(transpose_csr(ctx, L.P, L.R));
+    trace.mark(level, "transpose");
     // Galerkin product A_c = R (A P)
     DeviceCsr T;
     AMGB_TRY(spgemm(ctx, L.A, L.P, T, false));
+    trace.mark(level, "A*P");
     P->lv.emplace_back();
     Level& Lc = P->lv[level + 1];
     AMGB_TRY(spgemm(ctx, P->lv[level].R, T, Lc.A, true));
+    trace.mark(level, "R*(AP)");
     if (!d.keep_setup_intermediates) P->lv[level].mask.release();
   }
   return AMGB_OK;
@@ -1646,7 +1678,9 @@ int build_hierarchy(amgb_precond* P) {
     P->st_nnzP.push_back(L.P.nnz);
   }
   ctx->cur_level = 0;
+  StageTrace trace(ctx);
   AMGB_TRY(finish_solve_setup(P));
+  trace.mark(-1, "solve setup");
   AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return AMGB_OK;
 }

@@ -20,6 +20,8 @@ ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--max-steps", type=int, default=0)
 ap.add_argument("--timers", action="store_true", help="per-family CUDA-event timers (disables the V-cycle graph)")
 ap.add_argument("--kind", default="poisson", choices=["poisson", "elasticity"])
+ap.add_argument("--smoother", default="l1jacobi", choices=["l1jacobi", "chebyshev"])
+ap.add_argument("--agg", type=int, default=0, help="aggressive_coarsening_num_levels (testcase 3 passes 2)")
 args = ap.parse_args()
 
 epsv = ab.gen.checkerboard_epsv(4, 3, args.contrast)
@@ -30,8 +32,8 @@ else:
     s = ab.gen.poisson_q1(args.m, 4, 3, epsv)
 print(f"{args.kind} m={args.m}: n={s.n} nnz={s.nnz} generated in {time.perf_counter() - t_gen:.1f} s", flush=True)
 R = ab.RelaxationType
-data = ab.AdditionalData(True, args.theta, 0.9, 0, True, relaxation_type_up=R.l1scaledJacobi,
-                         relaxation_type_down=R.l1scaledJacobi)
+sm = R.Chebyshev if args.smoother == "chebyshev" else R.l1scaledJacobi
+data = ab.AdditionalData(True, args.theta, 0.9, args.agg, True, relaxation_type_up=sm, relaxation_type_down=sm)
 ctx = ab.Context(0)
 A = ab.SparseMatrix(ctx, s.rowptr32(), s.col, s.val)
 for rep in range(args.repeat):

@@ -52,7 +52,8 @@ def fn(rank, comm):
         t2 = time.perf_counter()
         res = dict(rows=list(P.level_stats()["rows"]), iters=ctl.last_step(), setup_ms=1e3 * (t1 - t0),
                    solve_ms=1e3 * (t2 - t1), res=ctl.last_value(),
-                   local=[P.level_dims(l)["n_local"] for l in range(P.num_levels)], x=x, hist=ctl.history)
+                   local=[P.level_dims(l)["n_local"] for l in range(min(P.num_levels, P.replicated_from))],
+                   x=x, hist=ctl.history)
         P.close()
     A.close()
     return res

@@ -1,6 +1,7 @@
 // Context, matrix residency, error reporting, prefix sums and the measurement
 // hooks of libamgb.so.  ABI documentation: include/amgb.h.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "amgb_internal.cuh"
@@ -271,10 +272,21 @@ int amgb_ctx_create(amgb_ctx** out, int device_id, void* stream) {
   }
   // keep freed blocks in the stream-ordered pool: the theta sweep re-allocates
   // the same hierarchy shapes over and over
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  // (a pool of its own per context: see amgb_ctx::pool; the default pool is the fallback)
+  uint64_t thr = UINT64_MAX;
+  cudaMemPoolProps props = {};
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = device_id;
+  if (!std::getenv("AMGB_SHARED_POOL") && cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess) {
+    cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  } else {
+    (void)cudaGetLastError();
+    ctx->pool = nullptr;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess)
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   ctx->pinned_bytes = 4096;
   if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) {
@@ -293,6 +305,7 @@ int amgb_ctx_destroy(amgb_ctx* ctx) {
   drain_timers(ctx);
   for (auto ev : ctx->free_events) cudaEventDestroy(ev);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);  // blocks still held by live objects stay valid until freed
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return AMGB_OK;

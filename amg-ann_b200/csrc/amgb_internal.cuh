@@ -67,6 +67,10 @@ struct amgb_ctx {
   double lvl_ms[amgb::F_COUNT][amgb::kTimerLevels] = {{0}};
   double lvl_bytes[amgb::F_COUNT][amgb::kTimerLevels] = {{0}};
   int64_t lvl_launches[amgb::F_COUNT][amgb::kTimerLevels] = {{0}};
+  // Private stream-ordered memory pool.  With the device's default pool, a block freed on
+  // one context's stream can be handed to another context with a hidden dependency on the
+  // first stream; contexts that run independent systems side by side must not couple.
+  cudaMemPool_t pool = nullptr;
   // small pinned staging area for device->host scalars
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -115,7 +119,8 @@ struct DevBuf {
     owns = true;
     n = count;
     if (count == 0) return AMGB_OK;
-    cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), c->stream);
+    cudaError_t e = c->pool ? cudaMallocFromPoolAsync((void**)&p, count * sizeof(T), c->pool, c->stream)
+                            : cudaMallocAsync((void**)&p, count * sizeof(T), c->stream);
     if (e != cudaSuccess) {
       p = nullptr;
       n = 0;

@@ -383,3 +383,36 @@ def test_chebyshev_is_rejected_on_the_coarse_grid_and_when_partitioned(gpu_ctx):
     A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
     with pytest.raises(ab.AmgbError):
         ab.PreconditionBoomerAMG().initialize(A, _cheby_data(relaxation_type_coarse=R.Chebyshev))
+
+
+def test_one_uploaded_matrix_serves_several_contexts_at_once(gpu_ctx):
+    """The independent systems of a theta sweep share one read-only matrix and run on
+    different contexts (streams, host threads) at the same time; every one of them gets
+    the bits of a sequential run."""
+    import threading
+    s = poisson(16, contrast=3.0)
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    thetas = [0.25, 0.5, 0.75, 0.9]
+    want = {}
+    for th in thetas:
+        x = s.x0.copy()
+        want[th] = (ab.amg_solve(device_data(th), 1e-8, A, s.rhs, x), x)
+    got, errs = {}, []
+
+    def lane(th):
+        try:
+            ctx = ab.Context(0)
+            x = s.x0.copy()
+            got[th] = (ab.amg_solve(device_data(th), 1e-8, A, s.rhs, x, ctx), x)
+            ctx.close()
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+    ts = [threading.Thread(target=lane, args=(th,)) for th in thetas]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for th in thetas:
+        assert got[th][0]["niters"] == want[th][0]["niters"]
+        assert np.array_equal(got[th][0]["p_res"], want[th][0]["p_res"])
+        assert np.array_equal(got[th][1], want[th][1])
+        assert np.array_equal(got[th][0]["nrows"], want[th][0]["nrows"])

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <vector>
 
+#include "amgb_dist.cuh"
 #include "amgb_internal.cuh"
 
 namespace amgb {
@@ -22,11 +23,12 @@ namespace {
 
 constexpr int kBlock = 256;
 
+// rows [row0, row0 + n) of a square matrix (row0 > 0: the owned rows of a rank's extended matrix)
 __global__ void __launch_bounds__(kBlock)
-cheby_scaling_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+cheby_scaling_kernel(int64_t n, int64_t row0, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
                      const double* __restrict__ val, double* __restrict__ ds) {
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
+  const int64_t i = row0 + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= row0 + n) return;
   double d = 0.0;
   for (int k = rp[i]; k < rp[i + 1]; ++k)
     if (col[k] == i) d = val[k];
@@ -35,12 +37,14 @@ cheby_scaling_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* _
 
 // hypre_ParVectorSetRandomValues(r, 1): r_i = 2 * hypre_Rand() - 1 with the multiplicative
 // generator 16807 mod 2^31-1 seeded with 1, i.e. value i comes from 16807^(i+1) mod m
+// (gid: global index of entry i on the row-partitioned path, so that every rank count draws
+// the same vector)
 __global__ void __launch_bounds__(kBlock)
-cheby_random_kernel(int64_t n, double* __restrict__ r) {
+cheby_random_kernel(int64_t n, const int32_t* __restrict__ gid, double* __restrict__ r) {
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
   const unsigned long long m = 2147483647ull;
-  unsigned long long e = (unsigned long long)i + 1ull, base = 16807ull, s = 1ull;
+  unsigned long long e = (unsigned long long)(gid ? (int64_t)gid[i] : i) + 1ull, base = 16807ull, s = 1ull;
   while (e) {
     if (e & 1ull) s = (s * base) % m;
     base = (base * base) % m;
@@ -76,8 +80,9 @@ constexpr int kSpBlock = 128;
 
 __global__ void __launch_bounds__(kSpBlock)
 cheby_scaled_spmv_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
-                         const double* __restrict__ val, const double* __restrict__ ds,
-                         const double* __restrict__ x, double* __restrict__ y, int stage) {
+                         const double* __restrict__ val, const double* __restrict__ ds_row,
+                         const double* __restrict__ ds, const double* __restrict__ x, double* __restrict__ y,
+                         int stage) {
   extern __shared__ double cheby_smem[];
   constexpr int kW = kSpBlock / 32;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,7 +109,7 @@ cheby_scaled_spmv_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_
     const int j = c[k];
     s = __dadd_rn(s, __dmul_rn(v[k], __dmul_rn(ds[j], x[j])));
   }
-  y[i] = __dmul_rn(ds[i], s);
+  y[i] = __dmul_rn(ds_row[i], s);
 }
 
 // p = r + beta p  (first step: p = r)
@@ -242,38 +247,56 @@ void cheby_coefficients(double max_eig, double min_eig, double fraction, int ord
 
 }  // namespace
 
-// level l of P: scaling (solve numbering), spectrum estimate, coefficients
+// Level l of P: scaling (solve numbering), spectrum estimate, coefficients.  On the
+// row-partitioned path the level's matrix is the rank's extended matrix (owned rows
+// [o0, o0 + nloc) with columns over the extended space): the vectors live on the extended
+// space, the direction's ghost entries are refreshed before every product, inner products
+// are the owned parts summed over the ranks in rank order.
 int cheby_setup_level(amgb_precond* P, int l) {
   amgb_ctx* ctx = P->ctx;
   Level& L = P->lv[l];
   const DeviceCsr& A = L.A;
-  const int64_t n = A.n;
   if (!A.rp.p) return set_error(ctx, AMGB_ERR_UNSUPPORTED, "Chebyshev smoother: level %d has no CSR operator", l);
+  amgb_dist_state* dist = P->dist && l < P->dist->replicated_from ? P->dist : nullptr;
+  DistLevel* D = dist ? &dist->dl[l] : nullptr;
+  amgb_comm* comm = dist ? dist->comm : nullptr;
+  const int64_t o0 = D ? D->o0 : 0, n = D ? D->nloc : A.n, next = D ? D->next : A.n;
+  const int64_t n_global = D ? D->own.n_global : A.n;
+  const int64_t own_nnz = D ? D->own.M.nnz : A.nnz;
   const unsigned vgrid = (unsigned)div_up(n, kBlock);
   const int64_t nblocks = div_up(n, kBlock);
   DevBuf<double> ds, r, p, s, partial;
-  AMGB_TRY(ds.alloc(ctx, n));
-  AMGB_TRY(r.alloc(ctx, n));
-  AMGB_TRY(p.alloc(ctx, n));
-  AMGB_TRY(s.alloc(ctx, n));
+  AMGB_TRY(ds.alloc_zero(ctx, next));
+  AMGB_TRY(r.alloc(ctx, next));
+  AMGB_TRY(p.alloc_zero(ctx, next));
+  AMGB_TRY(s.alloc(ctx, next));
   AMGB_TRY(partial.alloc(ctx, nblocks));
-  AMGB_LAUNCH(ctx, F_AUX, 12.0 * A.nnz + 8.0 * n, cheby_scaling_kernel, vgrid, kBlock, 0, n, A.rp.p, A.col.p, A.val.p,
-              ds.p);
-  AMGB_LAUNCH(ctx, F_AUX, 8.0 * n, cheby_random_kernel, vgrid, kBlock, 0, n, r.p);
+  AMGB_LAUNCH(ctx, F_AUX, 12.0 * own_nnz + 8.0 * n, cheby_scaling_kernel, vgrid, kBlock, 0, n, o0, A.rp.p, A.col.p,
+              A.val.p, ds.p);
+  AMGB_LAUNCH(ctx, F_AUX, 8.0 * next, cheby_random_kernel, (unsigned)div_up(next, kBlock), kBlock, 0, next,
+              D ? (const int32_t*)D->gid.p : (const int32_t*)nullptr, r.p);
   AMGB_CHECK_LAUNCH(ctx);
+  if (D) AMGB_TRY(plan_sync(ctx, comm, D->plan, ds.p, 8));
   std::vector<double> hp((size_t)nblocks);
   auto dot = [&](const double* x, const double* y, double* out) -> int {
-    AMGB_LAUNCH(ctx, F_AUX, 16.0 * n, cheby_dot_kernel, (unsigned)nblocks, kBlock, 0, n, x, y, partial.p);
+    AMGB_LAUNCH(ctx, F_AUX, 16.0 * n, cheby_dot_kernel, (unsigned)nblocks, kBlock, 0, n, x + o0, y + o0, partial.p);
     AMGB_CHECK_LAUNCH(ctx);
-    AMGB_CUDA(ctx, cudaMemcpyAsync(hp.data(), partial.p, (size_t)nblocks * sizeof(double), cudaMemcpyDeviceToHost,
-                                   ctx->stream));
+    if (nblocks)
+      AMGB_CUDA(ctx, cudaMemcpyAsync(hp.data(), partial.p, (size_t)nblocks * sizeof(double), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
     AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double t = 0.0;
     for (double v : hp) t = t + v;
+    if (comm) {
+      std::vector<double> all((size_t)comm->size);
+      AMGB_TRY(comm->allgather_host(ctx, &t, sizeof t, all.data()));
+      t = 0.0;
+      for (double v : all) t = t + v;
+    }
     *out = t;
     return AMGB_OK;
   };
-  const double avg = n > 0 ? double(A.nnz) / double(n) : 1.0;
+  const double avg = n > 0 ? double(own_nnz) / double(n) : 1.0;
   int stage = (int)(40.0 * avg) / 128 * 128 + 128;
   stage = std::min(std::max(stage, 256), 2048);
   const size_t smem = (size_t)(kSpBlock / 32) * stage * 12;
@@ -281,7 +304,7 @@ int cheby_setup_level(amgb_precond* P, int l) {
     AMGB_CUDA(ctx, cudaFuncSetAttribute(cheby_scaled_spmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         4 * 2048 * 12));
   int max_iter = 10;  // cheby_eig_est
-  if (n < max_iter) max_iter = (int)n;
+  if (n_global < max_iter) max_iter = (int)n_global;
   std::vector<double> tri(max_iter + 2, 0.0), off(max_iter + 2, 0.0);
   double gamma = 1.0;
   int it = 0;
@@ -290,10 +313,13 @@ int cheby_setup_level(amgb_precond* P, int l) {
     AMGB_TRY(dot(r.p, r.p, &gamma));
     if (!(gamma > 0.0)) break;
     const double beta = it == 0 ? 1.0 : gamma / gamma_old;
-    AMGB_LAUNCH(ctx, F_AUX, 24.0 * n, cheby_direction_kernel, vgrid, kBlock, 0, n, (const double*)r.p, beta,
-                it == 0 ? 1 : 0, p.p);
-    AMGB_LAUNCH(ctx, F_AUX, 12.0 * A.nnz + 32.0 * n, cheby_scaled_spmv_kernel, (unsigned)div_up(n, kSpBlock), kSpBlock,
-                smem, n, A.rp.p, A.col.p, A.val.p, (const double*)ds.p, (const double*)p.p, s.p, stage);
+    AMGB_LAUNCH(ctx, F_AUX, 24.0 * n, cheby_direction_kernel, vgrid, kBlock, 0, n, (const double*)(r.p + o0), beta,
+                it == 0 ? 1 : 0, p.p + o0);
+    AMGB_CHECK_LAUNCH(ctx);
+    if (D) AMGB_TRY(plan_sync(ctx, comm, D->plan, p.p, 8));
+    AMGB_LAUNCH(ctx, F_AUX, 12.0 * own_nnz + 32.0 * n, cheby_scaled_spmv_kernel, (unsigned)div_up(n, kSpBlock), kSpBlock,
+                smem, n, A.rp.p + o0, A.col.p, A.val.p, (const double*)(ds.p + o0), (const double*)ds.p,
+                (const double*)p.p, s.p + o0, stage);
     AMGB_CHECK_LAUNCH(ctx);
     double sdotp = 0.0;
     AMGB_TRY(dot(s.p, p.p, &sdotp));
@@ -305,7 +331,8 @@ int cheby_setup_level(amgb_precond* P, int l) {
     tri[it] += alphainv;
     off[it + 1] = alphainv;
     off[it] *= std::sqrt(beta);
-    AMGB_LAUNCH(ctx, F_AUX, 24.0 * n, cheby_residual_kernel, vgrid, kBlock, 0, n, alpha, (const double*)s.p, r.p);
+    AMGB_LAUNCH(ctx, F_AUX, 24.0 * n, cheby_residual_kernel, vgrid, kBlock, 0, n, alpha, (const double*)(s.p + o0),
+                r.p + o0);
     AMGB_CHECK_LAUNCH(ctx);
     ++it;
   }
@@ -317,14 +344,15 @@ int cheby_setup_level(amgb_precond* P, int l) {
     L.cheby_min_eig = tri[0];
   }
   cheby_coefficients(L.cheby_max_eig, L.cheby_min_eig, 0.3, 2, L.cheby_coefs, &L.cheby_degree);
-  // the sweeps run in the C/F-permuted numbering of the level
+  // the sweeps run in the C/F-permuted numbering of the level (owned rows; the work vectors
+  // that are gathered from carry the halo as well)
   AMGB_TRY(L.cheby_ds.alloc(ctx, n));
   AMGB_LAUNCH(ctx, F_AUX, 20.0 * n, cheby_gather_kernel, vgrid, kBlock, 0, n, (const int32_t*)L.perm.p,
-              (const double*)ds.p, L.cheby_ds.p);
+              (const double*)(ds.p + o0), L.cheby_ds.p);
   AMGB_CHECK_LAUNCH(ctx);
   AMGB_TRY(L.cheby_r.alloc(ctx, n));
-  AMGB_TRY(L.cheby_t[0].alloc(ctx, n));
-  if (L.cheby_degree > 1) AMGB_TRY(L.cheby_t[1].alloc(ctx, n));
+  AMGB_TRY(L.cheby_t[0].alloc(ctx, L.n_vec));
+  if (L.cheby_degree > 1) AMGB_TRY(L.cheby_t[1].alloc(ctx, L.n_vec));
   AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the temporaries go out of scope
   return AMGB_OK;
 }

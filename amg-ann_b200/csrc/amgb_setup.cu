@@ -1549,11 +1549,7 @@ int resolve_options(amgb_precond* P) {
     const bool jacobi_like = types[t] == 0 || types[t] == 18;
     const bool ok = jacobi_like || (t == 2 && types[t] == 9);
     if (ok) continue;
-    if (types[t] == 16 && t < 2) {  // Chebyshev on the way down / up (amgb_cheby.cu)
-      if (P->dist)
-        return set_error(ctx, AMGB_ERR_UNSUPPORTED, "the Chebyshev smoother is not available on the row-partitioned path");
-      continue;
-    }
+    if (types[t] == 16 && t < 2) continue;  // Chebyshev on the way down / up (amgb_cheby.cu)
     const bool sequential = types[t] == 1 || types[t] == 2 || types[t] == 3 || types[t] == 4 || types[t] == 6 ||
                             types[t] == 8 || types[t] == 13 || types[t] == 14;
     if (sequential && d.smoother_policy == AMGB_SMOOTHER_SUBSTITUTE) {

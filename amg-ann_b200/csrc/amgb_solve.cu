@@ -873,21 +873,21 @@ static int relax_cheby(amgb_precond* P, int l, const double* f, double* u, doubl
   if (u_is_zero) {
     AMGB_LAUNCH(ctx, F_VEC, 32.0 * n, cheby_zero_kernel, vgrid, kBlock, 0, n, f, ds, L.cheby_coefs[k], r, cur);
     AMGB_CHECK_LAUNCH(ctx);
-  } else {
-    AMGB_TRY(launch_sell(ctx, L.As, 0, n, u, u, 0, EpiChebyFirst{f, ds, r, cur, L.cheby_coefs[k]}, fam,
-                         mat + 40.0 * n));
+  } else {  // (row-partitioned path: the halo of the gather source is refreshed first)
+    AMGB_TRY(launch_sell_halo(P, l, L.As, 0, n, u, u, 0, EpiChebyFirst{f, ds, r, cur, L.cheby_coefs[k]}, fam,
+                              mat + 40.0 * n, u, u, 0, u));
   }
   for (int i = k - 1; i >= 1; --i) {
-    AMGB_TRY(launch_sell(ctx, L.As, 0, n, cur, cur, 0, EpiChebyMid{r, ds, nxt, L.cheby_coefs[i]}, fam,
-                         mat + 32.0 * n));
+    AMGB_TRY(launch_sell_halo(P, l, L.As, 0, n, cur, cur, 0, EpiChebyMid{r, ds, nxt, L.cheby_coefs[i]}, fam,
+                              mat + 32.0 * n, cur, cur, 0, cur));
     std::swap(cur, nxt);
   }
   if (k == 0) {
     AMGB_LAUNCH(ctx, F_VEC, 24.0 * n, add_kernel, vgrid, kBlock, 0, n, (const double*)u, (const double*)cur, out);
     AMGB_CHECK_LAUNCH(ctx);
   } else {
-    AMGB_TRY(launch_sell(ctx, L.As, 0, n, cur, cur, 0, EpiChebyLast{u, r, ds, out, L.cheby_coefs[0]}, fam,
-                         mat + 40.0 * n));
+    AMGB_TRY(launch_sell_halo(P, l, L.As, 0, n, cur, cur, 0, EpiChebyLast{u, r, ds, out, L.cheby_coefs[0]}, fam,
+                              mat + 40.0 * n, cur, cur, 0, cur));
   }
   return AMGB_OK;
 }
@@ -1613,11 +1613,13 @@ int finish_solve_setup_dist(amgb_precond* P) {
         AMGB_TRY(ds->repl_full.alloc(ctx, D.nc_global));
       }
     }
+    if (P->relax_down == 16) AMGB_TRY(cheby_setup_level(P, l));  // collective: inner products over all ranks
+    const int aux_type = P->relax_down == 16 ? (P->relax_coarse == 9 ? 0 : P->relax_coarse) : P->relax_down;
     AMGB_TRY(L.inv_relax.alloc(ctx, nloc));
     AMGB_DISPATCH_T(L.As.T, AMGB_LAUNCH(ctx, F_AUX, L.As.csr_bytes() + 8.0 * nloc, sell_aux_kernel<TT>,
                                         (unsigned)div_up(L.As.nslices * 32, kBlock), kBlock, 0,
                                         (int)L.As.nslices, (int)nloc, L.As.slice_ptr.p, L.As.col.p, L.As.val.p,
-                                        P->relax_down, L.inv_relax.p));
+                                        aux_type, L.inv_relax.p));
     AMGB_CHECK_LAUNCH(ctx);
     AMGB_TRY(L.tmp.alloc(ctx, L.n_vec));
     if (l > 0) {

@@ -180,3 +180,44 @@ def test_library_exchanges_still_work_without_peer_windows(gpu_ctx, monkeypatch)
         assert abs(p["niters"] - ctl1.last_step()) <= 1
         k = min(len(p["hist"]), len(ctl1.history))
         assert (np.abs(p["hist"][:k] - ctl1.history[:k]) <= 1e-10 * ctl1.history[:k]).all()
+
+
+@pytest.mark.parametrize("replicate_below", [0, 400])
+def test_chebyshev_smoother_partitioned_equals_single_device(gpu_ctx, replicate_below):
+    """Chebyshev (hypre relax type 16) on the row-partitioned path: the spectrum estimate is a
+    collective CG/Lanczos run, the sweeps exchange the halo of their gather source.  The
+    hierarchy is identical; coefficients and residuals agree to rounding (the inner products
+    are summed per rank, so the last bits depend on the partition)."""
+    from helpers import spd_laplacian
+    R = ab.RelaxationType
+    s = spd_laplacian(12, seed=4, decades=1.0)
+    data = device_data(0.25, relaxation_type_up=R.Chebyshev, relaxation_type_down=R.Chebyshev,
+                       dist_replicate_below=replicate_below)
+    A1, P1, ctl1, x1 = _single(gpu_ctx, s, data)
+    starts = [0, 500, 1100, s.n]
+    rp = s.rowptr
+
+    def fn(rank, comm):
+        b, e = starts[rank], starts[rank + 1]
+        A = dist.DistSparseMatrix(comm, s.n, b, e, (rp[b:e + 1] - rp[b]).astype(np.int64), s.col[rp[b]:rp[e]],
+                                  s.val[rp[b]:rp[e]])
+        P = dist.DistPreconditionBoomerAMG()
+        P.initialize(A, data)
+        ctl = ab.SolverControl(s.n, 1e-8)
+        x = s.x0[b:e].copy()
+        dist.DistSolverCG(ctl).solve(A, x, s.rhs[b:e], P)
+        out = dict(rows=P.level_stats()["rows"], x=x, hist=ctl.history, niters=ctl.last_step())
+        P.close()
+        A.close()
+        return out
+
+    parts = dist.run_local_group(3, fn)
+    for p in parts:
+        assert np.array_equal(p["rows"], P1.level_stats()["rows"])
+        assert abs(p["niters"] - ctl1.last_step()) <= 1
+        k = min(len(p["hist"]), len(ctl1.history))
+        d = np.abs(p["hist"][:k] - ctl1.history[:k])
+        assert (d[:10] <= 1e-10 * ctl1.history[:10]).all() and (d <= 1e-8 * ctl1.history[:k]).all()
+        assert np.array_equal(p["hist"], parts[0]["hist"])
+    x = np.concatenate([p["x"] for p in parts])
+    assert np.abs(x - x1).max() <= 1e-8 * np.abs(x1).max()

@@ -425,3 +425,23 @@ def test_chebyshev_smoothed_pcg_converges_to_the_direct_solution():
         assert rc == 0 and nit < 60
         xd = spl.spsolve(s.csr.tocsc(), s.rhs)
         assert np.abs(x - xd).max() <= 1e-6 * np.abs(xd).max()
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU restatement timed on the host cores) on a tiny
+    sample: one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-m", "8", "--cells", "12"], capture_output=True, text=True,
+                         timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "s/system" and line["higher_is_better"] is False
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"]
+    assert line["metric"] == "AMG-PCG setup+solve seconds per system" and "workload" in line["config"]

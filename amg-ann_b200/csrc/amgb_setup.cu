@@ -1068,6 +1068,7 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
   {
     auto kern = spgemm_symbolic_kernel<G, CAP_SYM>;
     const size_t smem = sizeof(unsigned) * (size_t)kGroups * CAP_SYM;
+    if (smem > 48 * 1024) AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, kern, grid, kSpThreads, smem, n, (const int32_t*)nullptr, A.rp.p, A.col.p,
                 B.rp.p, B.col.p, count.p, ovf1.p, info.p);
     AMGB_CHECK_LAUNCH(ctx);
@@ -1106,10 +1107,12 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
     const double bytes = in_bytes + 12.0 * nnz + 4.0 * n;
     if (sorted) {
       auto kern = spgemm_numeric_kernel<G, CAP_NUM, true>;
+      if (smem > 48 * 1024) AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       AMGB_LAUNCH(ctx, F_SPGEMM, bytes, kern, grid, kSpThreads, smem, n, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p,
                   B.val.p, C.rp.p, C.col.p, C.val.p, ovf1.p, info.p);
     } else {
       auto kern = spgemm_numeric_kernel<G, CAP_NUM, false>;
+      if (smem > 48 * 1024) AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       AMGB_LAUNCH(ctx, F_SPGEMM, bytes, kern, grid, kSpThreads, smem, n, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p,
                   B.val.p, C.rp.p, C.col.p, C.val.p, ovf1.p, info.p);
     }
@@ -1143,9 +1146,18 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
 
 // sorted = false: the caller does not need ascending columns (inner operand of R*(A*P))
 int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, bool sorted) {
+  const double avg_a = A.n > 0 ? double(A.nnz) / double(A.n) : 0.0;
   const double avg_b = B.n > 0 ? double(B.nnz) / double(B.n) : 0.0;
-  if (avg_b <= 8.0) return spgemm_impl<8, 256, 128>(ctx, A, B, C, sorted);
-  return spgemm_impl<32, 1024, 512>(ctx, A, B, C, sorted);
+  if (avg_b > 8.0) return spgemm_impl<32, 1024, 512>(ctx, A, B, C, sorted);
+  // short rows of B (A*P): 8 lanes per row; the table tier follows the expected row of the
+  // product (about a third of the products are distinct on the FE stencils measured: 27-point
+  // Poisson 120 -> 35).  Rows that outgrow their tier go to the one-warp-per-row second stage,
+  // which is much slower, so wide operators (3 DoF/node elasticity, coarse levels) start higher.
+  double est = avg_a * avg_b / 3.0;
+  if (const char* e = std::getenv("AMGB_SPGEMM_TIER")) est = e[0] == '0' ? 0.0 : (e[0] == '1' ? 100.0 : 1000.0);
+  if (est <= 50.0) return spgemm_impl<8, 256, 128>(ctx, A, B, C, sorted);
+  if (est <= 110.0) return spgemm_impl<8, 512, 256>(ctx, A, B, C, sorted);
+  return spgemm_impl<8, 1024, 512>(ctx, A, B, C, sorted);
 }
 
 // ---- setup stages as host functions (shared with the row-partitioned driver) ----

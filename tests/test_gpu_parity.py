@@ -416,3 +416,13 @@ def test_one_uploaded_matrix_serves_several_contexts_at_once(gpu_ctx):
         assert np.array_equal(got[th][0]["p_res"], want[th][0]["p_res"])
         assert np.array_equal(got[th][1], want[th][1])
         assert np.array_equal(got[th][0]["nrows"], want[th][0]["nrows"])
+
+
+@pytest.mark.parametrize("tier", ["1", "2"])
+def test_spgemm_table_tiers_give_the_same_hierarchy(gpu_ctx, monkeypatch, tier):
+    """AMGB_SPGEMM_TIER forces the wider first-stage hash tables of A*P (picked for wide
+    operators such as 3-DoF elasticity) on a small system: same bits as the oracle."""
+    monkeypatch.setenv("AMGB_SPGEMM_TIER", tier)
+    s = ab.gen.elasticity_q1(5, 2, 3, 10.0 ** ab.gen.checkerboard_epsv(2, 3, 2.0))
+    A, P, H = _both(gpu_ctx, s, device_data(0.25))
+    _assert_hierarchy_identical(P, H)

@@ -54,3 +54,31 @@ def spd_laplacian(m, seed=0, decades=2.0):
     return SimpleNamespace(n=n, nnz=A.nnz, rowptr=A.indptr.astype(np.int64), col=A.indices.astype(np.int32),
                            val=A.data.astype(np.float64), rhs=rng.normal(size=n), x0=np.zeros(n), csr=A,
                            rowptr32=lambda: A.indptr.astype(np.int32))
+
+
+def hub_leaf_csr(nh, nl, per_leaf, leaf_leaf, seed):
+    """SPD M-matrix on nh hubs + nl leaves: every leaf is coupled to `per_leaf` hubs and to about
+    `leaf_leaf` other leaves, hubs are not coupled to each other.  PMIS picks the hubs (largest
+    measures) as C points, so every leaf's interpolation row has `per_leaf` entries."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    n = nh + nl
+    rows, cols, vals = [], [], []
+    for leaf in range(nl):
+        for h in rng.choice(nh, size=per_leaf, replace=False):
+            w = -rng.uniform(0.5, 1.0)
+            rows += [nh + leaf, h]
+            cols += [h, nh + leaf]
+            vals += [w, w]
+        for o in rng.choice(nl, size=leaf_leaf, replace=False):
+            if o != leaf:
+                w = -rng.uniform(0.5, 1.0)
+                rows += [nh + leaf, nh + o]
+                cols += [nh + o, nh + leaf]
+                vals += [w, w]
+    B = sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr()
+    B.sum_duplicates()
+    d = -np.asarray(B.sum(axis=1)).ravel() + rng.random(n) * 0.1 + 1e-3
+    A = (B + sp.diags(d)).tocsr()
+    A.sort_indices()
+    return A

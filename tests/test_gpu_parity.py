@@ -426,3 +426,28 @@ def test_spgemm_table_tiers_give_the_same_hierarchy(gpu_ctx, monkeypatch, tier):
     s = ab.gen.elasticity_q1(5, 2, 3, 10.0 ** ab.gen.checkerboard_epsv(2, 3, 2.0))
     A, P, H = _both(gpu_ctx, s, device_data(0.25))
     _assert_hierarchy_identical(P, H)
+
+
+@pytest.mark.parametrize("nh,nl,per_leaf,leaf_leaf", [(100, 300, 30, 4), (160, 400, 70, 6)])
+def test_setup_long_interpolation_rows(gpu_ctx, nh, nl, per_leaf, leaf_leaf):
+    """Hub/leaf systems: every leaf depends strongly on 30 (70) hubs, which PMIS makes the C
+    points, and on a few other leaves.  Interpolation rows longer than the lane-parallel limit
+    (16) and than the shared-memory stage (48), rows of A spanning several 32-entry chunks,
+    transposed rows past the two-entries-per-lane rank sort.  Still the oracle's bits."""
+    from helpers import hub_leaf_csr
+    from types import SimpleNamespace
+    M = hub_leaf_csr(nh, nl, per_leaf, leaf_leaf, 5)
+    s = SimpleNamespace(n=M.shape[0], col=M.indices.astype(np.int32), val=M.data.astype(np.float64),
+                        rowptr32=lambda: M.indptr.astype(np.int32))
+    A, P, H = _both(gpu_ctx, s, device_data(0.05))
+    prp, _, _, nc = P.P(0)
+    assert nc == nh and np.diff(prp).max() == per_leaf      # the long-row routes are really taken
+    _assert_hierarchy_identical(P, H)
+    rhs = np.random.default_rng(1).normal(size=s.n)
+    ctl = ab.SolverControl(s.n, 1e-9)
+    x = np.zeros(s.n)
+    ab.SolverCG(ctl).solve(A, x, rhs, P)
+    rc, xo, nit, hist = H.cg_solve(rhs, np.zeros(s.n), abs_tol=1e-9)
+    assert rc == 0 and abs(ctl.last_step() - nit) <= 1
+    k = min(len(hist), len(ctl.history))
+    assert (np.abs(ctl.history[:k] - hist[:k]) <= 1e-9 * hist[:k]).all()

@@ -110,9 +110,13 @@ class Preconditioner {
   ~Preconditioner() { reset(); }
   Preconditioner(const Preconditioner&) = delete;
   Preconditioner& operator=(const Preconditioner&) = delete;
-  void initialize(const Matrix& A, const amgb_boomeramg_data& data) {
+  void initialize(const Matrix& A, const amgb_boomeramg_data& data) { initialize(A.context(), A, data); }
+  // On another context (stream, host thread) of the same device than the one that uploaded
+  // the matrix: an uploaded matrix is read-only, so the independent systems of a theta sweep
+  // can be in flight side by side (include/amgb.h, amgb_matrix_upload_csr).
+  void initialize(const Context& ctx, const Matrix& A, const amgb_boomeramg_data& data) {
     reset();
-    ctx_ = &A.context();
+    ctx_ = &ctx;
     ctx_->check(amgb_precond_initialize(ctx_->get(), A.get(), &data, &h_), "amgb_precond_initialize");
   }
   void reset() {

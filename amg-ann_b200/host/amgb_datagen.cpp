@@ -5,12 +5,15 @@
 //   amgb_datagen [--m 100] [--pattern-size 4] [--mode 3] [--contrast 6 | --seed S --eps-max 6]
 //                [--theta 0.05,0.96,0.05] [--max-row-sum 0.9] [--tol 1e-8] [--details 1]
 //                [--make-view 0|1] [--view-size 75] [--systems 1] [--threads 1]
-//                [--device-assembly 0|1] [--setting NAME] --out stats.csv
+//                [--theta-lanes 1] [--device-assembly 0|1] [--setting NAME] --out stats.csv
 //
 // --systems N --threads T: N independent systems (seeds S..S+N-1, ref 00_data-generation.py
 // :105-116 fans them out over processes) are processed by T host threads, each with its own
 // amgb context/stream on the same GPU, so small systems overlap on the device.  Rows of one
 // system are written contiguously; systems appear in completion order.
+// --theta-lanes L: the theta values of ONE system are independent too; L host threads (one
+// context/stream each) sweep them side by side on the shared, read-only device matrix.  Rows
+// keep the order of the sweep.
 #include <atomic>
 #include <cstring>
 #include <ctime>
@@ -26,7 +29,7 @@ namespace {
 
 struct Args {
   int m = 100, ps = 4, mode = 3, details = 1, make_view = 0, view_size = 75, systems = 1, threads = 1;
-  int device_assembly = 0;
+  int device_assembly = 0, theta_lanes = 1;
   double contrast = 6.0, eps_max = 6.0, t0 = 0.05, t1 = 0.96, dt = 0.05, mrs = 0.9, tol = 1e-8;
   long seed = -1;
   std::string out, setting = "synthetic";
@@ -51,6 +54,7 @@ bool parse(int argc, char** argv, Args& a) {
     else if (k == "--systems") a.systems = std::atoi(val());
     else if (k == "--threads") a.threads = std::atoi(val());
     else if (k == "--device-assembly") a.device_assembly = std::atoi(val());
+    else if (k == "--theta-lanes") a.theta_lanes = std::atoi(val());
     else if (k == "--setting") a.setting = val();
     else if (k == "--out") a.out = val();
     else return false;
@@ -107,15 +111,58 @@ void run_system(const Args& a, long seed, std::ostream& out, Totals& tot) {
     tot.views++;
     return;
   }
-  for (double t = a.t0; t <= a.t1; t += a.dt) {  // accumulation, as ref t2 main.cpp:443
-    solution = zero_solution;
-    const amgb::harness::BoomerAMGData data(true, t, a.mrs, 0, a.details != 0);
+  std::vector<double> thetas;
+  for (double t = a.t0; t <= a.t1; t += a.dt) thetas.push_back(t);  // accumulation, as ref t2 main.cpp:443
+  if (a.theta_lanes <= 1) {
+    for (double t : thetas) {
+      solution = zero_solution;
+      const amgb::harness::BoomerAMGData data(true, t, a.mrs, 0, a.details != 0);
+      print_stats();
+      amgb::harness::SolveRecord rec;
+      amgb::harness::amg_solve(data, a.tol, out, system_matrix, system_rhs, solution, &rec);
+      tot.setup_us += rec.t_setup_us;
+      tot.solve_us += rec.t_solve_us;
+      tot.solves++;
+    }
+    return;
+  }
+  // theta lanes: the matrix is uploaded once here, then only read
+  system_matrix.device();
+  std::vector<std::string> rows(thetas.size());
+  std::atomic<size_t> next{0};
+  std::mutex err_mutex;
+  std::string error;
+  auto lane = [&]() {
+    try {
+      PETScWrappers::MPI::Vector x(n);
+      for (;;) {
+        // largest theta (most iterations) first; the rows are emitted in sweep order below
+        const size_t k = next++;
+        if (k >= thetas.size()) break;
+        const size_t idx = thetas.size() - 1 - k;
+        x = zero_solution;
+        const amgb::harness::BoomerAMGData data(true, thetas[idx], a.mrs, 0, a.details != 0);
+        std::ostringstream row;
+        row << std::scientific << std::setprecision(17);
+        amgb::harness::SolveRecord rec;
+        amgb::harness::amg_solve(data, a.tol, row, system_matrix, system_rhs, x, &rec);
+        rows[idx] = row.str();
+        tot.setup_us += rec.t_setup_us;
+        tot.solve_us += rec.t_solve_us;
+        tot.solves++;
+      }
+    } catch (const std::exception& e) {
+      std::lock_guard<std::mutex> g(err_mutex);
+      error = e.what();
+    }
+  };
+  std::vector<std::thread> lanes;
+  for (int t = 0; t < a.theta_lanes; ++t) lanes.emplace_back(lane);
+  for (auto& t : lanes) t.join();
+  if (!error.empty()) throw std::runtime_error(error);
+  for (const std::string& r : rows) {
     print_stats();
-    amgb::harness::SolveRecord rec;
-    amgb::harness::amg_solve(data, a.tol, out, system_matrix, system_rhs, solution, &rec);
-    tot.setup_us += rec.t_setup_us;
-    tot.solve_us += rec.t_solve_us;
-    tot.solves++;
+    out << r;
   }
 }
 

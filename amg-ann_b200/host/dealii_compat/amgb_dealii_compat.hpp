@@ -393,7 +393,9 @@ class PreconditionBoomerAMG {
     data_ = data;
     matrix_ = &matrix;
     const amgb_boomeramg_data d = data.to_c();
-    prec_.initialize(matrix.device(), d);
+    // on the calling thread's context: threads that sweep theta over one matrix side by side
+    // share the (read-only) device copy and work on their own streams
+    prec_.initialize(amgb::compat::default_context(), matrix.device(), d);
     if (data.output_details) {
       const amgb::LevelStats st = prec_.level_stats();
       std::vector<int64_t> nnzP(st.rows.size(), 0);
@@ -436,7 +438,7 @@ class SolverCG {
   void solve(const MPI::SparseMatrix& A, MPI::Vector& x, const MPI::Vector& b,
              const PreconditionBoomerAMG& preconditioner) {
     const amgb::Matrix& Ad = A.device();
-    const amgb::Context& ctx = Ad.context();
+    const amgb::Context& ctx = preconditioner.backend().context();
     const int64_t max_steps = control_.max_steps();
     std::vector<double> hist((size_t)std::min<int64_t>(max_steps, (int64_t)1 << 22) + 1);
     int64_t nit = 0;

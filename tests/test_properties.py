@@ -10,7 +10,9 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 from helpers import device_data, random_spd_csr
 from oracle import binding as orc
 
-SETTINGS = dict(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+# derandomize: the same examples on every run (a CI gate must not depend on the draw)
+SETTINGS = dict(max_examples=12, deadline=None, derandomize=True, database=None,
+                suppress_health_check=[HealthCheck.too_slow])
 
 
 def _csr(n, density, seed):

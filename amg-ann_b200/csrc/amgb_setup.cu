@@ -1036,6 +1036,16 @@ spgemm_numeric_global_kernel(const int32_t* __restrict__ ovf_rows, int novf, int
     big_row(keys, vals, H, lgH, ovf_rows[idx], arp, acol, aval, brp, bcol, bval, crp, ccol, cval);
 }
 
+// 64-bit total of the row counts: the 32-bit scan below would wrap silently
+__global__ void __launch_bounds__(kBlock)
+sum_counts_kernel(int64_t n, const int32_t* __restrict__ count, unsigned long long* __restrict__ total) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  unsigned long long v = i < n ? (unsigned long long)count[i] : 0ull;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(total, v);
+}
+
 static int read_ovf(amgb_ctx* ctx, const int32_t* ovf_info, int* novf, int* maxv) {
   int32_t* info = (int32_t*)ctx->pinned;
   AMGB_CUDA(ctx, cudaMemcpyAsync(info, ovf_info, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1094,9 +1104,18 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
       }
     }
   }
+  DevBuf<unsigned long long> total;
+  AMGB_TRY(total.alloc_zero(ctx, 1));
+  AMGB_LAUNCH(ctx, F_SCAN, 4.0 * n, sum_counts_kernel, (unsigned)div_up(n, kBlock), kBlock, 0, n,
+              (const int32_t*)count.p, total.p);
   AMGB_TRY(exclusive_scan_i32(ctx, count.p, C.rp.p, n));
-  int32_t nnz = 0;
-  AMGB_TRY(read_i32(ctx, C.rp.p + n, &nnz));
+  int64_t nnz64 = 0;
+  AMGB_TRY(read_i64(ctx, (const int64_t*)total.p, &nnz64));
+  if (nnz64 > (int64_t)INT32_MAX)
+    return set_error(ctx, AMGB_ERR_RANGE,
+                     "a sparse product of the setup has %lld entries: row pointers are 32-bit, partition the system "
+                     "over more devices", (long long)nnz64);
+  const int32_t nnz = (int32_t)nnz64;
   C.nnz = nnz;
   AMGB_TRY(C.col.alloc(ctx, nnz));
   AMGB_TRY(C.val.alloc(ctx, nnz));

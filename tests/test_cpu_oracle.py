@@ -445,3 +445,25 @@ def test_reference_arm_prints_the_contract_line():
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"]
     assert line["metric"] == "AMG-PCG setup+solve seconds per system" and "workload" in line["config"]
+
+
+def test_chebyshev_coefficients_are_the_scaled_chebyshev_polynomial():
+    """The coefficients restated from hypre's par_cheby.c are checked against the definition:
+    the residual polynomial 1 - t p(t) of the order-2 smoother is T_2((theta - t)/delta) /
+    T_2(theta/delta) on [lower, upper] = [(1.1 max - min) 0.3 + min, 1.1 max]."""
+    from helpers import spd_laplacian
+    s = spd_laplacian(8, seed=7)
+    R = ab.RelaxationType
+    d = device_data(0.25, relaxation_type_up=R.Chebyshev, relaxation_type_down=R.Chebyshev)
+    H = orc.Hierarchy(s.rowptr32(), s.col, s.val, d.to_struct())
+    for l in range(H.num_levels):
+        mx, mn, c = H.level_cheby(l)
+        upper = 1.1 * mx
+        lower = (upper - mn) * 0.3 + mn
+        theta, delta = (upper + lower) / 2, (upper - lower) / 2
+        t = np.linspace(0.0, upper, 201)
+        T2 = lambda x: 2 * x * x - 1          # noqa: E731
+        want = T2((theta - t) / delta) / T2(theta / delta)
+        got = 1 - t * (c[0] + c[1] * t)
+        assert np.allclose(got, want, rtol=0, atol=1e-12)
+        assert np.abs(got[t >= lower]).max() <= 1.0 / T2(theta / delta) + 1e-12   # equioscillation bound

@@ -183,6 +183,19 @@ class Context:
         return out
 
 
+    def routes(self):
+        """{route name: times taken} since creation / reset_routes (include/amgb.h)."""
+        L = amgb_lib()
+        out = {}
+        for r in range(L.amgb_route_count()):
+            v = C.c_int64()
+            _chk(self._h, L.amgb_ctx_get_route(self._h, r, C.byref(v)), "get_route")
+            out[L.amgb_route_name(r).decode()] = v.value
+        return out
+
+    def reset_routes(self):
+        amgb_lib().amgb_ctx_reset_routes(self._h)
+
     def level_timers(self, max_levels=32):
         """{family: [dict(ms, launches, bytes) per level]} for launches timed with timers on."""
         L = amgb_lib()

@@ -92,7 +92,8 @@ AMGB_SYMBOLS = [
     "amgb_precond_get_A_csr", "amgb_precond_get_P_csr", "amgb_cg_solve",
     "amgb_cg_solve_device", "amgb_make_view", "amgb_make_view_normalized", "amgb_ctx_enable_timers",
     "amgb_ctx_reset_timers", "amgb_timer_count", "amgb_timer_name", "amgb_ctx_get_timer",
-    "amgb_ctx_get_timer_level",
+    "amgb_ctx_get_timer_level", "amgb_route_count", "amgb_route_name", "amgb_ctx_get_route",
+    "amgb_ctx_reset_routes",
     # row-partitioned path
     "amgb_nccl_unique_id", "amgb_comm_create_nccl", "amgb_local_group_create",
     "amgb_local_group_destroy", "amgb_local_group_abort", "amgb_comm_create_local", "amgb_comm_destroy", "amgb_comm_rank",
@@ -172,6 +173,10 @@ def amgb_lib():
         _sig(L.amgb_timer_name, C.c_char_p, C.c_int)
         _sig(L.amgb_ctx_get_timer, C.c_int, vp, C.c_int, c_f64p, c_i64p, c_f64p)
         _sig(L.amgb_ctx_get_timer_level, C.c_int, vp, C.c_int, C.c_int, c_f64p, c_i64p, c_f64p)
+        _sig(L.amgb_route_count, C.c_int)
+        _sig(L.amgb_route_name, C.c_char_p, C.c_int)
+        _sig(L.amgb_ctx_get_route, C.c_int, vp, C.c_int, c_i64p)
+        _sig(L.amgb_ctx_reset_routes, C.c_int, vp)
         _sig(L.amgb_nccl_unique_id, C.c_int, vp, C.c_int)
         _sig(L.amgb_comm_create_nccl, C.c_int, vp, C.c_int, C.c_int, vp, C.POINTER(vp))
         _sig(L.amgb_local_group_create, C.c_int, C.c_int, C.POINTER(vp))

@@ -214,11 +214,32 @@ static const char* kFamilyNames[F_COUNT] = {
     "coarsen",  "interp", "transpose", "spgemm",   "scan",    "aux",  "pool",
     "smooth_l0", "residual_l0", "restrict_l0", "prolong_l0"};
 
+static const char* kRouteNames[R_COUNT] = {
+    "sell_t1_stream",   "sell_t_multi",      "spgemm_g8_t128",  "spgemm_g8_t256",    "spgemm_g8_t512",
+    "spgemm_g32",       "spgemm_sym_big",    "spgemm_sym_global", "spgemm_num_big",  "spgemm_num_global",
+    "spgemm_rowreg",    "cycle_graph",       "cycle_tail_fused", "pcg_device_loop",  "dense_stepwise"};
+
 }  // namespace amgb
 
 using namespace amgb;
 
 extern "C" {
+
+int amgb_route_count(void) { return R_COUNT; }
+
+const char* amgb_route_name(int route) { return (route >= 0 && route < R_COUNT) ? kRouteNames[route] : ""; }
+
+int amgb_ctx_get_route(const amgb_ctx* ctx, int route, int64_t* count) {
+  if (!ctx || !count || route < 0 || route >= R_COUNT) return AMGB_ERR_BAD_ARG;
+  *count = ctx->routes[route];
+  return AMGB_OK;
+}
+
+int amgb_ctx_reset_routes(amgb_ctx* ctx) {
+  if (!ctx) return AMGB_ERR_BAD_ARG;
+  for (int r = 0; r < R_COUNT; ++r) ctx->routes[r] = 0;
+  return AMGB_OK;
+}
 
 int amgb_version(void) { return AMGB_VERSION; }
 

@@ -46,6 +46,28 @@ struct TimerRec {
 
 constexpr int kTimerLevels = 32;
 
+// Code routes taken on the host side of a context (amgb_route_name): which SELL layout,
+// which SpGEMM table tier / overflow stage, captured cycle ... so that parity tests at the
+// benchmarked sizes can assert that the routes carrying the benchmark were exercised.
+enum Route : int {
+  R_SELL_T1_STREAM = 0,  // operator stored with one lane per row (streaming loads)
+  R_SELL_T_MULTI,        // operator stored with several lanes per row
+  R_SPGEMM_G8_T128,      // A*P-type product, 8 lanes per row, numeric table 128 slots
+  R_SPGEMM_G8_T256,
+  R_SPGEMM_G8_T512,
+  R_SPGEMM_G32,          // long B rows: one warp per row
+  R_SPGEMM_SYM_BIG,      // symbolic overflow: big shared-memory table
+  R_SPGEMM_SYM_GLOBAL,   // symbolic overflow: global-memory table
+  R_SPGEMM_NUM_BIG,
+  R_SPGEMM_NUM_GLOBAL,
+  R_SPGEMM_ROWREG,       // short product rows accumulated in registers (no hash table)
+  R_CYCLE_GRAPH,         // V-cycle replayed from a captured CUDA graph
+  R_CYCLE_TAIL_FUSED,    // coarse levels of the cycle run inside one persistent kernel
+  R_PCG_DEVICE_LOOP,     // PCG iterations issued without a per-iteration host read
+  R_DENSE_STEPWISE,      // coarsest grid factorised by the grid-wide step kernels (n > 96)
+  R_COUNT
+};
+
 }  // namespace amgb
 
 struct amgb_ctx {
@@ -67,6 +89,7 @@ struct amgb_ctx {
   double lvl_ms[amgb::F_COUNT][amgb::kTimerLevels] = {{0}};
   double lvl_bytes[amgb::F_COUNT][amgb::kTimerLevels] = {{0}};
   int64_t lvl_launches[amgb::F_COUNT][amgb::kTimerLevels] = {{0}};
+  int64_t routes[amgb::R_COUNT] = {0};
   // Private stream-ordered memory pool.  With the device's default pool, a block freed on
   // one context's stream can be handed to another context with a hidden dependency on the
   // first stream; contexts that run independent systems side by side must not couple.

@@ -1084,6 +1084,7 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
     AMGB_CHECK_LAUNCH(ctx);
     AMGB_TRY(read_ovf(ctx, info.p, &novf, &maxv));
     if (novf > 0) {
+      ctx->routes[R_SPGEMM_SYM_BIG]++;
       auto big = spgemm_symbolic_kernel<32, kBigSym>;
       const size_t bsmem = sizeof(unsigned) * (size_t)(kSpThreads / 32) * kBigSym;
       AMGB_CUDA(ctx, cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
@@ -1096,6 +1097,7 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
         const long long want = std::min<long long>(2ll * maxv, 2ll * B.ncols);
         while ((1ll << lgH) < want) ++lgH;
         const int H = 1 << lgH;
+        ctx->routes[R_SPGEMM_SYM_GLOBAL]++;
         DevBuf<unsigned> tables;
         AMGB_TRY(tables.alloc(ctx, (size_t)fb_warps * H));
         AMGB_LAUNCH(ctx, F_SPGEMM, 0.0, spgemm_symbolic_global_kernel, fb_blocks, kSpThreads, 0, ovf2.p, novf, H, lgH,
@@ -1138,6 +1140,7 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
     AMGB_CHECK_LAUNCH(ctx);
     AMGB_TRY(read_ovf(ctx, info.p, &novf, &maxv));
     if (novf > 0) {
+      ctx->routes[R_SPGEMM_NUM_BIG]++;
       auto big = spgemm_numeric_big_kernel<kBigNum>;
       const size_t bsmem = (sizeof(unsigned) + sizeof(double)) * (size_t)(kSpThreads / 32) * kBigNum;
       AMGB_CUDA(ctx, cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
@@ -1150,6 +1153,7 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
         int lgH = 5;
         while ((1ll << lgH) < 2ll * maxv) ++lgH;
         const int H = 1 << lgH;
+        ctx->routes[R_SPGEMM_NUM_GLOBAL]++;
         DevBuf<unsigned> kt;
         DevBuf<double> vt;
         AMGB_TRY(kt.alloc(ctx, (size_t)fb_warps * H));
@@ -1167,13 +1171,17 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
 int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, bool sorted) {
   const double avg_a = A.n > 0 ? double(A.nnz) / double(A.n) : 0.0;
   const double avg_b = B.n > 0 ? double(B.nnz) / double(B.n) : 0.0;
-  if (avg_b > 8.0) return spgemm_impl<32, 1024, 512>(ctx, A, B, C, sorted);
+  if (avg_b > 8.0) {
+    ctx->routes[R_SPGEMM_G32]++;
+    return spgemm_impl<32, 1024, 512>(ctx, A, B, C, sorted);
+  }
   // short rows of B (A*P): 8 lanes per row; the table tier follows the expected row of the
   // product (about a third of the products are distinct on the FE stencils measured: 27-point
   // Poisson 120 -> 35).  Rows that outgrow their tier go to the one-warp-per-row second stage,
   // which is much slower, so wide operators (3 DoF/node elasticity, coarse levels) start higher.
   double est = avg_a * avg_b / 3.0;
   if (const char* e = std::getenv("AMGB_SPGEMM_TIER")) est = e[0] == '0' ? 0.0 : (e[0] == '1' ? 100.0 : 1000.0);
+  ctx->routes[est <= 50.0 ? R_SPGEMM_G8_T128 : (est <= 110.0 ? R_SPGEMM_G8_T256 : R_SPGEMM_G8_T512)]++;
   if (est <= 50.0) return spgemm_impl<8, 256, 128>(ctx, A, B, C, sorted);
   if (est <= 110.0) return spgemm_impl<8, 512, 256>(ctx, A, B, C, sorted);
   return spgemm_impl<8, 1024, 512>(ctx, A, B, C, sorted);

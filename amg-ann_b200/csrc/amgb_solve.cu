@@ -172,6 +172,7 @@ static int csr_to_sell(amgb_ctx* ctx, const DeviceCsr& A, const int32_t* row_per
   S.ncols = A.ncols;
   S.nnz = A.nnz;
   S.T = pick_T(A);
+  ctx->routes[S.T == 1 ? R_SELL_T1_STREAM : R_SELL_T_MULTI]++;
   S.nslices = div_up(A.n * S.T, 32);
   DevBuf<int32_t> width;
   AMGB_TRY(width.alloc(ctx, S.nslices));
@@ -665,6 +666,7 @@ static int setup_dense_from(amgb_precond* P, const DeviceCsr& CA) {
   if (n <= 96) {
     AMGB_LAUNCH(ctx, F_COARSE, 8.0 * n * n, dense_factor_kernel, 1, kBlock, 0, (int)n, P->dense.p);
   } else {
+    ctx->routes[R_DENSE_STEPWISE]++;
     DevBuf<double> fac;
     AMGB_TRY(fac.alloc(ctx, n));
     for (int k = 0; k + 1 < (int)n; ++k) {
@@ -1065,6 +1067,7 @@ int vcycle_apply(amgb_precond* P, double* z, const double* r) {
     P->graph_r = r;
   }
   AMGB_CUDA(ctx, cudaGraphLaunch(P->vcycle_graph, ctx->stream));
+  ctx->routes[R_CYCLE_GRAPH]++;
   ctx->launches += P->graph_kernels;
   for (int f = 0; f < F_COUNT; ++f) {
     ctx->fam_launches[f] += P->graph_fam_launches[f];

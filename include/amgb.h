@@ -341,6 +341,15 @@ int amgb_ctx_get_timer(amgb_ctx* ctx, int family, double* total_ms, int64_t* lau
 int amgb_ctx_get_timer_level(amgb_ctx* ctx, int family, int level, double* total_ms,
                              int64_t* launches, double* algorithmic_bytes);
 
+/* Code routes taken by the host side of a context since creation / last reset (which SELL
+ * layout, which SpGEMM table tier or overflow stage, captured cycle, fused coarse tail ...):
+ * lets the parity tests at the benchmarked sizes assert that the routes which carry the
+ * benchmark were the ones compared with the oracle.  Names: amgb_route_name. */
+int amgb_route_count(void);
+const char* amgb_route_name(int route);
+int amgb_ctx_get_route(const amgb_ctx* ctx, int route, int64_t* count);
+int amgb_ctx_reset_routes(amgb_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: minutes of CPU oracle time (still part of -m gpu; deselect with -m 'gpu and not slow')")
 
 
 def _ensure_built():

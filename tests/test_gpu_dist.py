@@ -23,7 +23,7 @@ def _single(gpu_ctx, s, data):
     return A, P, ctl, x
 
 
-def _run_partitioned(m, contrast, starts, data, solve=True):
+def _run_partitioned(m, contrast, starts, data, solve=True, device_ids=None):
     nranks = len(starts) - 1
 
     def fn(rank, comm):
@@ -54,7 +54,7 @@ def _run_partitioned(m, contrast, starts, data, solve=True):
         A.close()
         return out
 
-    return dist.run_local_group(nranks, fn)
+    return dist.run_local_group(nranks, fn, device_ids)
 
 
 def _assert_same_hierarchy(parts, P1):
@@ -221,3 +221,58 @@ def test_chebyshev_smoother_partitioned_equals_single_device(gpu_ctx, replicate_
         assert np.array_equal(p["hist"], parts[0]["hist"])
     x = np.concatenate([p["x"] for p in parts])
     assert np.abs(x - x1).max() <= 1e-8 * np.abs(x1).max()
+
+
+# ---- real multi-GPU variants (skipped on a one-GPU box; run with `gpurun --gpus 2`) ----
+def _device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("replicate_below", [0, 300])
+@pytest.mark.parametrize("m,theta,contrast", [(12, 0.25, 3.0), (16, 0.5, 6.0)])
+def test_partitioned_on_distinct_gpus_equals_single_device(gpu_ctx, m, theta, contrast, replicate_below):
+    """The ranks are host threads again, but every rank owns its own GPU: halo values, the
+    replication all-gather and the PCG scalars cross NVLink through the peer windows."""
+    ng = min(_device_count(), 4)
+    if ng < 2:
+        pytest.skip("needs at least 2 GPUs")
+    s = poisson(m, contrast=contrast)
+    data = device_data(theta, dist_replicate_below=replicate_below)
+    A1, P1, ctl1, x1 = _single(gpu_ctx, s, data)
+    parts = _run_partitioned(m, contrast, dist.slab_partition(m, ng), data, device_ids=list(range(ng)))
+    _assert_same_hierarchy(parts, P1)
+    for p in parts:
+        assert abs(p["niters"] - ctl1.last_step()) <= 1
+        k = min(len(p["hist"]), len(ctl1.history))
+        assert (np.abs(p["hist"][:k] - ctl1.history[:k]) <= 1e-10 * ctl1.history[:k]).all()
+        assert np.array_equal(p["hist"], parts[0]["hist"])
+    x = np.concatenate([p["x"] for p in parts])
+    assert np.abs(x - x1).max() <= 1e-9 * np.abs(x1).max()
+
+
+@pytest.mark.parametrize("peer", ["1", "0"])
+def test_partitioned_nccl_processes_equal_single_device(peer):
+    """One PROCESS per GPU over NCCL (the way bench.py --gpus N runs config 5): tools/dist_nccl.py
+    --check compares level sizes, iteration count and residual history with the single-device
+    run on rank 0.  peer=1: NVLink peer windows for the solve-phase exchanges; peer=0: NCCL."""
+    import json
+    import os
+    import subprocess
+    import sys
+    ng = min(_device_count(), 4)
+    if ng < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AMGB_PEER=peer, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ng}",
+           "--master-addr", "127.0.0.1", "--master-port", "29547" if peer == "1" else "29548",
+           os.path.join(root, "tools", "dist_nccl.py"), "--cells", "40", "--theta", "0.25", "--contrast", "3",
+           "--check"]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{\"check\"")]
+    assert line, out.stdout[-2000:]
+    chk = json.loads(line[-1])
+    assert chk["rows_equal"] and abs(chk["iters_single"] - chk["iters_dist"]) <= 1
+    assert chk["max_rel_hist_diff"] <= 1e-10

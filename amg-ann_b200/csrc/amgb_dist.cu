@@ -283,7 +283,7 @@ int plan_sync(amgb_ctx* ctx, amgb_comm* comm, HaloPlan& pl, void* per_point, int
 
 int plan_sync_split(amgb_ctx* ctx, amgb_comm* comm, HaloPlan& pl, const double* lo, const double* hi, int split,
                     double* dst) {
-  AMGB_LAUNCH(ctx, F_VEC, 20.0 * pl.send_total, pack_split_kernel, grid_for(pl.send_total), kBlock, 0, pl.send_total,
+  AMGB_LAUNCH(ctx, F_EXCHANGE, 20.0 * pl.send_total, pack_split_kernel, grid_for(pl.send_total), kBlock, 0, pl.send_total,
               pl.send_idx.p, lo, hi, split, (double*)pl.sendbuf.p);
   AMGB_CHECK_LAUNCH(ctx);
   return plan_exchange(ctx, comm, pl, dst, 8);

@@ -34,6 +34,7 @@ enum Family : int {
   F_RESIDUAL_L0,
   F_RESTRICT_L0,
   F_PROLONG_L0,
+  F_EXCHANGE,      // row-partitioned path: halo put / wait+unpack / scalar all-reduce kernels
   F_COUNT
 };
 

@@ -133,7 +133,7 @@ int peer_put(amgb_ctx* ctx, const PeerPlan& pl, const double* lo, const double* 
   if (pl.tab.npeers == 0) return AMGB_OK;
   // at least one block: it carries the flags even when nothing is sent
   const unsigned grid = pl.send_total > 0 ? (unsigned)div_up(pl.send_total, kBlock) : 1u;
-  AMGB_LAUNCH(ctx, F_VEC, 20.0 * pl.send_total, peer_put_kernel, grid, kBlock, 0, (int)pl.send_total, pl.send_idx, lo,
+  AMGB_LAUNCH(ctx, F_EXCHANGE, 20.0 * pl.send_total, peer_put_kernel, grid, kBlock, 0, (int)pl.send_total, pl.send_idx, lo,
               hi, split, pl.tab);
   AMGB_CHECK_LAUNCH(ctx);
   return AMGB_OK;
@@ -144,7 +144,7 @@ int peer_get(amgb_ctx* ctx, const PeerPlan& pl, double* dst) {
   if (pl.tab.npeers == 0) return AMGB_OK;
   int64_t grid = div_up(pl.recv_total, kBlock);
   grid = grid < 1 ? 1 : (grid > kGetBlocks ? kGetBlocks : grid);
-  AMGB_LAUNCH(ctx, F_VEC, 16.0 * pl.recv_total, peer_get_kernel, (unsigned)grid, kBlock, 0, (int)pl.recv_total, pl.tab,
+  AMGB_LAUNCH(ctx, F_EXCHANGE, 16.0 * pl.recv_total, peer_get_kernel, (unsigned)grid, kBlock, 0, (int)pl.recv_total, pl.tab,
               dst);
   AMGB_CHECK_LAUNCH(ctx);
   return AMGB_OK;
@@ -154,7 +154,7 @@ int peer_allreduce(amgb_ctx* ctx, const PeerPlan& pl, double* red, int count) {
   if (count > 8) return set_error(ctx, AMGB_ERR_BAD_ARG, "peer_allreduce: at most 8 values");
   AMGB_TRY(pl.comm->launch_fence());
   if (pl.tab.npeers == 0) return AMGB_OK;
-  AMGB_LAUNCH(ctx, F_VEC, 16.0 * count * (pl.tab.npeers + 1), peer_allreduce_kernel, 1, 64, 0, pl.tab, red, count);
+  AMGB_LAUNCH(ctx, F_EXCHANGE, 16.0 * count * (pl.tab.npeers + 1), peer_allreduce_kernel, 1, 64, 0, pl.tab, red, count);
   AMGB_CHECK_LAUNCH(ctx);
   return AMGB_OK;
 }

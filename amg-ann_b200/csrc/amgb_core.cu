@@ -326,6 +326,7 @@ int amgb_ctx_destroy(amgb_ctx* ctx) {
   drain_timers(ctx);
   for (auto ev : ctx->free_events) cudaEventDestroy(ev);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);  // blocks still held by live objects stay valid until freed
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -74,6 +74,7 @@ enum Route : int {
 struct amgb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // body of the PCG while-graph is captured here (created on demand)
   bool own_stream = false;
   int sm_count = 148;
   size_t l2_bytes = 0;
@@ -283,6 +284,11 @@ struct amgb_precond {
   double* graph_z = nullptr;
   const double* graph_r = nullptr;
   bool use_graph = true;
+  bool graph_loop = true;   // PCG iterations as a WHILE node of one graph (needs use_graph)
+  bool capturing = false;   // a caller's capture is open: the cycle is recorded inline
+  int64_t loop_kernels = 0; // launch accounting of one captured PCG step
+  int64_t loop_fam_launches[amgb::F_COUNT] = {0};
+  double loop_fam_bytes[amgb::F_COUNT] = {0};
   int64_t graph_kernels = 0;  // kernels inside the captured graph (launch accounting)
   int64_t graph_fam_launches[amgb::F_COUNT] = {0};
   double graph_fam_bytes[amgb::F_COUNT] = {0};

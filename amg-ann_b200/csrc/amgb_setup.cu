@@ -1736,6 +1736,7 @@ int amgb_precond_initialize(amgb_ctx* ctx, const amgb_matrix* A, const amgb_boom
   P->mat = A;
   P->data = *data;
   if (std::getenv("AMGB_NO_GRAPH")) P->use_graph = false;  // profiling aid: plain launches
+  if (std::getenv("AMGB_PCG_HOST_LOOP")) P->graph_loop = false;  // A/B aid: host-driven PCG iteration
   const int rc = build_hierarchy(P);
   if (rc != AMGB_OK) {
     cudaStreamSynchronize(ctx->stream);

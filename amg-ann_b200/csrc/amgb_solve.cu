@@ -1026,7 +1026,7 @@ static int vcycle_launches(amgb_precond* P, double* z, const double* r) {
 
 int vcycle_apply(amgb_precond* P, double* z, const double* r) {
   amgb_ctx* ctx = P->ctx;
-  if (!P->use_graph || ctx->timers_on) return vcycle_launches(P, z, r);
+  if (!P->use_graph || ctx->timers_on || P->capturing) return vcycle_launches(P, z, r);
   if (P->vcycle_graph && (P->graph_z != z || P->graph_r != r)) destroy_solve_state(P);
   if (!P->vcycle_graph) {
     // capture the whole cycle once: on the small levels it is launch-latency bound
@@ -1160,27 +1160,41 @@ finalize_alpha_kernel(const double* __restrict__ partial, int64_t m, double* sc,
   }
 }
 
+// The PCG loop can run as a WHILE node of a CUDA graph (cg_device): the kernel that closes an
+// iteration then also decides whether another one runs.
+struct PcgCond {
+  cudaGraphConditionalHandle handle;
+  int on;  // 0: the host loop reads the flags instead
+};
+
+// beta = (z, r), dp = ||z||: history, convergence / breakdown flags, iteration counter
+__device__ __forceinline__ void pcg_close_iteration(double zz, double zr, double* sc, int* fl, double* hist,
+                                                    int64_t hist_cap, double abs_tol, int first, int64_t max_steps,
+                                                    PcgCond c) {
+  const double dp = sqrt(zz);
+  sc[4] = dp;
+  sc[1] = sc[0];
+  sc[0] = zr;
+  const int it = first ? 0 : fl[1] + 1;
+  fl[1] = it;
+  if (it < hist_cap) hist[it] = dp;
+  if (dp != dp) {
+    fl[0] = 1;
+    fl[2] = AMGB_ERR_BREAKDOWN;
+  } else if (dp <= abs_tol) {
+    fl[0] = 1;
+  }
+  if (c.on) cudaGraphSetConditional(c.handle, (!fl[0] && it < max_steps) ? 1u : 0u);
+}
+
 __global__ void __launch_bounds__(kBlock)
 finalize_beta_kernel(const double* __restrict__ pzz, const double* __restrict__ pzr, int64_t m,
-                     double* sc, int* fl, double* hist, int64_t hist_cap, double abs_tol, int first) {
+                     double* sc, int* fl, double* hist, int64_t hist_cap, double abs_tol, int first,
+                     int64_t max_steps, PcgCond c) {
   __shared__ double ws[kWarps];
   const double zz = ordered_sum(pzz, m, ws);
   const double zr = ordered_sum(pzr, m, ws);
-  if (threadIdx.x == 0) {
-    const double dp = sqrt(zz);
-    sc[4] = dp;
-    sc[1] = sc[0];
-    sc[0] = zr;
-    const int it = first ? 0 : fl[1] + 1;
-    fl[1] = it;
-    if (it < hist_cap) hist[it] = dp;
-    if (dp != dp) {
-      fl[0] = 1;
-      fl[2] = AMGB_ERR_BREAKDOWN;
-    } else if (dp <= abs_tol) {
-      fl[0] = 1;
-    }
-  }
+  if (threadIdx.x == 0) pcg_close_iteration(zz, zr, sc, fl, hist, hist_cap, abs_tol, first, max_steps, c);
 }
 
 // Row-partitioned path: the block partials are summed locally (same fixed tree), the 1-2
@@ -1209,29 +1223,16 @@ __global__ void finalize_alpha_red_kernel(const double* __restrict__ red, double
 }
 
 __global__ void finalize_beta_red_kernel(const double* __restrict__ red, double* sc, int* fl, double* hist,
-                                         int64_t hist_cap, double abs_tol, int first) {
-  const double zz = red[0], zr = red[1];
-  const double dp = sqrt(zz);
-  sc[4] = dp;
-  sc[1] = sc[0];
-  sc[0] = zr;
-  const int it = first ? 0 : fl[1] + 1;
-  fl[1] = it;
-  if (it < hist_cap) hist[it] = dp;
-  if (dp != dp) {
-    fl[0] = 1;
-    fl[2] = AMGB_ERR_BREAKDOWN;
-  } else if (dp <= abs_tol) {
-    fl[0] = 1;
-  }
+                                         int64_t hist_cap, double abs_tol, int first, int64_t max_steps, PcgCond c) {
+  pcg_close_iteration(red[0], red[1], sc, fl, hist, hist_cap, abs_tol, first, max_steps, c);
 }
 
 __global__ void __launch_bounds__(kBlock)
 update_p_kernel(int64_t n, const double* __restrict__ z, double* __restrict__ p,
-                const double* __restrict__ sc, int first) {
+                const double* __restrict__ sc, const int* __restrict__ fl) {
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
-  if (first) {
+  if (fl[1] == 0) {  // first step: no previous direction
     p[i] = z[i];
   } else {
     const double bb = sc[0] / sc[1];
@@ -1268,8 +1269,110 @@ struct PcgFlags {
   int done, iters, status, pad;
 };
 
+// Records  prologue -> WHILE(cond) { body } -> epilogue  as one graph and launches it on the
+// context's stream.  The body is captured on a second stream into the body graph of the
+// conditional node (a stream carries one capture at a time), with the context's stream
+// pointer swapped for the duration, so every launch helper records into the right graph.
+// *ran = false (and nothing executed) when the graph could not be built: the caller then
+// runs the host loop.
+template <class Pro, class Body, class Epi>
+static int pcg_graph_loop(amgb_ctx* ctx, amgb_precond* P, PcgCond& cond, Pro&& prologue, Body&& body, Epi&& epilogue,
+                          bool* ran) {
+  *ran = false;
+  if (!ctx->stream2 && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) {
+    (void)cudaGetLastError();
+    P->graph_loop = false;
+    return AMGB_OK;
+  }
+  cudaStream_t main_stream = ctx->stream;
+  cudaGraph_t G = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  bool outer_open = false, inner_open = false;
+  int rc = AMGB_OK;
+  bool ok = cudaGraphCreate(&G, 0) == cudaSuccess &&
+            cudaGraphConditionalHandleCreate(&cond.handle, G, 0, 0) == cudaSuccess;
+  cond.on = 1;
+  const bool was_capturing = P->capturing;
+  P->capturing = true;  // the cycle is recorded inline, not as its own executable graph
+  if (ok) ok = outer_open = cudaStreamBeginCaptureToGraph(main_stream, G, nullptr, nullptr, 0,
+                                                          cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+  if (ok) rc = prologue();
+  if (ok && rc == AMGB_OK) {
+    cudaStreamCaptureStatus st;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t ndeps = 0;
+    cudaGraph_t cg = nullptr;
+    ok = cudaStreamGetCaptureInfo(main_stream, &st, nullptr, &cg, &deps, &ndeps) == cudaSuccess &&
+         st == cudaStreamCaptureStatusActive;
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = cond.handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t cnode = nullptr;
+    if (ok) ok = cudaGraphAddNode(&cnode, G, deps, ndeps, &np) == cudaSuccess;
+    if (ok) ok = cudaStreamUpdateCaptureDependencies(main_stream, &cnode, 1, cudaStreamSetCaptureDependencies) ==
+                 cudaSuccess;
+    if (ok) {
+      cudaGraph_t bg = np.conditional.phGraph_out[0];
+      const int64_t l0 = ctx->launches;
+      int64_t fam_l0[F_COUNT];
+      double fam_b0[F_COUNT];
+      for (int f = 0; f < F_COUNT; ++f) {
+        fam_l0[f] = ctx->fam_launches[f];
+        fam_b0[f] = ctx->fam_bytes[f];
+      }
+      ctx->stream = ctx->stream2;
+      ok = inner_open = cudaStreamBeginCaptureToGraph(ctx->stream, bg, nullptr, nullptr, 0,
+                                                      cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) rc = body();
+      if (inner_open) {
+        cudaGraph_t got = nullptr;
+        if (cudaStreamEndCapture(ctx->stream, &got) != cudaSuccess) ok = false;
+        inner_open = false;
+      }
+      ctx->stream = main_stream;
+      P->loop_kernels = ctx->launches - l0;
+      for (int f = 0; f < F_COUNT; ++f) {
+        P->loop_fam_launches[f] = ctx->fam_launches[f] - fam_l0[f];
+        P->loop_fam_bytes[f] = ctx->fam_bytes[f] - fam_b0[f];
+      }
+    }
+    if (ok && rc == AMGB_OK) rc = epilogue();
+  }
+  if (outer_open) {
+    cudaGraph_t got = nullptr;
+    if (cudaStreamEndCapture(main_stream, &got) != cudaSuccess) ok = false;
+  }
+  P->capturing = was_capturing;
+  if (ok && rc == AMGB_OK) ok = cudaGraphInstantiate(&exec, G, 0) == cudaSuccess;
+  if (ok && rc == AMGB_OK) ok = cudaGraphLaunch(exec, main_stream) == cudaSuccess;
+  if (ok && rc == AMGB_OK) {
+    const cudaError_t e = cudaStreamSynchronize(main_stream);
+    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "PCG graph", __FILE__, __LINE__);
+    *ran = true;
+  } else {
+    (void)cudaGetLastError();
+    if (rc == AMGB_OK) P->graph_loop = false;  // graph API refused: host loop from now on
+  }
+  if (exec) cudaGraphExecDestroy(exec);
+  if (G) cudaGraphDestroy(G);
+  return rc;
+}
+
+// History entries kept on the device: PCG needs tens of iterations; a buffer of max_steps + 1
+// = n + 1 entries (SolverControl(n, tol), ref amg_solver.h:33) would cost a 65 MB allocation and
+// memset inside the timed solve at m=200.
+constexpr int64_t kMaxHistory = 1 << 16;
+
 // x, b in the USER numbering (device; on the row-partitioned path: the owned slab);
 // everything inside runs in the permuted one.
+//
+// The iteration is either driven by the host (one 16-byte flag read per step), or -- whenever
+// the V-cycle is capturable -- recorded ONCE as a CUDA graph
+//     prologue -> WHILE(cond) { one PCG step } -> scatter
+// whose condition is set on the device by the kernel that closes a step
+// (pcg_close_iteration): no host round trip between the first residual and the solution.
 static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const double* b_user,
                      amgb_precond* P, int64_t max_steps, double abs_tol, double* res_hist, int64_t hist_cap,
                      int64_t* n_iters) {
@@ -1292,6 +1395,7 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
   AMGB_TRY(fl.alloc_zero(ctx, 4));
   int64_t cap = hist_cap > 0 && res_hist ? hist_cap : 1;
   if (cap > max_steps + 1) cap = max_steps + 1;
+  if (cap > kMaxHistory) cap = kMaxHistory;
   if (cap < 1) cap = 1;
   AMGB_TRY(hist.alloc_zero(ctx, cap));
   const int64_t dot_blocks = div_up(n, kDotChunk);
@@ -1301,6 +1405,13 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
   AMGB_TRY(pb.alloc(ctx, dot_blocks + 1));
   const unsigned vgrid = (unsigned)div_up(n, kBlock);
   double* red = ds ? ds->red.p : nullptr;
+  PcgCond cond{};
+  // the captured cycle belongs to this call's (z, r): dropped on every way out
+  struct SolveStateGuard {
+    amgb_precond* P;
+    ~SolveStateGuard() { destroy_solve_state(P); }
+  } guard{P};
+
   auto finalize_beta = [&](int first) -> int {
     if (ds) {
       AMGB_LAUNCH(ctx, F_VEC, 16.0 * dot_blocks, local_sums_kernel, 1, kBlock, 0, (const double*)pa.p,
@@ -1308,33 +1419,27 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
       AMGB_CHECK_LAUNCH(ctx);
       AMGB_TRY(reduce_scalars(P, red, 2));
       AMGB_LAUNCH(ctx, F_VEC, 16.0, finalize_beta_red_kernel, 1, 1, 0, (const double*)red, sc.p, fl.p, hist.p, cap,
-                  abs_tol, first);
+                  abs_tol, first, max_steps, cond);
     } else {
       AMGB_LAUNCH(ctx, F_VEC, 16.0 * dot_blocks, finalize_beta_kernel, 1, kBlock, 0, pa.p, pb.p, dot_blocks, sc.p,
-                  fl.p, hist.p, cap, abs_tol, first);
+                  fl.p, hist.p, cap, abs_tol, first, max_steps, cond);
     }
     AMGB_CHECK_LAUNCH(ctx);
     return AMGB_OK;
   };
-
-  AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, gather_kernel, vgrid, kBlock, 0, n, L0.perm.p, x_user, x.p);
-  AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, gather_kernel, vgrid, kBlock, 0, n, L0.perm.p, b_user, b.p);
   // r = b - A x ; z = M^{-1} r ; dp = ||z|| ; beta = (z, r)
-  AMGB_TRY(launch_sell_halo(P, 0, As, 0, (int)n, x.p, x.p, 0, EpiResidual{b.p, r.p}, F_RESIDUAL_L0,
-                            As.csr_bytes() + 24.0 * n, x.p, x.p, 0, x.p));
-  AMGB_TRY(vcycle_apply(P, z.p, r.p));
-  AMGB_LAUNCH(ctx, F_VEC, 16.0 * n, dot2_kernel, (unsigned)dot_blocks, kBlock, 0, n, z.p, r.p, pa.p, pb.p);
-  AMGB_TRY(finalize_beta(1));
-  PcgFlags* hf = (PcgFlags*)ctx->pinned;
-  auto read_flags = [&]() -> int {
-    AMGB_CUDA(ctx, cudaMemcpyAsync(hf, fl.p, sizeof(PcgFlags), cudaMemcpyDeviceToHost, ctx->stream));
-    AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return AMGB_OK;
+  auto prologue = [&]() -> int {
+    AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, gather_kernel, vgrid, kBlock, 0, n, L0.perm.p, x_user, x.p);
+    AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, gather_kernel, vgrid, kBlock, 0, n, L0.perm.p, b_user, b.p);
+    AMGB_TRY(launch_sell_halo(P, 0, As, 0, (int)n, x.p, x.p, 0, EpiResidual{b.p, r.p}, F_RESIDUAL_L0,
+                              As.csr_bytes() + 24.0 * n, x.p, x.p, 0, x.p));
+    AMGB_TRY(vcycle_apply(P, z.p, r.p));
+    AMGB_LAUNCH(ctx, F_VEC, 16.0 * n, dot2_kernel, (unsigned)dot_blocks, kBlock, 0, n, z.p, r.p, pa.p, pb.p);
+    return finalize_beta(1);
   };
-  AMGB_TRY(read_flags());
-  int64_t it = 0;
-  while (!hf->done && it < max_steps) {
-    AMGB_LAUNCH(ctx, F_VEC, 24.0 * n, update_p_kernel, vgrid, kBlock, 0, n, z.p, p.p, sc.p, it == 0 ? 1 : 0);
+  // one PCG step: p, w = A p, alpha, x, r, z = M^{-1} r, beta
+  auto body = [&]() -> int {
+    AMGB_LAUNCH(ctx, F_VEC, 24.0 * n, update_p_kernel, vgrid, kBlock, 0, n, z.p, p.p, sc.p, (const int*)fl.p);
     int64_t np = 0;  // partials of (p, w)
     const double spmv_bytes = As.csr_bytes() + 16.0 * n;
     if (ds && ds->window_slot >= 0 && As.has_interior && As.n >= ds->overlap_min_rows && n > 0) {
@@ -1365,24 +1470,58 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
     AMGB_CHECK_LAUNCH(ctx);
     AMGB_TRY(vcycle_apply(P, z.p, r.p));
     AMGB_LAUNCH(ctx, F_VEC, 16.0 * n, dot2_kernel, (unsigned)dot_blocks, kBlock, 0, n, z.p, r.p, pa.p, pb.p);
-    AMGB_TRY(finalize_beta(0));
+    return finalize_beta(0);
+  };
+  auto epilogue = [&]() -> int {
+    AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, scatter_kernel, vgrid, kBlock, 0, n, L0.perm.p, x.p, x_user);
+    AMGB_CHECK_LAUNCH(ctx);
+    return AMGB_OK;
+  };
+  PcgFlags* hf = (PcgFlags*)ctx->pinned;
+  auto read_flags = [&]() -> int {
+    AMGB_CUDA(ctx, cudaMemcpyAsync(hf, fl.p, sizeof(PcgFlags), cudaMemcpyDeviceToHost, ctx->stream));
+    AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AMGB_OK;
+  };
+
+  bool done_by_graph = false;
+  if (P->use_graph && P->graph_loop && !ctx->timers_on) {
+    int rc = pcg_graph_loop(ctx, P, cond, prologue, body, epilogue, &done_by_graph);
+    if (rc != AMGB_OK) return rc;
+    if (done_by_graph) {
+      AMGB_TRY(read_flags());
+      // the launch counters saw the captured step once; it ran hf->iters times
+      const int64_t extra = (int64_t)hf->iters - 1;
+      ctx->launches += extra * P->loop_kernels;
+      for (int f = 0; f < F_COUNT; ++f) {
+        ctx->fam_launches[f] += extra * P->loop_fam_launches[f];
+        ctx->fam_bytes[f] += double(extra) * P->loop_fam_bytes[f];
+      }
+      ctx->routes[R_PCG_DEVICE_LOOP]++;
+    }
+  }
+  if (!done_by_graph) {
+    cond.on = 0;
+    AMGB_TRY(prologue());
     AMGB_TRY(read_flags());
-    ++it;
+    int64_t it = 0;
+    while (!hf->done && it < max_steps) {
+      AMGB_TRY(body());
+      AMGB_TRY(read_flags());
+      ++it;
+    }
+    AMGB_TRY(epilogue());
   }
   *n_iters = hf->iters;
   const int status = hf->status;
   const bool done = hf->done != 0;
   const int iters = hf->iters;
-  AMGB_LAUNCH(ctx, F_VEC, 20.0 * n, scatter_kernel, vgrid, kBlock, 0, n, L0.perm.p, x.p, x_user);
-  AMGB_CHECK_LAUNCH(ctx);
   if (res_hist && hist_cap > 0) {
     int64_t k = iters + 1;
     if (k > cap) k = cap;
     AMGB_CUDA(ctx, cudaMemcpyAsync(res_hist, hist.p, k * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   }
   AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  // the graph was captured for this call's (z, r): drop it before they are freed
-  destroy_solve_state(P);
   if (ds) AMGB_TRY(peer_check(ctx, ds->peer_err));
   if (status != 0) return set_error(ctx, status, "PCG breakdown at iteration %d", iters);
   if (!done)

@@ -1014,7 +1014,7 @@ int amgb_dist_precond_initialize(amgb_ctx* ctx, const amgb_dist_matrix* A, const
   // communicator only enqueues stream work (NCCL).  Measured on 2 x B200 (m=160) the graph
   // with NCCL send/recv nodes is ~15 % SLOWER than plain launches, so it is opt-in.
   P->use_graph = A->comm->capturable() && std::getenv("AMGB_DIST_GRAPH") != nullptr;
-  if (std::getenv("AMGB_PCG_HOST_LOOP")) P->graph_loop = false;
+  P->graph_loop = std::getenv("AMGB_PCG_GRAPH_LOOP") != nullptr;
   P->dist = new amgb_dist_state;
   P->dist->comm = A->comm;
   P->dist->mat = A;

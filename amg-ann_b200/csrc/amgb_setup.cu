@@ -1036,6 +1036,159 @@ spgemm_numeric_global_kernel(const int32_t* __restrict__ ovf_rows, int novf, int
     big_row(keys, vals, H, lgH, ovf_rows[idx], arp, acol, aval, brp, bcol, bval, crp, ccol, cval);
 }
 
+
+// ---------------------------------------------------------------------------
+// Row-per-thread SpGEMM for products whose B rows are SHORT and whose product rows are
+// small (A*P on the finest levels of a 27-point operator: ~85 products, ~18 distinct
+// columns per row).  The sub-warp hash kernels above spend most of their issue slots on
+// idle lanes and per-entry barriers there (a P row has 1-4 entries for 8 lanes).  Here a
+// thread owns a row and a private hash table in shared memory, laid out bank-owned: slot s
+// of thread t lives at word s*blockDim + t, so thread t only ever touches bank t%32 and the
+// tables of a warp never conflict, whatever slots the lanes probe.  No atomics, no
+// barriers; the entries k of A's row are walked in order, so every C(i,c) accumulates
+// a_ik*b_kc in ascending k from 0.0 -- the oracle's Gustavson loop verbatim.  The emission
+// order (table order) is deterministic too: insertion is sequential.  Rows that outgrow the
+// table go to the overflow list of the second stage like in the sub-warp kernels.
+// ---------------------------------------------------------------------------
+constexpr int kRtThreads = 128;
+constexpr int kRtSymLg = 7, kRtSymSlots = 1 << kRtSymLg;   // count pass: 128 keys per row (64 KB per block)
+constexpr int kRtNumLg = 6, kRtNumSlots = 1 << kRtNumLg;   // numeric pass: 64 (key, value) slots per row (96 KB)
+constexpr int kRtNumMaxRow = 48;                           // longest product row accumulated here
+constexpr int kRtSymMaxRow = 112;                          // distinct columns the count table is allowed to hold
+
+__global__ void __launch_bounds__(kRtThreads)
+spgemm_rowthread_count_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
+                              const int32_t* __restrict__ brp, const int32_t* __restrict__ bcol,
+                              int32_t* __restrict__ count, int32_t* __restrict__ ovf_rows,
+                              int32_t* __restrict__ ovf_info) {
+  extern __shared__ unsigned rt_smem[];
+  const int64_t i = (int64_t)blockIdx.x * kRtThreads + threadIdx.x;
+  if (i >= n) return;
+  unsigned* keys = rt_smem + threadIdx.x;
+#pragma unroll 8
+  for (int t = 0; t < kRtSymSlots; ++t) keys[t * kRtThreads] = kEmpty;
+  int cnt = 0, ub = 0;
+  bool full = false;
+  const int ab = arp[i], ae = arp[i + 1];
+  int mb = 0, me = 0;
+  if (ab < ae) {
+    const int kk = acol[ab];
+    mb = brp[kk];
+    me = brp[kk + 1];
+  }
+  for (int k = ab; k < ae; ++k) {
+    int mb2 = 0, me2 = 0;  // the next B row's extent is fetched while this one is inserted
+    if (k + 1 < ae) {
+      const int kk2 = acol[k + 1];
+      mb2 = brp[kk2];
+      me2 = brp[kk2 + 1];
+    }
+    ub += me - mb;
+    if (!full)
+      for (int m = mb; m < me; ++m) {
+        const unsigned key = (unsigned)bcol[m];
+        int h = (int)((key * 2654435761u) >> (32 - kRtSymLg));
+        for (;;) {
+          const unsigned cur = keys[h * kRtThreads];
+          if (cur == key) break;
+          if (cur == kEmpty) {
+            keys[h * kRtThreads] = key;
+            ++cnt;
+            break;
+          }
+          h = (h + 1) & (kRtSymSlots - 1);
+        }
+        if (cnt > kRtSymMaxRow) {  // (an empty slot always remains: the probe loop terminates)
+          full = true;
+          break;
+        }
+      }
+    mb = mb2;
+    me = me2;
+  }
+  if (full) {
+    const int w = atomicAdd(&ovf_info[0], 1);
+    ovf_rows[w] = (int)i;
+    atomicMax(&ovf_info[1], ub);
+    count[i] = 0;
+  } else {
+    count[i] = cnt;
+  }
+}
+
+__global__ void __launch_bounds__(kRtThreads)
+spgemm_rowthread_numeric_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
+                                const double* __restrict__ aval, const int32_t* __restrict__ brp,
+                                const int32_t* __restrict__ bcol, const double* __restrict__ bval,
+                                const int32_t* __restrict__ crp, int32_t* __restrict__ ccol,
+                                double* __restrict__ cval, int32_t* __restrict__ ovf_rows,
+                                int32_t* __restrict__ ovf_info) {
+  extern __shared__ unsigned char rt_smem_raw[];
+  const int64_t i = (int64_t)blockIdx.x * kRtThreads + threadIdx.x;
+  if (i >= n) return;
+  const int out_b = crp[i], out_n = crp[i + 1] - out_b;
+  if (out_n == 0) return;
+  if (out_n > kRtNumMaxRow) {
+    const int w = atomicAdd(&ovf_info[0], 1);
+    ovf_rows[w] = (int)i;
+    atomicMax(&ovf_info[1], out_n);
+    return;
+  }
+  double* vals = reinterpret_cast<double*>(rt_smem_raw) + threadIdx.x;
+  unsigned* keys = reinterpret_cast<unsigned*>(rt_smem_raw + sizeof(double) * (size_t)kRtNumSlots * kRtThreads) + threadIdx.x;
+#pragma unroll 8
+  for (int t = 0; t < kRtNumSlots; ++t) keys[t * kRtThreads] = kEmpty;
+  const int ab = arp[i], ae = arp[i + 1];
+  int mb = 0, me = 0;
+  double a = 0.0;
+  if (ab < ae) {
+    const int kk = acol[ab];
+    a = aval[ab];
+    mb = brp[kk];
+    me = brp[kk + 1];
+  }
+  for (int k = ab; k < ae; ++k) {
+    int mb2 = 0, me2 = 0;
+    double a2 = 0.0;
+    if (k + 1 < ae) {
+      const int kk2 = acol[k + 1];
+      a2 = aval[k + 1];
+      mb2 = brp[kk2];
+      me2 = brp[kk2 + 1];
+    }
+    for (int m = mb; m < me; ++m) {
+      const unsigned key = (unsigned)bcol[m];
+      const double prod = __dmul_rn(a, bval[m]);
+      int h = (int)((key * 2654435761u) >> (32 - kRtNumLg));
+      for (;;) {
+        const unsigned cur = keys[h * kRtThreads];
+        if (cur == key) {
+          vals[h * kRtThreads] = __dadd_rn(vals[h * kRtThreads], prod);
+          break;
+        }
+        if (cur == kEmpty) {
+          keys[h * kRtThreads] = key;
+          vals[h * kRtThreads] = __dadd_rn(0.0, prod);
+          break;
+        }
+        h = (h + 1) & (kRtNumSlots - 1);
+      }
+    }
+    a = a2;
+    mb = mb2;
+    me = me2;
+  }
+  int w = out_b;
+  for (int t = 0; t < kRtNumSlots; ++t) {
+    const unsigned key = keys[t * kRtThreads];
+    if (key != kEmpty) {
+      ccol[w] = (int)key;
+      cval[w] = vals[t * kRtThreads];
+      ++w;
+    }
+  }
+}
+
 // 64-bit total of the row counts: the 32-bit scan below would wrap silently
 __global__ void __launch_bounds__(kBlock)
 sum_counts_kernel(int64_t n, const int32_t* __restrict__ count, unsigned long long* __restrict__ total) {
@@ -1056,8 +1209,10 @@ static int read_ovf(amgb_ctx* ctx, const int32_t* ovf_info, int* novf, int* maxv
 }
 
 // G: lanes per row; CAP_SYM / CAP_NUM: first-stage table capacities per row group
+// rowthread: the first stage of both passes is the row-per-thread kernel pair (unsorted output only)
 template <int G, int CAP_SYM, int CAP_NUM>
-static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, bool sorted) {
+static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, bool sorted,
+                       bool rowthread = false) {
   constexpr int kBigSym = 8192, kBigNum = 2048;  // second-stage capacities (one warp per row)
   const int64_t n = A.n;
   C.n = n;
@@ -1076,11 +1231,19 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
   int novf = 0, maxv = 0;
   // ---- symbolic
   {
-    auto kern = spgemm_symbolic_kernel<G, CAP_SYM>;
-    const size_t smem = sizeof(unsigned) * (size_t)kGroups * CAP_SYM;
-    if (smem > 48 * 1024) AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, kern, grid, kSpThreads, smem, n, (const int32_t*)nullptr, A.rp.p, A.col.p,
-                B.rp.p, B.col.p, count.p, ovf1.p, info.p);
+    if (rowthread) {
+      const size_t smem = sizeof(unsigned) * (size_t)kRtSymSlots * kRtThreads;
+      AMGB_CUDA(ctx, cudaFuncSetAttribute(spgemm_rowthread_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+      AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, spgemm_rowthread_count_kernel, (unsigned)div_up(n, kRtThreads), kRtThreads,
+                  smem, n, A.rp.p, A.col.p, B.rp.p, B.col.p, count.p, ovf1.p, info.p);
+    } else {
+      auto kern = spgemm_symbolic_kernel<G, CAP_SYM>;
+      const size_t smem = sizeof(unsigned) * (size_t)kGroups * CAP_SYM;
+      if (smem > 48 * 1024) AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, kern, grid, kSpThreads, smem, n, (const int32_t*)nullptr, A.rp.p, A.col.p,
+                  B.rp.p, B.col.p, count.p, ovf1.p, info.p);
+    }
     AMGB_CHECK_LAUNCH(ctx);
     AMGB_TRY(read_ovf(ctx, info.p, &novf, &maxv));
     if (novf > 0) {
@@ -1126,7 +1289,14 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
   {
     const size_t smem = (sizeof(unsigned) + sizeof(double)) * (size_t)kGroups * CAP_NUM;
     const double bytes = in_bytes + 12.0 * nnz + 4.0 * n;
-    if (sorted) {
+    if (rowthread) {
+      const size_t rsmem = (sizeof(unsigned) + sizeof(double)) * (size_t)kRtNumSlots * kRtThreads;
+      AMGB_CUDA(ctx, cudaFuncSetAttribute(spgemm_rowthread_numeric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)rsmem));
+      AMGB_LAUNCH(ctx, F_SPGEMM, bytes, spgemm_rowthread_numeric_kernel, (unsigned)div_up(n, kRtThreads), kRtThreads,
+                  rsmem, n, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p, ovf1.p,
+                  info.p);
+    } else if (sorted) {
       auto kern = spgemm_numeric_kernel<G, CAP_NUM, true>;
       if (smem > 48 * 1024) AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       AMGB_LAUNCH(ctx, F_SPGEMM, bytes, kern, grid, kSpThreads, smem, n, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p,
@@ -1181,6 +1351,14 @@ int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, 
   // which is much slower, so wide operators (3 DoF/node elasticity, coarse levels) start higher.
   double est = avg_a * avg_b / 3.0;
   if (const char* e = std::getenv("AMGB_SPGEMM_TIER")) est = e[0] == '0' ? 0.0 : (e[0] == '1' ? 100.0 : 1000.0);
+  // small product rows that need no column order (the inner operand A*P): one thread per row
+  // (AMGB_SPGEMM_ROWTHREAD=0 / =1: never / whenever the output may stay unsorted -- parity tests of both routes)
+  const char* rt_env = std::getenv("AMGB_SPGEMM_ROWTHREAD");
+  const bool rt = rt_env ? rt_env[0] == '1' : est <= 40.0;
+  if (rt && !sorted) {
+    ctx->routes[R_SPGEMM_ROWREG]++;
+    return spgemm_impl<8, 256, 128>(ctx, A, B, C, sorted, true);
+  }
   ctx->routes[est <= 50.0 ? R_SPGEMM_G8_T128 : (est <= 110.0 ? R_SPGEMM_G8_T256 : R_SPGEMM_G8_T512)]++;
   if (est <= 50.0) return spgemm_impl<8, 256, 128>(ctx, A, B, C, sorted);
   if (est <= 110.0) return spgemm_impl<8, 512, 256>(ctx, A, B, C, sorted);
@@ -1736,7 +1914,10 @@ int amgb_precond_initialize(amgb_ctx* ctx, const amgb_matrix* A, const amgb_boom
   P->mat = A;
   P->data = *data;
   if (std::getenv("AMGB_NO_GRAPH")) P->use_graph = false;  // profiling aid: plain launches
-  if (std::getenv("AMGB_PCG_HOST_LOOP")) P->graph_loop = false;  // A/B aid: host-driven PCG iteration
+  // PCG iterations as a WHILE node of one graph: opt-in.  Measured on B200 (m=200 sweep): 0.8 % faster
+  // with one system in flight, but graphs with conditional nodes do not overlap with the work of other
+  // streams, which costs the 6 % that three systems in flight gain.
+  P->graph_loop = std::getenv("AMGB_PCG_GRAPH_LOOP") != nullptr;
   const int rc = build_hierarchy(P);
   if (rc != AMGB_OK) {
     cudaStreamSynchronize(ctx->stream);

@@ -428,6 +428,36 @@ def test_spgemm_table_tiers_give_the_same_hierarchy(gpu_ctx, monkeypatch, tier):
     _assert_hierarchy_identical(P, H)
 
 
+@pytest.mark.parametrize("mode", ["0", "1"])
+@pytest.mark.parametrize("kind", ["poisson", "elasticity", "hub"])
+def test_spgemm_row_per_thread_and_sub_warp_routes_agree_with_the_oracle(gpu_ctx, monkeypatch, mode, kind):
+    """AMGB_SPGEMM_ROWTHREAD=1 sends every unsorted product (A*P) through the row-per-thread
+    kernels, =0 through the sub-warp hash kernels.  Elasticity and hub/leaf rows outgrow the
+    48-entry rows (and the hub rows the 112-column count table) of the row-per-thread tables, so
+    the overflow lists of both passes are exercised.  Same bits as the oracle either way."""
+    from helpers import hub_leaf_csr
+    from types import SimpleNamespace
+    monkeypatch.setenv("AMGB_SPGEMM_ROWTHREAD", mode)
+    if kind == "poisson":
+        s = poisson(14, contrast=3.0)
+        theta = 0.25
+    elif kind == "elasticity":
+        s = ab.gen.elasticity_q1(6, 2, 3, 10.0 ** ab.gen.checkerboard_epsv(2, 3, 2.0))
+        theta = 0.25
+    else:
+        M = hub_leaf_csr(300, 500, 60, 8, 7)
+        s = SimpleNamespace(n=M.shape[0], col=M.indices.astype(np.int32), val=M.data.astype(np.float64),
+                            rowptr32=lambda: M.indptr.astype(np.int32))
+        theta = 0.05
+    gpu_ctx.reset_routes()
+    A, P, H = _both(gpu_ctx, s, device_data(theta))
+    r = gpu_ctx.routes()
+    assert (r["spgemm_rowreg"] > 0) == (mode == "1"), r
+    if mode == "1" and kind != "poisson":
+        assert r["spgemm_num_big"] > 0, r          # rows past 48 entries went to the second stage
+    _assert_hierarchy_identical(P, H)
+
+
 @pytest.mark.parametrize("nh,nl,per_leaf,leaf_leaf", [(100, 300, 30, 4), (160, 400, 70, 6)])
 def test_setup_long_interpolation_rows(gpu_ctx, nh, nl, per_leaf, leaf_leaf):
     """Hub/leaf systems: every leaf depends strongly on 30 (70) hubs, which PMIS makes the C
@@ -454,3 +484,34 @@ def test_setup_long_interpolation_rows(gpu_ctx, nh, nl, per_leaf, leaf_leaf):
     # agreement to 1e-10 of the initial residual, and to 1e-6 of each entry down to 1e-10
     d = np.abs(ctl.history[:k] - hist[:k])
     assert (d <= RES_RTOL * hist[0]).all() and (d <= 1e-6 * hist[:k]).all()
+
+
+def test_pcg_as_a_while_graph_gives_the_same_history(gpu_ctx, monkeypatch):
+    """AMGB_PCG_GRAPH_LOOP=1: prologue, WHILE(not converged) { PCG step }, scatter as ONE graph
+    whose condition is set on the device; same residual history, iteration count and solution
+    bits as the host-driven loop, NoConvergence and immediate convergence included."""
+    s = poisson(16, contrast=4.0)
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    out = {}
+    for mode in ("host", "graph"):
+        if mode == "graph":
+            monkeypatch.setenv("AMGB_PCG_GRAPH_LOOP", "1")
+        gpu_ctx.reset_routes()
+        P = ab.PreconditionBoomerAMG()
+        P.initialize(A, device_data(0.5))
+        ctl = ab.SolverControl(s.n, 1e-8)
+        x = s.x0.copy()
+        ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+        assert (gpu_ctx.routes()["pcg_device_loop"] > 0) == (mode == "graph")
+        short = ab.SolverControl(3, 1e-30)
+        x3 = s.x0.copy()
+        with pytest.raises(ab.NoConvergence):
+            ab.SolverCG(short).solve(A, x3, s.rhs, P)
+        easy = ab.SolverControl(10, 1e30)
+        ab.SolverCG(easy).solve(A, s.x0.copy(), s.rhs, P)
+        out[mode] = (ctl.last_step(), ctl.history.copy(), x, short.last_step(), len(short.history), x3, easy.last_step())
+        P.close()
+    h, g = out["host"], out["graph"]
+    assert h[0] == g[0] and np.array_equal(h[1], g[1]) and np.array_equal(h[2], g[2])
+    assert (h[3], h[4]) == (g[3], g[4]) == (3, 4) and np.array_equal(h[5], g[5])
+    assert h[6] == g[6] == 0

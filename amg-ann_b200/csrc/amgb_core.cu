@@ -212,7 +212,7 @@ __global__ void rowptr64_to_32_kernel(const int64_t* __restrict__ in, int32_t* _
 static const char* kFamilyNames[F_COUNT] = {
     "spmv",     "smooth", "residual",  "restrict", "prolong", "vec",  "coarse", "strength",
     "coarsen",  "interp", "transpose", "spgemm",   "scan",    "aux",  "pool",
-    "smooth_l0", "residual_l0", "restrict_l0", "prolong_l0", "exchange"};
+    "smooth_l0", "residual_l0", "restrict_l0", "prolong_l0", "exchange", "tail"};
 
 static const char* kRouteNames[R_COUNT] = {
     "sell_t1_stream",   "sell_t_multi",      "spgemm_g8_t128",  "spgemm_g8_t256",    "spgemm_g8_t512",

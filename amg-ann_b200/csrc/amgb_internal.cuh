@@ -35,6 +35,7 @@ enum Family : int {
   F_RESTRICT_L0,
   F_PROLONG_L0,
   F_EXCHANGE,      // row-partitioned path: halo put / wait+unpack / scalar all-reduce kernels
+  F_TAIL,          // coarse tail of the cycle in one kernel (amgb_tail.cu)
   F_COUNT
 };
 
@@ -221,6 +222,23 @@ struct Level {
 
 int64_t div_up(int64_t a, int64_t b);
 
+// Coarse tail of the V-cycle as one kernel (amgb_tail.cu): byte offsets into the packed blob /
+// the kernel's shared memory.  POD: passed to the kernel by value.
+constexpr int kTailMaxLevels = 10;
+struct TailOpDesc {
+  int rows = 0, nnz = 0, off_rp = 0, off_col = 0, off_val = 0;
+};
+struct TailLevelDesc {
+  int n = 0, nC = 0;
+  TailOpDesc A, P, R;   // P: this level <- next; R: next <- this level
+  int off_inv = 0, off_u = 0, off_f = 0, off_t = 0;
+};
+struct TailDesc {
+  int nlev = 0, blob_bytes = 0, dense_n = 0, off_dense = 0;
+  double w = 1.0;
+  TailLevelDesc lv[kTailMaxLevels];
+};
+
 // Launch bookkeeping: counts the launch, optionally brackets it with events.
 struct LaunchScope {
   amgb_ctx* ctx;
@@ -277,6 +295,11 @@ struct amgb_precond {
   std::vector<amgb::Level> lv;
   amgb::DevBuf<double> dense;  // coarsest operator, LU in place (row-major)
   bool dense_ok = false;
+  // coarse tail: levels [tail_from, nl) run in one kernel from a packed blob (-1: none)
+  int tail_from = -1;
+  amgb::TailDesc tail_desc;
+  amgb::DevBuf<unsigned char> tail_blob;
+  size_t tail_smem = 0;
   // statistics
   std::vector<int64_t> st_rows, st_nnz, st_nnzP;
   // captured V-cycle (valid for the (z, r) pointer pair below)
@@ -331,6 +354,10 @@ int finish_solve_setup_range(amgb_precond* P, int l0);
 // z = M^{-1} r with z, r in the level-0 permuted numbering
 int vcycle_apply(amgb_precond* P, double* z_dev, const double* r_dev);
 int spmv(amgb_ctx* ctx, const DeviceCsr& A, const double* x, double* y, int family);
+// amgb_tail.cu
+int tail_plan(const amgb_precond* P, int l0);
+int tail_pack(amgb_precond* P);
+int tail_cycle(amgb_precond* P, const double* f, double* u);
 // amgb_cheby.cu: Chebyshev smoother data of level l (needs the level's CSR operator and perm)
 int cheby_setup_level(amgb_precond* P, int l);
 void destroy_solve_state(amgb_precond* P);

@@ -1,20 +1,22 @@
 // Matrix -> V x V four-channel image pooling, replacing ViewMaker::make_view
 // (ref common/view_maker.h:26-74: a single-threaded MatGetRow loop).
 //
-// Atomic-free and deterministic:
-//   * the V row-bins are contiguous row ranges (ref view_maker.h:41-45,52), so a
-//     CTA is given a tile of rows inside ONE row-bin and only needs V-wide
-//     accumulators;
-//   * each lane walks one CSR row; columns are ascending, so the row decomposes
-//     into runs of equal column-bin which the lane sums in CSR order in
-//     registers;
-//   * the warp advances over the column-bins in lock step (min over the lanes'
-//     next bin), reduces the 32 run partials with a fixed shuffle tree and lane 0
-//     adds the result to the warp-private shared-memory accumulators -- no two
-//     writers ever share an address;
-//   * warps, then tiles, are combined in index order.
-// count is integer-exact, max_pp / max_np are order-independent hence exact,
-// sum has a fixed (input-independent) association.
+// One streaming, atomic-free pass over the CSR entries:
+//   * the V row-bins are contiguous row ranges (ref view_maker.h:41-45,52), hence contiguous
+//     ENTRY ranges [rp[r0], rp[r1]); a CTA is given a slice of the entry range of ONE row-bin,
+//     so it only needs V-wide accumulators and never looks at row pointers again;
+//   * a lane loads 8 consecutive entries (two 16-byte column loads, four 16-byte value loads;
+//     a warp covers 256 consecutive entries = 3 KB, fully coalesced) and folds them into runs
+//     of equal column-bin in registers -- columns ascend within a row, so runs are long
+//     (9 entries and more on the FE stencils);
+//   * run #r of all lanes is combined across the warp by a segmented shuffle scan keyed on
+//     the bin, and the last lane of every segment adds the total to the WARP-PRIVATE
+//     shared-memory accumulators; two segments of one round that hit the same bin are
+//     committed in two steps (ranked with __match_any_sync), so no two writers ever share an
+//     address -- no atomics anywhere;
+//   * warps, then slices, are combined in index order.
+// count is integer-exact, max_pp / max_np are order-independent hence exact, sum has a
+// fixed (input-independent) association.
 #include <climits>
 
 #include "amgb_internal.cuh"
@@ -24,18 +26,33 @@ namespace amgb {
 constexpr int kPoolBlock = 256;
 constexpr int kPoolWarps = kPoolBlock / 32;
 constexpr int kMaxView = 512;
+constexpr int kPoolPerLane = 8;
+constexpr int kPoolWarpChunk = 32 * kPoolPerLane;            // entries per warp and iteration
+constexpr int kPoolBlockChunk = kPoolWarps * kPoolWarpChunk;  // entries per CTA and iteration
+constexpr size_t kPoolSmemMax = (size_t)kPoolWarps * kMaxView * (3 * sizeof(double) + sizeof(int));
 
 struct BinMap {
   int q, q1, p, t, V;
-  __device__ __forceinline__ int bin(int i) const { return i < t ? i / q1 : (i - t) / q + p; }
+  double rq, rq1;  // 1/q, 1/q1
+  // floor(i / d) for 0 <= i < 2^31 without an integer division: the quotient is a bin index
+  // (< 2^10), so the double product is within one of it and a single correction makes it exact
+  __device__ __forceinline__ static int div(int i, int d, double rd) {
+    int b = __double2int_rz(__int2double_rn(i) * rd);
+    const long long r = (long long)i - (long long)b * d;
+    if (r < 0) --b;
+    else if (r >= d) ++b;
+    return b;
+  }
+  __device__ __forceinline__ int bin(int i) const { return i < t ? div(i, q1, rq1) : div(i - t, q, rq) + p; }
   __host__ __device__ int row_begin(int br) const { return br < p ? br * q1 : t + (br - p) * q; }
 };
 
+template <bool VEC>
 __global__ void __launch_bounds__(kPoolBlock)
-pool_tiles_kernel(BinMap bm, int tiles, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
-                  const double* __restrict__ val, double* __restrict__ part_sum,
-                  long long* __restrict__ part_cnt, double* __restrict__ part_pp,
-                  double* __restrict__ part_np) {
+pool_entries_kernel(BinMap bm, int tiles, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                    const double* __restrict__ val, double* __restrict__ part_sum,
+                    long long* __restrict__ part_cnt, double* __restrict__ part_pp,
+                    double* __restrict__ part_np) {
   extern __shared__ unsigned char pool_smem[];
   const int V = bm.V;
   double* s_sum = reinterpret_cast<double*>(pool_smem);          // [warps][V]
@@ -44,6 +61,7 @@ pool_tiles_kernel(BinMap bm, int tiles, const int32_t* __restrict__ rp, const in
   int* s_cnt = reinterpret_cast<int*>(s_np + kPoolWarps * V);
   const int br = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned full = 0xffffffffu;
   for (int t = threadIdx.x; t < kPoolWarps * V; t += kPoolBlock) {
     s_sum[t] = 0.0;
     s_pp[t] = 0.0;
@@ -51,55 +69,100 @@ pool_tiles_kernel(BinMap bm, int tiles, const int32_t* __restrict__ rp, const in
     s_cnt[t] = 0;
   }
   __syncthreads();
-  const int r0 = bm.row_begin(br), r1 = bm.row_begin(br + 1);
-  const int per = (r1 - r0 + tiles - 1) / tiles;
-  const int tb = r0 + tile * per;
-  const int te = tb + per < r1 ? tb + per : r1;
+  const int e_lo = rp[bm.row_begin(br)], e_hi = rp[bm.row_begin(br + 1)];
+  // whole CTA-chunks (absolute multiples of kPoolBlockChunk, so every lane's 8 entries are
+  // 32-byte / 64-byte aligned) that overlap the entry range of this row-bin, split over the tiles
+  const int c_first = e_lo / kPoolBlockChunk, c_last = (int)(((long long)e_hi + kPoolBlockChunk - 1) / kPoolBlockChunk);
+  const int per = (c_last - c_first + tiles - 1) / tiles;
+  const int c0 = c_first + tile * per, c1 = min(c0 + per, c_last);
   double* w_sum = s_sum + warp * V;
   double* w_pp = s_pp + warp * V;
   double* w_np = s_np + warp * V;
   int* w_cnt = s_cnt + warp * V;
-  for (int base = tb + warp * 32; base < te; base += kPoolBlock) {
-    const int row = base + lane;
-    int k = 0, e = 0;
-    if (row < te) {
-      k = rp[row];
-      e = rp[row + 1];
+  for (int chunk = c0; chunk < c1; ++chunk) {
+    const long long base = (long long)chunk * kPoolBlockChunk + warp * kPoolWarpChunk + lane * kPoolPerLane;
+    int c[kPoolPerLane];
+    double v[kPoolPerLane];
+    const bool inside = base >= e_lo && base + kPoolPerLane <= e_hi;
+    if (VEC && inside) {
+      const int4 c0v = __ldcs(reinterpret_cast<const int4*>(col + base));
+      const int4 c1v = __ldcs(reinterpret_cast<const int4*>(col + base) + 1);
+      c[0] = c0v.x; c[1] = c0v.y; c[2] = c0v.z; c[3] = c0v.w;
+      c[4] = c1v.x; c[5] = c1v.y; c[6] = c1v.z; c[7] = c1v.w;
+#pragma unroll
+      for (int j = 0; j < kPoolPerLane; j += 2) {
+        const double2 vv = __ldcs(reinterpret_cast<const double2*>(val + base + j));
+        v[j] = vv.x;
+        v[j + 1] = vv.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kPoolPerLane; ++j) {
+        const long long k = base + j;
+        const bool ok = k >= e_lo && k < e_hi;
+        c[j] = ok ? __ldcs(col + k) : -1;
+        v[j] = ok ? __ldcs(val + k) : 0.0;
+      }
     }
-    int nb = k < e ? bm.bin(col[k]) : INT_MAX;
-    for (;;) {
-      int cur = nb;
+    // column bins; entries outside the row-bin's range (only at its two ends) get -1
+    int b[kPoolPerLane], nr = 0, prev = -2;
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) cur = min(cur, __shfl_xor_sync(0xffffffffu, cur, d));
-      if (cur == INT_MAX) break;
+    for (int j = 0; j < kPoolPerLane; ++j) {
+      b[j] = c[j] >= 0 ? bm.bin(c[j]) : -1;
+      if (b[j] >= 0 && b[j] != prev) {
+        ++nr;
+        prev = b[j];
+      }
+    }
+    const int rounds = __reduce_max_sync(full, nr);
+    for (int r = 0; r < rounds; ++r) {
+      // my run #r
+      int rb = -1, cnt = 0, idx = -1;
       double s = 0.0, pp = 0.0, np = 0.0;
-      int c = 0;
-      if (nb == cur) {
-        int b = cur;
-        while (k < e) {
-          b = bm.bin(col[k]);
-          if (b != cur) break;
-          const double v = val[k];
-          s += v;
-          ++c;
-          pp = fmax(pp, fmax(v, 0.0));
-          np = fmax(np, fmax(-v, 0.0));
-          ++k;
-        }
-        nb = k < e ? b : INT_MAX;
-      }
+      prev = -2;
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, d);
-        c += __shfl_xor_sync(0xffffffffu, c, d);
-        pp = fmax(pp, __shfl_xor_sync(0xffffffffu, pp, d));
-        np = fmax(np, __shfl_xor_sync(0xffffffffu, np, d));
+      for (int j = 0; j < kPoolPerLane; ++j) {
+        if (b[j] < 0) continue;
+        if (b[j] != prev) {
+          ++idx;
+          prev = b[j];
+        }
+        if (idx == r) {
+          rb = b[j];
+          s += v[j];
+          ++cnt;
+          pp = fmax(pp, fmax(v[j], 0.0));
+          np = fmax(np, fmax(-v[j], 0.0));
+        }
       }
-      if (lane == 0) {
-        w_sum[cur] += s;
-        w_cnt[cur] += c;
-        w_pp[cur] = fmax(w_pp[cur], pp);
-        w_np[cur] = fmax(w_np[cur], np);
+      // segments = maximal lane ranges with the same bin; inclusive segmented scan
+      const int left = __shfl_up_sync(full, rb, 1), right = __shfl_down_sync(full, rb, 1);
+      int flag = (lane == 0 || left != rb) ? 1 : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double s2 = __shfl_up_sync(full, s, d), pp2 = __shfl_up_sync(full, pp, d), np2 = __shfl_up_sync(full, np, d);
+        const int c2 = __shfl_up_sync(full, cnt, d), f2 = __shfl_up_sync(full, flag, d);
+        if (lane >= d && !flag) {
+          s = s2 + s;
+          cnt += c2;
+          pp = fmax(pp, pp2);
+          np = fmax(np, np2);
+          flag = f2;
+        }
+      }
+      const bool commit = rb >= 0 && (lane == 31 || right != rb);
+      // two segments of this round may address the same bin (a new row falling back to a lower bin)
+      const unsigned peers = __match_any_sync(full, commit ? rb : -1 - lane);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      const int steps = __reduce_max_sync(full, commit ? __popc(peers) : 0);
+      for (int g = 0; g < steps; ++g) {
+        if (commit && rank == g) {
+          w_sum[rb] += s;
+          w_cnt[rb] += cnt;
+          w_pp[rb] = fmax(w_pp[rb], pp);
+          w_np[rb] = fmax(w_np[rb], np);
+        }
+        __syncwarp();
       }
     }
   }
@@ -107,16 +170,16 @@ pool_tiles_kernel(BinMap bm, int tiles, const int32_t* __restrict__ rp, const in
   const size_t out = ((size_t)br * tiles + tile) * V;
   for (int bc = threadIdx.x; bc < V; bc += kPoolBlock) {
     double s = 0.0, pp = 0.0, np = 0.0;
-    long long c = 0;
+    long long cn = 0;
 #pragma unroll
     for (int w = 0; w < kPoolWarps; ++w) {
       s += s_sum[w * V + bc];
-      c += s_cnt[w * V + bc];
+      cn += s_cnt[w * V + bc];
       pp = fmax(pp, s_pp[w * V + bc]);
       np = fmax(np, s_np[w * V + bc]);
     }
     part_sum[out + bc] = s;
-    part_cnt[out + bc] = c;
+    part_cnt[out + bc] = cn;
     part_pp[out + bc] = pp;
     part_np[out + bc] = np;
   }
@@ -159,10 +222,12 @@ static int pool_to_device(amgb_ctx* ctx, const amgb_matrix* A, int V, double* d_
   bm.q1 = bm.q + 1;
   bm.p = n % V;
   bm.t = bm.q1 * bm.p;
-  int tiles = (int)div_up((int64_t)ctx->sm_count * 4, V);
-  const int max_rows_per_bin = bm.q1;
-  const int max_tiles = (int)div_up(max_rows_per_bin, kPoolBlock);
-  if (tiles > max_tiles) tiles = max_tiles;
+  bm.rq = bm.q > 0 ? 1.0 / bm.q : 0.0;  // (V > n: every row is a bin of its own, q is never divided by)
+  bm.rq1 = 1.0 / bm.q1;
+  // slices per row-bin: enough CTAs for every SM, at least a few CTA-chunks of entries each
+  int tiles = (int)div_up((int64_t)ctx->sm_count * 8, V);
+  const int64_t chunks_per_bin = div_up(div_up(A->A.nnz, V), kPoolBlockChunk);
+  if (tiles > chunks_per_bin / 4) tiles = (int)(chunks_per_bin / 4);
   if (tiles < 1) tiles = 1;
   const size_t vv = (size_t)V * V;
   const size_t np = (size_t)V * tiles * V;
@@ -173,25 +238,36 @@ static int pool_to_device(amgb_ctx* ctx, const amgb_matrix* A, int V, double* d_
   AMGB_TRY(p_np.alloc(ctx, np));
   AMGB_TRY(p_cnt.alloc(ctx, np));
   const size_t smem = (size_t)kPoolWarps * V * (3 * sizeof(double) + sizeof(int));
-  AMGB_CUDA(ctx, cudaFuncSetAttribute(pool_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaEvent_t e0, e1;
-  AMGB_CUDA(ctx, cudaEventCreate(&e0));
-  AMGB_CUDA(ctx, cudaEventCreate(&e1));
-  AMGB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  // (the limit is per function and device, shared by every host thread: always the maximum)
+  AMGB_CUDA(ctx, cudaFuncSetAttribute(pool_entries_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmemMax));
+  AMGB_CUDA(ctx, cudaFuncSetAttribute(pool_entries_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmemMax));
+  struct Events {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Events() {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } ev;
+  AMGB_CUDA(ctx, cudaEventCreate(&ev.a));
+  AMGB_CUDA(ctx, cudaEventCreate(&ev.b));
+  AMGB_CUDA(ctx, cudaEventRecord(ev.a, ctx->stream));
   // pooling reads 12*nnz + 4*(n+1), writes 28*V^2
   const double bytes = 12.0 * A->A.nnz + 4.0 * (n + 1) + 28.0 * vv;
-  AMGB_LAUNCH(ctx, F_POOL, bytes, pool_tiles_kernel, (unsigned)(V * tiles), kPoolBlock, smem, bm, tiles,
-              A->A.rp.p, A->A.col.p, A->A.val.p, p_sum.p, p_cnt.p, p_pp.p, p_np.p);
+  const bool vec = (reinterpret_cast<uintptr_t>(A->A.col.p) % 16 == 0) && (reinterpret_cast<uintptr_t>(A->A.val.p) % 16 == 0);
+  if (vec) {
+    AMGB_LAUNCH(ctx, F_POOL, bytes, pool_entries_kernel<true>, (unsigned)(V * tiles), kPoolBlock, smem, bm, tiles,
+                A->A.rp.p, A->A.col.p, A->A.val.p, p_sum.p, p_cnt.p, p_pp.p, p_np.p);
+  } else {
+    AMGB_LAUNCH(ctx, F_POOL, bytes, pool_entries_kernel<false>, (unsigned)(V * tiles), kPoolBlock, smem, bm, tiles,
+                A->A.rp.p, A->A.col.p, A->A.val.p, p_sum.p, p_cnt.p, p_pp.p, p_np.p);
+  }
   AMGB_LAUNCH(ctx, F_POOL, 28.0 * np + 28.0 * vv, pool_finalize_kernel, (unsigned)div_up(vv, kPoolBlock),
               kPoolBlock, 0, V, tiles, p_sum.p, p_cnt.p, p_pp.p, p_np.p, d_sum, d_cnt, d_pp, d_np);
-  cudaError_t le = cudaGetLastError();
-  if (le == cudaSuccess) le = cudaEventRecord(e1, ctx->stream);
-  if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
+  AMGB_CHECK_LAUNCH(ctx);
+  AMGB_CUDA(ctx, cudaEventRecord(ev.b, ctx->stream));
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   float ms = 0.f;
-  if (le == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  if (le != cudaSuccess) return cuda_fail(ctx, le, "pooling", __FILE__, __LINE__);
+  cudaEventElapsedTime(&ms, ev.a, ev.b);
   if (ms_out) *ms_out = ms;
   return AMGB_OK;
 }

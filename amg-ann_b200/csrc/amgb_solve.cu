@@ -699,11 +699,35 @@ int finish_solve_setup_range(amgb_precond* P, int l0) {
                 (const int32_t*)L.cf.p, (const int32_t*)L.f2c.p, (int)L.n_coarse, L.perm.p, L.inv_perm.p);
     AMGB_CHECK_LAUNCH(ctx);
   }
+  // the coarsest grid is factorised first: the tail is only planned on top of a dense solve
+  AMGB_TRY(setup_dense(P));
+  P->tail_from = P->dense_ok ? tail_plan(P, l0) : -1;
+  if (P->tail_from >= 0) AMGB_TRY(tail_pack(P));
+  const int n_sell = P->tail_from >= 0 ? P->tail_from : nl;  // levels with SELL operators of their own
   // 2. operators: A (rows, cols permuted), P (fine rows, coarse cols), R = P^T
   for (int l = l0; l < nl; ++l) {
     Level& L = P->lv[l];
     const int64_t n = L.A.n;
     ctx->cur_level = l;
+    if (l >= n_sell) {  // tail level: lives in the packed blob; only the first one exchanges vectors
+      if (l + 1 < nl) {
+        L.R.rp.release();
+        L.R.col.release();
+        L.R.val.release();
+        if (!P->data.keep_setup_intermediates) {
+          L.P.rp.release();
+          L.P.col.release();
+          L.P.val.release();
+        }
+      }
+      L.n_solve = L.n_vec = n;
+      if (l == n_sell && l > 0) {
+        AMGB_TRY(L.u.alloc(ctx, n));
+        AMGB_TRY(L.f.alloc(ctx, n));
+      }
+      L.f2c.release();
+      continue;
+    }
     AMGB_TRY(csr_to_sell(ctx, L.A, L.perm.p, L.inv_perm.p, L.As));
     if (l + 1 < nl) {
       Level& C = P->lv[l + 1];
@@ -736,7 +760,7 @@ int finish_solve_setup_range(amgb_precond* P, int l0) {
     L.f2c.release();
   }
   ctx->cur_level = 0;
-  return setup_dense(P);
+  return AMGB_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -941,6 +965,10 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
   Level& L = P->lv[l];
   const int nl = (int)P->lv.size();
   const int n = (int)L.n_solve;
+  if (l == P->tail_from && u_is_zero) {  // this level and everything below it: one kernel
+    ctx->cur_level = l;
+    return tail_cycle(P, f, u);
+  }
   if (l == nl - 1) {
     if (P->relax_coarse == 9 && P->dense_ok) {
       if (partitioned_level(P, l)) {
@@ -996,7 +1024,8 @@ static int cycle(amgb_precond* P, int l, double*& u, double*& alt, const double*
     AMGB_TRY(launch_sell_halo(P, l, L.Rs, 0, ncrs, alt, alt, 0, EpiStore{C.f.p}, l == 0 ? F_RESTRICT_L0 : F_RESTRICT,
                               L.Rs.csr_bytes() + 8.0 * n + 8.0 * ncrs, alt, alt, 0, alt));
   }
-  if (C.n_vec > 0) AMGB_CUDA(ctx, cudaMemsetAsync(C.u.p, 0, (size_t)C.n_vec * sizeof(double), ctx->stream));
+  if (C.n_vec > 0 && l + 1 != P->tail_from)  // (the fused tail starts from the zero guess by construction)
+    AMGB_CUDA(ctx, cudaMemsetAsync(C.u.p, 0, (size_t)C.n_vec * sizeof(double), ctx->stream));
   double* cu = C.u.p;
   double* calt = C.tmp.p;
   AMGB_TRY(cycle(P, l + 1, cu, calt, C.f.p, true));

@@ -515,3 +515,44 @@ def test_pcg_as_a_while_graph_gives_the_same_history(gpu_ctx, monkeypatch):
     assert h[0] == g[0] and np.array_equal(h[1], g[1]) and np.array_equal(h[2], g[2])
     assert (h[3], h[4]) == (g[3], g[4]) == (3, 4) and np.array_equal(h[5], g[5])
     assert h[6] == g[6] == 0
+
+
+@pytest.mark.parametrize("m,theta,contrast,relax", [(16, 0.25, 3.0, "l1"), (20, 0.5, 6.0, "l1"), (24, 0.25, 0.0, "jacobi"),
+                                                    (12, 0.9, 6.0, "l1")])
+def test_coarse_tail_in_one_kernel_matches_the_per_level_cycle(gpu_ctx, monkeypatch, m, theta, contrast, relax):
+    """Levels of a few hundred rows and below run in ONE kernel from shared memory
+    (amgb_tail.cu).  Same hierarchy; V-cycle and residual history agree with the per-level
+    launches (AMGB_NO_TAIL=1) to rounding and with the oracle to the north-star tolerance."""
+    s = poisson(m, contrast=contrast)
+    R = ab.RelaxationType
+    kw = dict(relaxation_type_up=R.Jacobi, relaxation_type_down=R.Jacobi, relax_weight=0.7) if relax == "jacobi" else {}
+    data = device_data(theta, **kw)
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    H = orc.Hierarchy(s.rowptr32(), s.col, s.val, data.to_struct())
+    r = np.random.default_rng(11).standard_normal(s.n)
+    zo = H.vmult(r)
+    rc, xo, nit, hist = H.cg_solve(s.rhs, s.x0, abs_tol=1e-8)
+    got = {}
+    for mode in ("tail", "levels"):
+        if mode == "levels":
+            monkeypatch.setenv("AMGB_NO_TAIL", "1")
+        gpu_ctx.reset_routes()
+        P = ab.PreconditionBoomerAMG()
+        P.initialize(A, data)
+        _assert_hierarchy_identical(P, H)
+        z = np.empty(s.n)
+        P.vmult(z, r)
+        ctl = ab.SolverControl(s.n, 1e-8)
+        x = s.x0.copy()
+        ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+        assert (gpu_ctx.routes()["cycle_tail_fused"] > 0) == (mode == "tail"), gpu_ctx.routes()
+        got[mode] = (z, ctl.history.copy(), ctl.last_step(), x)
+        P.close()
+    for mode in got:
+        z, h, it, x = got[mode]
+        assert np.abs(z - zo).max() <= 1e-12 * np.abs(zo).max(), mode
+        assert abs(it - nit) <= 1
+        k = min(len(hist), len(h))
+        assert (np.abs(h[:k] - hist[:k]) <= RES_RTOL * hist[:k]).all(), mode
+    k = min(len(got["tail"][1]), len(got["levels"][1]))
+    assert (np.abs(got["tail"][1][:k] - got["levels"][1][:k]) <= 1e-11 * got["levels"][1][:k]).all()

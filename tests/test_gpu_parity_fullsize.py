@@ -73,7 +73,7 @@ def test_config1_full_size_is_bit_exact(gpu_ctx, theta):
     A, P, H = _both(gpu_ctx, s, device_data(theta))
     _assert_levels_identical(P, H)
     routes = gpu_ctx.routes()
-    assert routes["spgemm_rowreg"] > 0 and routes["spgemm_g32"] > 0      # A*P (row per thread) and R*(AP)
+    assert routes["spgemm_g8_t128"] > 0 and routes["spgemm_g32"] > 0     # A*P tier and R*(AP)
     _assert_pcg_parity(gpu_ctx, A, P, H, s)
     r = gpu_ctx.routes()
     assert r["cycle_graph"] > 0 or r["pcg_device_loop"] > 0     # the cycle ran from a captured graph
@@ -146,7 +146,7 @@ def test_config2_m200_theta025_is_bit_exact(gpu_ctx):
     A, P, H = _both(gpu_ctx, s, device_data(0.25))
     routes = gpu_ctx.routes()
     assert routes["sell_t1_stream"] >= 2          # level-0 A and at least one more operator
-    assert routes["spgemm_rowreg"] > 0 and routes["spgemm_g32"] > 0
+    assert routes["spgemm_g8_t128"] > 0 and routes["spgemm_g32"] > 0
     _assert_levels_identical(P, H)
     it, rel = _assert_pcg_parity(gpu_ctx, A, P, H, s)
     assert it == 36                                # the count bench.py reports for theta = 0.25

@@ -64,7 +64,7 @@ class RelaxationType:
     none = 14
 
 
-COARSEN_FALGOUT, COARSEN_PMIS = 6, 8
+COARSEN_CLJP, COARSEN_FALGOUT, COARSEN_PMIS = 0, 6, 8
 INTERP_CLASSICAL = 0
 SMOOTHER_SUBSTITUTE, SMOOTHER_STRICT = 0, 1
 

@@ -9,11 +9,13 @@
 //     a warp covers 256 consecutive entries = 3 KB, fully coalesced) and folds them into runs
 //     of equal column-bin in registers -- columns ascend within a row, so runs are long
 //     (9 entries and more on the FE stencils);
-//   * run #r of all lanes is combined across the warp by a segmented shuffle scan keyed on
-//     the bin, and the last lane of every segment adds the total to the WARP-PRIVATE
-//     shared-memory accumulators; two segments of one round that hit the same bin are
-//     committed in two steps (ranked with __match_any_sync), so no two writers ever share an
-//     address -- no atomics anywhere;
+//   * the rows of a row-bin of a banded matrix meet the same two or three column bins over and
+//     over: the warp caches four bins (ids warp-uniform, partial sum / count / maxima
+//     lane-private in registers), so the steady state is loads, a bin computation and
+//     predicated register adds -- no cross-lane traffic at all;
+//   * a bin that is not cached is installed in a free slot, or makes the warp flush its slots
+//     first: a butterfly over the warp and ONE writer (lane 0) per bin into the WARP-PRIVATE
+//     shared-memory accumulators -- no two writers ever share an address, no atomics anywhere;
 //   * warps, then slices, are combined in index order.
 // count is integer-exact, max_pp / max_np are order-independent hence exact, sum has a
 // fixed (input-independent) association.
@@ -47,8 +49,44 @@ struct BinMap {
   __host__ __device__ int row_begin(int br) const { return br < p ? br * q1 : t + (br - p) * q; }
 };
 
+// One (bin, partial) slot of a lane.  The bin ids of the slots are WARP-UNIFORM (every lane caches
+// the same kPoolSlots bins), the partials are lane-private registers.
+struct PoolSlot {
+  double s, pp, np;
+  int cnt;
+  __device__ __forceinline__ void clear() { s = 0.0; pp = 0.0; np = 0.0; cnt = 0; }
+  __device__ __forceinline__ void add(double v) {
+    s += v;
+    ++cnt;
+    pp = fmax(pp, fmax(v, 0.0));
+    np = fmax(np, fmax(-v, 0.0));
+  }
+};
+
+// butterfly over the warp, then lane 0 adds the total to the warp's accumulators of `bin`
+__device__ __forceinline__ void pool_flush_slot(PoolSlot& a, int bin, int lane, double* w_sum, int* w_cnt, double* w_pp,
+                                                double* w_np) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    a.s += __shfl_xor_sync(full, a.s, d);
+    a.cnt += __shfl_xor_sync(full, a.cnt, d);
+    a.pp = fmax(a.pp, __shfl_xor_sync(full, a.pp, d));
+    a.np = fmax(a.np, __shfl_xor_sync(full, a.np, d));
+  }
+  if (lane == 0) {
+    w_sum[bin] += a.s;
+    w_cnt[bin] += a.cnt;
+    w_pp[bin] = fmax(w_pp[bin], a.pp);
+    w_np[bin] = fmax(w_np[bin], a.np);
+  }
+  a.clear();
+}
+
+constexpr int kPoolSlots = 4;
+
 template <bool VEC>
-__global__ void __launch_bounds__(kPoolBlock)
+__global__ void __launch_bounds__(kPoolBlock, 3)
 pool_entries_kernel(BinMap bm, int tiles, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
                     const double* __restrict__ val, double* __restrict__ part_sum,
                     long long* __restrict__ part_cnt, double* __restrict__ part_pp,
@@ -79,6 +117,18 @@ pool_entries_kernel(BinMap bm, int tiles, const int32_t* __restrict__ rp, const 
   double* w_pp = s_pp + warp * V;
   double* w_np = s_np + warp * V;
   int* w_cnt = s_cnt + warp * V;
+  // The rows of one row-bin of a banded matrix meet two or three column bins, over and over:
+  // the warp caches kPoolSlots bins (ids warp-uniform, partial sums lane-private in registers)
+  // and streams the entries into them without any cross-lane traffic.  A bin that is not cached
+  // is installed (free slot) or makes the warp flush all slots into its shared-memory
+  // accumulators first (butterfly + one writer per bin).
+  int key[kPoolSlots];
+  PoolSlot acc[kPoolSlots];
+#pragma unroll
+  for (int t = 0; t < kPoolSlots; ++t) {
+    key[t] = -2;  // free (never equal to a bin, nor to the -1 of an entry outside the range)
+    acc[t].clear();
+  }
   for (int chunk = c0; chunk < c1; ++chunk) {
     const long long base = (long long)chunk * kPoolBlockChunk + warp * kPoolWarpChunk + lane * kPoolPerLane;
     int c[kPoolPerLane];
@@ -105,67 +155,47 @@ pool_entries_kernel(BinMap bm, int tiles, const int32_t* __restrict__ rp, const 
       }
     }
     // column bins; entries outside the row-bin's range (only at its two ends) get -1
-    int b[kPoolPerLane], nr = 0, prev = -2;
+    int b[kPoolPerLane];
 #pragma unroll
-    for (int j = 0; j < kPoolPerLane; ++j) {
-      b[j] = c[j] >= 0 ? bm.bin(c[j]) : -1;
-      if (b[j] >= 0 && b[j] != prev) {
-        ++nr;
-        prev = b[j];
-      }
-    }
-    const int rounds = __reduce_max_sync(full, nr);
-    for (int r = 0; r < rounds; ++r) {
-      // my run #r
-      int rb = -1, cnt = 0, idx = -1;
-      double s = 0.0, pp = 0.0, np = 0.0;
-      prev = -2;
+    for (int j = 0; j < kPoolPerLane; ++j) b[j] = c[j] >= 0 ? bm.bin(c[j]) : -1;
+    for (;;) {
+      int missing = -1;  // a bin of mine that no slot holds
 #pragma unroll
       for (int j = 0; j < kPoolPerLane; ++j) {
-        if (b[j] < 0) continue;
-        if (b[j] != prev) {
-          ++idx;
-          prev = b[j];
-        }
-        if (idx == r) {
-          rb = b[j];
-          s += v[j];
-          ++cnt;
-          pp = fmax(pp, fmax(v[j], 0.0));
-          np = fmax(np, fmax(-v[j], 0.0));
-        }
-      }
-      // segments = maximal lane ranges with the same bin; inclusive segmented scan
-      const int left = __shfl_up_sync(full, rb, 1), right = __shfl_down_sync(full, rb, 1);
-      int flag = (lane == 0 || left != rb) ? 1 : 0;
+        bool hit = b[j] < 0;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const double s2 = __shfl_up_sync(full, s, d), pp2 = __shfl_up_sync(full, pp, d), np2 = __shfl_up_sync(full, np, d);
-        const int c2 = __shfl_up_sync(full, cnt, d), f2 = __shfl_up_sync(full, flag, d);
-        if (lane >= d && !flag) {
-          s = s2 + s;
-          cnt += c2;
-          pp = fmax(pp, pp2);
-          np = fmax(np, np2);
-          flag = f2;
-        }
+        for (int t = 0; t < kPoolSlots; ++t) hit |= b[j] == key[t];
+        if (!hit) missing = b[j];
       }
-      const bool commit = rb >= 0 && (lane == 31 || right != rb);
-      // two segments of this round may address the same bin (a new row falling back to a lower bin)
-      const unsigned peers = __match_any_sync(full, commit ? rb : -1 - lane);
-      const int rank = __popc(peers & ((1u << lane) - 1u));
-      const int steps = __reduce_max_sync(full, commit ? __popc(peers) : 0);
-      for (int g = 0; g < steps; ++g) {
-        if (commit && rank == g) {
-          w_sum[rb] += s;
-          w_cnt[rb] += cnt;
-          w_pp[rb] = fmax(w_pp[rb], pp);
-          w_np[rb] = fmax(w_np[rb], np);
+      const unsigned mm = __ballot_sync(full, missing >= 0);
+      if (mm == 0) break;
+      const int nb = __shfl_sync(full, missing, __ffs(mm) - 1);
+      bool placed = false;
+#pragma unroll
+      for (int t = 0; t < kPoolSlots; ++t)
+        if (!placed && key[t] < 0) {
+          key[t] = nb;
+          placed = true;
         }
-        __syncwarp();
+      if (!placed) {  // all slots busy: flush them and start over with the new bin
+#pragma unroll
+        for (int t = 0; t < kPoolSlots; ++t) {
+          pool_flush_slot(acc[t], key[t], lane, w_sum, w_cnt, w_pp, w_np);
+          key[t] = -2;
+        }
+        key[0] = nb;
       }
     }
+#pragma unroll
+    for (int j = 0; j < kPoolPerLane; ++j) {
+#pragma unroll
+      for (int t = 0; t < kPoolSlots; ++t)
+        if (b[j] == key[t]) acc[t].add(v[j]);
+    }
   }
+#pragma unroll
+  for (int t = 0; t < kPoolSlots; ++t)
+    if (key[t] >= 0) pool_flush_slot(acc[t], key[t], lane, w_sum, w_cnt, w_pp, w_np);
   __syncthreads();
   const size_t out = ((size_t)br * tiles + tile) * V;
   for (int bc = threadIdx.x; bc < V; bc += kPoolBlock) {

@@ -276,6 +276,139 @@ int coarsen_pmis(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const i
 }
 
 // ---------------------------------------------------------------------------
+// CLJP (coarsen type 0, hypre_BoomerAMGCoarsen): the parallel coarsening of the Falgout
+// family -- under Falgout (the reference's PCHYPRE default, serial on one rank) this routine
+// is the third stage.  Operation for operation oracle/amg_oracle.cpp::coarsen_cljp (restated
+// from memory like the rest; parity unpinned).  The measure of a point is the number of
+// strong connections INTO it that are still in the graph, plus the PMIS tie breaker; the
+// independent-set step is the PMIS one; what differs are the edge removals and measure
+// decrements after every round.  Measures change by exact decrements of 1.0 (atomicAdd of
+// -1.0 is exact here), so the splitting does not depend on the order of the threads.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+cljp_init_kernel(int64_t n, const int32_t* __restrict__ influence, const int32_t* __restrict__ has_strong,
+                 double* __restrict__ measure, int32_t* __restrict__ cf) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const bool any = has_strong[i] != 0;
+  cf[i] = any ? 0 : -3;  // rows without strong connections never coarsen (special F points)
+  measure[i] = any ? (double)influence[i] + hypre_rand_at(i) : 0.0;
+}
+
+__global__ void __launch_bounds__(kBlock)
+cljp_edges_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                  const uint8_t* __restrict__ mask, const int32_t* __restrict__ cf, uint8_t* __restrict__ edge) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  for (int k = rp[i]; k < rp[i + 1]; ++k) edge[k] = mask[k] && cf[col[k]] != -3;
+}
+
+// (1) undecided points nobody depends on any more, whose own dependencies are all accounted
+// for, become F; decided points leave the graph; counts the undecided ones
+__global__ void __launch_bounds__(kBlock)
+cljp_set_f_kernel(int64_t n, const int32_t* __restrict__ rp, const uint8_t* __restrict__ edge,
+                  int32_t* __restrict__ cf, double* __restrict__ measure, int32_t* __restrict__ undecided) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  int und = 0;
+  if (i < n) {
+    int c = cf[i];
+    if (c == 0 && measure[i] < 1.0) {
+      bool open = false;
+      for (int k = rp[i]; k < rp[i + 1] && !open; ++k) open = edge[k] != 0;
+      if (!open) {
+        c = -1;
+        cf[i] = -1;
+      }
+    }
+    if (c != 0) measure[i] = 0.0; else und = 1;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, und);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(undecided, __popc(b));
+}
+
+// (3) new C points drop their dependency edges and their targets lose one; (4) undecided
+// points drop the edges to C points and the edges to points they share a C point with
+__global__ void __launch_bounds__(kBlock)
+cljp_update_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                   const uint8_t* __restrict__ mask, const int32_t* __restrict__ cf,
+                   const int32_t* __restrict__ newc, uint8_t* __restrict__ edge, double* __restrict__ measure) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const int b = rp[i], e = rp[i + 1];
+  if (newc[i]) {
+    for (int k = b; k < e; ++k)
+      if (edge[k]) {
+        edge[k] = 0;
+        if (cf[col[k]] == 0) atomicAdd(&measure[col[k]], -1.0);
+      }
+    return;
+  }
+  if (cf[i] != 0) return;
+  for (int k = b; k < e; ++k)
+    if (mask[k] && cf[col[k]] > 0) edge[k] = 0;
+  for (int k = b; k < e; ++k) {
+    if (!edge[k]) continue;
+    const int j = col[k];
+    bool common = false;
+    for (int k2 = rp[j]; k2 < rp[j + 1] && !common; ++k2) {
+      if (!mask[k2]) continue;
+      const int c = col[k2];
+      if (cf[c] <= 0) continue;
+      // is c a strong dependency of i as well?  (row i is sorted by column)
+      int lo = b, hi = e;
+      while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (col[mid] < c) lo = mid + 1; else hi = mid;
+      }
+      common = lo < e && col[lo] == c && mask[lo];
+    }
+    if (common) {
+      edge[k] = 0;
+      atomicAdd(&measure[j], -1.0);
+    }
+  }
+}
+
+int coarsen_cljp(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const int32_t* has_strong, int32_t* cf) {
+  const int64_t n = A.n;
+  const unsigned grid = (unsigned)div_up(n, kBlock);
+  DevBuf<int32_t> influence, mark, undecided;
+  DevBuf<double> measure;
+  DevBuf<uint8_t> edge;
+  AMGB_TRY(influence.alloc_zero(ctx, n));
+  AMGB_TRY(mark.alloc(ctx, n));
+  AMGB_TRY(measure.alloc(ctx, n));
+  AMGB_TRY(undecided.alloc(ctx, 1));
+  AMGB_TRY(edge.alloc(ctx, A.nnz));
+  const double row_bytes = 5.0 * A.nnz + 4.0 * (n + 1);
+  AMGB_LAUNCH(ctx, F_COARSEN, row_bytes, pmis_influence_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p, mask,
+              influence.p);
+  AMGB_LAUNCH(ctx, F_COARSEN, 20.0 * n, cljp_init_kernel, grid, kBlock, 0, n, (const int32_t*)influence.p, has_strong,
+              measure.p, cf);
+  AMGB_LAUNCH(ctx, F_COARSEN, row_bytes + A.nnz, cljp_edges_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p, mask,
+              (const int32_t*)cf, edge.p);
+  AMGB_CHECK_LAUNCH(ctx);
+  for (int round = 0; round < 100000; ++round) {
+    AMGB_CUDA(ctx, cudaMemsetAsync(undecided.p, 0, sizeof(int32_t), ctx->stream));
+    AMGB_LAUNCH(ctx, F_COARSEN, A.nnz + 16.0 * n, cljp_set_f_kernel, grid, kBlock, 0, n, A.rp.p,
+                (const uint8_t*)edge.p, cf, measure.p, undecided.p);
+    AMGB_CHECK_LAUNCH(ctx);
+    int32_t und = 0;
+    AMGB_TRY(read_i32(ctx, undecided.p, &und));
+    if (und == 0) return AMGB_OK;
+    AMGB_LAUNCH(ctx, F_COARSEN, 16.0 * n, pmis_mark_kernel, grid, kBlock, 0, n, (const int32_t*)cf,
+                (const double*)measure.p, mark.p);
+    AMGB_LAUNCH(ctx, F_COARSEN, row_bytes, pmis_knockout_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p, mask,
+                (const int32_t*)cf, (const double*)measure.p, mark.p);
+    AMGB_LAUNCH(ctx, F_COARSEN, 12.0 * n, pmis_set_c_kernel, grid, kBlock, 0, n, (const int32_t*)mark.p, cf);
+    AMGB_LAUNCH(ctx, F_COARSEN, 2.0 * row_bytes, cljp_update_kernel, grid, kBlock, 0, n, A.rp.p, A.col.p, mask,
+                (const int32_t*)cf, (const int32_t*)mark.p, edge.p, measure.p);
+    AMGB_CHECK_LAUNCH(ctx);
+  }
+  return set_error(ctx, AMGB_ERR_BREAKDOWN, "CLJP did not terminate");
+}
+
+// ---------------------------------------------------------------------------
 // Interpolation type 0, modified classical (hypre_BoomerAMGBuildInterp).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock)
@@ -1752,10 +1885,13 @@ int resolve_options(amgb_precond* P) {
   const amgb_boomeramg_data& d = P->data;
   if (d.aggressive_coarsening_num_levels != 0 && P->dist)
     return set_error(ctx, AMGB_ERR_UNSUPPORTED, "aggressive coarsening is not available on the row-partitioned path");
-  if (d.coarsen_type != AMGB_COARSEN_PMIS)
+  if (d.coarsen_type != AMGB_COARSEN_PMIS && d.coarsen_type != AMGB_COARSEN_CLJP)
     return set_error(ctx, AMGB_ERR_UNSUPPORTED,
-                     "coarsen_type %d: only PMIS (8) runs on the device (Falgout/RS is sequential)",
-                     d.coarsen_type);
+                     "coarsen_type %d: PMIS (8) and CLJP (0) run on the device; the Ruge-Stueben passes of Falgout "
+                     "(6) are sequential -- CLJP is its parallel third stage", d.coarsen_type);
+  if (d.coarsen_type == AMGB_COARSEN_CLJP && (P->dist || d.aggressive_coarsening_num_levels != 0))
+    return set_error(ctx, AMGB_ERR_UNSUPPORTED,
+                     "CLJP coarsening: single device, without aggressive levels");
   if (d.interp_type != AMGB_INTERP_CLASSICAL)
     return set_error(ctx, AMGB_ERR_UNSUPPORTED, "interp_type %d not available", d.interp_type);
   if (d.max_levels < 1) return set_error(ctx, AMGB_ERR_BAD_ARG, "max_levels < 1");
@@ -1829,8 +1965,9 @@ int build_levels_from(amgb_precond* P, int level0) {
     trace.mark(level, "alloc");
     AMGB_TRY(run_strength(ctx, L.A, P->theta_eff, P->mrs_eff, L.mask.p, has_strong.p, diagv.p));
     trace.mark(level, "strength");
-    AMGB_TRY(coarsen_pmis(ctx, L.A, L.mask.p, has_strong.p, L.cf.p, nullptr));
-    trace.mark(level, "pmis");
+    if (d.coarsen_type == AMGB_COARSEN_CLJP) AMGB_TRY(coarsen_cljp(ctx, L.A, L.mask.p, has_strong.p, L.cf.p));
+    else AMGB_TRY(coarsen_pmis(ctx, L.A, L.mask.p, has_strong.p, L.cf.p, nullptr));
+    trace.mark(level, "coarsen");
     // coarse numbering: ascending fine index of the C points
     AMGB_TRY(L.f2c.alloc(ctx, n + 1));
     int32_t nc = 0;

@@ -1531,11 +1531,66 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
   }
   if (!done_by_graph) {
     cond.on = 0;
-    AMGB_TRY(prologue());
+    // One PCG step = ONE graph launch (vector kernels and the whole cycle recorded together): three
+    // host calls per step (launch, flag copy, synchronise) instead of nine.
+    const bool step_graph = P->use_graph && !ctx->timers_on;
+    const bool was_capturing = P->capturing;
+    if (step_graph) P->capturing = true;  // the single cycle of the prologue is not worth an executable graph
+    const int prc = prologue();
+    P->capturing = was_capturing;
+    AMGB_TRY(prc);
     AMGB_TRY(read_flags());
     int64_t it = 0;
+    cudaGraphExec_t step_exec = nullptr;
+    struct ExecGuard {
+      cudaGraphExec_t* e;
+      ~ExecGuard() { if (*e) cudaGraphExecDestroy(*e); }
+    } exec_guard{&step_exec};
+    int64_t step_kernels = 0, step_fam[F_COUNT] = {0};
+    double step_bytes[F_COUNT] = {0};
+    if (step_graph && !hf->done && it < max_steps) {
+      const int64_t l0 = ctx->launches;
+      int64_t fam_l0[F_COUNT];
+      double fam_b0[F_COUNT];
+      for (int f = 0; f < F_COUNT; ++f) {
+        fam_l0[f] = ctx->fam_launches[f];
+        fam_b0[f] = ctx->fam_bytes[f];
+      }
+      cudaGraph_t g = nullptr;
+      int brc = AMGB_OK;
+      if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        P->capturing = true;
+        brc = body();
+        P->capturing = was_capturing;
+        const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+        if (brc == AMGB_OK && ce == cudaSuccess && g) {
+          if (cudaGraphInstantiate(&step_exec, g, 0) != cudaSuccess) step_exec = nullptr;
+        }
+        if (g) cudaGraphDestroy(g);
+      }
+      (void)cudaGetLastError();
+      step_kernels = ctx->launches - l0;
+      ctx->launches = l0;
+      for (int f = 0; f < F_COUNT; ++f) {
+        step_fam[f] = ctx->fam_launches[f] - fam_l0[f];
+        step_bytes[f] = ctx->fam_bytes[f] - fam_b0[f];
+        ctx->fam_launches[f] = fam_l0[f];
+        ctx->fam_bytes[f] = fam_b0[f];
+      }
+      AMGB_TRY(brc);
+    }
     while (!hf->done && it < max_steps) {
-      AMGB_TRY(body());
+      if (step_exec) {
+        AMGB_CUDA(ctx, cudaGraphLaunch(step_exec, ctx->stream));
+        ctx->routes[R_CYCLE_GRAPH]++;
+        ctx->launches += step_kernels;
+        for (int f = 0; f < F_COUNT; ++f) {
+          ctx->fam_launches[f] += step_fam[f];
+          ctx->fam_bytes[f] += step_bytes[f];
+        }
+      } else {
+        AMGB_TRY(body());
+      }
       AMGB_TRY(read_flags());
       ++it;
     }

@@ -389,6 +389,120 @@ void coarsen_falgout(int64_t n, const int32_t* rp, const int32_t* col, const uin
 }
 
 // ---------------------------------------------------------------------------
+// A.3 CLJP (coarsen type 0): hypre_BoomerAMGCoarsen (par_coarsen.c) with CF_init = 0 on one
+// rank, restated from memory like the rest of the AMG part (PARITY UNPINNED).  It is the
+// parallel coarsening of the Falgout family (Falgout = Ruge first/second pass + this routine
+// with CF_init = 1).
+//   measure_i = |S^T_i| + hypre_Rand()  = number of PRESENT edges into i, plus the tie breaker.
+//   Every round:
+//   (1) undecided points with measure < 1 whose own dependency edges are all gone become F
+//       ("make sure all dependencies have been accounted for"); decided points leave the graph;
+//   (2) independent set among the points with measure > 1 (hypre_BoomerAMGIndepSet: along every
+//       strong connection, removed or not, the smaller measure is knocked out) -> new C points;
+//   (3) new C point i: every present edge i -> j is removed and undecided j loses one
+//       ("C points don't interpolate from neighbours that influence them");
+//   (4) undecided point i: edges to C points are removed; a present edge i -> j whose target j
+//       depends (any edge, removed or not) on a C point that i depends on too is removed and j
+//       loses one (i and j already share an interpolation point).
+// Measures only ever change by exact decrements of 1, so the result does not depend on the
+// order in which the points of a round are visited: the device kernels run (3) and (4) in
+// parallel and give the same splitting.
+// ---------------------------------------------------------------------------
+void coarsen_cljp(int64_t n, const int32_t* rp, const int32_t* col, const uint8_t* mask,
+                  std::vector<int32_t>& cf) {
+  std::vector<double> measure(n, 0.0);
+  for (int64_t i = 0; i < n; ++i)
+    for (int32_t k = rp[i]; k < rp[i + 1]; ++k)
+      if (mask[k]) measure[col[k]] += 1.0;
+  int64_t seed = kRandSeed;
+  for (int64_t i = 0; i < n; ++i) {
+    seed = rand_next(seed);
+    measure[i] += double(seed) / double(kRandM);
+  }
+  std::vector<uint8_t> edge(mask, mask + rp[n]);  // 1: strong connection still in the graph
+  cf.assign(n, 0);
+  // rows without strong connections are special F points from the start, as in the Ruge first
+  // pass that precedes this routine under Falgout (and as PMIS does): they never coarsen, and
+  // edges into them are dropped without touching any measure (the SF_PT branch of hypre's loop)
+  std::vector<int32_t> graph;
+  graph.reserve(n);
+  for (int64_t i = 0; i < n; ++i) {
+    bool any = false;
+    for (int32_t k = rp[i]; k < rp[i + 1] && !any; ++k) any = mask[k];
+    if (!any) {
+      cf[i] = -3;
+      measure[i] = 0.0;
+    } else {
+      graph.push_back((int32_t)i);
+    }
+  }
+  for (int64_t i = 0; i < n; ++i)
+    for (int32_t k = rp[i]; k < rp[i + 1]; ++k)
+      if (edge[k] && cf[col[k]] == -3) edge[k] = 0;
+  std::vector<int32_t> mark(n, 0);
+  std::vector<uint8_t> common(n, 0);
+  while (true) {
+    // (1) F points, graph update
+    size_t w = 0;
+    for (int32_t i : graph) {
+      if (cf[i] == 0 && measure[i] < 1.0) {
+        bool open = false;
+        for (int32_t k = rp[i]; k < rp[i + 1] && !open; ++k) open = edge[k] != 0;
+        if (!open) cf[i] = -1;
+      }
+      if (cf[i] != 0) measure[i] = 0.0;
+      else graph[w++] = i;
+    }
+    graph.resize(w);
+    if (graph.empty()) break;
+    // (2) independent set
+    for (int32_t i : graph) mark[i] = measure[i] > 1.0 ? 1 : 0;
+    for (int32_t i : graph) {
+      if (!(measure[i] > 1.0)) continue;
+      for (int32_t k = rp[i]; k < rp[i + 1]; ++k) {
+        if (!mask[k]) continue;
+        const int32_t j = col[k];
+        if (measure[j] > 1.0) {
+          if (measure[i] > measure[j]) mark[j] = 0;
+          else if (measure[j] > measure[i]) mark[i] = 0;
+        }
+      }
+    }
+    for (int32_t i : graph)
+      if (mark[i]) cf[i] = 1;
+    // (3), (4)
+    for (int32_t i : graph) {
+      if (cf[i] > 0) {
+        for (int32_t k = rp[i]; k < rp[i + 1]; ++k)
+          if (edge[k]) {
+            edge[k] = 0;
+            if (cf[col[k]] == 0) measure[col[k]] -= 1.0;
+          }
+        continue;
+      }
+      for (int32_t k = rp[i]; k < rp[i + 1]; ++k)
+        if (mask[k] && cf[col[k]] > 0) {
+          edge[k] = 0;
+          common[col[k]] = 1;
+        }
+      for (int32_t k = rp[i]; k < rp[i + 1]; ++k) {
+        if (!edge[k]) continue;
+        const int32_t j = col[k];
+        for (int32_t k2 = rp[j]; k2 < rp[j + 1]; ++k2)
+          if (mask[k2] && common[col[k2]]) {
+            edge[k] = 0;
+            measure[j] -= 1.0;
+            break;
+          }
+      }
+      for (int32_t k = rp[i]; k < rp[i + 1]; ++k)
+        if (mask[k]) common[col[k]] = 0;
+    }
+    for (int32_t i : graph) mark[i] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // A.3 aggressive coarsening (levels < agg_nl), restated from memory like the rest of the
 // AMG part (PARITY UNPINNED):
 //  * hypre_BoomerAMGCreate2ndS with num_paths = 1 (PCHYPRE default agg_num_paths): for a
@@ -1155,6 +1269,14 @@ int orc_coarsen_pmis(int64_t n, const int32_t* rowptr, const int32_t* col, const
   return 0;
 }
 
+int orc_coarsen_cljp(int64_t n, const int32_t* rowptr, const int32_t* col, const uint8_t* mask,
+                     int32_t* cf) {
+  std::vector<int32_t> c;
+  coarsen_cljp(n, rowptr, col, mask, c);
+  std::memcpy(cf, c.data(), n * sizeof(int32_t));
+  return 0;
+}
+
 int orc_coarsen_falgout(int64_t n, const int32_t* rowptr, const int32_t* col,
                         const uint8_t* mask, int32_t* cf) {
   std::vector<int32_t> c;
@@ -1205,6 +1327,8 @@ int orc_setup(int64_t n, const int32_t* rowptr, const int32_t* col, const double
       coarsen_pmis(L.A.n, L.A.rp.data(), L.A.col.data(), L.mask.data(), L.cf);
     else if (data->coarsen_type == AMGB_COARSEN_FALGOUT)
       coarsen_falgout(L.A.n, L.A.rp.data(), L.A.col.data(), L.mask.data(), L.cf);
+    else if (data->coarsen_type == AMGB_COARSEN_CLJP)
+      coarsen_cljp(L.A.n, L.A.rp.data(), L.A.col.data(), L.mask.data(), L.cf);
     else {
       delete h;
       return AMGB_ERR_UNSUPPORTED;

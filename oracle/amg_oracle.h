@@ -46,6 +46,8 @@ int orc_coarsen_pmis(int64_t n, const int32_t* rowptr, const int32_t* col,
                      const uint8_t* mask, int32_t* cf);
 /* hypre_BoomerAMGCoarsenFalgout (coarsen type 6) on one rank: Ruge first+second
  * pass, then CLJP with CF_init=1. */
+int orc_coarsen_cljp(int64_t n, const int32_t* rowptr, const int32_t* col,
+                     const uint8_t* mask, int32_t* cf);
 int orc_coarsen_falgout(int64_t n, const int32_t* rowptr, const int32_t* col,
                         const uint8_t* mask, int32_t* cf);
 

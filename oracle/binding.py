@@ -40,6 +40,7 @@ def lib():
         sig("orc_hypre_rand", C.c_double, C.c_int64)
         sig("orc_coarsen_pmis", C.c_int, C.c_int64, c_i32p, c_i32p, c_u8p, c_i32p)
         sig("orc_coarsen_falgout", C.c_int, C.c_int64, c_i32p, c_i32p, c_u8p, c_i32p)
+        sig("orc_coarsen_cljp", C.c_int, C.c_int64, c_i32p, c_i32p, c_u8p, c_i32p)
         sig("orc_setup", C.c_int, C.c_int64, c_i32p, c_i32p, c_f64p, vp, C.POINTER(vp))
         sig("orc_destroy", None, vp)
         sig("orc_num_levels", C.c_int, vp)
@@ -88,7 +89,7 @@ def coarsen(rowptr, col, mask, kind="pmis"):
     cl = np.ascontiguousarray(col, dtype=np.int32)
     mk = np.ascontiguousarray(mask, dtype=np.uint8)
     cf = np.empty(len(rp) - 1, dtype=np.int32)
-    fn = lib().orc_coarsen_pmis if kind == "pmis" else lib().orc_coarsen_falgout
+    fn = {"pmis": lib().orc_coarsen_pmis, "cljp": lib().orc_coarsen_cljp}.get(kind, lib().orc_coarsen_falgout)
     fn(len(rp) - 1, _p(rp, c_i32p), _p(cl, c_i32p), _p(mk, c_u8p), _p(cf, c_i32p))
     return cf
 

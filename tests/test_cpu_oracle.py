@@ -467,3 +467,25 @@ def test_chebyshev_coefficients_are_the_scaled_chebyshev_polynomial():
         got = 1 - t * (c[0] + c[1] * t)
         assert np.allclose(got, want, rtol=0, atol=1e-12)
         assert np.abs(got[t >= lower]).max() <= 1.0 / T2(theta / delta) + 1e-12   # equioscillation bound
+
+
+@pytest.mark.parametrize("m,theta,contrast", [(8, 0.25, 0.0), (10, 0.5, 4.0), (12, 0.25, 6.0)])
+def test_cljp_splitting_properties(m, theta, contrast):
+    """CLJP (coarsen type 0, the parallel stage of the Falgout family) in the oracle: every point is
+    decided; rows without strong connections are special F points; every ordinary F point keeps
+    a strong C neighbour to interpolate from; the coarse grid is denser than the PMIS one."""
+    import amg_ann_b200 as ab
+    from oracle import binding as orc
+    epsv = ab.gen.checkerboard_epsv(2, 3, contrast) if contrast else None
+    s = ab.gen.poisson_q1(m, 2, 3, epsv) if contrast else ab.gen.poisson_q1(m)
+    rp = s.rowptr32()
+    mask = orc.strength(rp, s.col, s.val, theta)
+    cf = orc.coarsen(rp, s.col, mask, "cljp")
+    assert set(np.unique(cf)) <= {1, -1, -3}
+    strong_rows = np.add.reduceat(mask.astype(np.int64), rp[:-1]) > 0
+    assert ((cf == -3) == ~strong_rows).all()
+    is_c = cf > 0
+    has_c = np.add.reduceat((mask.astype(bool) & is_c[s.col]).astype(np.int64), rp[:-1]) > 0
+    assert has_c[(cf == -1)].all()          # every ordinary F point interpolates from at least one C point
+    pm = orc.coarsen(rp, s.col, mask, "pmis")
+    assert (cf > 0).sum() > (pm > 0).sum()  # denser coarse grids than PMIS: that is what buys the convergence

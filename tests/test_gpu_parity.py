@@ -556,3 +556,46 @@ def test_coarse_tail_in_one_kernel_matches_the_per_level_cycle(gpu_ctx, monkeypa
         assert (np.abs(h[:k] - hist[:k]) <= RES_RTOL * hist[:k]).all(), mode
     k = min(len(got["tail"][1]), len(got["levels"][1]))
     assert (np.abs(got["tail"][1][:k] - got["levels"][1][:k]) <= 1e-11 * got["levels"][1][:k]).all()
+
+
+# ---- CLJP coarsening (hypre coarsen type 0): the parallel member of the Falgout family ----
+@pytest.mark.parametrize("m,theta,contrast", [(8, 0.25, 0.0), (12, 0.5, 3.0), (16, 0.25, 6.0), (14, 0.7, 0.0), (10, 0.05, 6.0)])
+def test_cljp_coarsening_is_bit_exact(gpu_ctx, m, theta, contrast):
+    """coarsen_type = CLJP on the device against the oracle's CLJP: C/F splittings, operators and
+    interpolation bit-identical on every level; PCG history to the north-star tolerance."""
+    s = poisson(m, contrast=contrast)
+    data = device_data(theta, coarsen_type=ab.COARSEN_CLJP)
+    A, P, H = _both(gpu_ctx, s, data)
+    _assert_hierarchy_identical(P, H)
+    cf = P.cf_marker(0)
+    assert set(np.unique(cf)) <= {1, -1, -3}
+    ctl = ab.SolverControl(s.n, 1e-8)
+    x = s.x0.copy()
+    ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+    rc, xo, nit, hist = H.cg_solve(s.rhs, s.x0, abs_tol=1e-8)
+    assert rc == 0 and abs(ctl.last_step() - nit) <= 1
+    k = min(len(hist), len(ctl.history))
+    assert (np.abs(ctl.history[:k] - hist[:k]) <= RES_RTOL * hist[:k]).all()
+    # the point of this family: fewer iterations than PMIS at a higher operator complexity
+    Pm = ab.PreconditionBoomerAMG()
+    Pm.initialize(A, device_data(theta))
+    assert P.level_stats()["operator"] > Pm.level_stats()["operator"]
+
+
+def test_cljp_on_an_unstructured_system(gpu_ctx):
+    M = random_spd_csr(3000, 0.003, 11)
+    class S:
+        n = M.shape[0]; col = M.indices; val = M.data
+        def rowptr32(self): return M.indptr.astype(np.int32)
+    A, P, H = _both(gpu_ctx, S(), device_data(0.25, coarsen_type=ab.COARSEN_CLJP))
+    _assert_hierarchy_identical(P, H)
+
+
+def test_cljp_is_refused_where_it_is_not_implemented(gpu_ctx):
+    s = poisson(6)
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    d = device_data(0.25, coarsen_type=ab.COARSEN_CLJP)
+    d.aggressive_coarsening_num_levels = 1
+    with pytest.raises(ab.AmgbError) as e:
+        ab.PreconditionBoomerAMG().initialize(A, d)
+    assert e.value.status == -5

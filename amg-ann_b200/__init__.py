@@ -262,6 +262,33 @@ class SparseMatrix:
         _chk(ctx._h, rc, "amgb_matrix_assemble_poisson_q1")
         return self
 
+    @classmethod
+    def assemble_elasticity_q1(cls, ctx, m, pattern_size=1, mode=1, young=None, rhs_ptr=0, x0_ptr=0):
+        """On-device assembly of the Q1 elasticity system (ref t3 main.cpp:320-342): matrix and x0
+        bit-identical to gen.elasticity_q1, rhs to rounding.  rhs_ptr / x0_ptr: device pointers to
+        3 (m+1)^3 doubles, or 0."""
+        if young is None:
+            young = np.ones(pattern_size ** mode)
+        young = np.ascontiguousarray(young, dtype=np.float64)
+        self = cls.__new__(cls)
+        self.ctx, self.n = ctx, 3 * (m + 1) ** 3
+        self._h = C.c_void_p()
+        rc = amgb_lib().amgb_matrix_assemble_elasticity_q1(ctx._h, m, pattern_size, mode, _p(young, c_f64p), len(young),
+                                                           C.byref(self._h), C.c_void_p(rhs_ptr), C.c_void_p(x0_ptr))
+        _chk(ctx._h, rc, "amgb_matrix_assemble_elasticity_q1")
+        return self
+
+    def permuted(self, new_to_old):
+        """Q A Q^T on the device for a DoF renumbering given as new -> old (a permutation)."""
+        perm = np.ascontiguousarray(new_to_old, dtype=np.int32)
+        assert len(perm) == self.n
+        out = SparseMatrix.__new__(SparseMatrix)
+        out.ctx, out.n = self.ctx, self.n
+        out._h = C.c_void_p()
+        rc = amgb_lib().amgb_matrix_permute(self.ctx._h, self._h, _p(perm, c_i32p), C.byref(out._h))
+        _chk(self.ctx._h, rc, "amgb_matrix_permute")
+        return out
+
     def download(self):
         n, nnz = C.c_int64(), C.c_int64()
         amgb_lib().amgb_matrix_dims(self._h, C.byref(n), C.byref(nnz))
@@ -292,6 +319,16 @@ class SparseMatrix:
         _chk(self.ctx._h, amgb_lib().amgb_matrix_vmult(self.ctx._h, self._h, _p(y, c_f64p),
                                                        _p(x, c_f64p)), "amgb_matrix_vmult")
         return y
+
+
+def numbering_dealii_q1(ctx, coarse_cells, refinements):
+    """new -> lexicographic node id of deal.II's distribute_dofs numbering for Q1 on
+    subdivided_hyper_cube(coarse_cells) refined `refinements` times (include/amgb.h)."""
+    m = coarse_cells << refinements
+    out = np.empty((m + 1) ** 3, dtype=np.int32)
+    _chk(ctx._h, amgb_lib().amgb_numbering_dealii_q1(ctx._h, coarse_cells, refinements, _p(out, c_i32p)),
+         "amgb_numbering_dealii_q1")
+    return out
 
 
 class PreconditionBoomerAMG:

@@ -74,6 +74,7 @@ def gen_lib():
              c_i64p, c_i32p, c_f64p, c_f64p, c_f64p)
         _sig(L.amgb_gen_random_vec, C.c_int, C.c_int64, C.c_int64, C.c_double, c_f64p)
         _sig(L.amgb_gen_checkerboard_epsv, C.c_int, C.c_int, C.c_int, C.c_double, c_f64p)
+        _sig(L.amgb_gen_cuthill_mckee, C.c_int, C.c_int64, c_i64p, c_i32p, C.c_int, c_i32p)
         _gen = L
     return _gen
 
@@ -82,8 +83,8 @@ AMGB_SYMBOLS = [
     "amgb_ctx_create", "amgb_ctx_destroy", "amgb_ctx_synchronize", "amgb_last_error",
     "amgb_status_string", "amgb_version", "amgb_ctx_kernel_launches",
     "amgb_ctx_reset_kernel_launches", "amgb_matrix_upload_csr", "amgb_matrix_upload_csr64",
-    "amgb_matrix_wrap_device_csr", "amgb_matrix_destroy", "amgb_matrix_dims",
-    "amgb_matrix_assemble_poisson_q1", "amgb_matrix_assemble_poisson_q1_hostvec", "amgb_matrix_download_csr", "amgb_dist_matrix_assemble_poisson_q1",
+    "amgb_matrix_wrap_device_csr", "amgb_matrix_destroy", "amgb_matrix_dims", "amgb_numbering_dealii_q1", "amgb_matrix_permute",
+    "amgb_matrix_assemble_poisson_q1", "amgb_matrix_assemble_elasticity_q1", "amgb_matrix_assemble_poisson_q1_hostvec", "amgb_matrix_download_csr", "amgb_dist_matrix_assemble_poisson_q1",
     "amgb_matrix_vmult", "amgb_boomeramg_data_default", "amgb_precond_initialize",
     "amgb_precond_destroy", "amgb_precond_vmult", "amgb_precond_vmult_device",
     "amgb_precond_num_levels", "amgb_precond_level_stats", "amgb_precond_level_row_stats",
@@ -97,7 +98,7 @@ AMGB_SYMBOLS = [
     # row-partitioned path
     "amgb_nccl_unique_id", "amgb_comm_create_nccl", "amgb_local_group_create",
     "amgb_local_group_destroy", "amgb_local_group_abort", "amgb_comm_create_local", "amgb_comm_destroy", "amgb_comm_rank",
-    "amgb_comm_size", "amgb_dist_matrix_create", "amgb_dist_matrix_destroy",
+    "amgb_comm_size", "amgb_dist_matrix_create", "amgb_dist_matrix_destroy", "amgb_dist_make_view",
     "amgb_dist_precond_initialize", "amgb_dist_cg_solve", "amgb_dist_cg_solve_device",
     "amgb_dist_precond_level_dims", "amgb_dist_precond_replicated_from", "amgb_dist_precond_get_cf_marker",
     "amgb_dist_precond_get_A_rows", "amgb_dist_precond_get_P_rows",
@@ -135,12 +136,16 @@ def amgb_lib():
              C.POINTER(vp))
         _sig(L.amgb_matrix_assemble_poisson_q1, C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, c_f64p, C.c_int64,
              C.POINTER(vp), vp, vp)
+        _sig(L.amgb_matrix_assemble_elasticity_q1, C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, c_f64p, C.c_int64,
+             C.POINTER(vp), vp, vp)
         _sig(L.amgb_matrix_assemble_poisson_q1_hostvec, C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, c_f64p,
              C.c_int64, C.POINTER(vp), c_f64p, c_f64p)
         _sig(L.amgb_matrix_download_csr, C.c_int, vp, c_i32p, c_i32p, c_f64p)
         _sig(L.amgb_dist_matrix_assemble_poisson_q1, C.c_int, vp, vp, C.c_int32, C.c_int32, C.c_int32, c_f64p,
              C.c_int64, C.c_int64, C.c_int64, C.POINTER(vp), vp, vp)
         _sig(L.amgb_matrix_destroy, C.c_int, vp)
+        _sig(L.amgb_numbering_dealii_q1, C.c_int, vp, C.c_int32, C.c_int32, c_i32p)
+        _sig(L.amgb_matrix_permute, C.c_int, vp, vp, c_i32p, C.POINTER(vp))
         _sig(L.amgb_matrix_dims, C.c_int, vp, c_i64p, c_i64p)
         _sig(L.amgb_matrix_vmult, C.c_int, vp, vp, c_f64p, c_f64p)
         _sig(L.amgb_boomeramg_data_default, C.c_int, C.POINTER(BoomerAMGDataStruct))
@@ -189,6 +194,7 @@ def amgb_lib():
         _sig(L.amgb_dist_matrix_create, C.c_int, vp, vp, C.c_int64, C.c_int64, C.c_int64, c_i64p,
              c_i32p, c_f64p, C.POINTER(vp))
         _sig(L.amgb_dist_matrix_destroy, C.c_int, vp)
+        _sig(L.amgb_dist_make_view, C.c_int, vp, vp, C.c_int32, c_f64p, c_i64p, c_f64p, c_f64p, c_f64p)
         _sig(L.amgb_dist_precond_initialize, C.c_int, vp, vp, C.POINTER(BoomerAMGDataStruct),
              C.POINTER(vp))
         _sig(L.amgb_dist_cg_solve, C.c_int, vp, c_f64p, c_f64p, vp, C.c_int64, C.c_double, c_f64p,

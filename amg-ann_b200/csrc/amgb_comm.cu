@@ -85,8 +85,10 @@ struct NcclComm : amgb_comm {
   int alltoallv(amgb_ctx* ctx, const void* send, const size_t* scount, const size_t* sdispl, void* recv,
                 const size_t* rcount, const size_t* rdispl) override {
     NcclApi& n = nccl_api();
-    if (scount[rank] != rcount[rank]) return set_error(ctx, AMGB_ERR_COMM, "alltoallv: self counts differ");
-    if (scount[rank])
+    // (an inconsistent self count is reported AFTER the exchange with the peers has been posted:
+    // leaving early would strand them in their receives)
+    const bool self_bad = scount[rank] != rcount[rank];
+    if (!self_bad && scount[rank])
       AMGB_CUDA(ctx, cudaMemcpyAsync((char*)recv + rdispl[rank], (const char*)send + sdispl[rank], scount[rank],
                                      cudaMemcpyDeviceToDevice, ctx->stream));
     AMGB_NCCL(ctx, n.GroupStart());
@@ -96,6 +98,7 @@ struct NcclComm : amgb_comm {
       if (rcount[q]) AMGB_NCCL(ctx, n.Recv((char*)recv + rdispl[q], rcount[q], kNcclChar, q, comm, ctx->stream));
     }
     AMGB_NCCL(ctx, n.GroupEnd());
+    if (self_bad) return set_error(ctx, AMGB_ERR_COMM, "alltoallv: self counts differ");
     return AMGB_OK;
   }
   int allgather_host(amgb_ctx* ctx, const void* mine, size_t bytes, void* all) override {

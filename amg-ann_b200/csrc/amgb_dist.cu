@@ -940,20 +940,44 @@ void amgb_dist_state_destroy(amgb_dist_state* s) { delete s; }
 
 extern "C" {
 
+// COLLECTIVE, including its failures: every rank first contributes its row range and a local
+// verdict to one all-gather, so a rank with bad arguments cannot leave while its peers wait in a
+// collective for it -- all ranks return an error together (the offending rank with its own
+// message, the others AMGB_ERR_COMM naming it).
 int amgb_dist_matrix_create(amgb_ctx* ctx, amgb_comm* comm, int64_t n_global, int64_t row_begin, int64_t row_end,
                             const int64_t* rowptr_local, const int32_t* col_global, const double* val,
                             amgb_dist_matrix** out) {
-  if (!ctx || !comm || !rowptr_local || !out || row_begin < 0 || row_end < row_begin || row_end > n_global)
-    return AMGB_ERR_BAD_ARG;
+  if (!ctx || !comm || !out) return AMGB_ERR_BAD_ARG;  // (no communicator to agree on anything)
   *out = nullptr;
-  if (n_global >= (int64_t(1) << 31))
-    return set_error(ctx, AMGB_ERR_RANGE, "n_global=%lld: global ids are 32-bit", (long long)n_global);
   cudaSetDevice(ctx->device);
-  const int64_t nloc = row_end - row_begin, nnz = rowptr_local[nloc];
-  if (nnz >= (int64_t(1) << 31))
-    return set_error(ctx, AMGB_ERR_RANGE, "local nnz=%lld does not fit 32-bit row pointers: use more ranks",
-                     (long long)nnz);
-  if (nnz > 0 && (!col_global || !val)) return AMGB_ERR_BAD_ARG;
+  int local = AMGB_OK;
+  int64_t nloc = 0, nnz = 0;
+  if (!rowptr_local || row_begin < 0 || row_end < row_begin || row_end > n_global) {
+    local = set_error(ctx, AMGB_ERR_BAD_ARG, "bad row range [%lld, %lld) of %lld or null row pointers",
+                      (long long)row_begin, (long long)row_end, (long long)n_global);
+  } else if (n_global >= (int64_t(1) << 31)) {
+    local = set_error(ctx, AMGB_ERR_RANGE, "n_global=%lld: global ids are 32-bit", (long long)n_global);
+  } else {
+    nloc = row_end - row_begin;
+    nnz = rowptr_local[nloc];
+    if (nnz >= (int64_t(1) << 31))
+      local = set_error(ctx, AMGB_ERR_RANGE, "local nnz=%lld does not fit 32-bit row pointers: use more ranks",
+                        (long long)nnz);
+    else if (nnz > 0 && (!col_global || !val))
+      local = set_error(ctx, AMGB_ERR_BAD_ARG, "null column / value arrays");
+  }
+  const int64_t mine[2] = {row_begin, (int64_t)local};
+  std::vector<int64_t> all(2 * (size_t)comm->size);
+  AMGB_TRY(comm->allgather_host(ctx, mine, sizeof mine, all.data()));
+  for (int q = 0; q < comm->size; ++q)
+    if (all[2 * q + 1] != AMGB_OK) {
+      if (local != AMGB_OK) return local;
+      return set_error(ctx, AMGB_ERR_COMM, "rank %d rejected its part of the matrix (status %lld)", q,
+                       (long long)all[2 * q + 1]);
+    }
+  for (int q = 0; q + 1 < comm->size; ++q)
+    if (all[2 * q] > all[2 * (q + 1)])  // (the same verdict on every rank: computed from the gathered ranges)
+      return set_error(ctx, AMGB_ERR_BAD_ARG, "row ranges must ascend with the rank");
   amgb_dist_matrix* M = new amgb_dist_matrix;
   M->ctx = ctx;
   M->comm = comm;
@@ -961,34 +985,34 @@ int amgb_dist_matrix_create(amgb_ctx* ctx, amgb_comm* comm, int64_t n_global, in
   o.n_global = n_global;
   o.g0 = row_begin;
   o.starts.assign(comm->size + 1, 0);
-  std::vector<int64_t> begins(comm->size);
-  int rc = comm->allgather_host(ctx, &row_begin, sizeof(int64_t), begins.data());
-  for (int q = 0; q < comm->size; ++q) o.starts[q] = begins[q];
+  for (int q = 0; q < comm->size; ++q) o.starts[q] = all[2 * q];
   o.starts[comm->size] = n_global;
-  for (int q = 0; q < comm->size && rc == AMGB_OK; ++q)
-    if (o.starts[q] > o.starts[q + 1]) rc = set_error(ctx, AMGB_ERR_BAD_ARG, "row ranges must ascend with the rank");
   o.M.n = nloc;
   o.M.ncols = n_global;
   o.M.nnz = nnz;
   std::vector<int32_t> rp32(nloc + 1);
   for (int64_t i = 0; i <= nloc; ++i) rp32[i] = (int32_t)rowptr_local[i];
-  if (rc == AMGB_OK) rc = o.M.rp.alloc(ctx, nloc + 1);
+  int rc = o.M.rp.alloc(ctx, nloc + 1);
   if (rc == AMGB_OK) rc = o.M.col.alloc(ctx, nnz);
   if (rc == AMGB_OK) rc = o.M.val.alloc(ctx, nnz);
+  cudaError_t e = cudaSuccess;
+  if (rc == AMGB_OK) {
+    e = cudaMemcpyAsync(o.M.rp.p, rp32.data(), (nloc + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz)
+      e = cudaMemcpyAsync(o.M.col.p, col_global, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz)
+      e = cudaMemcpyAsync(o.M.val.p, val, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "distributed matrix upload", __FILE__, __LINE__);
+  }
+  // an allocation or copy failure is a local event too: agree on it before anyone goes on
+  int64_t good = rc == AMGB_OK ? 1 : 0;
+  const int arc = allreduce_min_i64_host(ctx, comm, &good);
+  if (rc == AMGB_OK && arc != AMGB_OK) rc = arc;
+  if (rc == AMGB_OK && !good) rc = set_error(ctx, AMGB_ERR_COMM, "another rank could not upload its part of the matrix");
   if (rc != AMGB_OK) {
     delete M;
     return rc;
-  }
-  cudaError_t e = cudaMemcpyAsync(o.M.rp.p, rp32.data(), (nloc + 1) * sizeof(int32_t), cudaMemcpyHostToDevice,
-                                  ctx->stream);
-  if (e == cudaSuccess && nnz)
-    e = cudaMemcpyAsync(o.M.col.p, col_global, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess && nnz)
-    e = cudaMemcpyAsync(o.M.val.p, val, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e != cudaSuccess) {
-    delete M;
-    return cuda_fail(ctx, e, "distributed matrix upload", __FILE__, __LINE__);
   }
   *out = M;
   return AMGB_OK;

@@ -21,6 +21,9 @@
 // fixed (input-independent) association.
 #include <climits>
 
+#include <vector>
+
+#include "amgb_dist.cuh"
 #include "amgb_internal.cuh"
 
 namespace amgb {
@@ -87,7 +90,8 @@ constexpr int kPoolSlots = 4;
 
 template <bool VEC>
 __global__ void __launch_bounds__(kPoolBlock, 3)
-pool_entries_kernel(BinMap bm, int tiles, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+pool_entries_kernel(BinMap bm, int tiles, long long g0, int nloc, const int32_t* __restrict__ rp,
+                    const int32_t* __restrict__ col,
                     const double* __restrict__ val, double* __restrict__ part_sum,
                     long long* __restrict__ part_cnt, double* __restrict__ part_pp,
                     double* __restrict__ part_np) {
@@ -107,7 +111,9 @@ pool_entries_kernel(BinMap bm, int tiles, const int32_t* __restrict__ rp, const 
     s_cnt[t] = 0;
   }
   __syncthreads();
-  const int e_lo = rp[bm.row_begin(br)], e_hi = rp[bm.row_begin(br + 1)];
+  // rows [g0, g0 + nloc) of the global matrix are held here (a single device holds all of them)
+  const long long rb0 = (long long)bm.row_begin(br) - g0, rb1 = (long long)bm.row_begin(br + 1) - g0;
+  const int e_lo = rp[rb0 < 0 ? 0 : (rb0 > nloc ? nloc : (int)rb0)], e_hi = rp[rb1 < 0 ? 0 : (rb1 > nloc ? nloc : (int)rb1)];
   // whole CTA-chunks (absolute multiples of kPoolBlockChunk, so every lane's 8 entries are
   // 32-byte / 64-byte aligned) that overlap the entry range of this row-bin, split over the tiles
   const int c_first = e_lo / kPoolBlockChunk, c_last = (int)(((long long)e_hi + kPoolBlockChunk - 1) / kPoolBlockChunk);
@@ -158,14 +164,23 @@ pool_entries_kernel(BinMap bm, int tiles, const int32_t* __restrict__ rp, const 
     int b[kPoolPerLane];
 #pragma unroll
     for (int j = 0; j < kPoolPerLane; ++j) b[j] = c[j] >= 0 ? bm.bin(c[j]) : -1;
+    // Every pass adds the entries whose bin is cached and consumes them (b = -1); what is left
+    // names a bin to install -- in a free slot, or after flushing all slots when none is free.
+    // One new bin per pass, so a chunk with k uncached bins takes k + 1 passes; the steady state
+    // of a banded matrix is a single pass and a single vote.
     for (;;) {
       int missing = -1;  // a bin of mine that no slot holds
 #pragma unroll
       for (int j = 0; j < kPoolPerLane; ++j) {
-        bool hit = b[j] < 0;
+        if (b[j] < 0) continue;
+        bool hit = false;
 #pragma unroll
-        for (int t = 0; t < kPoolSlots; ++t) hit |= b[j] == key[t];
-        if (!hit) missing = b[j];
+        for (int t = 0; t < kPoolSlots; ++t)
+          if (b[j] == key[t]) {
+            acc[t].add(v[j]);
+            hit = true;
+          }
+        if (hit) b[j] = -1; else missing = b[j];
       }
       const unsigned mm = __ballot_sync(full, missing >= 0);
       if (mm == 0) break;
@@ -185,12 +200,6 @@ pool_entries_kernel(BinMap bm, int tiles, const int32_t* __restrict__ rp, const 
         }
         key[0] = nb;
       }
-    }
-#pragma unroll
-    for (int j = 0; j < kPoolPerLane; ++j) {
-#pragma unroll
-      for (int t = 0; t < kPoolSlots; ++t)
-        if (b[j] == key[t]) acc[t].add(v[j]);
     }
   }
 #pragma unroll
@@ -243,9 +252,10 @@ pool_finalize_kernel(int V, int tiles, const double* __restrict__ part_sum,
 using namespace amgb;
 
 // Pooling into device buffers (vv = V*V entries each); ms: device time of the pass.
-static int pool_to_device(amgb_ctx* ctx, const amgb_matrix* A, int V, double* d_sum, long long* d_cnt, double* d_pp,
-                          double* d_np, float* ms_out) {
-  const int n = (int)A->A.n;
+// M: the rows [g0, g0 + M.n) of the n_global x n_global matrix, GLOBAL column ids
+static int pool_to_device(amgb_ctx* ctx, const amgb::DeviceCsr& M, int64_t n_global, int64_t g0, int V, double* d_sum,
+                          long long* d_cnt, double* d_pp, double* d_np, float* ms_out) {
+  const int n = (int)n_global;
   BinMap bm;
   bm.V = V;
   bm.q = n / V;
@@ -256,7 +266,7 @@ static int pool_to_device(amgb_ctx* ctx, const amgb_matrix* A, int V, double* d_
   bm.rq1 = 1.0 / bm.q1;
   // slices per row-bin: enough CTAs for every SM, at least a few CTA-chunks of entries each
   int tiles = (int)div_up((int64_t)ctx->sm_count * 8, V);
-  const int64_t chunks_per_bin = div_up(div_up(A->A.nnz, V), kPoolBlockChunk);
+  const int64_t chunks_per_bin = div_up(div_up(M.nnz, V), kPoolBlockChunk);
   if (tiles > chunks_per_bin / 4) tiles = (int)(chunks_per_bin / 4);
   if (tiles < 1) tiles = 1;
   const size_t vv = (size_t)V * V;
@@ -282,14 +292,14 @@ static int pool_to_device(amgb_ctx* ctx, const amgb_matrix* A, int V, double* d_
   AMGB_CUDA(ctx, cudaEventCreate(&ev.b));
   AMGB_CUDA(ctx, cudaEventRecord(ev.a, ctx->stream));
   // pooling reads 12*nnz + 4*(n+1), writes 28*V^2
-  const double bytes = 12.0 * A->A.nnz + 4.0 * (n + 1) + 28.0 * vv;
-  const bool vec = (reinterpret_cast<uintptr_t>(A->A.col.p) % 16 == 0) && (reinterpret_cast<uintptr_t>(A->A.val.p) % 16 == 0);
+  const double bytes = 12.0 * M.nnz + 4.0 * (M.n + 1) + 28.0 * vv;
+  const bool vec = (reinterpret_cast<uintptr_t>(M.col.p) % 16 == 0) && (reinterpret_cast<uintptr_t>(M.val.p) % 16 == 0);
   if (vec) {
     AMGB_LAUNCH(ctx, F_POOL, bytes, pool_entries_kernel<true>, (unsigned)(V * tiles), kPoolBlock, smem, bm, tiles,
-                A->A.rp.p, A->A.col.p, A->A.val.p, p_sum.p, p_cnt.p, p_pp.p, p_np.p);
+                (long long)g0, (int)M.n, M.rp.p, M.col.p, M.val.p, p_sum.p, p_cnt.p, p_pp.p, p_np.p);
   } else {
     AMGB_LAUNCH(ctx, F_POOL, bytes, pool_entries_kernel<false>, (unsigned)(V * tiles), kPoolBlock, smem, bm, tiles,
-                A->A.rp.p, A->A.col.p, A->A.val.p, p_sum.p, p_cnt.p, p_pp.p, p_np.p);
+                (long long)g0, (int)M.n, M.rp.p, M.col.p, M.val.p, p_sum.p, p_cnt.p, p_pp.p, p_np.p);
   }
   AMGB_LAUNCH(ctx, F_POOL, 28.0 * np + 28.0 * vv, pool_finalize_kernel, (unsigned)div_up(vv, kPoolBlock),
               kPoolBlock, 0, V, tiles, p_sum.p, p_cnt.p, p_pp.p, p_np.p, d_sum, d_cnt, d_pp, d_np);
@@ -316,13 +326,76 @@ extern "C" int amgb_make_view(amgb_ctx* ctx, const amgb_matrix* A, int32_t view_
   AMGB_TRY(d_np.alloc(ctx, vv));
   AMGB_TRY(d_cnt.alloc(ctx, vv));
   float ms = 0.f;
-  AMGB_TRY(pool_to_device(ctx, A, view_size, d_sum.p, d_cnt.p, d_pp.p, d_np.p, &ms));
+  AMGB_TRY(pool_to_device(ctx, A->A, A->A.n, 0, view_size, d_sum.p, d_cnt.p, d_pp.p, d_np.p, &ms));
   AMGB_CUDA(ctx, cudaMemcpyAsync(sum, d_sum.p, vv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   AMGB_CUDA(ctx, cudaMemcpyAsync(count, d_cnt.p, vv * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   AMGB_CUDA(ctx, cudaMemcpyAsync(max_pp, d_pp.p, vv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   AMGB_CUDA(ctx, cudaMemcpyAsync(max_np, d_np.p, vv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (t_us) *t_us = (double)ms * 1000.0;
+  return AMGB_OK;
+}
+
+// Pooled image of a ROW-PARTITIONED matrix (ref common/view_maker.h:41-65 on an MPI matrix): every
+// rank pools the rows it owns into the global V x V bins (global row and column ids), then the four
+// channels are combined over the ranks in rank order -- sums and counts added, maxima maxed -- so
+// every rank returns the same image.  Collective.
+extern "C" int amgb_dist_make_view(amgb_ctx* ctx, const amgb_dist_matrix* A, int32_t view_size, double* sum,
+                                   int64_t* count, double* max_pp, double* max_np, double* t_us) {
+  if (!ctx || !A || !sum || !count || !max_pp || !max_np || view_size < 1) return AMGB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  amgb_comm* comm = A->comm;
+  const size_t vv = (size_t)view_size * view_size;
+  int rc = view_size > kMaxView ? set_error(ctx, AMGB_ERR_UNSUPPORTED, "view_size %d > %d", view_size, kMaxView) : AMGB_OK;
+  // layout of one rank's contribution: [sum | max_pp | max_np | count (as int64)]
+  std::vector<double> mine(4 * vv, 0.0);
+  float ms = 0.f;
+  if (rc == AMGB_OK) {
+    DevBuf<double> d_sum, d_pp, d_np;
+    DevBuf<long long> d_cnt;
+    rc = d_sum.alloc(ctx, vv);
+    if (rc == AMGB_OK) rc = d_pp.alloc(ctx, vv);
+    if (rc == AMGB_OK) rc = d_np.alloc(ctx, vv);
+    if (rc == AMGB_OK) rc = d_cnt.alloc(ctx, vv);
+    if (rc == AMGB_OK)
+      rc = pool_to_device(ctx, A->own.M, A->own.n_global, A->own.g0, view_size, d_sum.p, d_cnt.p, d_pp.p, d_np.p, &ms);
+    if (rc == AMGB_OK) {
+      cudaError_t e = cudaMemcpyAsync(mine.data(), d_sum.p, vv * 8, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(mine.data() + vv, d_pp.p, vv * 8, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(mine.data() + 2 * vv, d_np.p, vv * 8, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(mine.data() + 3 * vv, d_cnt.p, vv * 8, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) rc = cuda_fail(ctx, e, "pooled image download", __FILE__, __LINE__);
+    }
+  }
+  // a local failure is agreed on before the exchange, so no rank waits for one that has left
+  int64_t good = rc == AMGB_OK ? 1 : 0;
+  const int arc = allreduce_min_i64_host(ctx, comm, &good);
+  if (rc == AMGB_OK && arc != AMGB_OK) rc = arc;
+  if (rc == AMGB_OK && !good) rc = set_error(ctx, AMGB_ERR_COMM, "another rank could not pool its rows");
+  if (rc != AMGB_OK) return rc;
+  std::vector<double> all(4 * vv * (size_t)comm->size);
+  AMGB_TRY(comm->allgather_host(ctx, mine.data(), mine.size() * sizeof(double), all.data()));
+  for (size_t i = 0; i < vv; ++i) {
+    double s = 0.0, pp = 0.0, np = 0.0;
+    int64_t c = 0;
+    for (int q = 0; q < comm->size; ++q) {
+      const double* r = all.data() + (size_t)q * 4 * vv;
+      s += r[i];
+      pp = pp > r[vv + i] ? pp : r[vv + i];
+      np = np > r[2 * vv + i] ? np : r[2 * vv + i];
+      c += reinterpret_cast<const int64_t*>(r + 3 * vv)[i];
+    }
+    sum[i] = s;
+    max_pp[i] = pp;
+    max_np[i] = np;
+    count[i] = c;
+  }
+  double t = ms * 1000.0;  // device time of the local pass, max over the ranks
+  std::vector<double> ts(comm->size);
+  AMGB_TRY(comm->allgather_host(ctx, &t, sizeof t, ts.data()));
+  for (double v : ts) t = v > t ? v : t;
+  if (t_us) *t_us = t;
   return AMGB_OK;
 }
 
@@ -394,7 +467,7 @@ extern "C" int amgb_make_view_normalized(amgb_ctx* ctx, const amgb_matrix* A, in
   AMGB_TRY(d_cnt.alloc(ctx, vv));
   AMGB_TRY(d_out.alloc(ctx, vv * 4));
   float ms = 0.f;
-  AMGB_TRY(pool_to_device(ctx, A, view_size, d_sum.p, d_cnt.p, d_pp.p, d_np.p, &ms));
+  AMGB_TRY(pool_to_device(ctx, A->A, A->A.n, 0, view_size, d_sum.p, d_cnt.p, d_pp.p, d_np.p, &ms));
   AMGB_LAUNCH(ctx, F_POOL, 60.0 * vv, view_normalize_kernel, 4, kPoolBlock, 0, (int)vv, mode,
               count_channel_as_reference, d_sum.p, d_cnt.p, d_pp.p, d_np.p, d_out.p);
   AMGB_CHECK_LAUNCH(ctx);

@@ -813,6 +813,149 @@ int transpose_csr(amgb_ctx* ctx, const DeviceCsr& P, DeviceCsr& R) {
 }
 
 // ---------------------------------------------------------------------------
+// DoF numberings of the step before the path as permutations applied on
+// the device.  The generators number nodes lexicographically; the reference's matrices come
+// out of deal.II in the order DoFHandler::distribute_dofs hands out indices: active cells in
+// refinement-tree order (GridGenerator::subdivided_hyper_cube(c) cells lexicographic, the 8
+// children of a refined cell consecutive, x fastest), the 8 vertices of a cell in
+// lexicographic order, a vertex numbered when it is first met (ref testcase2-diffusion-
+// structured/src/main.cpp:423-425 mesh, :230-232 distribute_dofs + subdomain_wise).  Restated
+// from memory of deal.II (not installed here); closed form, no sort: the traversal rank of a
+// cell is (coarse lexicographic index) * 8^r + Morton code of its position inside the coarse
+// cell; a cell introduces a vertex iff it has the smallest rank among the cells that share it;
+// an exclusive scan over the cells in traversal order turns the per-cell counts into numbers.
+// ---------------------------------------------------------------------------
+struct TreeGrid {
+  int c, r, m;  // coarse cells per direction, refinements, m = c << r
+  __device__ __forceinline__ long long rank_of(int cx, int cy, int cz) const {
+    const int X = cx >> r, Y = cy >> r, Z = cz >> r, mask = (1 << r) - 1;
+    const int lx = cx & mask, ly = cy & mask, lz = cz & mask;
+    long long mo = 0;
+    for (int b = 0; b < r; ++b)
+      mo |= ((long long)((lx >> b) & 1) << (3 * b)) | ((long long)((ly >> b) & 1) << (3 * b + 1)) |
+            ((long long)((lz >> b) & 1) << (3 * b + 2));
+    return (((long long)X + (long long)c * (Y + (long long)c * Z)) << (3 * r)) + mo;
+  }
+  __device__ __forceinline__ void cell_of(long long t, int& cx, int& cy, int& cz) const {
+    const long long mo = t & ((1ll << (3 * r)) - 1);
+    long long cc = t >> (3 * r);
+    const int X = (int)(cc % c);
+    cc /= c;
+    const int Y = (int)(cc % c), Z = (int)(cc / c);
+    int lx = 0, ly = 0, lz = 0;
+    for (int b = 0; b < r; ++b) {
+      lx |= (int)((mo >> (3 * b)) & 1) << b;
+      ly |= (int)((mo >> (3 * b + 1)) & 1) << b;
+      lz |= (int)((mo >> (3 * b + 2)) & 1) << b;
+    }
+    cx = (X << r) + lx;
+    cy = (Y << r) + ly;
+    cz = (Z << r) + lz;
+  }
+  // is cell (cx,cy,cz) with rank t the first one in traversal order that touches vertex (vx,vy,vz)?
+  __device__ __forceinline__ bool introduces(long long t, int vx, int vy, int vz) const {
+    for (int dz = -1; dz <= 0; ++dz)
+      for (int dy = -1; dy <= 0; ++dy)
+        for (int dx = -1; dx <= 0; ++dx) {
+          const int ox = vx + dx, oy = vy + dy, oz = vz + dz;
+          if (ox < 0 || oy < 0 || oz < 0 || ox >= m || oy >= m || oz >= m) continue;
+          if (rank_of(ox, oy, oz) < t) return false;
+        }
+    return true;
+  }
+};
+
+__global__ void __launch_bounds__(kBlock)
+tree_count_kernel(TreeGrid g, long long ncells, int32_t* __restrict__ count) {
+  const long long t = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (t >= ncells) return;
+  int cx, cy, cz, c = 0;
+  g.cell_of(t, cx, cy, cz);
+  for (int v = 0; v < 8; ++v) c += g.introduces(t, cx + (v & 1), cy + ((v >> 1) & 1), cz + ((v >> 2) & 1)) ? 1 : 0;
+  count[t] = c;
+}
+
+__global__ void __launch_bounds__(kBlock)
+tree_number_kernel(TreeGrid g, long long ncells, const int32_t* __restrict__ first, int32_t* __restrict__ new_to_lex) {
+  const long long t = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (t >= ncells) return;
+  int cx, cy, cz;
+  g.cell_of(t, cx, cy, cz);
+  int next = first[t];
+  const long long N = g.m + 1;
+  for (int v = 0; v < 8; ++v) {
+    const int vx = cx + (v & 1), vy = cy + ((v >> 1) & 1), vz = cz + ((v >> 2) & 1);
+    if (g.introduces(t, vx, vy, vz)) new_to_lex[next++] = (int32_t)(vx + N * (vy + N * (long long)vz));
+  }
+}
+
+// ---- B = Q A Q^T for a renumbering given as new -> old ----
+__global__ void __launch_bounds__(kBlock)
+invert_perm_kernel(int64_t n, const int32_t* __restrict__ new_to_old, int32_t* __restrict__ old_to_new,
+                   int32_t* __restrict__ bad) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const int32_t o = new_to_old[i];
+  if (o < 0 || o >= n) {
+    atomicAdd(bad, 1);
+    return;
+  }
+  if (atomicExch(&old_to_new[o], (int32_t)i) != -1) atomicAdd(bad, 1);  // hit twice: not a permutation
+}
+
+__global__ void __launch_bounds__(kBlock)
+perm_row_len_kernel(int64_t n, const int32_t* __restrict__ new_to_old, const int32_t* __restrict__ rp,
+                    int32_t* __restrict__ len) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i < n) len[i] = rp[new_to_old[i] + 1] - rp[new_to_old[i]];
+}
+
+__global__ void __launch_bounds__(kBlock)
+perm_fill_kernel(int64_t n, const int32_t* __restrict__ new_to_old, const int32_t* __restrict__ old_to_new,
+                 const int32_t* __restrict__ rp, const int32_t* __restrict__ col, const double* __restrict__ val,
+                 const int32_t* __restrict__ brp, int32_t* __restrict__ bcol, double* __restrict__ bval) {
+  const int64_t i = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const int o = new_to_old[i], b = rp[o], len = rp[o + 1] - b, w = brp[i];
+  for (int t = lane; t < len; t += 32) {
+    bcol[w + t] = old_to_new[col[b + t]];
+    bval[w + t] = val[b + t];
+  }
+}
+
+int permute_csr(amgb_ctx* ctx, const DeviceCsr& A, const int32_t* new_to_old_device, DeviceCsr& B) {
+  const int64_t n = A.n;
+  const unsigned grid = (unsigned)div_up(n, kBlock);
+  DevBuf<int32_t> inv, len, bad;
+  AMGB_TRY(inv.alloc(ctx, n));
+  AMGB_TRY(len.alloc(ctx, n));
+  AMGB_TRY(bad.alloc_zero(ctx, 1));
+  AMGB_CUDA(ctx, cudaMemsetAsync(inv.p, 0xff, n * sizeof(int32_t), ctx->stream));
+  AMGB_LAUNCH(ctx, F_AUX, 12.0 * n, invert_perm_kernel, grid, kBlock, 0, n, new_to_old_device, inv.p, bad.p);
+  AMGB_CHECK_LAUNCH(ctx);
+  int32_t nbad = 0;
+  AMGB_TRY(read_i32(ctx, bad.p, &nbad));
+  if (nbad) return set_error(ctx, AMGB_ERR_BAD_ARG, "renumbering is not a permutation of 0..n-1");
+  B.n = B.ncols = n;
+  B.nnz = A.nnz;
+  AMGB_TRY(B.rp.alloc(ctx, n + 1));
+  AMGB_TRY(B.col.alloc(ctx, A.nnz));
+  AMGB_TRY(B.val.alloc(ctx, A.nnz));
+  AMGB_LAUNCH(ctx, F_AUX, 12.0 * n, perm_row_len_kernel, grid, kBlock, 0, n, new_to_old_device,
+              (const int32_t*)A.rp.p, len.p);
+  AMGB_TRY(exclusive_scan_i32(ctx, len.p, B.rp.p, n));
+  AMGB_LAUNCH(ctx, F_AUX, 24.0 * A.nnz, perm_fill_kernel, (unsigned)div_up(n * 32, kBlock), kBlock, 0, n,
+              new_to_old_device, (const int32_t*)inv.p, (const int32_t*)A.rp.p, (const int32_t*)A.col.p,
+              (const double*)A.val.p, (const int32_t*)B.rp.p, B.col.p, B.val.p);
+  AMGB_LAUNCH(ctx, F_AUX, 24.0 * A.nnz, sort_rows_kernel, (unsigned)div_up(n * 32, kBlock), kBlock, 0, n,
+              (const int32_t*)B.rp.p, B.col.p, B.val.p);
+  AMGB_CHECK_LAUNCH(ctx);
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMGB_OK;
+}
+
+// ---------------------------------------------------------------------------
 // SpGEMM C = A*B: two-phase hash (count, then fill).  G lanes cooperate on one output
 // row (G = 8 for short B rows such as A*P, 32 otherwise), so a warp works on 32/G rows
 // at once; hash tables live in shared memory and are sized per row, with two fall-back
@@ -2075,6 +2218,46 @@ int amgb_precond_destroy(amgb_precond* P) {
   if (P->dist) amgb_dist_state_destroy(P->dist);
   P->dist = nullptr;
   delete P;
+  return AMGB_OK;
+}
+
+int amgb_numbering_dealii_q1(amgb_ctx* ctx, int32_t coarse_cells, int32_t refinements, int32_t* new_to_lex) {
+  if (!ctx || !new_to_lex || coarse_cells < 1 || refinements < 0 || refinements > 10) return AMGB_ERR_BAD_ARG;
+  cudaSetDevice(ctx->device);
+  const int64_t m = (int64_t)coarse_cells << refinements, ncells = m * m * m, n = (m + 1) * (m + 1) * (m + 1);
+  if (n >= (int64_t(1) << 31)) return set_error(ctx, AMGB_ERR_RANGE, "%lld nodes: ids are 32-bit", (long long)n);
+  TreeGrid g{coarse_cells, refinements, (int)m};
+  DevBuf<int32_t> count, first, out;
+  AMGB_TRY(count.alloc(ctx, ncells));
+  AMGB_TRY(first.alloc(ctx, ncells + 1));
+  AMGB_TRY(out.alloc(ctx, n));
+  const unsigned grid = (unsigned)div_up(ncells, kBlock);
+  AMGB_LAUNCH(ctx, F_AUX, 4.0 * ncells, tree_count_kernel, grid, kBlock, 0, g, (long long)ncells, count.p);
+  AMGB_TRY(exclusive_scan_i32(ctx, count.p, first.p, ncells));
+  AMGB_LAUNCH(ctx, F_AUX, 8.0 * ncells + 4.0 * n, tree_number_kernel, grid, kBlock, 0, g, (long long)ncells,
+              (const int32_t*)first.p, out.p);
+  AMGB_CHECK_LAUNCH(ctx);
+  AMGB_CUDA(ctx, cudaMemcpyAsync(new_to_lex, out.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMGB_OK;
+}
+
+int amgb_matrix_permute(amgb_ctx* ctx, const amgb_matrix* A, const int32_t* new_to_old, amgb_matrix** out) {
+  if (!ctx || !A || !new_to_old || !out) return AMGB_ERR_BAD_ARG;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  DevBuf<int32_t> perm;
+  AMGB_TRY(perm.alloc(ctx, A->A.n));
+  AMGB_CUDA(ctx, cudaMemcpyAsync(perm.p, new_to_old, A->A.n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  amgb_matrix* M = new amgb_matrix;
+  M->ctx = ctx;
+  const int rc = permute_csr(ctx, A->A, perm.p, M->A);
+  if (rc != AMGB_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    delete M;
+    return rc;
+  }
+  *out = M;
   return AMGB_OK;
 }
 

@@ -7,6 +7,7 @@
 // number of OpenMP threads.
 #include "amgb_gen.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <random>
@@ -388,6 +389,46 @@ int amgb_gen_elasticity_q1(int m, int pattern_size, int mode, const double* youn
       if (x0) x0[row] = 0.0;
     }
   }
+  return kOk;
+}
+
+int amgb_gen_cuthill_mckee(int64_t n, const int64_t* rowptr, const int32_t* col, int reversed,
+                           int32_t* new_to_old) {
+  if (n < 0 || !rowptr || (n > 0 && !new_to_old) || n >= (int64_t(1) << 31)) return kBadArg;
+  std::vector<uint8_t> done(n, 0);
+  std::vector<int32_t> front, next;
+  int64_t numbered = 0, scan_from = 0;
+  auto degree = [&](int32_t i) { return rowptr[i + 1] - rowptr[i]; };
+  while (numbered < n) {
+    // starting point of the next component: smallest coordination number, lowest index
+    int32_t start = -1;
+    for (int64_t i = scan_from; i < n; ++i)
+      if (!done[i] && (start < 0 || degree((int32_t)i) < degree(start))) start = (int32_t)i;
+    while (scan_from < n && done[scan_from]) ++scan_from;
+    done[start] = 1;
+    new_to_old[numbered++] = start;
+    front.assign(1, start);
+    while (!front.empty()) {
+      next.clear();
+      for (int32_t i : front)
+        for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+          const int32_t j = col[k];
+          if (j < 0 || j >= n) return kBadArg;
+          if (!done[j]) {
+            done[j] = 1;
+            next.push_back(j);
+          }
+        }
+      // by coordination number, ties by index (deal.II: sorted list fed into a multimap)
+      std::sort(next.begin(), next.end(), [&](int32_t a, int32_t b) {
+        const int64_t da = degree(a), db = degree(b);
+        return da != db ? da < db : a < b;
+      });
+      for (int32_t j : next) new_to_old[numbered++] = j;
+      front.swap(next);
+    }
+  }
+  if (reversed) std::reverse(new_to_old, new_to_old + n);
   return kOk;
 }
 

@@ -151,6 +151,18 @@ class DistSparseMatrix:
     def n_local(self):
         return self.row_end - self.row_begin
 
+    def make_view(self, view_size):
+        """Pooled image of the whole partitioned matrix (collective; ref common/view_maker.h:26-74):
+        returns (sum, count, max_pp, max_np, device_us), each V*V row-major."""
+        vv = int(view_size) ** 2
+        s, c = np.zeros(vv), np.zeros(vv, dtype=np.int64)
+        pp, npv = np.zeros(vv), np.zeros(vv)
+        t = C.c_double()
+        rc = amgb_lib().amgb_dist_make_view(self.ctx._h, self._h, int(view_size), _p(s, c_f64p), _p(c, c_i64p),
+                                            _p(pp, c_f64p), _p(npv, c_f64p), C.byref(t))
+        _chk(self.ctx._h, rc, "amgb_dist_make_view")
+        return s, c, pp, npv, t.value
+
     def close(self):
         if self._h:
             amgb_lib().amgb_dist_matrix_destroy(self._h)

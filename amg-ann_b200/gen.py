@@ -122,3 +122,15 @@ def theta_sweep(start, stop, step):
         out.append(t)
         t += step
     return out
+
+
+def cuthill_mckee(rowptr, col, reversed=False):
+    """deal.II-style Cuthill-McKee renumbering (include/amgb_gen.h): new -> old."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    n = len(rowptr) - 1
+    out = np.empty(n, dtype=np.int32)
+    rc = gen_lib().amgb_gen_cuthill_mckee(n, _p(rowptr, c_i64p), _p(col, c_i32p), int(bool(reversed)), _p(out, c_i32p))
+    if rc:
+        raise ValueError(f"amgb_gen_cuthill_mckee -> {rc}")
+    return out

@@ -163,12 +163,33 @@ int amgb_matrix_wrap_device_csr(amgb_ctx* ctx, int64_t n, int64_t nnz,
 int amgb_matrix_assemble_poisson_q1(amgb_ctx* ctx, int32_t m, int32_t pattern_size, int32_t mode,
                                     const double* epsv, int64_t n_epsv, amgb_matrix** out,
                                     double* rhs_device, double* x0_device);
+/* On-device assembly of the Q1 vector-elasticity system of the reference's testcase 3 (3 DoFs per node,
+ * interleaved; ref testcase3-elasticity-structured/src/main.cpp:320-342; E = 1000 * young[pattern cell],
+ * nu = 0.29, :48-49,88-99; constrained DoFs condensed out, :264-268; lexicographic node numbering).
+ * Matrix and initial guess are bit-identical to the host generator of include/amgb_gen.h; the body
+ * force is evaluated with the device's sin/cos, so the right-hand side agrees to rounding.
+ * rhs_device / x0_device: device arrays of n = 3 (m+1)^3 doubles, or NULL. */
+int amgb_matrix_assemble_elasticity_q1(amgb_ctx* ctx, int32_t m, int32_t pattern_size, int32_t mode,
+                                       const double* young, int64_t n_young, amgb_matrix** out,
+                                       double* rhs_device, double* x0_device);
 /* Same, returning the right-hand side and the initial guess in HOST arrays (n doubles, or NULL). */
 int amgb_matrix_assemble_poisson_q1_hostvec(amgb_ctx* ctx, int32_t m, int32_t pattern_size, int32_t mode,
                                             const double* epsv, int64_t n_epsv, amgb_matrix** out,
                                             double* rhs_host, double* x0_host);
 /* CSR of a resident matrix back to host arrays (any pointer may be NULL). */
 int amgb_matrix_download_csr(const amgb_matrix* A, int32_t* rowptr, int32_t* col, double* val);
+/* ---- DoF numberings of the step before the path ---- */
+/* The numbering deal.II's DoFHandler::distribute_dofs gives Q1 DoFs on
+ * GridGenerator::subdivided_hyper_cube(coarse_cells) refined `refinements` times (ref testcase2-
+ * diffusion-structured/src/main.cpp:423-425,230-232): active cells in refinement-tree order, the 8
+ * vertices of a cell in lexicographic order, a vertex numbered when first met.  Restated from memory of
+ * deal.II; computed on the device in closed form.  new_to_lex: HOST array of (m+1)^3 entries,
+ * m = coarse_cells << refinements; new_to_lex[k] = lexicographic id of the node that DoF k sits on. */
+int amgb_numbering_dealii_q1(amgb_ctx* ctx, int32_t coarse_cells, int32_t refinements, int32_t* new_to_lex);
+/* B = Q A Q^T: rows and columns renumbered (new_to_old: HOST array, a permutation of 0..n-1; anything
+ * else is AMGB_ERR_BAD_ARG), columns of every row ascending again.  Applies any DoF renumbering
+ * (the one above, Cuthill-McKee from include/amgb_gen.h, ...) to a resident matrix on the device. */
+int amgb_matrix_permute(amgb_ctx* ctx, const amgb_matrix* A, const int32_t* new_to_old, amgb_matrix** out);
 int amgb_matrix_destroy(amgb_matrix* A);
 int amgb_matrix_dims(const amgb_matrix* A, int64_t* n, int64_t* nnz);
 /* y = A x (host vectors); the plain SpMV, exposed for parity tests. */
@@ -302,6 +323,13 @@ int amgb_dist_matrix_assemble_poisson_q1(amgb_ctx* ctx, amgb_comm* comm, int32_t
                                          int64_t row_begin, int64_t row_end, amgb_dist_matrix** out,
                                          double* rhs_device, double* x0_device);
 int amgb_dist_matrix_destroy(amgb_dist_matrix* A);
+/* Pooled image of the partitioned matrix (ref common/view_maker.h:26-74 run on an MPI matrix: every
+ * rank bins the rows it owns, :41-65): local pass on every rank's device, then the four channels are
+ * combined over the ranks in rank order (sum and count added, maxima maxed).  Collective; every rank
+ * receives the whole V x V image.  count / max_pp / max_np are identical to amgb_make_view of the
+ * assembled matrix, sum agrees to rounding. */
+int amgb_dist_make_view(amgb_ctx* ctx, const amgb_dist_matrix* A, int32_t view_size, double* sum,
+                        int64_t* count, double* max_pp, double* max_np, double* t_us);
 /* initialize() on the partitioned matrix; the result is used with the amgb_precond_*
  * queries (level statistics are global) and destroyed with amgb_precond_destroy. */
 int amgb_dist_precond_initialize(amgb_ctx* ctx, const amgb_dist_matrix* A,

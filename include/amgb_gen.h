@@ -66,6 +66,17 @@ int amgb_gen_random_vec(int64_t seed, int64_t len, double max, double* out);
 int amgb_gen_checkerboard_epsv(int pattern_size, int mode, double contrast_exp,
                                double* out);
 
+/* Cuthill-McKee renumbering of a symmetric-pattern CSR matrix as deal.II's
+ * DoFRenumbering::Cuthill_McKee / SparsityTools::reorder_Cuthill_McKee does it (ref testcase1-.../
+ * src/main.cpp:183-184, testcase3-.../src/main.cpp:249-250; restated from memory of deal.II): start
+ * from the unnumbered point of smallest coordination number (lowest index among ties), then level by
+ * level: the unnumbered neighbours of the previous front, ordered by coordination number and, among
+ * equals, by index.  Components that are not connected are started the same way.  new_to_old[k] = old
+ * index of the point numbered k; reversed != 0 gives reverse Cuthill-McKee.  Apply with
+ * amgb_matrix_permute (include/amgb.h). */
+int amgb_gen_cuthill_mckee(int64_t n, const int64_t* rowptr, const int32_t* col, int reversed,
+                           int32_t* new_to_old);
+
 #ifdef __cplusplus
 }
 #endif

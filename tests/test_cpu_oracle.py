@@ -489,3 +489,17 @@ def test_cljp_splitting_properties(m, theta, contrast):
     assert has_c[(cf == -1)].all()          # every ordinary F point interpolates from at least one C point
     pm = orc.coarsen(rp, s.col, mask, "pmis")
     assert (cf > 0).sum() > (pm > 0).sum()  # denser coarse grids than PMIS: that is what buys the convergence
+
+
+def test_cuthill_mckee_is_a_level_ordering():
+    """include/amgb_gen.h amgb_gen_cuthill_mckee on a path graph and on a 2-component graph."""
+    import amg_ann_b200 as ab
+    import scipy.sparse as sp
+    n = 9
+    P = sp.diags([np.ones(n - 1), np.ones(n), np.ones(n - 1)], [-1, 0, 1]).tocsr()
+    perm = ab.gen.cuthill_mckee(P.indptr, P.indices)
+    assert list(perm) == list(range(n))               # starts at an end point (degree 2), walks the path
+    B = sp.block_diag([P, P]).tocsr()
+    perm = ab.gen.cuthill_mckee(B.indptr, B.indices)
+    assert sorted(perm) == list(range(2 * n)) and list(perm[:n]) == list(range(n))
+    assert list(ab.gen.cuthill_mckee(B.indptr, B.indices, reversed=True)) == list(perm[::-1])

@@ -74,3 +74,21 @@ def test_device_assembly_of_slabs_feeds_the_partitioned_path(gpu_ctx):
     x1 = whole.x0.copy()
     row = ab.amg_solve(device_data(0.25), 1e-8, A1, whole.rhs, x1)
     assert all(abs(p["niters"] - row["niters"]) <= 1 for p in parts)
+
+
+@pytest.mark.parametrize("m,ps,mode", [(2, 1, 1), (5, 2, 3), (8, 4, 3), (11, 3, 2)])
+def test_device_elasticity_assembly_equals_host_generator(gpu_ctx, m, ps, mode):
+    """Q1 elasticity (ref t3 main.cpp:320-342) assembled on the device: pattern, values and the
+    initial guess are the host generator's bit for bit; the right-hand side (device sin/cos in
+    the body force) agrees to rounding."""
+    young = 10.0 ** ab.gen.random_vec(5, ps ** mode, 2.0)
+    s = ab.gen.elasticity_q1(m, ps, mode, young)
+    rhs = torch.empty(s.n, dtype=torch.float64, device="cuda")
+    x0 = torch.empty(s.n, dtype=torch.float64, device="cuda")
+    A = ab.SparseMatrix.assemble_elasticity_q1(gpu_ctx, m, ps, mode, young, rhs.data_ptr(), x0.data_ptr())
+    rp, cl, vl = A.download()
+    assert np.array_equal(rp, s.rowptr32()) and np.array_equal(cl, s.col)
+    assert np.array_equal(vl, s.val), np.abs(vl - s.val).max()
+    assert np.array_equal(x0.cpu().numpy(), s.x0)
+    r = rhs.cpu().numpy()
+    assert np.abs(r - s.rhs).max() <= 1e-11 * max(1.0, np.abs(s.rhs).max())

@@ -223,6 +223,54 @@ def test_chebyshev_smoother_partitioned_equals_single_device(gpu_ctx, replicate_
     assert np.abs(x - x1).max() <= 1e-8 * np.abs(x1).max()
 
 
+@pytest.mark.parametrize("m,V,nranks", [(10, 20, 3), (14, 75, 2), (6, 50, 4)])
+def test_pooled_image_of_a_partitioned_matrix(gpu_ctx, m, V, nranks):
+    """amgb_dist_make_view: local pooling of the owned rows + combination over the ranks = the image
+    of the assembled matrix (count / maxima exact, sum to rounding), the same on every rank."""
+    s = poisson(m, contrast=4.0)
+    A1 = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    vm = ab.ViewMaker(V).make_view(A1)
+    starts = dist.slab_partition(m, nranks) if nranks < 4 else [0, 17, 100, 101, s.n]
+
+    def fn(rank, comm):
+        b, e = starts[rank], starts[rank + 1]
+        sl = ab.gen.poisson_q1(m, 2, 3, ab.gen.checkerboard_epsv(2, 3, 4.0), row_begin=b, row_end=e)
+        A = dist.DistSparseMatrix(comm, sl.n, b, e, sl.rowptr, sl.col, sl.val)
+        out = A.make_view(V)
+        A.close()
+        return out
+
+    parts = dist.run_local_group(nranks, fn)
+    for sm, cnt, pp, npv, _ in parts:
+        assert np.array_equal(cnt, vm.count) and cnt.sum() == s.nnz
+        assert np.array_equal(pp, vm.max_pp) and np.array_equal(npv, vm.max_np)
+        assert np.allclose(sm, vm.view, rtol=0, atol=1e-13 * np.abs(s.val).sum())
+        assert np.array_equal(sm, parts[0][0])
+
+
+def test_a_rank_with_bad_arguments_fails_on_every_rank_together(gpu_ctx):
+    """amgb_dist_matrix_create is collective including its failures: the rank whose arguments are
+    wrong and its peers all come back with an error from the same all-gather; nobody is left
+    waiting in a collective (the group is NOT aborted by the test: the library must agree)."""
+    m = 6
+    starts = dist.slab_partition(m, 2)
+
+    def fn(rank, comm):
+        b, e = starts[rank], starts[rank + 1]
+        sl = ab.gen.poisson_q1(m, row_begin=b, row_end=e)
+        try:
+            if rank == 1:   # row range past the end of the matrix
+                dist.DistSparseMatrix(comm, sl.n, b, sl.n + 5, sl.rowptr, sl.col, sl.val)
+            else:
+                dist.DistSparseMatrix(comm, sl.n, b, e, sl.rowptr, sl.col, sl.val)
+        except ab.AmgbError as err:
+            return err.status
+        return 0
+
+    out = dist.run_local_group(2, fn)
+    assert out == [-9, -1]     # peer: AMGB_ERR_COMM naming the rank; offender: AMGB_ERR_BAD_ARG
+
+
 # ---- real multi-GPU variants (skipped on a one-GPU box; run with `gpurun --gpus 2`) ----
 def _device_count():
     import torch

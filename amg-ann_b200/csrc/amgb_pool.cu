@@ -5,10 +5,9 @@
 //   * the V row-bins are contiguous row ranges (ref view_maker.h:41-45,52), hence contiguous
 //     ENTRY ranges [rp[r0], rp[r1]); a CTA is given a slice of the entry range of ONE row-bin,
 //     so it only needs V-wide accumulators and never looks at row pointers again;
-//   * a lane loads 8 consecutive entries (two 16-byte column loads, four 16-byte value loads;
-//     a warp covers 256 consecutive entries = 3 KB, fully coalesced) and folds them into runs
-//     of equal column-bin in registers -- columns ascend within a row, so runs are long
-//     (9 entries and more on the FE stencils);
+//   * a warp covers 256 consecutive entries per iteration (3 KB) with four pairs of load
+//     instructions, each one contiguous run (8 bytes of columns and 16 bytes of values per
+//     lane), 8 entries per lane;
 //   * the rows of a row-bin of a banded matrix meet the same two or three column bins over and
 //     over: the warp caches four bins (ids warp-uniform, partial sum / count / maxima
 //     lane-private in registers), so the steady state is loads, a bin computation and
@@ -61,8 +60,8 @@ struct PoolSlot {
   __device__ __forceinline__ void add(double v) {
     s += v;
     ++cnt;
-    pp = fmax(pp, fmax(v, 0.0));
-    np = fmax(np, fmax(-v, 0.0));
+    pp = fmax(pp, v);    // (v < 0 leaves pp, which starts at 0, alone: max(pp, max(v, 0)) == max(pp, v))
+    np = fmax(np, -v);
   }
 };
 
@@ -114,8 +113,8 @@ pool_entries_kernel(BinMap bm, int tiles, long long g0, int nloc, const int32_t*
   // rows [g0, g0 + nloc) of the global matrix are held here (a single device holds all of them)
   const long long rb0 = (long long)bm.row_begin(br) - g0, rb1 = (long long)bm.row_begin(br + 1) - g0;
   const int e_lo = rp[rb0 < 0 ? 0 : (rb0 > nloc ? nloc : (int)rb0)], e_hi = rp[rb1 < 0 ? 0 : (rb1 > nloc ? nloc : (int)rb1)];
-  // whole CTA-chunks (absolute multiples of kPoolBlockChunk, so every lane's 8 entries are
-  // 32-byte / 64-byte aligned) that overlap the entry range of this row-bin, split over the tiles
+  // whole CTA-chunks (absolute multiples of kPoolBlockChunk, so every lane's entry pairs are
+  // 8-byte / 16-byte aligned) that overlap the entry range of this row-bin, split over the tiles
   const int c_first = e_lo / kPoolBlockChunk, c_last = (int)(((long long)e_hi + kPoolBlockChunk - 1) / kPoolBlockChunk);
   const int per = (c_last - c_first + tiles - 1) / tiles;
   const int c0 = c_first + tile * per, c1 = min(c0 + per, c_last);
@@ -136,28 +135,28 @@ pool_entries_kernel(BinMap bm, int tiles, long long g0, int nloc, const int32_t*
     acc[t].clear();
   }
   for (int chunk = c0; chunk < c1; ++chunk) {
-    const long long base = (long long)chunk * kPoolBlockChunk + warp * kPoolWarpChunk + lane * kPoolPerLane;
+    // entries 64 j + 2 lane + {0, 1} of the warp's 256, j = 0..3: every load instruction of the warp is
+    // one contiguous run (8 bytes per lane for the columns, 16 for the values)
+    const long long wbase = (long long)chunk * kPoolBlockChunk + warp * kPoolWarpChunk + 2 * lane;
     int c[kPoolPerLane];
     double v[kPoolPerLane];
-    const bool inside = base >= e_lo && base + kPoolPerLane <= e_hi;
-    if (VEC && inside) {
-      const int4 c0v = __ldcs(reinterpret_cast<const int4*>(col + base));
-      const int4 c1v = __ldcs(reinterpret_cast<const int4*>(col + base) + 1);
-      c[0] = c0v.x; c[1] = c0v.y; c[2] = c0v.z; c[3] = c0v.w;
-      c[4] = c1v.x; c[5] = c1v.y; c[6] = c1v.z; c[7] = c1v.w;
 #pragma unroll
-      for (int j = 0; j < kPoolPerLane; j += 2) {
-        const double2 vv = __ldcs(reinterpret_cast<const double2*>(val + base + j));
+    for (int j = 0; j < kPoolPerLane; j += 2) {
+      const long long k = wbase + 32 * j;
+      if (VEC && k >= e_lo && k + 2 <= e_hi) {
+        const int2 cc = __ldcs(reinterpret_cast<const int2*>(col + k));
+        const double2 vv = __ldcs(reinterpret_cast<const double2*>(val + k));
+        c[j] = cc.x;
+        c[j + 1] = cc.y;
         v[j] = vv.x;
         v[j + 1] = vv.y;
-      }
-    } else {
+      } else {
 #pragma unroll
-      for (int j = 0; j < kPoolPerLane; ++j) {
-        const long long k = base + j;
-        const bool ok = k >= e_lo && k < e_hi;
-        c[j] = ok ? __ldcs(col + k) : -1;
-        v[j] = ok ? __ldcs(val + k) : 0.0;
+        for (int u = 0; u < 2; ++u) {
+          const bool ok = k + u >= e_lo && k + u < e_hi;
+          c[j + u] = ok ? __ldcs(col + k + u) : -1;
+          v[j + u] = ok ? __ldcs(val + k + u) : 0.0;
+        }
       }
     }
     // column bins; entries outside the row-bin's range (only at its two ends) get -1
@@ -265,7 +264,7 @@ static int pool_to_device(amgb_ctx* ctx, const amgb::DeviceCsr& M, int64_t n_glo
   bm.rq = bm.q > 0 ? 1.0 / bm.q : 0.0;  // (V > n: every row is a bin of its own, q is never divided by)
   bm.rq1 = 1.0 / bm.q1;
   // slices per row-bin: enough CTAs for every SM, at least a few CTA-chunks of entries each
-  int tiles = (int)div_up((int64_t)ctx->sm_count * 8, V);
+  int tiles = (int)div_up((int64_t)ctx->sm_count * 12, V);
   const int64_t chunks_per_bin = div_up(div_up(M.nnz, V), kPoolBlockChunk);
   if (tiles > chunks_per_bin / 4) tiles = (int)(chunks_per_bin / 4);
   if (tiles < 1) tiles = 1;

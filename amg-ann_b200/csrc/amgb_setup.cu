@@ -454,10 +454,11 @@ interp_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __r
                    const double* __restrict__ val, const uint8_t* __restrict__ mask,
                    const int32_t* __restrict__ cf, const int32_t* __restrict__ f2c,
                    const double* __restrict__ diagv, const int32_t* __restrict__ prp, int32_t* pcol,
-                   double* pval, int64_t row_begin) {
+                   double* pval, int64_t row_begin, const uint8_t* __restrict__ only) {
   const int64_t i = row_begin + (((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= n) return;
+  if (only && !only[i]) return;  // second stage of the grouped kernel: the rows it left behind
   const unsigned full = 0xffffffffu;
   const int jb = prp[i];
   const int len = prp[i + 1] - jb;
@@ -698,6 +699,206 @@ interp_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __r
   for (int t = lane; t < len; t += 32) {
     pval[jb + t] = diagonal == 0.0 ? 0.0 : myv[t] / nd;
     pcol[jb + t] = f2c[myc[t]];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Grouped interpolation kernel (first stage of build_interp): 8 lanes per row, 4 rows per
+// warp, working on a COMPACTED copy of the operator.
+//
+// What row i needs from the row of a strong F neighbour k are the entries a_kc with c a C
+// point and sign(a_kk) a_kc < 0 -- on a 27-point operator about 4 of 27.  They are gathered
+// once per level (interp_ac_*: "A_C", ascending columns like A), so that the pair (i, k)
+// costs a walk over ~4 entries by ONE lane instead of a warp-wide pass over 27; the eight
+// lanes of a group take the strong F neighbours of an 8-entry chunk of row i side by side.
+// Every sum keeps the oracle's order: sum_k runs over A_C[k] in column order; P(i,p) and the
+// diagonal receive their terms entry by entry of row i (the chunk's entries are applied one
+// after the other, the matches of one entry in parallel -- they address distinct P entries).
+// Rows with more than 32 interpolation points, or with a neighbour matching more than 8 of
+// them, are left to interp_fill_kernel (flagged in `todo`).
+// ---------------------------------------------------------------------------
+constexpr int kIgLanes = 8;
+constexpr int kIgRows = kBlock / kIgLanes;  // rows per block
+constexpr int kIgMaxP = 32;                 // interpolation points per row
+constexpr int kIgMaxMatch = 8;              // matches of one neighbour
+
+__global__ void __launch_bounds__(kBlock)
+interp_ac_count_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                       const double* __restrict__ val, const int32_t* __restrict__ cf,
+                       const double* __restrict__ diagv, int32_t* __restrict__ count) {
+  const int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (k >= n) return;
+  int c = 0;
+  if (cf[k] <= 0) {  // only F rows are ever distributed
+    const bool neg = diagv[k] < 0;
+    for (int e = rp[k]; e < rp[k + 1]; ++e) {
+      const double v = val[e];
+      c += (cf[col[e]] > 0 && (neg ? v > 0 : v < 0)) ? 1 : 0;
+    }
+  }
+  count[k] = c;
+}
+
+__global__ void __launch_bounds__(kBlock)
+interp_ac_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                      const double* __restrict__ val, const int32_t* __restrict__ cf,
+                      const double* __restrict__ diagv, const int32_t* __restrict__ acrp,
+                      int32_t* __restrict__ accol, double* __restrict__ acval) {
+  const int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (k >= n || cf[k] > 0) return;
+  const bool neg = diagv[k] < 0;
+  int w = acrp[k];
+  for (int e = rp[k]; e < rp[k + 1]; ++e) {
+    const double v = val[e];
+    const int c = col[e];
+    if (cf[c] > 0 && (neg ? v > 0 : v < 0)) {
+      accol[w] = c;
+      acval[w] = v;
+      ++w;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+interp_fill_group_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                         const double* __restrict__ val, const uint8_t* __restrict__ mask,
+                         const int32_t* __restrict__ cf, const int32_t* __restrict__ f2c,
+                         const int32_t* __restrict__ acrp, const int32_t* __restrict__ accol,
+                         const double* __restrict__ acval, const int32_t* __restrict__ prp,
+                         int32_t* __restrict__ pcol, double* __restrict__ pval, int64_t row_begin,
+                         uint8_t* __restrict__ todo, int32_t* __restrict__ n_todo) {
+  __shared__ int32_t s_cs[kIgRows][kIgMaxP];                      // interpolation points (fine ids, ascending)
+  __shared__ double s_pv[kIgRows][kIgMaxP];                       // P entries under construction
+  __shared__ int32_t s_mpos[kIgRows][kIgLanes][kIgMaxMatch];      // matches of the chunk's neighbours: P position
+  __shared__ double s_mval[kIgRows][kIgLanes][kIgMaxMatch];       // ... and a_kc
+  const int g = threadIdx.x / kIgLanes, q = threadIdx.x % kIgLanes;
+  const int64_t i = row_begin + (int64_t)blockIdx.x * kIgRows + g;
+  const unsigned gm = 0xffu << ((threadIdx.x & 31) / kIgLanes * kIgLanes);
+  if (i >= n) return;  // (whole groups leave together)
+  const int jb = prp[i], len = prp[i + 1] - jb;
+  if (cf[i] > 0) {
+    if (q == 0) {
+      pcol[jb] = f2c[i];
+      pval[jb] = 1.0;
+    }
+    return;
+  }
+  if (len > kIgMaxP) {
+    if (q == 0) {
+      todo[i] = 1;
+      atomicAdd(n_todo, 1);
+    }
+    return;
+  }
+  int32_t* cs = s_cs[g];
+  double* pv = s_pv[g];
+  const int b = rp[i], e = rp[i + 1];
+  // phase 0: diagonal, interpolation points in row order
+  double diagonal = 0.0;
+  {
+    int base = 0;
+    for (int kb = b; kb < e; kb += kIgLanes) {
+      const int k = kb + q;
+      int i1 = -1;
+      double a = 0.0;
+      bool isc = false;
+      if (k < e) {
+        i1 = col[k];
+        a = val[k];
+        isc = i1 != (int)i && mask[k] && cf[i1] > 0;
+      }
+      const unsigned sh = (threadIdx.x & 31) / kIgLanes * kIgLanes;
+      const unsigned dm = (__ballot_sync(gm, k < e && i1 == (int)i) >> sh) & 0xffu;
+      if (dm) diagonal = __shfl_sync(gm, a, __ffs(dm) - 1, kIgLanes);
+      const unsigned cm = (__ballot_sync(gm, isc) >> sh) & 0xffu;
+      if (isc) {
+        const int pos = base + __popc(cm & ((1u << q) - 1u));
+        cs[pos] = i1;
+        pv[pos] = 0.0;
+      }
+      base += __popc(cm);
+    }
+  }
+  __syncwarp(gm);
+  // phase 1: the entries of row i, 8 at a time
+  bool overflow = false;
+  int seen_c = 0;
+  for (int kb = b; kb < e; kb += kIgLanes) {
+    const int k = kb + q;
+    int i1 = -1, c1 = -3, strong = 0;
+    double a = 0.0;
+    if (k < e) {
+      i1 = col[k];
+      a = val[k];
+      strong = mask[k];
+      c1 = cf[i1];
+    }
+    const bool offd = k < e && i1 != (int)i;
+    const bool is_c = offd && strong && c1 > 0;
+    const bool is_sf = offd && strong && c1 <= 0 && c1 != -3;
+    const bool is_weak = offd && !strong && c1 != -3;
+    // my neighbour's share: sum over the interpolation points it meets, in column order
+    double dist = 0.0;
+    int nmatch = 0;
+    bool zero = false;
+    if (is_sf) {
+      double sum = 0.0;
+      for (int t = acrp[i1]; t < acrp[i1 + 1]; ++t) {
+        const int pos = find_sorted(cs, len, accol[t]);
+        if (pos >= 0) {
+          const double v = acval[t];
+          sum = __dadd_rn(sum, v);
+          if (nmatch < kIgMaxMatch) {
+            s_mpos[g][q][nmatch] = pos;
+            s_mval[g][q][nmatch] = v;
+          }
+          ++nmatch;
+        }
+      }
+      if (nmatch > kIgMaxMatch) overflow = true;
+      if (sum != 0) dist = a / sum; else zero = true;
+    }
+    const unsigned sh = (threadIdx.x & 31) / kIgLanes * kIgLanes;
+    if ((__ballot_sync(gm, overflow) >> sh) & 0xffu) {
+      overflow = true;
+      break;
+    }
+    __syncwarp(gm);
+    // apply the chunk's entries one after the other
+    const unsigned cmask = (__ballot_sync(gm, is_c) >> sh) & 0xffu;
+    const unsigned fmask = (__ballot_sync(gm, is_sf && !zero) >> sh) & 0xffu;
+    const unsigned dmask = (__ballot_sync(gm, is_weak || (is_sf && zero)) >> sh) & 0xffu;
+    for (unsigned todo_m = cmask | fmask | dmask; todo_m; todo_m &= todo_m - 1) {
+      const int t = __ffs(todo_m) - 1;
+      const double at = __shfl_sync(gm, a, t, kIgLanes);
+      if ((cmask >> t) & 1u) {
+        if (q == 0) pv[seen_c] = __dadd_rn(pv[seen_c], at);
+        ++seen_c;
+      } else if ((fmask >> t) & 1u) {
+        const double dt = __shfl_sync(gm, dist, t, kIgLanes);
+        const int nm = __shfl_sync(gm, nmatch, t, kIgLanes);
+        if (q < nm) {  // nm <= 8: one match per lane, distinct P entries
+          const int pos = s_mpos[g][t][q];
+          pv[pos] = __dadd_rn(pv[pos], __dmul_rn(dt, s_mval[g][t][q]));
+        }
+      } else {
+        diagonal = __dadd_rn(diagonal, at);  // (kept identically by every lane of the group)
+      }
+      __syncwarp(gm);
+    }
+  }
+  if (overflow) {
+    if (q == 0) {
+      todo[i] = 1;
+      atomicAdd(n_todo, 1);
+    }
+    return;
+  }
+  // phase 2: scale, renumber to coarse ids
+  const double nd = -diagonal;
+  for (int t = q; t < len; t += kIgLanes) {
+    pval[jb + t] = diagonal == 0.0 ? 0.0 : pv[t] / nd;
+    pcol[jb + t] = f2c[cs[t]];
   }
 }
 
@@ -1638,6 +1839,7 @@ int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, 
     return spgemm_impl<8, 256, 128>(ctx, A, B, C, sorted, true);
   }
   ctx->routes[est <= 50.0 ? R_SPGEMM_G8_T128 : (est <= 110.0 ? R_SPGEMM_G8_T256 : R_SPGEMM_G8_T512)]++;
+  if (est <= 50.0 && avg_b <= 4.0 && std::getenv("AMGB_SPGEMM_G4")) return spgemm_impl<4, 256, 128>(ctx, A, B, C, sorted);
   if (est <= 50.0) return spgemm_impl<8, 256, 128>(ctx, A, B, C, sorted);
   if (est <= 110.0) return spgemm_impl<8, 512, 256>(ctx, A, B, C, sorted);
   return spgemm_impl<8, 1024, 512>(ctx, A, B, C, sorted);
@@ -1684,10 +1886,43 @@ int build_interp(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const i
   AMGB_TRY(P.col.alloc(ctx, nnzp));
   AMGB_TRY(P.val.alloc(ctx, nnzp));
   const int64_t rows = row_end - row_begin;
-  AMGB_LAUNCH(ctx, F_INTERP, 13.0 * A.nnz + 12.0 * nnzp + 16.0 * n, interp_fill_kernel,
-              (unsigned)div_up(rows * 32, kBlock), kBlock, 0, row_end, A.rp.p, A.col.p, A.val.p, mask, cf, col_id,
-              diagv, P.rp.p, P.col.p, P.val.p, row_begin);
+  const double fill_bytes = 13.0 * A.nnz + 12.0 * nnzp + 16.0 * n;
+  if (std::getenv("AMGB_INTERP_WARP")) {  // A/B and parity aid: the warp-per-row kernel alone
+    AMGB_LAUNCH(ctx, F_INTERP, fill_bytes, interp_fill_kernel, (unsigned)div_up(rows * 32, kBlock), kBlock, 0,
+                row_end, A.rp.p, A.col.p, A.val.p, mask, cf, col_id, diagv, P.rp.p, P.col.p, P.val.p, row_begin,
+                (const uint8_t*)nullptr);
+    AMGB_CHECK_LAUNCH(ctx);
+    return AMGB_OK;
+  }
+  // compacted C-column, sign-filtered rows of the F points
+  DevBuf<int32_t> account, acrp, accol, n_todo;
+  DevBuf<double> acval;
+  DevBuf<uint8_t> todo;
+  AMGB_TRY(account.alloc(ctx, n));
+  AMGB_TRY(acrp.alloc(ctx, n + 1));
+  AMGB_LAUNCH(ctx, F_INTERP, 12.0 * A.nnz + 16.0 * n, interp_ac_count_kernel, (unsigned)div_up(n, kBlock), kBlock, 0, n,
+              A.rp.p, A.col.p, A.val.p, cf, diagv, account.p);
+  AMGB_TRY(exclusive_scan_i32(ctx, account.p, acrp.p, n));
+  int32_t nnzac = 0;
+  AMGB_TRY(read_i32(ctx, acrp.p + n, &nnzac));
+  AMGB_TRY(accol.alloc(ctx, nnzac));
+  AMGB_TRY(acval.alloc(ctx, nnzac));
+  AMGB_TRY(todo.alloc_zero(ctx, n));
+  AMGB_TRY(n_todo.alloc_zero(ctx, 1));
+  AMGB_LAUNCH(ctx, F_INTERP, 12.0 * A.nnz + 12.0 * nnzac, interp_ac_fill_kernel, (unsigned)div_up(n, kBlock), kBlock, 0,
+              n, A.rp.p, A.col.p, A.val.p, cf, diagv, (const int32_t*)acrp.p, accol.p, acval.p);
+  AMGB_LAUNCH(ctx, F_INTERP, fill_bytes, interp_fill_group_kernel, (unsigned)div_up(rows, kIgRows), kBlock, 0, row_end,
+              A.rp.p, A.col.p, A.val.p, mask, cf, col_id, (const int32_t*)acrp.p, (const int32_t*)accol.p,
+              (const double*)acval.p, (const int32_t*)P.rp.p, P.col.p, P.val.p, row_begin, todo.p, n_todo.p);
   AMGB_CHECK_LAUNCH(ctx);
+  int32_t left = 0;
+  AMGB_TRY(read_i32(ctx, n_todo.p, &left));
+  if (left > 0) {  // rows with many interpolation points: the warp-per-row kernel
+    AMGB_LAUNCH(ctx, F_INTERP, 0.0, interp_fill_kernel, (unsigned)div_up(rows * 32, kBlock), kBlock, 0, row_end, A.rp.p,
+                A.col.p, A.val.p, mask, cf, col_id, diagv, P.rp.p, P.col.p, P.val.p, row_begin, (const uint8_t*)todo.p);
+    AMGB_CHECK_LAUNCH(ctx);
+    AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `todo` goes out of scope
+  }
   return AMGB_OK;
 }
 

@@ -599,3 +599,24 @@ def test_cljp_is_refused_where_it_is_not_implemented(gpu_ctx):
     with pytest.raises(ab.AmgbError) as e:
         ab.PreconditionBoomerAMG().initialize(A, d)
     assert e.value.status == -5
+
+
+@pytest.mark.parametrize("kind", ["poisson", "elasticity", "hub"])
+def test_warp_per_row_interpolation_kernel_alone_agrees_with_the_oracle(gpu_ctx, monkeypatch, kind):
+    """AMGB_INTERP_WARP=1 builds every interpolation row with the warp-per-row kernel (otherwise the
+    second stage of the grouped kernel, which only sees rows with more than 32 interpolation points
+    or a neighbour matching more than 8 of them).  Same bits as the oracle."""
+    from helpers import hub_leaf_csr
+    from types import SimpleNamespace
+    monkeypatch.setenv("AMGB_INTERP_WARP", "1")
+    if kind == "poisson":
+        s, theta = poisson(14, contrast=3.0), 0.25
+    elif kind == "elasticity":
+        s, theta = ab.gen.elasticity_q1(6, 2, 3, 10.0 ** ab.gen.checkerboard_epsv(2, 3, 2.0)), 0.25
+    else:
+        M = hub_leaf_csr(160, 400, 70, 6, 5)
+        s = SimpleNamespace(n=M.shape[0], col=M.indices.astype(np.int32), val=M.data.astype(np.float64),
+                            rowptr32=lambda: M.indptr.astype(np.int32))
+        theta = 0.05
+    A, P, H = _both(gpu_ctx, s, device_data(theta))
+    _assert_hierarchy_identical(P, H)

@@ -208,6 +208,9 @@ struct Level {
   DevBuf<int32_t> perm;      // new -> old
   DevBuf<int32_t> inv_perm;  // old -> new
   Sell As, Ps, Rs;
+  // F rows x C columns block of As: all a pre-smoothing F half sweep from the zero guess needs
+  // (the F columns multiply zeros), ~1/6 of the entries of the F rows on a 27-point operator
+  Sell Afc;
   DevBuf<double> inv_relax;  // new order: 1/l1 (type 18) or 1/diag (type 0); 0 = skip row
   DevBuf<double> u, f, tmp;  // new order
   // Chebyshev smoother (relax type 16; amgb_cheby.cu): 1/sqrt(diag) in the solve numbering,

@@ -1839,7 +1839,6 @@ int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, 
     return spgemm_impl<8, 256, 128>(ctx, A, B, C, sorted, true);
   }
   ctx->routes[est <= 50.0 ? R_SPGEMM_G8_T128 : (est <= 110.0 ? R_SPGEMM_G8_T256 : R_SPGEMM_G8_T512)]++;
-  if (est <= 50.0 && avg_b <= 4.0 && std::getenv("AMGB_SPGEMM_G4")) return spgemm_impl<4, 256, 128>(ctx, A, B, C, sorted);
   if (est <= 50.0) return spgemm_impl<8, 256, 128>(ctx, A, B, C, sorted);
   if (est <= 110.0) return spgemm_impl<8, 512, 256>(ctx, A, B, C, sorted);
   return spgemm_impl<8, 1024, 512>(ctx, A, B, C, sorted);

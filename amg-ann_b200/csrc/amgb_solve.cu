@@ -87,10 +87,13 @@ build_perm_kernel(int64_t n, const int32_t* __restrict__ cf, const int32_t* __re
 }
 
 // one warp per slice of 32/T rows: width = ceil(longest row / T), in 32-element units
+// col_lt >= 0: only the entries whose (mapped) column is < col_lt are kept, and only in rows >= col_lt
+// (the F rows x C columns block of a C/F-permuted operator)
 template <int T>
 __global__ void __launch_bounds__(kBlock)
 sell_width_kernel(int64_t n, int64_t nslices, const int32_t* __restrict__ perm,
-                  const int32_t* __restrict__ rp, int32_t* __restrict__ width) {
+                  const int32_t* __restrict__ rp, int32_t* __restrict__ width, const int32_t* __restrict__ col,
+                  const int32_t* __restrict__ colmap, int col_lt) {
   const int64_t s = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (s >= nslices) return;
@@ -99,6 +102,12 @@ sell_width_kernel(int64_t n, int64_t nslices, const int32_t* __restrict__ perm,
   if (row < n) {
     const int old = perm ? perm[row] : (int)row;
     len = rp[old + 1] - rp[old];
+    if (col_lt >= 0) {
+      int kept = 0;
+      if (row >= col_lt && lane % T == 0)
+        for (int k = rp[old]; k < rp[old] + len; ++k) kept += (colmap ? colmap[col[k]] : col[k]) < col_lt;
+      len = kept;  // (the other lanes of the row contribute 0 to the max below)
+    }
   }
   len = (len + T - 1) / T;
 #pragma unroll
@@ -112,7 +121,7 @@ sell_fill_kernel(int64_t n, int64_t ncols, int64_t nslices, const int32_t* __res
                  const int32_t* __restrict__ colmap, const int32_t* __restrict__ rp,
                  const int32_t* __restrict__ col, const double* __restrict__ val,
                  const int32_t* __restrict__ slice_ptr, int32_t* __restrict__ scol,
-                 double* __restrict__ sval) {
+                 double* __restrict__ sval, int col_lt) {
   const int64_t s = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (s >= nslices) return;
@@ -127,6 +136,26 @@ sell_fill_kernel(int64_t n, int64_t ncols, int64_t nslices, const int32_t* __res
   const int w = slice_ptr[s + 1] - slice_ptr[s];
   const int64_t base = (int64_t)slice_ptr[s] * 32 + lane;
   const int pad_col = row < ncols ? (int)row : 0;
+  if (col_lt >= 0) {
+    // filtered block: lane t of the row walks the whole row and keeps the kept entries number t, t+T, ...
+    int kept = 0, ju = 0;
+    if (row >= col_lt)
+      for (int k = b; k < b + len; ++k) {
+        const int c = colmap ? colmap[col[k]] : col[k];
+        if (c >= col_lt) continue;
+        if (kept % T == t) {
+          scol[base + (int64_t)ju * 32] = c;
+          sval[base + (int64_t)ju * 32] = val[k];
+          ++ju;
+        }
+        ++kept;
+      }
+    for (; ju < w; ++ju) {
+      scol[base + (int64_t)ju * 32] = 0;
+      sval[base + (int64_t)ju * 32] = 0.0;
+    }
+    return;
+  }
   for (int ju = 0; ju < w; ++ju) {
     const int j = ju * T + t;
     int c = pad_col;
@@ -166,20 +195,22 @@ static int pick_T(const DeviceCsr& A) {
     default: { constexpr int TT = 32; CALL; } break; \
   }
 
+// col_lt >= 0: the block (rows >= col_lt) x (columns < col_lt) only, T lanes per row as given
 static int csr_to_sell(amgb_ctx* ctx, const DeviceCsr& A, const int32_t* row_perm, const int32_t* colmap,
-                       Sell& S) {
+                       Sell& S, int col_lt = -1, int T_block = 1) {
   S.n = A.n;
   S.ncols = A.ncols;
   S.nnz = A.nnz;
-  S.T = pick_T(A);
+  S.T = col_lt >= 0 ? T_block : pick_T(A);
   ctx->routes[S.T == 1 ? R_SELL_T1_STREAM : R_SELL_T_MULTI]++;
   S.nslices = div_up(A.n * S.T, 32);
   DevBuf<int32_t> width;
   AMGB_TRY(width.alloc(ctx, S.nslices));
   AMGB_TRY(S.slice_ptr.alloc(ctx, S.nslices + 1));
   const unsigned grid = (unsigned)div_up(S.nslices * 32, kBlock);
-  AMGB_DISPATCH_T(S.T, AMGB_LAUNCH(ctx, F_AUX, 8.0 * A.n, sell_width_kernel<TT>, grid, kBlock, 0, A.n,
-                                   S.nslices, row_perm, A.rp.p, width.p));
+  AMGB_DISPATCH_T(S.T, AMGB_LAUNCH(ctx, F_AUX, 8.0 * A.n + (col_lt >= 0 ? 4.0 * A.nnz : 0.0), sell_width_kernel<TT>, grid,
+                                   kBlock, 0, A.n, S.nslices, row_perm, A.rp.p, width.p, (const int32_t*)A.col.p, colmap,
+                                   col_lt));
   AMGB_TRY(exclusive_scan_i32(ctx, width.p, S.slice_ptr.p, S.nslices));
   int32_t total = 0;
   AMGB_TRY(read_i32(ctx, S.slice_ptr.p + S.nslices, &total));
@@ -188,8 +219,11 @@ static int csr_to_sell(amgb_ctx* ctx, const DeviceCsr& A, const int32_t* row_per
   AMGB_TRY(S.val.alloc(ctx, S.padded));
   AMGB_DISPATCH_T(S.T, AMGB_LAUNCH(ctx, F_AUX, 12.0 * A.nnz + 12.0 * S.padded, sell_fill_kernel<TT>, grid,
                                    kBlock, 0, A.n, A.ncols, S.nslices, row_perm, colmap, A.rp.p, A.col.p,
-                                   A.val.p, S.slice_ptr.p, S.col.p, S.val.p));
+                                   A.val.p, S.slice_ptr.p, S.col.p, S.val.p, col_lt));
   AMGB_CHECK_LAUNCH(ctx);
+  if (col_lt >= 0) {  // entries really stored, for the byte accounting (padding included: it is read)
+    S.nnz = S.padded;
+  }
   return AMGB_OK;
 }
 
@@ -223,6 +257,16 @@ struct EpiJacobi {  // out = u_old + w (f - A u) inv_relax  (hypre relax types 0
   double w;
   __device__ __forceinline__ void store(int row, double s) const {
     out[row] = u_old[row] + w * (f[row] - s) * inv_relax[row];
+  }
+};
+
+struct EpiJacobiZero {  // the same from the zero guess: out = 0 + w (f - A_FC u_C) inv_relax
+  const double* f;
+  const double* inv_relax;
+  double* out;
+  double w;
+  __device__ __forceinline__ void store(int row, double s) const {
+    out[row] = 0.0 + w * (f[row] - s) * inv_relax[row];
   }
 };
 
@@ -729,6 +773,11 @@ int finish_solve_setup_range(amgb_precond* P, int l0) {
       continue;
     }
     AMGB_TRY(csr_to_sell(ctx, L.A, L.perm.p, L.inv_perm.p, L.As));
+    if (l + 1 < nl && L.n_coarse > 0 && L.n_coarse < n && P->data.relax_order == 1 &&
+        (P->relax_down == 0 || P->relax_down == 18) && !std::getenv("AMGB_NO_AFC")) {
+      // (the rows of the block are ~6 times shorter than those of A: a quarter of its lanes per row)
+      AMGB_TRY(csr_to_sell(ctx, L.A, L.perm.p, L.inv_perm.p, L.Afc, (int)L.n_coarse, L.As.T >= 8 ? L.As.T / 4 : 1));
+    }
     if (l + 1 < nl) {
       Level& C = P->lv[l + 1];
       AMGB_TRY(csr_to_sell(ctx, L.P, L.perm.p, C.inv_perm.p, L.Ps));
@@ -941,6 +990,12 @@ static int relax_if(amgb_precond* P, int l, const double* f, double* u, double* 
     if (cycle_param < 2) {  // down: C then F
       if (u_is_zero) AMGB_TRY(relax_zero(ctx, L, 0, nC, f, w, out));
       else AMGB_TRY(launch_sell_halo(P, l, L.As, 0, nC, u, u, 0, epi, fam, bytes_c, u, u, 0, u));
+      if (u_is_zero && L.Afc.n > 0 && !partitioned_level(P, l)) {
+        // from the zero guess the F columns multiply zeros: the F rows x C columns block is all there is
+        AMGB_TRY(launch_sell(ctx, L.Afc, nC, n, out, out, 0, EpiJacobiZero{f, L.inv_relax.p, out, w}, fam,
+                             12.0 * L.Afc.padded + 4.0 * (n - nC) + 24.0 * (n - nC) + 8.0 * nC));
+        return AMGB_OK;
+      }
       // halo C points: fresh; halo F points: old
       AMGB_TRY(launch_sell_halo(P, l, L.As, nC, n, out, u, nC, epi, fam, bytes_f, out, u, nC, u));
     } else {  // up: F then C

@@ -7,13 +7,11 @@
 //     so it only needs V-wide accumulators and never looks at row pointers again;
 //   * a warp covers 256 consecutive entries per iteration (3 KB) with four pairs of load
 //     instructions, each one contiguous run (8 bytes of columns and 16 bytes of values per
-//     lane); a transpose through shared memory leaves every lane with 8 CONSECUTIVE entries,
-//     which it folds into at most two runs of equal column bin (columns ascend within a row):
-//     one bin computation per run, range checks for the rest;
+//     lane), 8 entries per lane;
 //   * the rows of a row-bin of a banded matrix meet the same two or three column bins over and
 //     over: the warp caches four bins (ids warp-uniform, partial sum / count / maxima
-//     lane-private in registers), so the steady state is loads, the run folding and two
-//     predicated merges per lane -- no cross-lane traffic beyond one vote;
+//     lane-private in registers), so the steady state is loads, a bin computation and
+//     predicated register adds -- no cross-lane traffic at all;
 //   * a bin that is not cached is installed in a free slot, or makes the warp flush its slots
 //     first: a butterfly over the warp and ONE writer (lane 0) per bin into the WARP-PRIVATE
 //     shared-memory accumulators -- no two writers ever share an address, no atomics anywhere;
@@ -65,12 +63,6 @@ struct PoolSlot {
     pp = fmax(pp, v);    // (v < 0 leaves pp, which starts at 0, alone: max(pp, max(v, 0)) == max(pp, v))
     np = fmax(np, -v);
   }
-  __device__ __forceinline__ void merge(const PoolSlot& o) {
-    s += o.s;
-    cnt += o.cnt;
-    pp = fmax(pp, o.pp);
-    np = fmax(np, o.np);
-  }
 };
 
 // butterfly over the warp, then lane 0 adds the total to the warp's accumulators of `bin`
@@ -94,44 +86,15 @@ __device__ __forceinline__ void pool_flush_slot(PoolSlot& a, int bin, int lane, 
 }
 
 constexpr int kPoolSlots = 4;
-constexpr int kPoolStage = kPoolWarpChunk + kPoolWarpChunk / 8;  // one pad word per 8 entries: conflict-free reads
-
-// The warp's cache of bins (ids in `key`, warp-uniform; partials in `acc`, lane-private).  `missing`
-// is a bin this lane still needs (or -1): installs it for the whole warp -- in a free slot, or in
-// slot 0 after flushing every slot.  Returns false when no lane misses anything.
-__device__ __forceinline__ bool pool_install(int missing, int (&key)[kPoolSlots], PoolSlot (&acc)[kPoolSlots], int lane,
-                                             double* w_sum, int* w_cnt, double* w_pp, double* w_np) {
-  const unsigned full = 0xffffffffu;
-  const unsigned mm = __ballot_sync(full, missing >= 0);
-  if (mm == 0) return false;
-  const int nb = __shfl_sync(full, missing, __ffs(mm) - 1);
-  bool placed = false;
-#pragma unroll
-  for (int t = 0; t < kPoolSlots; ++t)
-    if (!placed && key[t] < 0) {
-      key[t] = nb;
-      placed = true;
-    }
-  if (!placed) {
-#pragma unroll
-    for (int t = 0; t < kPoolSlots; ++t) {
-      pool_flush_slot(acc[t], key[t], lane, w_sum, w_cnt, w_pp, w_np);
-      key[t] = -2;
-    }
-    key[0] = nb;
-  }
-  return true;
-}
 
 template <bool VEC>
-__global__ void __launch_bounds__(kPoolBlock, 2)
+__global__ void __launch_bounds__(kPoolBlock, 3)
 pool_entries_kernel(BinMap bm, int tiles, long long g0, int nloc, const int32_t* __restrict__ rp,
-                    const int32_t* __restrict__ col, const double* __restrict__ val, double* __restrict__ part_sum,
+                    const int32_t* __restrict__ col,
+                    const double* __restrict__ val, double* __restrict__ part_sum,
                     long long* __restrict__ part_cnt, double* __restrict__ part_pp,
                     double* __restrict__ part_np) {
   extern __shared__ unsigned char pool_smem[];
-  __shared__ int32_t st_c[kPoolWarps][kPoolStage];
-  __shared__ double st_v[kPoolWarps][kPoolStage];
   const int V = bm.V;
   double* s_sum = reinterpret_cast<double*>(pool_smem);          // [warps][V]
   double* s_pp = s_sum + kPoolWarps * V;
@@ -159,125 +122,86 @@ pool_entries_kernel(BinMap bm, int tiles, long long g0, int nloc, const int32_t*
   double* w_pp = s_pp + warp * V;
   double* w_np = s_np + warp * V;
   int* w_cnt = s_cnt + warp * V;
-  int32_t* stc = st_c[warp];
-  double* stv = st_v[warp];
   // The rows of one row-bin of a banded matrix meet two or three column bins, over and over:
   // the warp caches kPoolSlots bins (ids warp-uniform, partial sums lane-private in registers)
-  // and streams the entries into them without any cross-lane traffic.
-  int key[kPoolSlots];
+  // and streams the entries into them without any cross-lane traffic.  A bin that is not cached
+  // is installed (free slot) or makes the warp flush all slots into its shared-memory
+  // accumulators first (butterfly + one writer per bin).
+  // (a slot is kept as the COLUMN RANGE of its bin: an entry is matched with two integer compares, the
+  // division of BinMap::bin is only paid when a bin is installed)
+  int key[kPoolSlots], lo[kPoolSlots], hi[kPoolSlots];
   PoolSlot acc[kPoolSlots];
 #pragma unroll
   for (int t = 0; t < kPoolSlots; ++t) {
-    key[t] = -2;  // free (never equal to a bin, nor to the -1 of an entry outside the range)
+    key[t] = -2;  // free
+    lo[t] = hi[t] = 0;
     acc[t].clear();
   }
   for (int chunk = c0; chunk < c1; ++chunk) {
-    // (a) the warp's 256 entries: four pairs of fully coalesced loads (8 B of columns, 16 B of values per
-    //     lane), transposed through shared memory so that every lane ends up with 8 CONSECUTIVE entries
-    const long long wbase = (long long)chunk * kPoolBlockChunk + warp * kPoolWarpChunk;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = 64 * j + 2 * lane;
-      const long long k = wbase + e;
-      int ca, cb;
-      double va, vb;
-      if (VEC && k >= e_lo && k + 2 <= e_hi) {
-        const int2 cc = __ldcs(reinterpret_cast<const int2*>(col + k));
-        const double2 vv = __ldcs(reinterpret_cast<const double2*>(val + k));
-        ca = cc.x; cb = cc.y; va = vv.x; vb = vv.y;
-      } else {
-        const bool oa = k >= e_lo && k < e_hi, ob = k + 1 >= e_lo && k + 1 < e_hi;
-        ca = oa ? __ldcs(col + k) : -1;
-        va = oa ? __ldcs(val + k) : 0.0;
-        cb = ob ? __ldcs(col + k + 1) : -1;
-        vb = ob ? __ldcs(val + k + 1) : 0.0;
-      }
-      const int p = e + (e >> 3);  // e and e+1 share e/8
-      stc[p] = ca;
-      stc[p + 1] = cb;
-      stv[p] = va;
-      stv[p + 1] = vb;
-    }
-    __syncwarp();
+    // entries 64 j + 2 lane + {0, 1} of the warp's 256, j = 0..3: every load instruction of the warp is
+    // one contiguous run (8 bytes per lane for the columns, 16 for the values)
+    const long long wbase = (long long)chunk * kPoolBlockChunk + warp * kPoolWarpChunk + 2 * lane;
     int c[kPoolPerLane];
     double v[kPoolPerLane];
 #pragma unroll
-    for (int u = 0; u < kPoolPerLane; ++u) {
-      c[u] = stc[9 * lane + u];
-      v[u] = stv[9 * lane + u];
-    }
-    __syncwarp();
-    // (b) my 8 entries as at most two runs of equal column bin (columns ascend within a row, a row of a
-    //     27-point operator changes bin at most once per 9 entries); one division per run, range checks after
-    PoolSlot ra, rb;
-    ra.clear();
-    rb.clear();
-    int ba = -1, bb = -1, lo = 0, hi = 0, state = 0;
-    bool complex_lane = false;
+    for (int j = 0; j < kPoolPerLane; j += 2) {
+      const long long k = wbase + 32 * j;
+      if (VEC && k >= e_lo && k + 2 <= e_hi) {
+        const int2 cc = __ldcs(reinterpret_cast<const int2*>(col + k));
+        const double2 vv = __ldcs(reinterpret_cast<const double2*>(val + k));
+        c[j] = cc.x;
+        c[j + 1] = cc.y;
+        v[j] = vv.x;
+        v[j + 1] = vv.y;
+      } else {
 #pragma unroll
-    for (int u = 0; u < kPoolPerLane; ++u) {
-      if (c[u] < 0) continue;
-      if (state == 0 || c[u] < lo || c[u] >= hi) {
-        if (state == 2) {
-          complex_lane = true;
-        } else {
-          const int nbin = bm.bin(c[u]);
-          lo = bm.row_begin(nbin);
-          hi = bm.row_begin(nbin + 1);
-          if (state == 0) ba = nbin; else bb = nbin;
-          ++state;
+        for (int u = 0; u < 2; ++u) {
+          const bool ok = k + u >= e_lo && k + u < e_hi;
+          c[j + u] = ok ? __ldcs(col + k + u) : -1;  // (outside the row-bin's entry range: only at its two ends)
+          v[j + u] = ok ? __ldcs(val + k + u) : 0.0;
         }
       }
-      if (state == 1) ra.add(v[u]); else rb.add(v[u]);
     }
-    if (!__any_sync(full, complex_lane)) {
-      // (c) the common case: two items per lane go into the cached bins
-      for (;;) {
-        int missing = -1;
-        if (ba >= 0) {
-          bool hit = false;
+    // Every pass adds the entries whose column lies in a cached bin and consumes them (c = -1); what is
+    // left names a bin to install -- in a free slot, or after flushing all slots when none is free.
+    // One new bin per pass, so a chunk with k uncached bins takes k + 1 passes; the steady state of a
+    // banded matrix is a single pass and a single vote.
+    for (;;) {
+      int missing = -1;  // a column of mine that no cached bin covers
 #pragma unroll
-          for (int t = 0; t < kPoolSlots; ++t)
-            if (ba == key[t]) {
-              acc[t].merge(ra);
-              hit = true;
-            }
-          if (hit) ba = -1; else missing = ba;
-        }
-        if (bb >= 0) {
-          bool hit = false;
+      for (int j = 0; j < kPoolPerLane; ++j) {
+        if (c[j] < 0) continue;
+        bool hit = false;
 #pragma unroll
-          for (int t = 0; t < kPoolSlots; ++t)
-            if (bb == key[t]) {
-              acc[t].merge(rb);
-              hit = true;
-            }
-          if (hit) bb = -1; else missing = bb;
-        }
-        if (!pool_install(missing, key, acc, lane, w_sum, w_cnt, w_pp, w_np)) break;
+        for (int t = 0; t < kPoolSlots; ++t)
+          if (c[j] >= lo[t] && c[j] < hi[t]) {
+            acc[t].add(v[j]);
+            hit = true;
+          }
+        if (hit) c[j] = -1; else missing = c[j];
       }
-    } else {
-      // (d) some lane holds three or more runs (short rows, unstructured columns): entry by entry.
-      // Every pass adds the entries whose bin is cached and consumes them (b = -1); one new bin is
-      // installed per pass, so the loop ends after (uncached bins + 1) passes.
-      int b[kPoolPerLane];
+      const unsigned mm = __ballot_sync(full, missing >= 0);
+      if (mm == 0) break;
+      const int nb = bm.bin(__shfl_sync(full, missing, __ffs(mm) - 1));
+      bool placed = false;
 #pragma unroll
-      for (int u = 0; u < kPoolPerLane; ++u) b[u] = c[u] >= 0 ? bm.bin(c[u]) : -1;
-      for (;;) {
-        int missing = -1;
-#pragma unroll
-        for (int u = 0; u < kPoolPerLane; ++u) {
-          if (b[u] < 0) continue;
-          bool hit = false;
-#pragma unroll
-          for (int t = 0; t < kPoolSlots; ++t)
-            if (b[u] == key[t]) {
-              acc[t].add(v[u]);
-              hit = true;
-            }
-          if (hit) b[u] = -1; else missing = b[u];
+      for (int t = 0; t < kPoolSlots; ++t)
+        if (!placed && key[t] < 0) {
+          key[t] = nb;
+          placed = true;
         }
-        if (!pool_install(missing, key, acc, lane, w_sum, w_cnt, w_pp, w_np)) break;
+      if (!placed) {  // all slots busy: flush them and start over with the new bin
+#pragma unroll
+        for (int t = 0; t < kPoolSlots; ++t) {
+          pool_flush_slot(acc[t], key[t], lane, w_sum, w_cnt, w_pp, w_np);
+          key[t] = -2;
+        }
+        key[0] = nb;
+      }
+#pragma unroll
+      for (int t = 0; t < kPoolSlots; ++t) {
+        lo[t] = key[t] >= 0 ? bm.row_begin(key[t]) : 0;
+        hi[t] = key[t] >= 0 ? bm.row_begin(key[t] + 1) : 0;
       }
     }
   }

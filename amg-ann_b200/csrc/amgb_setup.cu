@@ -1233,11 +1233,6 @@ __device__ __forceinline__ int row_upper_bound(int b, int e, int gl, unsigned gm
   return group_sum<G>(ub, gm);
 }
 
-// Short B rows (A*P: 1-4 entries) held in registers: every lane of the group fetches the first
-// kPre entries of the B row of ITS A entry right after the preload of the A entries, so the B rows of a
-// whole chunk are in flight together; the ordered walk over the chunk then only shuffles.
-constexpr int kPre = 4;
-
 // number of distinct columns of row i of A*B, or -1 if the table overflowed
 template <int G>
 __device__ __forceinline__ int symbolic_row(unsigned* keys, int H, int lgH, int b, int e, int gl,
@@ -1255,35 +1250,12 @@ __device__ __forceinline__ int symbolic_row(unsigned* keys, int H, int lgH, int 
       my_bb = brp[kk];
       my_len = brp[kk + 1] - my_bb;
     }
-    int pre[kPre];
-    if (G <= 8) {
-#pragma unroll
-      for (int m = 0; m < kPre; ++m) pre[m] = m < my_len ? bcol[my_bb + m] : 0;
-    }
     const int steps = min(G, e - kb);
     for (int t = 0; t < steps; ++t) {
       const int bb = __shfl_sync(gm, my_bb, t, G), len = __shfl_sync(gm, my_len, t, G);
-      if (G <= 8) {
-        // entry m of the row goes to lane m: it comes out of lane t's registers
-        int mine = 0;
-#pragma unroll
-        for (int m = 0; m < kPre; ++m) {
-          const int c = __shfl_sync(gm, pre[m], t, G);
-          if (gl == m) mine = c;
-        }
-        if (gl < len && gl < kPre) {
-          const int r = hash_insert(keys, H, lgH, (unsigned)mine);
-          if (r < 0) fail = 1; else cnt += r;
-        }
-        for (int m = kPre + gl; m < len; m += G) {  // (longer rows: the rest from memory)
-          const int r = hash_insert(keys, H, lgH, (unsigned)bcol[bb + m]);
-          if (r < 0) fail = 1; else cnt += r;
-        }
-      } else {
-        for (int m = gl; m < len; m += G) {
-          const int r = hash_insert(keys, H, lgH, (unsigned)bcol[bb + m]);
-          if (r < 0) fail = 1; else cnt += r;
-        }
+      for (int m = gl; m < len; m += G) {
+        const int r = hash_insert(keys, H, lgH, (unsigned)bcol[bb + m]);
+        if (r < 0) fail = 1; else cnt += r;
       }
     }
     if (__any_sync(gm, fail)) {  // group-uniform: the table is full
@@ -1352,22 +1324,6 @@ spgemm_symbolic_global_kernel(const int32_t* __restrict__ ovf_rows, int novf, in
   }
 }
 
-__device__ __forceinline__ void table_add(unsigned* keys, double* vals, int H, int lgH, unsigned key, double prod) {
-  int h = hash_slot(key, lgH);
-  for (;;) {
-    const unsigned old = atomicCAS(&keys[h], kEmpty, key);
-    if (old == kEmpty) {
-      vals[h] = __dadd_rn(0.0, prod);
-      return;
-    }
-    if (old == key) {
-      vals[h] = __dadd_rn(vals[h], prod);
-      return;
-    }
-    h = (h + 1) & (H - 1);
-  }
-}
-
 // accumulate row i of A*B into the (keys, vals) table, ascending k
 template <int G>
 __device__ __forceinline__ void accumulate_row(unsigned* keys, double* vals, int H, int lgH, int b, int e, int gl,
@@ -1386,37 +1342,26 @@ __device__ __forceinline__ void accumulate_row(unsigned* keys, double* vals, int
       my_bb = brp[kk];
       my_len = brp[kk + 1] - my_bb;
     }
-    int prec[kPre];
-    double prev[kPre];
-    if (G <= 8) {  // the first entries of MY B row, already multiplied by my A entry (one rounding, as before)
-#pragma unroll
-      for (int m = 0; m < kPre; ++m) {
-        prec[m] = m < my_len ? bcol[my_bb + m] : 0;
-        prev[m] = m < my_len ? __dmul_rn(my_a, bval[my_bb + m]) : 0.0;
-      }
-    }
     const int steps = min(G, e - kb);
     for (int t = 0; t < steps; ++t) {
       const int bb = __shfl_sync(gm, my_bb, t, G), len = __shfl_sync(gm, my_len, t, G);
       const double a = __shfl_sync(gm, my_a, t, G);
-      if (G <= 8) {
-        int mc = 0;
-        double mp = 0.0;
-#pragma unroll
-        for (int m = 0; m < kPre; ++m) {
-          const int c = __shfl_sync(gm, prec[m], t, G);
-          const double pr = __shfl_sync(gm, prev[m], t, G);
-          if (gl == m) {
-            mc = c;
-            mp = pr;
+      for (int m = gl; m < len; m += G) {
+        const unsigned key = (unsigned)bcol[bb + m];
+        const double prod = __dmul_rn(a, bval[bb + m]);
+        int h = hash_slot(key, lgH);
+        for (;;) {
+          const unsigned old = atomicCAS(&keys[h], kEmpty, key);
+          if (old == kEmpty) {
+            vals[h] = __dadd_rn(0.0, prod);
+            break;
           }
+          if (old == key) {
+            vals[h] = __dadd_rn(vals[h], prod);
+            break;
+          }
+          h = (h + 1) & (H - 1);
         }
-        if (gl < len && gl < kPre) table_add(keys, vals, H, lgH, (unsigned)mc, mp);
-        for (int m = kPre + gl; m < len; m += G)
-          table_add(keys, vals, H, lgH, (unsigned)bcol[bb + m], __dmul_rn(a, bval[bb + m]));
-      } else {
-        for (int m = gl; m < len; m += G)
-          table_add(keys, vals, H, lgH, (unsigned)bcol[bb + m], __dmul_rn(a, bval[bb + m]));
       }
       __syncwarp(gm);  // orders the accumulation over k
     }
@@ -2595,7 +2540,9 @@ int amgb_precond_effective_relax(const amgb_precond* P, int32_t* down, int32_t* 
   if (!P) return AMGB_ERR_BAD_ARG;
   if (down) *down = P->relax_down;
   if (up) *up = P->relax_up;
-  if (coarse) *coarse = P->relax_coarse;
+  // (Gaussian elimination needs a coarsest grid of at most 1024 rows; beyond that the coarsest level is
+  // relaxed with the sweeps of the way down, and that is what is reported)
+  if (coarse) *coarse = (P->relax_coarse == 9 && !P->dense_ok && !P->lv.empty()) ? P->relax_down : P->relax_coarse;
   return AMGB_OK;
 }
 

@@ -794,7 +794,13 @@ int finish_solve_setup_range(amgb_precond* P, int l0) {
     L.n_solve = L.n_vec = n;
     if (P->relax_down == 16) AMGB_TRY(cheby_setup_level(P, l));
     // (with Chebyshev on the way down and up, inv_relax only serves a Jacobi-type coarse relaxation)
-    const int aux_type = P->relax_down == 16 ? (P->relax_coarse == 9 ? 0 : P->relax_coarse) : P->relax_down;
+    // scaling of the Jacobi-type relaxation of this level: the coarsest level is relaxed with the COARSE
+    // type when that is a Jacobi-type one (relax_coarse may differ from relax_down: 0 vs 18); with
+    // Chebyshev on the way down and up, 1/diag only serves such a coarse relaxation (or the sweeps that
+    // stand in for Gaussian elimination when the coarsest grid is too large for it)
+    const bool coarsest = l == nl - 1;
+    int aux_type = P->relax_down == 16 ? 0 : P->relax_down;
+    if (coarsest && (P->relax_coarse == 0 || P->relax_coarse == 18)) aux_type = P->relax_coarse;
     AMGB_TRY(L.inv_relax.alloc(ctx, n));
     AMGB_DISPATCH_T(L.As.T, AMGB_LAUNCH(ctx, F_AUX, L.As.csr_bytes() + 8.0 * n, sell_aux_kernel<TT>,
                                         (unsigned)div_up(L.As.nslices * 32, kBlock), kBlock, 0,
@@ -1895,7 +1901,13 @@ int finish_solve_setup_dist(amgb_precond* P) {
       }
     }
     if (P->relax_down == 16) AMGB_TRY(cheby_setup_level(P, l));  // collective: inner products over all ranks
-    const int aux_type = P->relax_down == 16 ? (P->relax_coarse == 9 ? 0 : P->relax_coarse) : P->relax_down;
+    // scaling of the Jacobi-type relaxation of this level: the coarsest level is relaxed with the COARSE
+    // type when that is a Jacobi-type one (relax_coarse may differ from relax_down: 0 vs 18); with
+    // Chebyshev on the way down and up, 1/diag only serves such a coarse relaxation (or the sweeps that
+    // stand in for Gaussian elimination when the coarsest grid is too large for it)
+    const bool coarsest = l == nl - 1;
+    int aux_type = P->relax_down == 16 ? 0 : P->relax_down;
+    if (coarsest && (P->relax_coarse == 0 || P->relax_coarse == 18)) aux_type = P->relax_coarse;
     AMGB_TRY(L.inv_relax.alloc(ctx, nloc));
     AMGB_DISPATCH_T(L.As.T, AMGB_LAUNCH(ctx, F_AUX, L.As.csr_bytes() + 8.0 * nloc, sell_aux_kernel<TT>,
                                         (unsigned)div_up(L.As.nslices * 32, kBlock), kBlock, 0,

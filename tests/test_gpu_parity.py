@@ -238,6 +238,7 @@ def test_truncated_hierarchy_dense_or_relaxed_coarsest(gpu_ctx, m, max_levels):
 
 @pytest.mark.parametrize("kw", [dict(w_cycle=True), dict(n_sweeps=2), dict(max_iter=2),
                                 dict(relaxation_type_coarse=ab.RelaxationType.l1scaledJacobi, n_sweeps_coarse=3),
+                                dict(relaxation_type_coarse=ab.RelaxationType.Jacobi, n_sweeps_coarse=2, relax_weight=0.8),
                                 dict(max_coarse_size=60), dict(max_row_sum=1.0)])
 def test_cycle_options_of_additional_data(gpu_ctx, kw):
     """The remaining deal.II AdditionalData / PCHYPRE knobs: W-cycle,

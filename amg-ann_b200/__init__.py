@@ -477,7 +477,7 @@ class SolverCG:
     def solve(self, A, x, b, preconditioner):
         assert x.dtype == np.float64 and x.flags.c_contiguous
         b = np.ascontiguousarray(b, dtype=np.float64)
-        cap = min(self.control.max_steps, 1 << 20) + 1
+        cap = min(self.control.max_steps, 65535) + 1   # the library keeps at most 65 536 entries
         hist = np.zeros(cap)
         nit = C.c_int64()
         ctx = preconditioner.ctx or A.ctx

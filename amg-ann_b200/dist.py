@@ -272,7 +272,7 @@ class DistSolverCG:
     def solve(self, A, x_local, b_local, preconditioner):
         assert x_local.dtype == np.float64 and x_local.flags.c_contiguous
         b = np.ascontiguousarray(b_local, dtype=np.float64)
-        cap = min(self.control.max_steps, 1 << 20) + 1
+        cap = min(self.control.max_steps, 65535) + 1   # the library keeps at most 65 536 entries
         hist = np.zeros(cap)
         nit = C.c_int64()
         rc = amgb_lib().amgb_dist_cg_solve(A.ctx._h, _p(x_local, c_f64p), _p(b, c_f64p), preconditioner._h,

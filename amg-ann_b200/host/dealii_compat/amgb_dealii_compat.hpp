@@ -440,7 +440,9 @@ class SolverCG {
     const amgb::Matrix& Ad = A.device();
     const amgb::Context& ctx = preconditioner.backend().context();
     const int64_t max_steps = control_.max_steps();
-    std::vector<double> hist((size_t)std::min<int64_t>(max_steps, (int64_t)1 << 22) + 1);
+    // (the library keeps at most 65 536 history entries; sized outside of nothing bigger than that, so
+    // the timed solve does not pay for zero-filling max_steps = n doubles)
+    std::vector<double> hist((size_t)std::min<int64_t>(max_steps, (int64_t)65535) + 1);
     int64_t nit = 0;
     const int rc = amgb_cg_solve(ctx.get(), Ad.get(), x.data(), b.data(), preconditioner.backend().get(), max_steps,
                                  control_.tolerance(), hist.data(), (int64_t)hist.size(), &nit);

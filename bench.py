@@ -278,21 +278,21 @@ def run_reference(args):
 
 def cpu_baseline_port(ab, m_full, nnz_full):
     """The oracle with the DEVICE algorithm on one core over the sweep's theta mix (every
-    third value) at m=56, scaled with the exponent measured against m=36."""
+    third value) at m=64, scaled with the exponent measured against m=44."""
     thetas = ab.gen.theta_sweep(*map(float, THETA))
     sel = thetas[::3]
     t0 = time.perf_counter()
-    s_a, s_b = make_system(ab, 36), make_system(ab, 56)
+    s_a, s_b = make_system(ab, 44), make_system(ab, 64)
     sec_a, _ = cpu_sample(s_a, sel, "port", 1)
     sec_b, recs = cpu_sample(s_b, sel, "port", 1)
     expo = scaling_exponent(sec_a, s_a.nnz, sec_b, s_b.nnz)
     used = min(max(expo, 1.0), 1.3)
     scale = (nnz_full / s_b.nnz) ** used
     return {"value": sec_b * scale, "unit": "s/system", "cores": 1, "kind": "port",
-            "sample": (f"oracle ({DEVICE_ALGO}, same options as the device) at m=56 ({s_b.n} DoFs), theta in "
+            "sample": (f"oracle ({DEVICE_ALGO}, same options as the device) at m=64 ({s_b.n} DoFs), theta in "
                        f"{[round(t, 2) for t in sel]} (every third value of the sweep), 1 thread; measured "
                        f"{sec_b:.3f} s/system, scaled to m={m_full} by (nnz ratio {nnz_full / s_b.nnz:.1f})^{used:.3f} "
-                       f"(exponent measured between m=36 and m=56: {expo:.3f})"),
+                       f"(exponent measured between m=44 and m=64: {expo:.3f})"),
             "measured_s_per_system_at_sample": sec_b,
             "iters_at_sample": {f"{r['theta']:.2f}": r["iters"] for r in recs},
             "wall_s": round(time.perf_counter() - t0, 2)}

@@ -157,6 +157,10 @@ class Context:
     def synchronize(self):
         _chk(self._h, amgb_lib().amgb_ctx_synchronize(self._h), "amgb_ctx_synchronize")
 
+    def reserve(self, nbytes):
+        """Grow the context's memory pool to nbytes up front (include/amgb.h amgb_ctx_reserve)."""
+        _chk(self._h, amgb_lib().amgb_ctx_reserve(self._h, int(nbytes)), "amgb_ctx_reserve")
+
     def kernel_launches(self):
         v = C.c_int64()
         _chk(self._h, amgb_lib().amgb_ctx_kernel_launches(self._h, C.byref(v)), "kernel_launches")

@@ -80,7 +80,7 @@ def gen_lib():
 
 
 AMGB_SYMBOLS = [
-    "amgb_ctx_create", "amgb_ctx_destroy", "amgb_ctx_synchronize", "amgb_last_error",
+    "amgb_ctx_create", "amgb_ctx_destroy", "amgb_ctx_synchronize", "amgb_ctx_reserve", "amgb_last_error",
     "amgb_status_string", "amgb_version", "amgb_ctx_kernel_launches",
     "amgb_ctx_reset_kernel_launches", "amgb_matrix_upload_csr", "amgb_matrix_upload_csr64",
     "amgb_matrix_wrap_device_csr", "amgb_matrix_destroy", "amgb_matrix_dims", "amgb_numbering_dealii_q1", "amgb_matrix_permute",
@@ -123,6 +123,7 @@ def amgb_lib():
         _sig(L.amgb_ctx_create, C.c_int, C.POINTER(vp), C.c_int, vp)
         _sig(L.amgb_ctx_destroy, C.c_int, vp)
         _sig(L.amgb_ctx_synchronize, C.c_int, vp)
+        _sig(L.amgb_ctx_reserve, C.c_int, vp, C.c_int64)
         _sig(L.amgb_last_error, C.c_char_p, vp)
         _sig(L.amgb_status_string, C.c_char_p, C.c_int)
         _sig(L.amgb_version, C.c_int)

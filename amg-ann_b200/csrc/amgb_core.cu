@@ -333,6 +333,20 @@ int amgb_ctx_destroy(amgb_ctx* ctx) {
   return AMGB_OK;
 }
 
+int amgb_ctx_reserve(amgb_ctx* ctx, int64_t bytes) {
+  if (!ctx || bytes < 0) return AMGB_ERR_BAD_ARG;
+  if (bytes == 0) return AMGB_OK;
+  cudaSetDevice(ctx->device);
+  // one allocation of the whole amount, freed at once: the pool keeps the memory (release threshold =
+  // infinity), so the hierarchy of the first initialize() is carved out of it instead of growing the
+  // pool allocation by allocation
+  DevBuf<char> b;
+  AMGB_TRY(b.alloc(ctx, (size_t)bytes));
+  b.release();
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AMGB_OK;
+}
+
 int amgb_ctx_synchronize(amgb_ctx* ctx) {
   if (!ctx) return AMGB_ERR_BAD_ARG;
   AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

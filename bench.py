@@ -398,11 +398,18 @@ def extra_config3(ab, L, ctx, m=187):
     d_x0 = torch.from_numpy(s.x0).cuda()
     d_x = torch.empty_like(d_x0)
     out = {}
+    ctx.reserve(int(3.2 * 12 * s.nnz))     # the pool grown once instead of allocation by allocation
     for agg in (0, 2):
+        # the first pass pays for kernel loading and whatever the pool still has to grow: reported, not hidden
+        t0 = time.perf_counter()
+        first = timed_solve(ab, L, ctx, A, s.n, d_b, d_x0, d_x, device_options(ab, 0.25, agg), reps=1)
+        first_wall = time.perf_counter() - t0
         r = timed_solve(ab, L, ctx, A, s.n, d_b, d_x0, d_x, device_options(ab, 0.25, agg), reps=1)
         out[f"config3_m{m}_agg{agg}"] = dict(
             workload=f"Q1 elasticity m={m} ({s.n} DoFs, {s.nnz} nnz), theta=0.25, aggressive levels {agg}, {DEVICE_ALGO}",
-            host_generation_s=round(t_gen, 1), **r)
+            host_generation_s=round(t_gen, 1), first_pass={"setup_ms": round(first["setup_ms"], 1),
+                                                          "solve_ms": round(first["solve_ms"], 1),
+                                                          "wall_s": round(first_wall, 2)}, **r)
     A.close()
     return out
 

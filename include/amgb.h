@@ -131,6 +131,10 @@ typedef struct amgb_precond amgb_precond;
 int amgb_ctx_create(amgb_ctx** out, int device_id, void* stream);
 int amgb_ctx_destroy(amgb_ctx* ctx);
 int amgb_ctx_synchronize(amgb_ctx* ctx);
+/* Grow the context's memory pool to `bytes` now (one allocation, freed into the pool), so that the
+ * first initialize() of a large system does not pay for growing it step by step: a hierarchy needs
+ * about 3.5 x the bytes of its CSR matrix (setup intermediates included).  Optional. */
+int amgb_ctx_reserve(amgb_ctx* ctx, int64_t bytes);
 /* Last error text of this context (never NULL). */
 const char* amgb_last_error(const amgb_ctx* ctx);
 const char* amgb_status_string(int status);

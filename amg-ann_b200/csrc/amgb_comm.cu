@@ -180,6 +180,7 @@ struct Slot {
   const size_t* sdispl = nullptr;
   const void* host = nullptr;
   std::vector<double> red;
+  int device = 0;  // device of the rank's buffers
 };
 
 }  // namespace amgb
@@ -201,6 +202,7 @@ struct LocalComm : amgb_comm {
     me.send = send;
     me.scount = scount;
     me.sdispl = sdispl;
+    me.device = ctx->device;
     AMGB_BARRIER(ctx, g);
     int rc = AMGB_OK;
     for (int q = 0; q < size && rc == AMGB_OK; ++q) {
@@ -210,10 +212,17 @@ struct LocalComm : amgb_comm {
                        s.scount[rank], rank, rcount[q]);
         break;
       }
-      if (rcount[q] &&
-          cudaMemcpyAsync((char*)recv + rdispl[q], (const char*)s.send + s.sdispl[rank], rcount[q],
-                          cudaMemcpyDefault, ctx->stream) != cudaSuccess)
-        rc = set_error(ctx, AMGB_ERR_CUDA, "alltoallv copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+      // (ranks on different devices: the sender's buffer comes from ITS context's memory pool, which a
+      // plain unified-addressing copy may not reach; the peer copy works with or without peer access)
+      if (rcount[q]) {
+        const cudaError_t ce =
+            s.device == ctx->device
+                ? cudaMemcpyAsync((char*)recv + rdispl[q], (const char*)s.send + s.sdispl[rank], rcount[q],
+                                  cudaMemcpyDefault, ctx->stream)
+                : cudaMemcpyPeerAsync((char*)recv + rdispl[q], ctx->device, (const char*)s.send + s.sdispl[rank],
+                                      s.device, rcount[q], ctx->stream);
+        if (ce != cudaSuccess) rc = set_error(ctx, AMGB_ERR_CUDA, "alltoallv copy failed: %s", cudaGetErrorString(ce));
+      }
     }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == AMGB_OK)
       rc = set_error(ctx, AMGB_ERR_CUDA, "alltoallv sync failed");

@@ -1317,27 +1317,53 @@ __global__ void finalize_beta_red_kernel(const double* __restrict__ red, double*
   pcg_close_iteration(red[0], red[1], sc, fl, hist, hist_cap, abs_tol, first, max_steps, c);
 }
 
+// The two streaming vector updates of a PCG step: two elements per thread as 16-byte accesses,
+// several blocks' worth per thread (grid-stride), so enough loads are in flight per SM.
 __global__ void __launch_bounds__(kBlock)
 update_p_kernel(int64_t n, const double* __restrict__ z, double* __restrict__ p,
                 const double* __restrict__ sc, const int* __restrict__ fl) {
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
-  if (fl[1] == 0) {  // first step: no previous direction
-    p[i] = z[i];
-  } else {
-    const double bb = sc[0] / sc[1];
-    p[i] = z[i] + bb * p[i];
+  const bool first = fl[1] == 0;  // first step: no previous direction
+  const double bb = first ? 0.0 : sc[0] / sc[1];
+  const int64_t n2 = n >> 1;
+  const double2* __restrict__ z2 = reinterpret_cast<const double2*>(z);
+  double2* __restrict__ p2 = reinterpret_cast<double2*>(p);
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (int64_t)gridDim.x * kBlock) {
+    const double2 zz = z2[i];
+    double2 pp = p2[i];
+    if (first) {
+      pp = zz;
+    } else {
+      pp.x = zz.x + bb * pp.x;
+      pp.y = zz.y + bb * pp.y;
+    }
+    p2[i] = pp;
   }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = first ? z[n - 1] : z[n - 1] + bb * p[n - 1];
 }
 
 __global__ void __launch_bounds__(kBlock)
 axpy2_kernel(int64_t n, const double* __restrict__ p, const double* __restrict__ w,
              double* __restrict__ x, double* __restrict__ r, const double* __restrict__ sc) {
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
   const double alpha = sc[3];
-  x[i] += alpha * p[i];
-  r[i] -= alpha * w[i];
+  const int64_t n2 = n >> 1;
+  const double2* __restrict__ p2 = reinterpret_cast<const double2*>(p);
+  const double2* __restrict__ w2 = reinterpret_cast<const double2*>(w);
+  double2* __restrict__ x2 = reinterpret_cast<double2*>(x);
+  double2* __restrict__ r2 = reinterpret_cast<double2*>(r);
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n2; i += (int64_t)gridDim.x * kBlock) {
+    const double2 pp = p2[i], ww = w2[i];
+    double2 xx = x2[i], rr = r2[i];
+    xx.x += alpha * pp.x;
+    xx.y += alpha * pp.y;
+    rr.x -= alpha * ww.x;
+    rr.y -= alpha * ww.y;
+    x2[i] = xx;
+    r2[i] = rr;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    x[n - 1] += alpha * p[n - 1];
+    r[n - 1] -= alpha * w[n - 1];
+  }
 }
 
 // out[k] = in[perm[k]]  /  out[perm[k]] = in[k]
@@ -1494,6 +1520,8 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
   AMGB_TRY(pa.alloc(ctx, (spmv_blocks > dot_blocks ? spmv_blocks : dot_blocks) + 16));
   AMGB_TRY(pb.alloc(ctx, dot_blocks + 1));
   const unsigned vgrid = (unsigned)div_up(n, kBlock);
+  // streaming updates: two elements per thread, at most 16 blocks per SM (grid-stride beyond that)
+  const unsigned sgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(div_up(n / 2 + 1, kBlock), (int64_t)ctx->sm_count * 16));
   double* red = ds ? ds->red.p : nullptr;
   PcgCond cond{};
   // the captured cycle belongs to this call's (z, r): dropped on every way out
@@ -1529,7 +1557,7 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
   };
   // one PCG step: p, w = A p, alpha, x, r, z = M^{-1} r, beta
   auto body = [&]() -> int {
-    AMGB_LAUNCH(ctx, F_VEC, 24.0 * n, update_p_kernel, vgrid, kBlock, 0, n, z.p, p.p, sc.p, (const int*)fl.p);
+    AMGB_LAUNCH(ctx, F_VEC, 24.0 * n, update_p_kernel, sgrid, kBlock, 0, n, z.p, p.p, sc.p, (const int*)fl.p);
     int64_t np = 0;  // partials of (p, w)
     const double spmv_bytes = As.csr_bytes() + 16.0 * n;
     if (ds && ds->window_slot >= 0 && As.has_interior && As.n >= ds->overlap_min_rows && n > 0) {
@@ -1556,7 +1584,7 @@ static int cg_device(amgb_ctx* ctx, const amgb_matrix* A, double* x_user, const 
     } else {
       AMGB_LAUNCH(ctx, F_VEC, 8.0 * np, finalize_alpha_kernel, 1, kBlock, 0, pa.p, np, sc.p, fl.p);
     }
-    AMGB_LAUNCH(ctx, F_VEC, 48.0 * n, axpy2_kernel, vgrid, kBlock, 0, n, p.p, w.p, x.p, r.p, sc.p);
+    AMGB_LAUNCH(ctx, F_VEC, 48.0 * n, axpy2_kernel, sgrid, kBlock, 0, n, p.p, w.p, x.p, r.p, sc.p);
     AMGB_CHECK_LAUNCH(ctx);
     AMGB_TRY(vcycle_apply(P, z.p, r.p));
     AMGB_LAUNCH(ctx, F_VEC, 16.0 * n, dot2_kernel, (unsigned)dot_blocks, kBlock, 0, n, z.p, r.p, pa.p, pb.p);

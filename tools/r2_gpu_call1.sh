@@ -1,0 +1,24 @@
+#!/bin/bash
+# One gpurun call: GPU test suite, default bench line, per-family timers, ncu launch list and
+# one --set full capture of the top kernels (each ncu pass only after the plain run exited 0).
+set -u
+O=gpurun_out
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > $O/r2_box.txt 2>&1
+( time timeout 1500 python -m pytest tests -m gpu -x -q ) > $O/r2_pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> $O/r2_pytest_gpu.log
+( time timeout 1200 python bench.py ) > $O/r2_bench_n1.json 2> $O/r2_bench_n1.err
+echo "bench rc=$?" >> $O/r2_bench_n1.err
+timeout 300 python tools/run_one.py --m 200 --mode full --repeat 2 --timers > $O/r2_timers_m200_theta0.25.log 2>&1
+if AMGB_NO_GRAPH=1 timeout 300 python tools/run_one.py --m 200 --mode full --max-steps 3 > $O/r2_runone_plain.log 2>&1; then
+  AMGB_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
+      --log-file $O/r2_launches_full_m200.csv python tools/run_one.py --m 200 --mode full --max-steps 3 > $O/r2_ncu_launches.log 2>&1
+  AMGB_NO_GRAPH=1 timeout 900 ncu --set full --clock-control none --import-source on \
+      -k 'regex:sell_rows_kernel<1|sell_spmv_dot|spgemm_numeric|spgemm_symbolic|interp_fill|interp_ac|strength_kernel' -c 100 \
+      -o $O/r2_full_m200 -f python tools/run_one.py --m 200 --mode full --max-steps 2 > $O/r2_ncu_full.log 2>&1
+fi
+if timeout 120 python tools/run_one.py --m 200 --mode pool > $O/r2_pool_plain.log 2>&1; then
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:pool_ -c 4 \
+      -o $O/r2_full_pool_m200 -f python tools/run_one.py --m 200 --mode pool > $O/r2_ncu_pool.log 2>&1
+fi
+ls -la $O

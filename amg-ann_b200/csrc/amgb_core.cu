@@ -217,7 +217,8 @@ static const char* kFamilyNames[F_COUNT] = {
 static const char* kRouteNames[R_COUNT] = {
     "sell_t1_stream",   "sell_t_multi",      "spgemm_g8_t128",  "spgemm_g8_t256",    "spgemm_g8_t512",
     "spgemm_g32",       "spgemm_sym_big",    "spgemm_sym_global", "spgemm_num_big",  "spgemm_num_global",
-    "spgemm_rowreg",    "cycle_graph",       "cycle_tail_fused", "pcg_device_loop",  "dense_stepwise"};
+    "spgemm_rowreg",    "cycle_graph",       "cycle_tail_fused", "pcg_device_loop",  "dense_stepwise",
+    "spgemm_flat"};
 
 }  // namespace amgb
 

@@ -67,6 +67,7 @@ enum Route : int {
   R_CYCLE_TAIL_FUSED,    // coarse levels of the cycle run inside one persistent kernel
   R_PCG_DEVICE_LOOP,     // PCG iterations issued without a per-iteration host read
   R_DENSE_STEPWISE,      // coarsest grid factorised by the grid-wide step kernels (n > 96)
+  R_SPGEMM_FLAT,         // A*P-type product through the flattened first-stage kernels
   R_COUNT
 };
 

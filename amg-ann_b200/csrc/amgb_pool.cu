@@ -57,11 +57,14 @@ struct PoolSlot {
   double s, pp, np;
   int cnt;
   __device__ __forceinline__ void clear() { s = 0.0; pp = 0.0; np = 0.0; cnt = 0; }
+  // (plain compare + select: fmax() carries NaN quieting, ten instructions a piece on sm_100 and two
+  // of them per slot and entry made the kernel issue-bound; a NaN entry is ignored either way)
   __device__ __forceinline__ void add(double v) {
     s += v;
     ++cnt;
-    pp = fmax(pp, v);    // (v < 0 leaves pp, which starts at 0, alone: max(pp, max(v, 0)) == max(pp, v))
-    np = fmax(np, -v);
+    pp = v > pp ? v : pp;    // (v < 0 leaves pp, which starts at 0, alone: max(pp, max(v, 0)) == max(pp, v))
+    const double nv = -v;
+    np = nv > np ? nv : np;
   }
 };
 
@@ -143,6 +146,20 @@ pool_entries_kernel(BinMap bm, int tiles, long long g0, int nloc, const int32_t*
     const long long wbase = (long long)chunk * kPoolBlockChunk + warp * kPoolWarpChunk + 2 * lane;
     int c[kPoolPerLane];
     double v[kPoolPerLane];
+    // (warp-uniform: the warp's 256 entries lie inside the row-bin's entry range -- everywhere but at
+    // its two ends -- so the four load pairs need no per-lane range checks)
+    const long long w0 = wbase - 2 * lane;
+    if (VEC && w0 >= e_lo && w0 + kPoolWarpChunk <= e_hi) {
+#pragma unroll
+      for (int j = 0; j < kPoolPerLane; j += 2) {
+        const int2 cc = __ldcs(reinterpret_cast<const int2*>(col + wbase + 32 * j));
+        const double2 vv = __ldcs(reinterpret_cast<const double2*>(val + wbase + 32 * j));
+        c[j] = cc.x;
+        c[j + 1] = cc.y;
+        v[j] = vv.x;
+        v[j + 1] = vv.y;
+      }
+    } else
 #pragma unroll
     for (int j = 0; j < kPoolPerLane; j += 2) {
       const long long k = wbase + 32 * j;

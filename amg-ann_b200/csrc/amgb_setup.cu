@@ -1679,6 +1679,344 @@ spgemm_rowthread_numeric_kernel(int64_t n, const int32_t* __restrict__ arp, cons
   }
 }
 
+// ---------------------------------------------------------------------------
+// Flattened first stage for products with SHORT B rows (A*P; B rows of 1-4 entries).
+// The sub-warp kernels above walk A's row entry by entry: one dependent global load of a
+// B row, one group barrier and mostly idle lanes per entry (27 steps for a 27-point row).
+// Here the products of (up to) 32 A entries are numbered p = 0..np-1 in (k, m) order by
+// group-wide scans of the B-row lengths; a byte map p -> A entry and the per-entry
+// (B offset - first p, a_ik) descriptors live in shared memory, so that lane gl of the
+// group takes the products p = base + gl: every lane is busy, the loads of several
+// batches are in flight together and nothing waits on a barrier per A entry.
+// Order: the products of one batch with the same column are found with match.any and
+// added by the first of their lanes in lane order = ascending p = ascending k, starting
+// from the table value; batches follow each other.  Every C(i,c) therefore accumulates
+// a_ik*b_kc in ascending k from 0.0, the oracle's Gustavson loop, bit for bit.
+// Rows whose chunk has more than S products (or whose table would not fit CAP) go to the
+// overflow list of the second stage like in the sub-warp kernels.
+// ---------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ int group_excl_scan(int v, int gl, unsigned gm, int* total) {
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < G; d <<= 1) {
+    const int t = __shfl_up_sync(gm, incl, d, G);
+    if (gl >= d) incl += t;
+  }
+  *total = __shfl_sync(gm, incl, G - 1, G);
+  return incl - v;
+}
+
+constexpr int kFlatChunk = 32;  // A-row entries numbered together
+
+// entry-wise variant: the table only (the chunk descriptors sit between values and keys, the map is not touched)
+template <int G, int CAP>
+constexpr size_t entry_smem_bytes() {
+  constexpr size_t groups = kSpThreads / G;
+  return groups * (sizeof(double) * (CAP + kFlatChunk) + sizeof(unsigned) * CAP);
+}
+
+template <int G, int CAP, int S, bool NUMERIC>
+constexpr size_t flat_smem_bytes() {
+  constexpr size_t groups = kSpThreads / G;
+  return groups * ((NUMERIC ? sizeof(double) * (CAP + kFlatChunk) : 0) + sizeof(unsigned) * CAP +
+                   sizeof(int) * kFlatChunk + S);
+}
+
+// Control flow is WARP-UNIFORM: the groups of a warp run every loop to the warp's maximum trip
+// count with their own lanes predicated off, and every collective (scan shuffles, match.any,
+// votes, barriers) names the full warp -- the group is folded into the matched value.  With
+// group masks the compiler has to run the groups' collectives one group after the other (ncu:
+// 8 of 32 threads per issued instruction in the batch loop), which costs more than it saves.
+// ENTRY (numeric pass only): the entry-by-entry accumulation of the sub-warp kernels (one B row per
+// step, the group's lanes spread over it) inside the same warp-uniform skeleton.
+template <int G, int CAP, int S, bool NUMERIC, bool SORT, bool ENTRY = false>
+__global__ void __launch_bounds__(kSpThreads)
+spgemm_flat_kernel(int64_t n, const int32_t* __restrict__ arp, const int32_t* __restrict__ acol,
+                   const double* __restrict__ aval, const int32_t* __restrict__ brp,
+                   const int32_t* __restrict__ bcol, const double* __restrict__ bval,
+                   const int32_t* __restrict__ crp, int32_t* __restrict__ ccol, double* __restrict__ cval,
+                   int32_t* __restrict__ count, int32_t* __restrict__ ovf_rows, int32_t* __restrict__ ovf_info) {
+  extern __shared__ unsigned char smem_raw[];
+  constexpr int kGroups = kSpThreads / G;
+  constexpr int R = kFlatChunk / G;  // A entries per lane and chunk
+  constexpr int U = 4;               // batches whose B loads are in flight together
+  static_assert(kFlatChunk <= 256, "byte map");
+  const unsigned full = 0xffffffffu;
+  const int g = threadIdx.x / G, gl = threadIdx.x % G;
+  const int lane = threadIdx.x & 31;
+  const int sh = lane - gl;  // first lane of my group
+  const unsigned glow = G == 32 ? full : ((1u << G) - 1u);
+  const int64_t i = (int64_t)blockIdx.x * kGroups + g;
+  constexpr size_t off8 = NUMERIC ? sizeof(double) * (size_t)kGroups * (CAP + kFlatChunk) : 0;
+  double* vals = reinterpret_cast<double*>(smem_raw) + (size_t)g * CAP;
+  double* da = reinterpret_cast<double*>(smem_raw) + (size_t)kGroups * CAP + (size_t)g * kFlatChunk;
+  unsigned* keys = reinterpret_cast<unsigned*>(smem_raw + off8) + (size_t)g * CAP;
+  int* db = reinterpret_cast<int*>(smem_raw + off8 + sizeof(unsigned) * (size_t)kGroups * CAP) + (size_t)g * kFlatChunk;
+  unsigned char* kmap = smem_raw + off8 + (sizeof(unsigned) * CAP + sizeof(int) * kFlatChunk) * (size_t)kGroups + (size_t)g * S;
+
+  // group state (uniform within the group): live = this group still accumulates its row
+  bool live = i < n;
+  int b = 0, e = 0, out_b = 0, out_n = 0, lgH = 3;
+  bool table_ready = false;
+  if (live) {
+    b = arp[i];
+    e = arp[i + 1];
+  }
+  if (NUMERIC) {
+    if (live) {
+      out_b = crp[i];
+      out_n = crp[i + 1] - out_b;
+      if (out_n == 0) live = false;
+    }
+    if (live) {
+      lgH = ceil_log2(2 * out_n);
+      if ((1 << lgH) < G) lgH = ceil_log2(G);  // the compaction reads the table G slots at a time
+      if ((1 << lgH) > CAP) {
+        if (gl == 0) {
+          const int w = atomicAdd(&ovf_info[0], 1);
+          ovf_rows[w] = (int)i;
+          atomicMax(&ovf_info[1], out_n);
+        }
+        live = false;
+      }
+    }
+    if (live)
+      for (int t = gl; t < (1 << lgH); t += G) keys[t] = kEmpty;
+    table_ready = true;
+  } else if (live && b == e) {
+    if (gl == 0) count[i] = 0;
+    live = false;
+  }
+  if (!live) e = b;
+  int cnt = 0, fail = 0;
+  const int maxlen = __reduce_max_sync(full, e - b);
+  if constexpr (ENTRY) {
+    static_assert(NUMERIC, "the count pass has no entry-by-entry variant here");
+    const int H = 1 << lgH;
+    for (int kb = 0; kb < maxlen; kb += G) {
+      const int k = b + kb + gl;
+      int my_bb = 0, my_len = 0;
+      double my_a = 0.0;
+      if (k < e) {
+        const int kk = acol[k];
+        my_a = aval[k];
+        my_bb = brp[kk];
+        my_len = brp[kk + 1] - my_bb;
+      }
+      const int steps = min(G, maxlen - kb);  // warp-uniform
+      for (int t = 0; t < steps; ++t) {
+        const int bb = __shfl_sync(full, my_bb, t, G), len = __shfl_sync(full, my_len, t, G);
+        const double a = __shfl_sync(full, my_a, t, G);
+        for (int m = gl; m < len; m += G) {  // (len = 0 past the end of my row)
+          const unsigned key = (unsigned)bcol[bb + m];
+          const double prod = __dmul_rn(a, bval[bb + m]);
+          int h = hash_slot(key, lgH);
+          for (;;) {
+            const unsigned old = atomicCAS(&keys[h], kEmpty, key);
+            if (old == kEmpty) {
+              vals[h] = __dadd_rn(0.0, prod);
+              break;
+            }
+            if (old == key) {
+              vals[h] = __dadd_rn(vals[h], prod);
+              break;
+            }
+            h = (h + 1) & (H - 1);
+          }
+        }
+        __syncwarp();  // orders the accumulation over k
+      }
+    }
+  } else
+  for (int kb = 0; kb < maxlen; kb += kFlatChunk) {
+    // ---- number the products of this chunk
+    int bb[R], len[R], off[R];
+    double a[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int k = b + kb + r * G + gl;
+      bb[r] = 0;
+      len[r] = 0;
+      a[r] = 0.0;
+      if (k < e) {
+        const int kk = acol[k];
+        if (NUMERIC) a[r] = aval[k];
+        bb[r] = brp[kk];
+        len[r] = brp[kk + 1] - bb[r];
+      }
+    }
+    int np = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      int incl = len[r];
+#pragma unroll
+      for (int d = 1; d < G; d <<= 1) {
+        const int t = __shfl_up_sync(full, incl, d, G);
+        if (gl >= d) incl += t;
+      }
+      off[r] = np + incl - len[r];
+      np += __shfl_sync(full, incl, G - 1, G);
+    }
+    if (np > S) {  // group-uniform: the row goes to the second stage
+      fail = 1;
+      np = 0;
+      e = b;
+    }
+    if (!table_ready && np > 0) {  // count pass: the table follows the products of the (usually only) chunk
+      lgH = e - b <= kFlatChunk ? ceil_log2(2 * np) : ceil_log2(CAP);
+      if (lgH < 3) lgH = 3;
+      if ((1 << lgH) > CAP) lgH = ceil_log2(CAP);
+      for (int t = gl; t < (1 << lgH); t += G) keys[t] = kEmpty;
+      table_ready = true;
+    }
+    __syncwarp();  // the previous chunk's batches are done with the map
+    if (np > 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int idx = r * G + gl;
+        if (len[r] > 0) {
+          db[idx] = bb[r] - off[r];
+          if (NUMERIC) da[idx] = a[r];
+          for (int m = 0; m < len[r]; ++m) kmap[off[r] + m] = (unsigned char)idx;
+        }
+      }
+    }
+    __syncwarp();
+    const int H = 1 << lgH;
+    const int npmax = __reduce_max_sync(full, np);
+    // ---- batches of G products per group, U batches loaded together
+    for (int base = 0; base < npmax; base += G * U) {
+      unsigned key[U];
+      double prod[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = base + u * G + gl;
+        key[u] = 0x80000000u | (unsigned)lane;  // no column: matches nothing
+        prod[u] = 0.0;
+        if (p < np) {
+          const int idx = kmap[p];
+          const int addr = db[idx] + p;
+          key[u] = (unsigned)bcol[addr];
+          if (NUMERIC) prod[u] = __dmul_rn(da[idx], bval[addr]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (base + u * G >= npmax) break;  // warp-uniform
+        const bool has = base + u * G + gl < np;
+        if (!NUMERIC) {
+          if (has) {
+            const int r = hash_insert(keys, H, lgH, key[u]);
+            if (r < 0) fail = 1; else cnt += r;
+          }
+        } else {
+          // equal columns of MY group: the group's first lane rides in the upper half of the matched value
+          const unsigned same = __match_any_sync(full, ((unsigned long long)sh << 32) | key[u]);
+          const bool lead = has && (same & (0u - same)) == (1u << lane);
+          unsigned rest = 0;
+          int h = 0;
+          double acc = 0.0;
+          if (lead) {
+            h = hash_slot(key[u], lgH);
+            for (;;) {
+              const unsigned old = atomicCAS(&keys[h], kEmpty, key[u]);
+              if (old == kEmpty) {
+                acc = __dadd_rn(0.0, prod[u]);
+                break;
+              }
+              if (old == key[u]) {
+                acc = __dadd_rn(vals[h], prod[u]);
+                break;
+              }
+              h = (h + 1) & (H - 1);
+            }
+            rest = same & (same - 1);
+          }
+          while (__any_sync(full, rest != 0)) {  // the other products of my column, in lane order
+            const int src = rest ? __ffs(rest) - 1 : lane;
+            const double v = __shfl_sync(full, prod[u], src);
+            if (rest) {
+              acc = __dadd_rn(acc, v);
+              rest &= rest - 1;
+            }
+          }
+          if (lead) vals[h] = acc;
+          __syncwarp();  // orders the batches
+        }
+      }
+    }
+  }
+  __syncwarp();
+  fail = ((__ballot_sync(full, fail != 0) >> sh) & glow) != 0;
+  if (!NUMERIC) {
+#pragma unroll
+    for (int d = G / 2; d > 0; d >>= 1) cnt += __shfl_xor_sync(full, cnt, d, G);
+    int ub = 0;
+    if (__any_sync(full, fail)) {  // upper bound of the rows handed to the second stage
+      const int b0 = i < n ? arp[i] : 0, e0 = i < n ? arp[i + 1] : 0;
+      const int lmax = __reduce_max_sync(full, fail ? e0 - b0 : 0);
+      for (int k0 = 0; k0 < lmax; k0 += G) {
+        const int k = b0 + k0 + gl;
+        if (fail && k < e0) {
+          const int kk = acol[k];
+          ub += brp[kk + 1] - brp[kk];
+        }
+      }
+#pragma unroll
+      for (int d = G / 2; d > 0; d >>= 1) ub += __shfl_xor_sync(full, ub, d, G);
+    }
+    if (gl == 0 && i < n && (live || fail)) {
+      if (fail) {
+        const int w = atomicAdd(&ovf_info[0], 1);
+        ovf_rows[w] = (int)i;
+        atomicMax(&ovf_info[1], ub);
+        count[i] = 0;
+      } else {
+        count[i] = cnt;
+      }
+    }
+    return;
+  }
+  if (fail) {
+    if (gl == 0) {
+      const int w = atomicAdd(&ovf_info[0], 1);
+      ovf_rows[w] = (int)i;
+      atomicMax(&ovf_info[1], out_n);
+    }
+    live = false;
+  }
+  // ---- in-place compaction of the occupied slots to the front, then the row (rank sort if SORT)
+  const int H = live ? (1 << lgH) : 0;
+  const int Hmax = __reduce_max_sync(full, H);
+  int outp = 0;
+  for (int tb = 0; tb < Hmax; tb += G) {
+    const int idx = tb + gl;
+    const unsigned key = idx < H ? keys[idx] : kEmpty;
+    const double v = idx < H ? vals[idx] : 0.0;
+    const bool occ = key != kEmpty;
+    const unsigned om = (__ballot_sync(full, occ) >> sh) & glow;
+    if (occ) {  // (write positions never run ahead of the chunk just read)
+      const int w = outp + __popc(om & ((1u << gl) - 1u));
+      keys[w] = key;
+      vals[w] = v;
+    }
+    outp += __popc(om);
+    __syncwarp();
+  }
+  if (!live) return;
+  for (int t = gl; t < out_n; t += G) {
+    const unsigned key = keys[t];
+    int pos = t;
+    if (SORT) {
+      pos = 0;
+      for (int u = 0; u < out_n; ++u) pos += keys[u] < key ? 1 : 0;
+    }
+    ccol[out_b + pos] = (int)key;
+    cval[out_b + pos] = vals[t];
+  }
+}
+
 // 64-bit total of the row counts: the 32-bit scan below would wrap silently
 __global__ void __launch_bounds__(kBlock)
 sum_counts_kernel(int64_t n, const int32_t* __restrict__ count, unsigned long long* __restrict__ total) {
@@ -1702,8 +2040,9 @@ static int read_ovf(amgb_ctx* ctx, const int32_t* ovf_info, int* novf, int* maxv
 // rowthread: the first stage of both passes is the row-per-thread kernel pair (unsorted output only)
 template <int G, int CAP_SYM, int CAP_NUM>
 static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, bool sorted,
-                       bool rowthread = false) {
+                       bool rowthread = false, int flat = 0 /* 1: flattened count pass, 2: flattened numeric pass, 4: entry-wise numeric pass in the warp-uniform kernel */) {
   constexpr int kBigSym = 8192, kBigNum = 2048;  // second-stage capacities (one warp per row)
+  constexpr int kFlatS = 2 * CAP_NUM;            // products of one 32-entry chunk of an A row (flat kernels)
   const int64_t n = A.n;
   C.n = n;
   C.ncols = B.ncols;
@@ -1727,6 +2066,12 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
                                           (int)smem));
       AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, spgemm_rowthread_count_kernel, (unsigned)div_up(n, kRtThreads), kRtThreads,
                   smem, n, A.rp.p, A.col.p, B.rp.p, B.col.p, count.p, ovf1.p, info.p);
+    } else if (flat & 1) {
+      auto kern = spgemm_flat_kernel<G, CAP_SYM, kFlatS, false, false>;
+      constexpr size_t smem = flat_smem_bytes<G, CAP_SYM, kFlatS, false>();
+      if (smem > 48 * 1024) AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      AMGB_LAUNCH(ctx, F_SPGEMM, in_bytes, kern, grid, kSpThreads, smem, n, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p,
+                  B.val.p, (const int32_t*)nullptr, (int32_t*)nullptr, (double*)nullptr, count.p, ovf1.p, info.p);
     } else {
       auto kern = spgemm_symbolic_kernel<G, CAP_SYM>;
       const size_t smem = sizeof(unsigned) * (size_t)kGroups * CAP_SYM;
@@ -1786,6 +2131,30 @@ static int spgemm_impl(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, De
       AMGB_LAUNCH(ctx, F_SPGEMM, bytes, spgemm_rowthread_numeric_kernel, (unsigned)div_up(n, kRtThreads), kRtThreads,
                   rsmem, n, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p, B.val.p, C.rp.p, C.col.p, C.val.p, ovf1.p,
                   info.p);
+    } else if ((flat & 2) && sorted) {
+      auto kern = spgemm_flat_kernel<G, CAP_NUM, kFlatS, true, true>;
+      constexpr size_t fsmem = flat_smem_bytes<G, CAP_NUM, kFlatS, true>();
+      if (fsmem > 48 * 1024) AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      AMGB_LAUNCH(ctx, F_SPGEMM, bytes, kern, grid, kSpThreads, fsmem, n, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p,
+                  B.val.p, C.rp.p, C.col.p, C.val.p, (int32_t*)nullptr, ovf1.p, info.p);
+    } else if (flat & 2) {
+      auto kern = spgemm_flat_kernel<G, CAP_NUM, kFlatS, true, false>;
+      constexpr size_t fsmem = flat_smem_bytes<G, CAP_NUM, kFlatS, true>();
+      if (fsmem > 48 * 1024) AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      AMGB_LAUNCH(ctx, F_SPGEMM, bytes, kern, grid, kSpThreads, fsmem, n, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p,
+                  B.val.p, C.rp.p, C.col.p, C.val.p, (int32_t*)nullptr, ovf1.p, info.p);
+    } else if ((flat & 4) && sorted) {
+      auto kern = spgemm_flat_kernel<G, CAP_NUM, kFlatS, true, true, true>;
+      constexpr size_t fsmem = entry_smem_bytes<G, CAP_NUM>();
+      if (fsmem > 48 * 1024) AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      AMGB_LAUNCH(ctx, F_SPGEMM, bytes, kern, grid, kSpThreads, fsmem, n, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p,
+                  B.val.p, C.rp.p, C.col.p, C.val.p, (int32_t*)nullptr, ovf1.p, info.p);
+    } else if (flat & 4) {
+      auto kern = spgemm_flat_kernel<G, CAP_NUM, kFlatS, true, false, true>;
+      constexpr size_t fsmem = entry_smem_bytes<G, CAP_NUM>();
+      if (fsmem > 48 * 1024) AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      AMGB_LAUNCH(ctx, F_SPGEMM, bytes, kern, grid, kSpThreads, fsmem, n, A.rp.p, A.col.p, A.val.p, B.rp.p, B.col.p,
+                  B.val.p, C.rp.p, C.col.p, C.val.p, (int32_t*)nullptr, ovf1.p, info.p);
     } else if (sorted) {
       auto kern = spgemm_numeric_kernel<G, CAP_NUM, true>;
       if (smem > 48 * 1024) AMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1833,7 +2202,9 @@ int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, 
   const double avg_b = B.n > 0 ? double(B.nnz) / double(B.n) : 0.0;
   if (avg_b > 8.0) {
     ctx->routes[R_SPGEMM_G32]++;
-    return spgemm_impl<32, 1024, 512>(ctx, A, B, C, sorted);
+    // AMGB_SPGEMM_FLAT=2: the flattened first stage with one warp per row here too (experiment)
+    const char* f32 = std::getenv("AMGB_SPGEMM_FLAT");
+    return spgemm_impl<32, 1024, 512>(ctx, A, B, C, sorted, false, (f32 && f32[0] == '2') ? 3 : 0);
   }
   // short rows of B (A*P): 8 lanes per row; the table tier follows the expected row of the
   // product (about a third of the products are distinct on the FE stencils measured: 27-point
@@ -1852,9 +2223,23 @@ int spgemm(amgb_ctx* ctx, const DeviceCsr& A, const DeviceCsr& B, DeviceCsr& C, 
     return spgemm_impl<8, 256, 128>(ctx, A, B, C, sorted, true);
   }
   ctx->routes[est <= 50.0 ? R_SPGEMM_G8_T128 : (est <= 110.0 ? R_SPGEMM_G8_T256 : R_SPGEMM_G8_T512)]++;
-  if (est <= 50.0) return spgemm_impl<8, 256, 128>(ctx, A, B, C, sorted);
-  if (est <= 110.0) return spgemm_impl<8, 512, 256>(ctx, A, B, C, sorted);
-  return spgemm_impl<8, 1024, 512>(ctx, A, B, C, sorted);
+  // First stage: the flattened kernels cost per PRODUCT (batches of 8 per row), the entry-by-entry
+  // accumulation per A ENTRY (one step each); both run in the warp-uniform kernel.  Measured on
+  // B200 at m = 200 (profiles/r2_spgemm_variants.md): the flattened count pass wins everywhere
+  // (level 0: 3.9 against 4.9 ms for the sub-warp kernel); the flattened numeric pass wins where
+  // B's rows are short or A's rows long (level 0 at theta = 0.7, 1.85 entries per P row: 18.0
+  // against 18.2 ms for the level's four kernels; level 1, 46 entries per A row: 4.7 against 5.0)
+  // and loses at 2.7 entries per P row (level 0 at theta = 0.25: 25.7 against 22.9 ms).
+  // AMGB_SPGEMM_FLAT = 0: the sub-warp kernels of round 1; 1: flattened, both passes; 4: flattened
+  // count pass + entry-by-entry numeric pass; 2: as 1, and the one-warp-per-row products too (the
+  // parity tests compare every variant with the oracle).
+  const char* fl_env = std::getenv("AMGB_SPGEMM_FLAT");
+  int flat = 1 | ((avg_b <= 2.0 || avg_a > 40.0) ? 2 : 4);
+  if (fl_env) flat = fl_env[0] == '0' ? 0 : (fl_env[0] == '4' ? 5 : 3);
+  if (flat) ctx->routes[R_SPGEMM_FLAT]++;
+  if (est <= 50.0) return spgemm_impl<8, 256, 128>(ctx, A, B, C, sorted, false, flat);
+  if (est <= 110.0) return spgemm_impl<8, 512, 256>(ctx, A, B, C, sorted, false, flat);
+  return spgemm_impl<8, 1024, 512>(ctx, A, B, C, sorted, false, flat);
 }
 
 // ---- setup stages as host functions (shared with the row-partitioned driver) ----

@@ -459,6 +459,45 @@ def test_spgemm_row_per_thread_and_sub_warp_routes_agree_with_the_oracle(gpu_ctx
     _assert_hierarchy_identical(P, H)
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "2", "4", "auto"])
+@pytest.mark.parametrize("kind", ["poisson", "elasticity", "hub", "aggressive"])
+def test_spgemm_flattened_and_entrywise_first_stages_agree_with_the_oracle(gpu_ctx, monkeypatch, mode, kind):
+    """AMGB_SPGEMM_FLAT: 1 = the flattened first-stage kernels for A*P-type products (products
+    of a 32-entry chunk numbered by scans, match.any batches), 0 = the entry-by-entry sub-warp
+    kernels, 2 = flattened with one warp per row for R*(AP) too, 4 = flattened count pass and
+    the entry-by-entry numeric pass inside the warp-uniform kernel, unset = picked per product.  Hub/leaf rows span
+    several chunks and outgrow the product stage (overflow list); the aggressive levels send
+    SORTED products through the same kernels.  Same bits as the oracle every way."""
+    from helpers import hub_leaf_csr
+    from types import SimpleNamespace
+    if mode == "auto":
+        monkeypatch.delenv("AMGB_SPGEMM_FLAT", raising=False)
+    else:
+        monkeypatch.setenv("AMGB_SPGEMM_FLAT", mode)
+    agg = 0
+    if kind == "poisson":
+        s = poisson(14, contrast=3.0)
+        theta = 0.25
+    elif kind == "aggressive":
+        s = poisson(12, contrast=2.0)
+        theta, agg = 0.25, 1
+    elif kind == "elasticity":
+        s = ab.gen.elasticity_q1(6, 2, 3, 10.0 ** ab.gen.checkerboard_epsv(2, 3, 2.0))
+        theta = 0.25
+    else:
+        M = hub_leaf_csr(300, 500, 60, 8, 7)
+        s = SimpleNamespace(n=M.shape[0], col=M.indices.astype(np.int32), val=M.data.astype(np.float64),
+                            rowptr32=lambda: M.indptr.astype(np.int32))
+        theta = 0.05
+    gpu_ctx.reset_routes()
+    data = device_data(theta)
+    data.aggressive_coarsening_num_levels = agg
+    A, P, H = _both(gpu_ctx, s, data)
+    r = gpu_ctx.routes()
+    assert (r["spgemm_flat"] > 0) == (mode != "0"), r
+    _assert_hierarchy_identical(P, H)
+
+
 @pytest.mark.parametrize("nh,nl,per_leaf,leaf_leaf", [(100, 300, 30, 4), (160, 400, 70, 6)])
 def test_setup_long_interpolation_rows(gpu_ctx, nh, nl, per_leaf, leaf_leaf):
     """Hub/leaf systems: every leaf depends strongly on 30 (70) hubs, which PMIS makes the C

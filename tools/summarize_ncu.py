@@ -61,12 +61,20 @@ WANT = [
     ("launch__grid_size", "grid"),
     ("launch__block_size", "block"),
     ("smsp__cycles_active.avg", "smsp cycles"),
+    ("smsp__inst_executed.sum", "warp inst"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long sb"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short sb"),
+    ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall branch"),
 ]
 
 
 def full(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True,
-                         check=True).stdout
+    if path.endswith(".csv"):   # already exported on the GPU box (ncu -i rep --page raw --csv)
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True,
+                             check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     cols = [(hdr.index(m), lbl) for m, lbl in WANT if m in hdr]

@@ -539,20 +539,35 @@ class ViewMaker:
 from . import dist  # noqa: E402  (row-partitioned front end; needs the names above)
 
 
-def amg_solve(data, rtol, A, b, x, ctx=None):
+class _NoLock:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def amg_solve(data, rtol, A, b, x, ctx=None, phase_locks=None):
     """Python mirror of ref common/amg_solver.h:22-92: timed initialize + timed
     cg.solve, returning the CSV fields as a dict instead of scraping stdout.
-    ctx: context (stream) to run on when several systems share one uploaded matrix."""
+    ctx: context (stream) to run on when several systems share one uploaded matrix.
+    phase_locks: (setup_lock, solve_lock) shared by the host threads that run the systems of
+    a sweep side by side on one GPU: at most one system is in its (latency- and
+    instruction-bound) setup and one in its (bandwidth-bound) solve at any time, so the two
+    phases that overlap are always complementary; the timed intervals exclude the waiting."""
+    setup_lock, solve_lock = phase_locks if phase_locks else (_NoLock(), _NoLock())
     control = SolverControl(A.m(), rtol)
     cg = SolverCG(control)
     prec = PreconditionBoomerAMG()
-    t1 = time.perf_counter()
-    prec.initialize(A, data, ctx)
-    prec.ctx.synchronize()
-    t2 = time.perf_counter()
-    t3 = time.perf_counter()
-    cg.solve(A, x, b, prec)
-    t4 = time.perf_counter()
+    with setup_lock:
+        t1 = time.perf_counter()
+        prec.initialize(A, data, ctx)
+        prec.ctx.synchronize()
+        t2 = time.perf_counter()
+    with solve_lock:
+        t3 = time.perf_counter()
+        cg.solve(A, x, b, prec)
+        t4 = time.perf_counter()
     row = dict(theta=data.strong_threshold, maxrowsum=data.max_row_sum,
                symop=int(data.symmetric_operator),
                agg_nl=data.aggressive_coarsening_num_levels, tol=rtol,

@@ -42,6 +42,8 @@ class Context {
     if (rc != AMGB_OK) throw Error(rc, where, amgb_last_error(h_));
   }
   void synchronize() const { check(amgb_ctx_synchronize(h_), "amgb_ctx_synchronize"); }
+  // grow the context's memory pool once, up front (amgb_ctx_reserve)
+  void reserve(int64_t bytes) const { check(amgb_ctx_reserve(h_, bytes), "amgb_ctx_reserve"); }
   int64_t kernel_launches() const {
     int64_t v = 0;
     check(amgb_ctx_kernel_launches(h_, &v), "amgb_ctx_kernel_launches");

@@ -134,6 +134,7 @@ void run_system(const Args& a, long seed, std::ostream& out, Totals& tot) {
   std::string error;
   auto lane = [&]() {
     try {
+      amgb::compat::default_context().reserve(110 * nnz + (int64_t(64) << 20));  // this lane's pool, grown once
       PETScWrappers::MPI::Vector x(n);
       for (;;) {
         // largest theta (most iterations) first; the rows are emitted in sweep order below
@@ -192,6 +193,12 @@ int main(int argc, char** argv) {
     const auto w0 = std::chrono::high_resolution_clock::now();
     auto worker = [&]() {
       try {
+        {  // this thread's pool grown once (matrix + hierarchy + work vectors of one system) instead of
+           // allocation by allocation: pool growth stalls every lane of the device
+          int64_t n = 0, nnz = 0;
+          if (amgb_gen_sizes(0, a.m, &n, &nnz) == 0)
+            amgb::compat::default_context().reserve(130 * nnz + (int64_t(64) << 20));
+        }
         for (;;) {
           const int s = next++;
           if (s >= a.systems) break;

@@ -628,25 +628,50 @@ def run_gpu(args):
     lane_streams = [stream] + [torch.cuda.Stream() for _ in range(lanes - 1)]
     lane_ctx = [ctx] + [ab.Context(local, st.cuda_stream) for st in lane_streams[1:]]
     lane_x = [d_x] + [torch.empty_like(d_x0) for _ in range(lanes - 1)]
+    # every lane's pool grown once, up front, instead of allocation by allocation: measured at m = 200 with
+    # 3 lanes, a sweep takes 4.53 +- 0.005 s with the reserve and 4.5 ... 7.4 s without (pool growth
+    # stalls every lane; which lane grows when depends on the order the lanes pick their systems in)
+    reserve = int(args.reserve_gb * 2 ** 30) if args.reserve_gb >= 0 else 100 * nnz
+    if reserve > 0:
+        for c in lane_ctx:
+            c.reserve(reserve)
+
+    # phase locks (--phases 1): of the systems in flight at most one is in its setup and one in
+    # its solve, so what overlaps on the GPU is always an instruction/latency-bound setup with a
+    # bandwidth-bound solve (two or three solves side by side only share the same HBM)
+    class _Free:
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+    phases = bool(args.phases) and lanes > 1
+    setup_lock = threading.Lock() if phases else _Free()
+    solve_lock = threading.Lock() if phases else _Free()
+    phase_locks = (setup_lock, solve_lock) if phases else None
 
     def solve_device(w, th, profile=None):
         c = lane_ctx[w]
         h, k = np.zeros(4096), C.c_int64()
-        with torch.cuda.stream(lane_streams[w]):
-            lane_x[w].copy_(d_x0)                # solution = m_zero_solution (t2 main.cpp:446)
-        t0 = time.perf_counter()
-        P = ab.PreconditionBoomerAMG()
-        P.initialize(A_dev, device_options(ab, th), c)
-        t1 = time.perf_counter()
-        rc = L.amgb_cg_solve_device(c._h, A_dev._h, C.c_void_p(lane_x[w].data_ptr()),
-                                    C.c_void_p(d_b.data_ptr()), P._h, n, TOL,
-                                    h.ctypes.data_as(c_f64p), len(h), C.byref(k))
-        t2 = time.perf_counter()
+        with setup_lock:
+            with torch.cuda.stream(lane_streams[w]):
+                lane_x[w].copy_(d_x0)                # solution = m_zero_solution (t2 main.cpp:446)
+            t0 = time.perf_counter()
+            P = ab.PreconditionBoomerAMG()
+            P.initialize(A_dev, device_options(ab, th), c)
+            c.synchronize()
+            t1 = time.perf_counter()
+        with solve_lock:
+            t1s = time.perf_counter()
+            rc = L.amgb_cg_solve_device(c._h, A_dev._h, C.c_void_p(lane_x[w].data_ptr()),
+                                        C.c_void_p(d_b.data_ptr()), P._h, n, TOL,
+                                        h.ctypes.data_as(c_f64p), len(h), C.byref(k))
+            t2 = time.perf_counter()
         if rc != 0:
             raise RuntimeError(f"amgb_cg_solve_device -> {rc}: {L.amgb_last_error(c._h).decode()}")
+        if os.environ.get("BENCH_DEBUG"):
+            print(f"[bench]   lane {w} theta {th:.2f}: setup {1e3 * (t1 - t0):7.1f} ms, solve {1e3 * (t2 - t1s):7.1f} ms "
+                  f"({k.value} it), started {t0 - t_start:8.3f}", file=sys.stderr, flush=True)
         results[th] = (k.value, P.level_stats() if th == thetas[0] else None)
         if profile is not None:
-            profile[th] = (t1 - t0, t2 - t1, k.value)
+            profile[th] = (t1 - t0, t2 - t1s, k.value)
         P.close()
 
     def fan_out(solve):
@@ -693,7 +718,7 @@ def run_gpu(args):
         def solve_host(w, th):
             h_x = h_xs[w]
             h_x[...] = h_x0
-            row = ab.amg_solve(device_options(ab, th), TOL, A, h_b, h_x, lane_ctx[w])  # x,b H2D; x,hist D2H
+            row = ab.amg_solve(device_options(ab, th), TOL, A, h_b, h_x, lane_ctx[w], phase_locks)  # x,b H2D; x,hist D2H
             with mlock:
                 moved["h2d"] += h_b.nbytes + h_x.nbytes
                 moved["d2h"] += h_x.nbytes + 8 * (row["niters"] + 1)
@@ -720,7 +745,10 @@ def run_gpu(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
+            t_fn = time.perf_counter()
             fn()
+            if os.environ.get("BENCH_DEBUG"):
+                print(f"[bench] {fn.__name__}: {time.perf_counter() - t_fn:.3f} s wall", file=sys.stderr, flush=True)
         e1.record(stream)
         barrier()
         launches = sum(c.kernel_launches() for c in lane_ctx)
@@ -824,6 +852,7 @@ def run_gpu(args):
                 "config": {"workload": workload_name(args.m), "n": n, "nnz": nnz, "systems_per_step": nsys,
                            "per_gpu": "one matrix + full theta sweep per rank",
                            "systems_in_flight": lanes,
+                           "phase_locks": phases,
                            "l2": "inputs (2.6 GB CSR) exceed the 126 MB L2; no flush needed",
                            "iters": iters,
                            "levels_theta0.05": [int(r) for r in st0["rows"]] if st0 else None,
@@ -892,6 +921,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--streams", type=int, default=3,
                     help="independent systems of the sweep kept in flight per GPU (host threads, one stream each)")
+    ap.add_argument("--reserve-gb", type=float, default=-1.0,
+                    help="memory pool of every lane pre-grown to this size (default: 100 bytes per matrix entry)")
+    ap.add_argument("--phases", type=int, default=0,
+                    help="1: the systems in flight take turns per phase (one setup and one solve at a time); 0: free-running lanes")
     ap.add_argument("--workload", default="sweep", choices=["sweep", "partitioned"],
                     help="sweep: config 2 theta sweep, one system per GPU (default, the headline metric); "
                          "partitioned: config 5 only, one system row-partitioned over all GPUs (use --cells 464)")

@@ -2832,6 +2832,23 @@ int amgb_precond_initialize(amgb_ctx* ctx, const amgb_matrix* A, const amgb_boom
   // with one system in flight, but graphs with conditional nodes do not overlap with the work of other
   // streams, which costs the 6 % that three systems in flight gain.
   P->graph_loop = std::getenv("AMGB_PCG_GRAPH_LOOP") != nullptr;
+  // The context's private pool is grown ONCE to what a hierarchy of this matrix takes (about 100 bytes
+  // per entry: Galerkin intermediates, CSR + SELL operators, work vectors) instead of allocation by
+  // allocation: growing a pool stalls the whole device, so with several contexts running systems side
+  // by side a theta sweep at m = 200 took 4.5 ... 7.4 s instead of 4.53 s (bench.py --reserve-gb 0).
+  // Skipped when that is more than a third of the free memory (amgb_ctx_reserve is the explicit call).
+  if (ctx->pool && !std::getenv("AMGB_NO_AUTO_RESERVE")) {
+    const uint64_t want = 100ull * (uint64_t)A->A.nnz + (64ull << 20);
+    uint64_t have = 0;
+    if (cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &have) == cudaSuccess && have < want / 2) {
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && want < free_b / 3) {
+        const int rrc = amgb_ctx_reserve(ctx, (int64_t)want);
+        if (rrc != AMGB_OK) (void)cudaGetLastError();  // best effort: the setup allocates on demand
+      }
+    }
+    (void)cudaGetLastError();
+  }
   const int rc = build_hierarchy(P);
   if (rc != AMGB_OK) {
     cudaStreamSynchronize(ctx->stream);

@@ -86,6 +86,58 @@ build_perm_kernel(int64_t n, const int32_t* __restrict__ cf, const int32_t* __re
   perm[ni] = (int)i;
 }
 
+// Rows of similar length next to each other (SELL-C-sigma): inside the C block and inside the F block
+// of the C/F numbering, every window of kSortWindow consecutive positions is ordered by descending
+// (row length of A, row length of P), ties in the order they had.  A slice then holds rows of (nearly)
+// one length: on the irregular coarse operators the padding of A goes from 1.2-1.5x to 1.03x, on the
+// finest level (all rows 27 long) the second key takes P's padding from 2.2x to 1.1x.  The numbering
+// of the solve phase is ours to choose.  Opt-in: see finish_solve_setup_range for the measurement.
+constexpr int kSortWindow = 1024;
+
+__global__ void __launch_bounds__(kSortWindow)
+perm_window_sort_kernel(int lo, int hi, const int32_t* __restrict__ arp, const int32_t* __restrict__ prp,
+                        int32_t* __restrict__ perm) {
+  __shared__ unsigned s_key[kSortWindow];
+  __shared__ int32_t s_row[kSortWindow];
+  const int t = threadIdx.x;
+  const int pos = lo + blockIdx.x * kSortWindow + t;
+  int row = -1;
+  unsigned key = 0;  // (positions past the block's end sort last)
+  if (pos < hi) {
+    row = perm[pos];
+    const int la = min(arp[row + 1] - arp[row], 32767);
+    const int lp = prp ? min(prp[row + 1] - prp[row], 63) : 0;
+    key = 0x80000000u | ((unsigned)la << 16) | ((unsigned)lp << 10) | (unsigned)(kSortWindow - 1 - t);
+  }
+  s_key[t] = key;
+  s_row[t] = row;
+  __syncthreads();
+  for (int kk = 2; kk <= kSortWindow; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      const int x = t ^ j;
+      if (x > t) {
+        const unsigned kt = s_key[t], kx = s_key[x];
+        const bool desc = (t & kk) == 0;  // descending runs first: the whole window ends up descending
+        if ((kt < kx) == desc) {
+          s_key[t] = kx;
+          s_key[x] = kt;
+          const int32_t r = s_row[t];
+          s_row[t] = s_row[x];
+          s_row[x] = r;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (pos < hi) perm[pos] = s_row[t];
+}
+
+__global__ void __launch_bounds__(kBlock)
+invert_perm_kernel(int64_t n, const int32_t* __restrict__ perm, int32_t* __restrict__ inv_perm) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i < n) inv_perm[perm[i]] = (int)i;
+}
+
 // one warp per slice of 32/T rows: width = ceil(longest row / T), in 32-element units
 // col_lt >= 0: only the entries whose (mapped) column is < col_lt are kept, and only in rows >= col_lt
 // (the F rows x C columns block of a C/F-permuted operator)
@@ -748,6 +800,27 @@ int finish_solve_setup_range(amgb_precond* P, int l0) {
   P->tail_from = P->dense_ok ? tail_plan(P, l0) : -1;
   if (P->tail_from >= 0) AMGB_TRY(tail_pack(P));
   const int n_sell = P->tail_from >= 0 ? P->tail_from : nl;  // levels with SELL operators of their own
+  // 1b. rows of similar length next to each other on the levels with SELL operators: opt-in
+  // (AMGB_ROW_SORT=1).  Measured on B200 at m = 200: the padding goes away as computed (level-0
+  // prolongation 162 -> 129 us) but the coarse-level sweeps are bound by their gathers, not by the
+  // matrix stream, and lose what locality the window order costs (level 1: 7.14 -> 7.31 ms per solve);
+  // one solve 104.5 -> 103.6 ms at theta = 0.25, 287 -> 290 ms at theta = 0.7, and 2 ms more setup.
+  if (std::getenv("AMGB_ROW_SORT"))
+    for (int l = l0; l < n_sell; ++l) {
+      Level& L = P->lv[l];
+      const int n = (int)L.A.n;
+      if (n < 2 * kSortWindow || !L.cf.p) continue;
+      const int nC = (int)L.n_coarse;
+      const int32_t* prp = l + 1 < nl ? L.P.rp.p : nullptr;
+      ctx->cur_level = l;
+      AMGB_LAUNCH(ctx, F_AUX, 16.0 * nC, perm_window_sort_kernel, (unsigned)div_up(nC, kSortWindow), kSortWindow, 0, 0, nC,
+                  (const int32_t*)L.A.rp.p, prp, L.perm.p);
+      AMGB_LAUNCH(ctx, F_AUX, 16.0 * (n - nC), perm_window_sort_kernel, (unsigned)div_up(n - nC, kSortWindow),
+                  kSortWindow, 0, nC, n, (const int32_t*)L.A.rp.p, prp, L.perm.p);
+      AMGB_LAUNCH(ctx, F_AUX, 8.0 * n, invert_perm_kernel, (unsigned)div_up(n, kBlock), kBlock, 0, (int64_t)n,
+                  (const int32_t*)L.perm.p, L.inv_perm.p);
+      AMGB_CHECK_LAUNCH(ctx);
+    }
   // 2. operators: A (rows, cols permuted), P (fine rows, coarse cols), R = P^T
   for (int l = l0; l < nl; ++l) {
     Level& L = P->lv[l];

@@ -660,3 +660,39 @@ def test_warp_per_row_interpolation_kernel_alone_agrees_with_the_oracle(gpu_ctx,
         theta = 0.05
     A, P, H = _both(gpu_ctx, s, device_data(theta))
     _assert_hierarchy_identical(P, H)
+
+
+@pytest.mark.parametrize("m,theta,contrast", [(24, 0.25, 3.0), (30, 0.6, 6.0)])
+def test_window_sorted_solve_numbering_agrees_with_the_oracle(gpu_ctx, monkeypatch, m, theta, contrast):
+    """AMGB_ROW_SORT=1: inside the C block and the F block of the solve numbering, windows of 1024
+    rows are ordered by (row length of A, row length of P) -- SELL-C-sigma.  The hierarchy is
+    untouched (it lives in the original numbering); V-cycle and residual history agree with the
+    oracle to the north-star tolerance and with the unsorted numbering to rounding."""
+    s = poisson(m, contrast=contrast)
+    data = device_data(theta)
+    A = ab.SparseMatrix(gpu_ctx, s.rowptr32(), s.col, s.val)
+    H = orc.Hierarchy(s.rowptr32(), s.col, s.val, data.to_struct())
+    r = np.random.default_rng(5).standard_normal(s.n)
+    zo = H.vmult(r)
+    rc, xo, nit, hist = H.cg_solve(s.rhs, s.x0, abs_tol=1e-8)
+    hs = {}
+    for mode in ("plain", "sorted"):
+        if mode == "sorted":
+            monkeypatch.setenv("AMGB_ROW_SORT", "1")
+        P = ab.PreconditionBoomerAMG()
+        P.initialize(A, data)
+        _assert_hierarchy_identical(P, H)
+        z = np.empty(s.n)
+        P.vmult(z, r)
+        assert np.abs(z - zo).max() <= 1e-12 * np.abs(zo).max(), mode
+        ctl = ab.SolverControl(s.n, 1e-8)
+        x = s.x0.copy()
+        ab.SolverCG(ctl).solve(A, x, s.rhs, P)
+        assert abs(ctl.last_step() - nit) <= 1
+        k = min(len(hist), len(ctl.history))
+        assert (np.abs(ctl.history[:k] - hist[:k]) <= RES_RTOL * hist[:k]).all(), mode
+        assert np.abs(x - xo).max() <= 1e-9 * np.abs(xo).max()
+        hs[mode] = ctl.history.copy()
+        P.close()
+    k = min(len(hs["plain"]), len(hs["sorted"]))
+    assert (np.abs(hs["plain"][:k] - hs["sorted"][:k]) <= 1e-11 * hs["plain"][:k]).all()

@@ -173,9 +173,44 @@ __global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(const int32_t* _
   if (blockIdx.x == nblocks - 1 && threadIdx.x == 0) out[n] = block_sums[nblocks];
 }
 
+// short inputs: the whole scan in ONE block, tile after tile with a running carry (one launch and no
+// block-sum buffer instead of three launches: the coarse levels of a hierarchy are launch-bound)
+constexpr int64_t kScanSmall = 8 * kScanTile;
+
+__global__ void __launch_bounds__(kScanBlock) scan_small_kernel(const int32_t* __restrict__ in, int64_t n,
+                                                                int32_t* __restrict__ out) {
+  int carry = 0;
+  for (int64_t tile = 0; tile < n; tile += kScanTile) {
+    const int64_t base = tile + (int64_t)threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      const int64_t i = base + k;
+      v[k] = i < n ? in[i] : 0;
+      s += v[k];
+    }
+    int total;
+    int ex = block_excl_scan(s, &total) + carry;  // (ends with a barrier: the tile is read before it is written)
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      const int64_t i = base + k;
+      if (i < n) out[i] = ex;
+      ex += v[k];
+    }
+    carry += total;
+  }
+  if (threadIdx.x == 0) out[n] = carry;
+}
+
 int exclusive_scan_i32(amgb_ctx* ctx, const int32_t* in, int32_t* out, int64_t n) {
   if (n <= 0) {
     AMGB_CUDA(ctx, cudaMemsetAsync(out, 0, sizeof(int32_t), ctx->stream));
+    return AMGB_OK;
+  }
+  if (n <= kScanSmall) {
+    AMGB_LAUNCH(ctx, F_SCAN, 8.0 * n, scan_small_kernel, 1, kScanBlock, 0, in, n, out);
+    AMGB_CHECK_LAUNCH(ctx);
     return AMGB_OK;
   }
   const int64_t nblocks = div_up(n, kScanTile);

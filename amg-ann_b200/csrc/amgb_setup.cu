@@ -228,9 +228,90 @@ cpoint_flag_kernel(int64_t n, const int32_t* __restrict__ cf, int32_t* __restric
   if (i < n) flag[i] = cf[i] > 0 ? 1 : 0;
 }
 
+// Small levels: the whole coarsening -- influence counts, measures, every round -- in ONE block with
+// block barriers between the phases (the phases are the kernels above, row for row).  A level of a
+// few thousand rows is launch-bound: ~6 rounds of four kernels, a memset and a host read each become
+// one launch and no host round trip.  Same splitting: no phase depends on the order of the threads.
+constexpr int kPmisSmallThreads = 256;
+constexpr int64_t kPmisSmallRows = 2048;
+
+__global__ void __launch_bounds__(kPmisSmallThreads)
+pmis_small_kernel(int n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                  const uint8_t* __restrict__ mask, const int32_t* __restrict__ has_strong,
+                  int32_t* influence /* zeroed */, double* measure, int32_t* mark, int32_t* cf) {
+  const int t = threadIdx.x;
+  for (int i = t; i < n; i += kPmisSmallThreads)
+    for (int k = rp[i]; k < rp[i + 1]; ++k)
+      if (mask[k]) atomicAdd(&influence[col[k]], 1);
+  __syncthreads();
+  for (int i = t; i < n; i += kPmisSmallThreads) {
+    double m = (double)influence[i] + hypre_rand_at(i);
+    int c = 0;
+    if (!has_strong[i]) {
+      c = -3;
+      m = 0.0;
+    } else if (m < 1.0) {
+      c = -1;
+      m = 0.0;
+    }
+    measure[i] = m;
+    cf[i] = c;
+  }
+  __syncthreads();
+  for (int round = 0; round < 100000; ++round) {
+    for (int i = t; i < n; i += kPmisSmallThreads) mark[i] = (cf[i] == 0 && measure[i] > 1.0) ? 1 : 0;
+    __syncthreads();
+    for (int i = t; i < n; i += kPmisSmallThreads) {
+      if (cf[i] != 0) continue;
+      const double mi = measure[i];
+      if (!(mi > 1.0)) continue;
+      bool lose = false;
+      for (int k = rp[i]; k < rp[i + 1]; ++k) {
+        if (!mask[k]) continue;
+        const int j = col[k];
+        const double mj = measure[j];
+        if (mj > 1.0) {
+          if (mi > mj) mark[j] = 0;
+          else if (mj > mi) lose = true;
+        }
+      }
+      if (lose) mark[i] = 0;
+    }
+    __syncthreads();
+    for (int i = t; i < n; i += kPmisSmallThreads)
+      if (cf[i] == 0 && mark[i]) cf[i] = 1;
+    __syncthreads();
+    int und = 0;
+    for (int i = t; i < n; i += kPmisSmallThreads) {
+      int c = cf[i];
+      if (c == 0) {
+        for (int k = rp[i]; k < rp[i + 1]; ++k)
+          if (mask[k] && cf[col[k]] > 0) {
+            c = -1;
+            break;
+          }
+        if (c != 0) cf[i] = c;
+      }
+      if (c != 0) measure[i] = 0.0; else und = 1;
+    }
+    if (__syncthreads_count(und) == 0) break;
+  }
+}
+
 int coarsen_pmis(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const int32_t* has_strong, int32_t* cf,
                  DistHooks* hooks) {
   const int64_t n = A.n;
+  if (!hooks && n <= kPmisSmallRows && !std::getenv("AMGB_NO_SMALL_LEVELS")) {
+    DevBuf<int32_t> influence, mark;
+    DevBuf<double> measure;
+    AMGB_TRY(influence.alloc_zero(ctx, n));
+    AMGB_TRY(mark.alloc(ctx, n));
+    AMGB_TRY(measure.alloc(ctx, n));
+    AMGB_LAUNCH(ctx, F_COARSEN, 40.0 * A.nnz + 60.0 * n, pmis_small_kernel, 1, kPmisSmallThreads, 0, (int)n, A.rp.p,
+                A.col.p, mask, has_strong, influence.p, measure.p, mark.p, cf);
+    AMGB_CHECK_LAUNCH(ctx);
+    return AMGB_OK;
+  }
   const int64_t own_begin = hooks ? hooks->own_begin : 0, own_end = hooks ? hooks->own_end : n;
   const unsigned grid = (unsigned)div_up(n, kBlock);
   DevBuf<int32_t> influence, mark, undecided;

@@ -191,6 +191,8 @@ int main(int argc, char** argv) {
     std::atomic<int> next{0};
     std::string error;
     const auto w0 = std::chrono::high_resolution_clock::now();
+    int warm_threads = 0, warm_solves = 0;  // (under file_mutex)
+    double warm_wall = 0.0;
     auto worker = [&]() {
       try {
         {  // this thread's pool grown once (matrix + hierarchy + work vectors of one system) instead of
@@ -199,6 +201,7 @@ int main(int argc, char** argv) {
           if (amgb_gen_sizes(0, a.m, &n, &nnz) == 0)
             amgb::compat::default_context().reserve(130 * nnz + (int64_t(64) << 20));
         }
+        bool first = true;
         for (;;) {
           const int s = next++;
           if (s >= a.systems) break;
@@ -206,6 +209,13 @@ int main(int argc, char** argv) {
           run_system(a, a.seed >= 0 ? a.seed + s : (a.systems > 1 ? s : -1), rows, tot);
           std::lock_guard<std::mutex> g(file_mutex);
           file << rows.str();
+          if (first) {  // this thread is warm (context, pool, kernels loaded): steady state starts when all are
+            first = false;
+            if (++warm_threads == std::min(a.threads, a.systems)) {
+              warm_wall = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - w0).count();
+              warm_solves = tot.solves.load();
+            }
+          }
         }
       } catch (const std::exception& e) {
         std::lock_guard<std::mutex> g(file_mutex);
@@ -218,10 +228,15 @@ int main(int argc, char** argv) {
     for (auto& t : pool) t.join();
     const double wall = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - w0).count();
     if (!error.empty()) throw std::runtime_error(error);
+    // steady state: from the moment every thread has finished its first system (process start-up, context
+    // creation and the first launch of every kernel are behind it) to the end
+    const double steady_s = warm_wall > 0 ? wall - warm_wall : 0.0;
+    const int steady_solves = warm_wall > 0 ? tot.solves.load() - warm_solves : 0;
     std::printf("{\"systems\": %d, \"solves\": %d, \"views\": %d, \"threads\": %d, \"wall_s\": %.6f, "
-                "\"setup_s\": %.6f, \"solve_s\": %.6f, \"view_device_s\": %.6f}\n",
+                "\"setup_s\": %.6f, \"solve_s\": %.6f, \"view_device_s\": %.6f, \"steady_s\": %.6f, "
+                "\"steady_solves\": %d}\n",
                 a.systems, tot.solves.load(), tot.views.load(), a.threads, wall, tot.setup_us / 1e6,
-                tot.solve_us / 1e6, tot.view_us / 1e6);
+                tot.solve_us / 1e6, tot.view_us / 1e6, steady_s, steady_solves);
   } catch (const std::exception& e) {  // ref t2 main.cpp:540-544
     std::cerr << "Exception on processing: " << e.what() << std::endl;
     return 1;

@@ -380,6 +380,9 @@ def extra_config4(systems=64, threads=8):
                         f"{threads} host threads / contexts on one GPU, device assembly, CSV rows written",
             "solves": j["solves"], "wall_s": round(j["wall_s"], 3),
             "systems_per_s": round(j["solves"] / j["wall_s"], 1),
+            "steady_systems_per_s": (round(j["steady_solves"] / j["steady_s"], 1) if j.get("steady_s", 0) > 0 else None),
+            "steady_note": "from the moment every host thread has finished its first system (process start-up, "
+                           "contexts, first launch of every kernel) to the end",
             "sum_setup_s": round(j["setup_s"], 3), "sum_solve_s": round(j["solve_s"], 3),
             "images": jv["views"] if jv else None,
             "images_per_s": round(jv["views"] / jv["wall_s"], 1) if jv else None,

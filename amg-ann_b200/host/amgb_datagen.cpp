@@ -198,7 +198,7 @@ int main(int argc, char** argv) {
         {  // this thread's pool grown once (matrix + hierarchy + work vectors of one system) instead of
            // allocation by allocation: pool growth stalls every lane of the device
           int64_t n = 0, nnz = 0;
-          if (amgb_gen_sizes(0, a.m, &n, &nnz) == 0)
+          if (!a.make_view && amgb_gen_sizes(0, a.m, &n, &nnz) == 0)  // (pooling allocates a few KB: nothing to reserve)
             amgb::compat::default_context().reserve(130 * nnz + (int64_t(64) << 20));
         }
         bool first = true;

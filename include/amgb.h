@@ -131,9 +131,12 @@ typedef struct amgb_precond amgb_precond;
 int amgb_ctx_create(amgb_ctx** out, int device_id, void* stream);
 int amgb_ctx_destroy(amgb_ctx* ctx);
 int amgb_ctx_synchronize(amgb_ctx* ctx);
-/* Grow the context's memory pool to `bytes` now (one allocation, freed into the pool), so that the
- * first initialize() of a large system does not pay for growing it step by step: a hierarchy needs
- * about 3.5 x the bytes of its CSR matrix (setup intermediates included).  Optional. */
+/* Grow the context's memory pool to `bytes` now (one allocation, freed into the pool), so that
+ * initialize() does not grow it step by step: growing a pool stalls the whole device, which is what
+ * made sweeps with several contexts on one GPU erratic (4.5 ... 7.4 s for a config-2 sweep instead of
+ * 4.53 s).  A hierarchy needs about 100 bytes per matrix entry (setup intermediates included).
+ * Optional: the first amgb_precond_initialize() of a context reserves that much by itself when it is
+ * less than a third of the free device memory (AMGB_NO_AUTO_RESERVE=1 turns that off). */
 int amgb_ctx_reserve(amgb_ctx* ctx, int64_t bytes);
 /* Last error text of this context (never NULL). */
 const char* amgb_last_error(const amgb_ctx* ctx);

@@ -16,3 +16,6 @@ dump build/amgb_setup.o _ZN4amgb24interp_fill_group_kernelElPKiS1_PKdPKhS1_S1_S1
 dump build/amgb_setup.o _ZN4amgb18interp_fill_kernelElPKiS1_PKdPKhS1_S1_S3_S1_PiPdlS5_ interp_fill_kernel
 dump build/amgb_pool.o _ZN4amgb19pool_entries_kernelILb0EEEvNS_6BinMapEixiPKiS3_PKdPdPxS6_S6_ pool_entries_kernel
 dump build/amgb_tail.o _ZN4amgb17cycle_tail_kernelENS_8TailDescEPKhPKdS4_Pd cycle_tail_kernel
+dump build/amgb_setup.o _ZN4amgb18spgemm_flat_kernelILi8ELi256ELi256ELb0ELb0ELb0EEEvlPKiS2_PKdS2_S2_S4_S2_PiPdS5_S5_S5_ spgemm_flat_kernel_G8_count
+dump build/amgb_setup.o _ZN4amgb18spgemm_flat_kernelILi8ELi128ELi256ELb1ELb0ELb0EEEvlPKiS2_PKdS2_S2_S4_S2_PiPdS5_S5_S5_ spgemm_flat_kernel_G8_numeric_flattened
+dump build/amgb_setup.o _ZN4amgb18spgemm_flat_kernelILi8ELi128ELi256ELb1ELb0ELb1EEEvlPKiS2_PKdS2_S2_S4_S2_PiPdS5_S5_S5_ spgemm_flat_kernel_G8_numeric_entrywise

@@ -840,6 +840,10 @@ interp_ac_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* 
   }
 }
 
+// Control flow is warp-uniform (see spgemm_flat_kernel): the four rows of a warp run every loop to the
+// warp's maximum trip count with their own lanes predicated off, and ballots / shuffles / barriers name
+// the full warp -- with group masks the four groups were serialised through every collective (ncu,
+// round-2 start: 15.7 of 32 threads per issued instruction).
 __global__ void __launch_bounds__(kBlock)
 interp_fill_group_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
                          const double* __restrict__ val, const uint8_t* __restrict__ mask,
@@ -852,34 +856,43 @@ interp_fill_group_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_
   __shared__ double s_pv[kIgRows][kIgMaxP];                       // P entries under construction
   __shared__ int32_t s_mpos[kIgRows][kIgLanes][kIgMaxMatch];      // matches of the chunk's neighbours: P position
   __shared__ double s_mval[kIgRows][kIgLanes][kIgMaxMatch];       // ... and a_kc
+  const unsigned full = 0xffffffffu;
   const int g = threadIdx.x / kIgLanes, q = threadIdx.x % kIgLanes;
   const int64_t i = row_begin + (int64_t)blockIdx.x * kIgRows + g;
-  const unsigned gm = 0xffu << ((threadIdx.x & 31) / kIgLanes * kIgLanes);
-  if (i >= n) return;  // (whole groups leave together)
-  const int jb = prp[i], len = prp[i + 1] - jb;
-  if (cf[i] > 0) {
-    if (q == 0) {
-      pcol[jb] = f2c[i];
-      pval[jb] = 1.0;
+  const unsigned sh = (threadIdx.x & 31) / kIgLanes * kIgLanes;
+  bool live = i < n;  // group-uniform
+  int jb = 0, len = 0;
+  if (live) {
+    jb = prp[i];
+    len = prp[i + 1] - jb;
+    if (cf[i] > 0) {
+      if (q == 0) {
+        pcol[jb] = f2c[i];
+        pval[jb] = 1.0;
+      }
+      live = false;
+    } else if (len > kIgMaxP) {
+      if (q == 0) {
+        todo[i] = 1;
+        atomicAdd(n_todo, 1);
+      }
+      live = false;
     }
-    return;
-  }
-  if (len > kIgMaxP) {
-    if (q == 0) {
-      todo[i] = 1;
-      atomicAdd(n_todo, 1);
-    }
-    return;
   }
   int32_t* cs = s_cs[g];
   double* pv = s_pv[g];
-  const int b = rp[i], e = rp[i + 1];
+  int b = 0, e = 0;
+  if (live) {
+    b = rp[i];
+    e = rp[i + 1];
+  }
+  const int maxlen = __reduce_max_sync(full, e - b);
   // phase 0: diagonal, interpolation points in row order
   double diagonal = 0.0;
   {
     int base = 0;
-    for (int kb = b; kb < e; kb += kIgLanes) {
-      const int k = kb + q;
+    for (int kb = 0; kb < maxlen; kb += kIgLanes) {
+      const int k = b + kb + q;
       int i1 = -1;
       double a = 0.0;
       bool isc = false;
@@ -888,10 +901,10 @@ interp_fill_group_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_
         a = val[k];
         isc = i1 != (int)i && mask[k] && cf[i1] > 0;
       }
-      const unsigned sh = (threadIdx.x & 31) / kIgLanes * kIgLanes;
-      const unsigned dm = (__ballot_sync(gm, k < e && i1 == (int)i) >> sh) & 0xffu;
-      if (dm) diagonal = __shfl_sync(gm, a, __ffs(dm) - 1, kIgLanes);
-      const unsigned cm = (__ballot_sync(gm, isc) >> sh) & 0xffu;
+      const unsigned dm = (__ballot_sync(full, k < e && i1 == (int)i) >> sh) & 0xffu;
+      const double dv = __shfl_sync(full, a, dm ? __ffs(dm) - 1 : 0, kIgLanes);
+      if (dm) diagonal = dv;
+      const unsigned cm = (__ballot_sync(full, isc) >> sh) & 0xffu;
       if (isc) {
         const int pos = base + __popc(cm & ((1u << q) - 1u));
         cs[pos] = i1;
@@ -900,12 +913,12 @@ interp_fill_group_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_
       base += __popc(cm);
     }
   }
-  __syncwarp(gm);
+  __syncwarp();
   // phase 1: the entries of row i, 8 at a time
   bool overflow = false;
   int seen_c = 0;
-  for (int kb = b; kb < e; kb += kIgLanes) {
-    const int k = kb + q;
+  for (int kb = 0; kb < maxlen; kb += kIgLanes) {
+    const int k = b + kb + q;
     int i1 = -1, c1 = -3, strong = 0;
     double a = 0.0;
     if (k < e) {
@@ -952,35 +965,38 @@ interp_fill_group_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_
       if (nmatch > kIgMaxMatch) overflow = true;
       if (sum != 0) dist = a / sum; else zero = true;
     }
-    const unsigned sh = (threadIdx.x & 31) / kIgLanes * kIgLanes;
-    if ((__ballot_sync(gm, overflow) >> sh) & 0xffu) {
+    if ((__ballot_sync(full, overflow) >> sh) & 0xffu) {  // this row goes to the warp-per-row kernel
       overflow = true;
-      break;
+      e = b;  // (nothing more is read; the rest of the loops run empty for this group)
     }
-    __syncwarp(gm);
+    __syncwarp();
     // apply the chunk's entries one after the other
-    const unsigned cmask = (__ballot_sync(gm, is_c) >> sh) & 0xffu;
-    const unsigned fmask = (__ballot_sync(gm, is_sf && !zero) >> sh) & 0xffu;
-    const unsigned dmask = (__ballot_sync(gm, is_weak || (is_sf && zero)) >> sh) & 0xffu;
-    for (unsigned todo_m = cmask | fmask | dmask; todo_m; todo_m &= todo_m - 1) {
-      const int t = __ffs(todo_m) - 1;
-      const double at = __shfl_sync(gm, a, t, kIgLanes);
+    // (every lane of the warp takes part in the ballots; an overflowed group then drops its bits)
+    unsigned cmask = (__ballot_sync(full, is_c) >> sh) & 0xffu;
+    unsigned fmask = (__ballot_sync(full, is_sf && !zero) >> sh) & 0xffu;
+    unsigned dmask = (__ballot_sync(full, is_weak || (is_sf && zero)) >> sh) & 0xffu;
+    if (overflow) cmask = fmask = dmask = 0u;
+    const unsigned any_m = cmask | fmask | dmask;
+    const int tmax = __reduce_max_sync(full, 32 - __clz(any_m));
+    for (int t = 0; t < tmax; ++t) {
+      const double at = __shfl_sync(full, a, t, kIgLanes);
+      const double dt = __shfl_sync(full, dist, t, kIgLanes);
+      const int nm = __shfl_sync(full, nmatch, t, kIgLanes);
       if ((cmask >> t) & 1u) {
         if (q == 0) pv[seen_c] = __dadd_rn(pv[seen_c], at);
         ++seen_c;
       } else if ((fmask >> t) & 1u) {
-        const double dt = __shfl_sync(gm, dist, t, kIgLanes);
-        const int nm = __shfl_sync(gm, nmatch, t, kIgLanes);
         if (q < nm) {  // nm <= 8: one match per lane, distinct P entries
           const int pos = s_mpos[g][t][q];
           pv[pos] = __dadd_rn(pv[pos], __dmul_rn(dt, s_mval[g][t][q]));
         }
-      } else {
+      } else if ((dmask >> t) & 1u) {
         diagonal = __dadd_rn(diagonal, at);  // (kept identically by every lane of the group)
       }
-      __syncwarp(gm);
+      __syncwarp();
     }
   }
+  if (!live) return;
   if (overflow) {
     if (q == 0) {
       todo[i] = 1;

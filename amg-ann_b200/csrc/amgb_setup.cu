@@ -95,9 +95,26 @@ strength_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __rest
   const int64_t i = r0 + lane;
   const bool staged = cnt <= stage;
   if (staged) {
-    for (int t = lane; t < cnt; t += 32) {
-      my_col[t] = col[eb + t];
-      my_val[t] = val[eb + t];
+    // eight coalesced load pairs in flight per lane (12 warps per SM fit: the copy has to cover the HBM
+    // latency with loads in flight, not with occupancy)
+    constexpr int kU = 8;
+    for (int t0 = 0; t0 < cnt; t0 += 32 * kU) {
+      int cc[kU];
+      double vv[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int t = t0 + u * 32 + lane;
+        cc[u] = t < cnt ? col[eb + t] : 0;
+        vv[u] = t < cnt ? val[eb + t] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int t = t0 + u * 32 + lane;
+        if (t < cnt) {
+          my_col[t] = cc[u];
+          my_val[t] = vv[u];
+        }
+      }
     }
     __syncwarp();
   }

@@ -66,7 +66,7 @@ class RelaxationType:
 
 COARSEN_CLJP, COARSEN_FALGOUT, COARSEN_PMIS = 0, 6, 8
 INTERP_CLASSICAL = 0
-SMOOTHER_SUBSTITUTE, SMOOTHER_STRICT = 0, 1
+SMOOTHER_SUBSTITUTE, SMOOTHER_STRICT, SMOOTHER_MULTICOLOR = 0, 1, 2
 
 
 class AdditionalData:
@@ -432,6 +432,15 @@ class PreconditionBoomerAMG:
         _chk(self.ctx._h, amgb_lib().amgb_precond_get_cf_marker(self._h, level, _p(out, c_i32p)),
              "get_cf_marker")
         return out
+
+    def colors(self, level):
+        """multicolour Gauss-Seidel (SMOOTHER_MULTICOLOR): (colour of every point, number of colours)"""
+        n, _, _, _ = self.level_dims(level)
+        out = np.empty(n, dtype=np.int32)
+        nc = C.c_int32()
+        _chk(self.ctx._h, amgb_lib().amgb_precond_get_colors(self._h, level, _p(out, c_i32p), C.byref(nc)),
+             "get_colors")
+        return out, nc.value
 
     def A(self, level):
         n, nnz, _, _ = self.level_dims(level)

@@ -89,7 +89,7 @@ AMGB_SYMBOLS = [
     "amgb_precond_destroy", "amgb_precond_vmult", "amgb_precond_vmult_device",
     "amgb_precond_num_levels", "amgb_precond_level_stats", "amgb_precond_level_row_stats",
     "amgb_precond_effective_relax", "amgb_precond_level_cheby",
-    "amgb_precond_level_dims", "amgb_precond_get_strength_mask", "amgb_precond_get_cf_marker",
+    "amgb_precond_level_dims", "amgb_precond_get_strength_mask", "amgb_precond_get_cf_marker", "amgb_precond_get_colors",
     "amgb_precond_get_A_csr", "amgb_precond_get_P_csr", "amgb_cg_solve",
     "amgb_cg_solve_device", "amgb_make_view", "amgb_make_view_normalized", "amgb_ctx_enable_timers",
     "amgb_ctx_reset_timers", "amgb_timer_count", "amgb_timer_name", "amgb_ctx_get_timer",
@@ -164,6 +164,7 @@ def amgb_lib():
         _sig(L.amgb_precond_level_dims, C.c_int, vp, C.c_int32, c_i64p, c_i64p, c_i64p, c_i64p)
         _sig(L.amgb_precond_get_strength_mask, C.c_int, vp, C.c_int32, c_u8p)
         _sig(L.amgb_precond_get_cf_marker, C.c_int, vp, C.c_int32, c_i32p)
+        _sig(L.amgb_precond_get_colors, C.c_int, vp, C.c_int32, c_i32p, c_i32p)
         _sig(L.amgb_precond_get_A_csr, C.c_int, vp, C.c_int32, c_i32p, c_i32p, c_f64p)
         _sig(L.amgb_precond_get_P_csr, C.c_int, vp, C.c_int32, c_i32p, c_i32p, c_f64p)
         _sig(L.amgb_cg_solve, C.c_int, vp, vp, c_f64p, c_f64p, vp, C.c_int64, C.c_double,

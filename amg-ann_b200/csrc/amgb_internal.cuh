@@ -213,6 +213,10 @@ struct Level {
   // (the F columns multiply zeros), ~1/6 of the entries of the F rows on a 27-point operator
   Sell Afc;
   DevBuf<double> inv_relax;  // new order: 1/l1 (type 18) or 1/diag (type 0); 0 = skip row
+  // multicolour Gauss-Seidel (relax types 103 / 104 / 106): colour of every point (original numbering);
+  // the solve numbering is then by colour, colour c = rows [color_ptr[c], color_ptr[c + 1])
+  DevBuf<int32_t> color;
+  std::vector<int> color_ptr;
   DevBuf<double> u, f, tmp;  // new order
   // Chebyshev smoother (relax type 16; amgb_cheby.cu): 1/sqrt(diag) in the solve numbering,
   // spectrum estimates of D^-1/2 A D^-1/2, coefficients of p in u += p(A) r, work vectors

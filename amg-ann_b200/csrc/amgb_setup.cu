@@ -2796,15 +2796,27 @@ int resolve_options(amgb_precond* P) {
     if (types[t] == 16 && t < 2) continue;  // Chebyshev on the way down / up (amgb_cheby.cu)
     const bool sequential = types[t] == 1 || types[t] == 2 || types[t] == 3 || types[t] == 4 || types[t] == 6 ||
                             types[t] == 8 || types[t] == 13 || types[t] == 14;
-    if (sequential && d.smoother_policy == AMGB_SMOOTHER_SUBSTITUTE) {
+    if (d.smoother_policy == AMGB_SMOOTHER_MULTICOLOR && (types[t] == 3 || types[t] == 4 || types[t] == 6)) {
+      if (P->dist)
+        return set_error(ctx, AMGB_ERR_UNSUPPORTED, "multicolour Gauss-Seidel is not available on the row-partitioned path");
+      types[t] += 100;  // the same Gauss-Seidel sweep in multicolour order (AMGB_RELAX_MC_*)
+      continue;
+    }
+    if (sequential && (d.smoother_policy == AMGB_SMOOTHER_SUBSTITUTE || d.smoother_policy == AMGB_SMOOTHER_MULTICOLOR)) {
       types[t] = 18;  // l1-scaled Jacobi, C/F ordered when relax_order == 1
       continue;
     }
     return set_error(ctx, AMGB_ERR_UNSUPPORTED, "relaxation type (hypre %d) not available on the device",
                      types[t]);
   }
-  if (types[0] != types[1])
+  const bool mc_pair = types[0] >= AMGB_RELAX_MC_FORWARD && types[1] >= AMGB_RELAX_MC_FORWARD;  // (forward down, backward up)
+  if (types[0] != types[1] && !mc_pair)
     return set_error(ctx, AMGB_ERR_UNSUPPORTED, "different up/down smoothers are not supported");
+  if ((types[0] >= AMGB_RELAX_MC_FORWARD) != (types[1] >= AMGB_RELAX_MC_FORWARD))
+    return set_error(ctx, AMGB_ERR_UNSUPPORTED, "multicolour Gauss-Seidel on the way down needs it on the way up too");
+  if (types[2] >= AMGB_RELAX_MC_FORWARD && types[0] < AMGB_RELAX_MC_FORWARD)
+    return set_error(ctx, AMGB_ERR_UNSUPPORTED,
+                     "multicolour Gauss-Seidel on the coarsest grid only: the levels are numbered either by colour or C/F");
   P->relax_down = types[0];
   P->relax_up = types[1];
   P->relax_coarse = types[2];
@@ -3049,6 +3061,20 @@ int amgb_precond_level_stats(const amgb_precond* P, int32_t capacity, int32_t* n
   if (grid_complexity) *grid_complexity = sr / double(P->st_rows[0]);
   if (operator_complexity) *operator_complexity = sa / double(P->st_nnz[0]);
   if (memory_complexity) *memory_complexity = (sa + sp) / double(P->st_nnz[0]);
+  return AMGB_OK;
+}
+
+int amgb_precond_get_colors(const amgb_precond* P, int32_t level, int32_t* colors, int32_t* n_colors) {
+  if (!P) return AMGB_ERR_BAD_ARG;
+  if (level < 0 || level >= (int)P->lv.size() || !P->lv[level].color.p) return AMGB_ERR_RANGE;
+  const Level& L = P->lv[level];
+  if (n_colors) *n_colors = (int32_t)L.color_ptr.size() - 1;
+  if (colors) {
+    cudaSetDevice(P->ctx->device);
+    AMGB_CUDA(P->ctx, cudaMemcpyAsync(colors, L.color.p, (size_t)L.A.n * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                      P->ctx->stream));
+    AMGB_CUDA(P->ctx, cudaStreamSynchronize(P->ctx->stream));
+  }
   return AMGB_OK;
 }
 

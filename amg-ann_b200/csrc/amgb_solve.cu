@@ -138,6 +138,117 @@ invert_perm_kernel(int64_t n, const int32_t* __restrict__ perm, int32_t* __restr
   if (i < n) inv_perm[perm[i]] = (int)i;
 }
 
+// ---------------------------------------------------------------------------
+// Multicolour Gauss-Seidel (smoother_policy = AMGB_SMOOTHER_MULTICOLOR, relax types 103 / 104 / 106):
+// greedy colouring of the level's graph, operation for operation oracle/amg_oracle.cpp::multicolor.
+// Rounds: every uncoloured point whose priority (a hash of the index, ties to the larger index) is the
+// largest among its uncoloured neighbours takes the smallest colour none of its coloured neighbours
+// has.  Two neighbours are never selected in the same round and the selection is written to `next`
+// before it is applied, so the colouring does not depend on the order of the threads.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t color_priority(int64_t i) {
+  uint32_t h = (uint32_t)(i + 1) * 2654435761u;
+  h ^= h >> 15;
+  h *= 2246822519u;
+  h ^= h >> 13;
+  return h;
+}
+
+__global__ void __launch_bounds__(kBlock)
+color_round_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                   const int32_t* __restrict__ color, int32_t* __restrict__ next, int32_t* __restrict__ info) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  next[i] = -1;
+  if (color[i] >= 0) return;
+  const uint32_t pi = color_priority(i);
+  bool is_max = true;
+  unsigned long long used = 0ull;
+  for (int k = rp[i]; k < rp[i + 1]; ++k) {
+    const int j = col[k];
+    if (j == (int)i) continue;
+    const int cj = color[j];
+    if (cj >= 0) {
+      used |= 1ull << cj;
+    } else {
+      const uint32_t pj = color_priority(j);
+      if (pj > pi || (pj == pi && j > (int)i)) is_max = false;
+    }
+  }
+  if (!is_max) return;
+  const int c = __ffsll((long long)~used) - 1;  // lowest colour not in use (-1: all 64 taken)
+  if (c < 0) {
+    info[1] = 1;
+    return;
+  }
+  next[i] = c;
+  atomicAdd(&info[0], 1);
+  atomicMax(&info[2], c + 1);
+}
+
+__global__ void __launch_bounds__(kBlock)
+color_apply_kernel(int64_t n, const int32_t* __restrict__ next, int32_t* __restrict__ color) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i < n && next[i] >= 0) color[i] = next[i];
+}
+
+__global__ void __launch_bounds__(kBlock)
+color_flag_kernel(int64_t n, const int32_t* __restrict__ color, int c, int32_t* __restrict__ flag) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i < n) flag[i] = color[i] == c ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kBlock)
+color_place_kernel(int64_t n, const int32_t* __restrict__ color, int c, const int32_t* __restrict__ pos, int base,
+                   int32_t* __restrict__ perm, int32_t* __restrict__ inv_perm) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n || color[i] != c) return;
+  const int ni = base + pos[i];
+  inv_perm[i] = ni;
+  perm[ni] = (int)i;
+}
+
+// colours of level L (kept in L.color) and the solve numbering by (colour, index)
+static int color_level(amgb_ctx* ctx, Level& L) {
+  const int64_t n = L.A.n;
+  const unsigned grid = (unsigned)div_up(n, kBlock);
+  DevBuf<int32_t> next, info, pos;
+  AMGB_TRY(L.color.alloc(ctx, n));
+  AMGB_TRY(next.alloc(ctx, n));
+  AMGB_TRY(pos.alloc(ctx, n + 1));
+  AMGB_TRY(info.alloc_zero(ctx, 4));
+  AMGB_CUDA(ctx, cudaMemsetAsync(L.color.p, 0xff, (size_t)n * sizeof(int32_t), ctx->stream));  // -1
+  int32_t* h = (int32_t*)ctx->pinned;
+  int64_t done = 0;
+  int ncolors = 0;
+  for (int round = 0; done < n; ++round) {
+    if (round > 100000) return set_error(ctx, AMGB_ERR_BREAKDOWN, "multicolouring did not terminate");
+    AMGB_LAUNCH(ctx, F_AUX, 8.0 * L.A.nnz + 12.0 * n, color_round_kernel, grid, kBlock, 0, n, (const int32_t*)L.A.rp.p,
+                (const int32_t*)L.A.col.p, (const int32_t*)L.color.p, next.p, info.p);
+    AMGB_LAUNCH(ctx, F_AUX, 8.0 * n, color_apply_kernel, grid, kBlock, 0, n, (const int32_t*)next.p, L.color.p);
+    AMGB_CHECK_LAUNCH(ctx);
+    AMGB_CUDA(ctx, cudaMemcpyAsync(h, info.p, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h[1]) return set_error(ctx, AMGB_ERR_RANGE, "multicolouring needs more than 64 colours");
+    if (h[0] == done) return set_error(ctx, AMGB_ERR_BREAKDOWN, "multicolouring stalled");
+    done = h[0];
+    ncolors = h[2];
+  }
+  L.color_ptr.assign(1, 0);
+  for (int c = 0; c < ncolors; ++c) {
+    AMGB_LAUNCH(ctx, F_AUX, 8.0 * n, color_flag_kernel, grid, kBlock, 0, n, (const int32_t*)L.color.p, c, next.p);
+    AMGB_TRY(exclusive_scan_i32(ctx, next.p, pos.p, n));
+    int32_t cnt = 0;
+    AMGB_TRY(read_i32(ctx, pos.p + n, &cnt));
+    AMGB_LAUNCH(ctx, F_AUX, 16.0 * n, color_place_kernel, grid, kBlock, 0, n, (const int32_t*)L.color.p, c,
+                (const int32_t*)pos.p, L.color_ptr.back(), L.perm.p, L.inv_perm.p);
+    AMGB_CHECK_LAUNCH(ctx);
+    L.color_ptr.push_back(L.color_ptr.back() + cnt);
+  }
+  if (L.color_ptr.back() != (int)n) return set_error(ctx, AMGB_ERR_BREAKDOWN, "multicolouring lost points");
+  return AMGB_OK;
+}
+
 // one warp per slice of 32/T rows: width = ceil(longest row / T), in 32-element units
 // col_lt >= 0: only the entries whose (mapped) column is < col_lt are kept, and only in rows >= col_lt
 // (the F rows x C columns block of a C/F-permuted operator)
@@ -795,6 +906,15 @@ int finish_solve_setup_range(amgb_precond* P, int l0) {
                 (const int32_t*)L.cf.p, (const int32_t*)L.f2c.p, (int)L.n_coarse, L.perm.p, L.inv_perm.p);
     AMGB_CHECK_LAUNCH(ctx);
   }
+  // multicolour Gauss-Seidel: the solve numbering is by colour instead of C/F (the coarsest level keeps
+  // the identity when it is solved directly)
+  const bool mc = P->relax_down >= AMGB_RELAX_MC_FORWARD || P->relax_coarse >= AMGB_RELAX_MC_FORWARD;
+  if (mc)
+    for (int l = l0; l < nl; ++l) {
+      if (l == nl - 1 && P->relax_coarse == 9 && P->lv[l].A.n <= kMaxDenseCoarse) continue;
+      ctx->cur_level = l;
+      AMGB_TRY(color_level(ctx, P->lv[l]));
+    }
   // the coarsest grid is factorised first: the tail is only planned on top of a dense solve
   AMGB_TRY(setup_dense(P));
   P->tail_from = P->dense_ok ? tail_plan(P, l0) : -1;
@@ -805,7 +925,7 @@ int finish_solve_setup_range(amgb_precond* P, int l0) {
   // prolongation 162 -> 129 us) but the coarse-level sweeps are bound by their gathers, not by the
   // matrix stream, and lose what locality the window order costs (level 1: 7.14 -> 7.31 ms per solve);
   // one solve 104.5 -> 103.6 ms at theta = 0.25, 287 -> 290 ms at theta = 0.7, and 2 ms more setup.
-  if (std::getenv("AMGB_ROW_SORT"))
+  if (std::getenv("AMGB_ROW_SORT") && !mc)
     for (int l = l0; l < n_sell; ++l) {
       Level& L = P->lv[l];
       const int n = (int)L.A.n;
@@ -1046,8 +1166,43 @@ static int relax_cheby(amgb_precond* P, int l, const double* f, double* u, doubl
   return AMGB_OK;
 }
 
+// Gauss-Seidel in multicolour order (relax types 103 / 104 / 106; oracle relax_multicolor): the level is
+// numbered by colour, a colour is a contiguous row range whose rows only read other colours, so one
+// in-place Jacobi-type launch per colour IS the Gauss-Seidel sweep.  Forward = colours ascending,
+// backward = descending, symmetric = both.
+static int relax_multicolor(amgb_precond* P, int l, int type, const double* f, const double* u, double* out,
+                            bool u_is_zero) {
+  Level& L = P->lv[l];
+  amgb_ctx* ctx = P->ctx;
+  ctx->cur_level = l;
+  const int n = (int)L.n_solve;
+  if (n == 0) return AMGB_OK;
+  if (u_is_zero) AMGB_CUDA(ctx, cudaMemsetAsync(out, 0, (size_t)n * sizeof(double), ctx->stream));
+  else AMGB_CUDA(ctx, cudaMemcpyAsync(out, u, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  const int nc = (int)L.color_ptr.size() - 1;
+  const int fam = l == 0 ? F_SMOOTH_L0 : F_SMOOTH;
+  const double mat = L.As.csr_bytes();
+  auto sweep = [&](int c) -> int {
+    const int lo = L.color_ptr[c], hi = L.color_ptr[c + 1];
+    const double share = n > 0 ? double(hi - lo) / double(n) : 0.0;
+    return launch_sell(ctx, L.As, lo, hi, out, out, 0, EpiJacobi{f, out, L.inv_relax.p, out, 1.0}, fam,
+                       share * mat + 32.0 * (hi - lo));
+  };
+  if (type != AMGB_RELAX_MC_BACKWARD)
+    for (int c = 0; c < nc; ++c) AMGB_TRY(sweep(c));
+  if (type != AMGB_RELAX_MC_FORWARD)
+    for (int c = nc - 1; c >= 0; --c) AMGB_TRY(sweep(c));
+  return AMGB_OK;
+}
+
 static int relax_if(amgb_precond* P, int l, const double* f, double* u, double* out, int cycle_param,
                     bool u_is_zero = false) {
+  {
+    const int type = cycle_param == 1 ? P->relax_down
+                                      : (cycle_param == 2 ? P->relax_up
+                                                          : (P->relax_coarse == 9 ? P->relax_down : P->relax_coarse));
+    if (type >= AMGB_RELAX_MC_FORWARD) return relax_multicolor(P, l, type, f, u, out, u_is_zero);
+  }
   if (P->relax_down == 16 && (cycle_param < 3 || P->relax_coarse == 9))
     return relax_cheby(P, l, f, u, out, u_is_zero);
   // on the row-partitioned path the halo of `u` is refreshed here, overlapped with the rows that do not need it

@@ -79,8 +79,17 @@ enum { AMGB_INTERP_CLASSICAL = 0, AMGB_INTERP_DIRECT = 3, AMGB_INTERP_EXT_I = 6 
  * (the reference default: hybrid symmetric Gauss-Seidel, hypre relax type 6). */
 enum {
   AMGB_SMOOTHER_SUBSTITUTE = 0, /* run C/F-ordered l1-scaled Jacobi instead (hypre's own GPU choice) */
-  AMGB_SMOOTHER_STRICT = 1      /* return AMGB_ERR_UNSUPPORTED */
+  AMGB_SMOOTHER_STRICT = 1,     /* return AMGB_ERR_UNSUPPORTED */
+  AMGB_SMOOTHER_MULTICOLOR = 2  /* Gauss-Seidel types 3 / 4 / 6 (forward / backward / symmetric): run the
+                                   same sweep in MULTICOLOUR order -- a true Gauss-Seidel sweep whose
+                                   unknowns are ordered by the colours of a greedy colouring of the
+                                   level's graph (colour by colour, every colour in parallel) instead of
+                                   by index; reported as 103 / 104 / 106 by amgb_precond_effective_relax.
+                                   The other sequential types (l1 variants, 1, 2) are substituted as under
+                                   AMGB_SMOOTHER_SUBSTITUTE.  Needs a structurally symmetric operator. */
 };
+/* relax type codes reported for the multicolour sweeps (outside hypre's numbering) */
+enum { AMGB_RELAX_MC_FORWARD = 103, AMGB_RELAX_MC_BACKWARD = 104, AMGB_RELAX_MC_SYMMETRIC = 106 };
 
 /*
  * Parameter pack of initialize().  The first twelve fields are deal.II's
@@ -228,6 +237,9 @@ int amgb_precond_level_row_stats(const amgb_precond* P, int32_t level, int32_t* 
  * of the polynomial (coefs needs room for 4; n_coefs = hypre's cheby_order, default 2). */
 int amgb_precond_level_cheby(const amgb_precond* P, int32_t level, double* max_eig, double* min_eig,
                              double* coefs, int32_t* n_coefs);
+/* Multicolour Gauss-Seidel (AMGB_SMOOTHER_MULTICOLOR): colour of every point of a level (original
+ * numbering, 0 .. n_colors-1), or AMGB_ERR_RANGE when the level has no colouring. */
+int amgb_precond_get_colors(const amgb_precond* P, int32_t level, int32_t* colors, int32_t* n_colors);
 /* hypre relax type actually run on the device for down/up/coarse (after the
  * smoother policy was applied). */
 int amgb_precond_effective_relax(const amgb_precond* P, int32_t* down, int32_t* up,

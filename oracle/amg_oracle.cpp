@@ -844,6 +844,8 @@ struct Level {
   std::vector<uint8_t> mask;
   std::vector<int32_t> cf;       // as returned by the coarsening (+1,-1,-3)
   std::vector<int32_t> cf_relax; // -3 folded into -1 (end of BuildInterp)
+  std::vector<int32_t> color;    // multicolour Gauss-Seidel: colour of every point
+  int32_t ncolors = 0;
   std::vector<double> diag, l1;
   std::vector<double> u, f, tmp; // work vectors
   // Chebyshev smoother (relax type 16): 1/sqrt(diag), spectrum estimates, polynomial
@@ -1101,6 +1103,79 @@ void cheby_relax(const Level& L, const double* f, double* u, double* tmp) {
   for (int64_t i = 0; i < n; ++i) u[i] = u[i] + ds[i] * q[i];
 }
 
+// Greedy multicolouring (AMGB_SMOOTHER_MULTICOLOR; not part of hypre: the device's parallel order for
+// the reference's Gauss-Seidel sweeps).  Rounds: every uncoloured point whose priority is the largest
+// among its uncoloured neighbours takes the smallest colour none of its (already coloured) neighbours
+// has.  The priority is a hash of the index, ties go to the larger index; two neighbours are never
+// selected in the same round, so the result does not depend on the order of evaluation.  Neighbours =
+// the columns of the row (the operator is assumed structurally symmetric).
+inline uint32_t color_priority(int64_t i) {
+  uint32_t h = (uint32_t)(i + 1) * 2654435761u;
+  h ^= h >> 15;
+  h *= 2246822519u;
+  h ^= h >> 13;
+  return h;
+}
+
+int multicolor(const Csr& A, std::vector<int32_t>& color, int32_t* ncolors) {
+  const int64_t n = A.n;
+  color.assign(n, -1);
+  std::vector<int32_t> next(n, -1);
+  int64_t left = n;
+  int32_t nc = 0;
+  while (left > 0) {
+    for (int64_t i = 0; i < n; ++i) {
+      if (color[i] >= 0) continue;
+      const uint32_t pi = color_priority(i);
+      bool is_max = true;
+      uint64_t used = 0;
+      for (int32_t k = A.rp[i]; k < A.rp[i + 1]; ++k) {
+        const int64_t j = A.col[k];
+        if (j == i) continue;
+        if (color[j] >= 0) {
+          used |= 1ull << color[j];
+        } else {
+          const uint32_t pj = color_priority(j);
+          if (pj > pi || (pj == pi && j > i)) is_max = false;
+        }
+      }
+      if (is_max) {
+        int32_t c = 0;
+        while (c < 64 && ((used >> c) & 1ull)) ++c;
+        if (c >= 64) return AMGB_ERR_RANGE;
+        next[i] = c;
+      }
+    }
+    for (int64_t i = 0; i < n; ++i)
+      if (color[i] < 0 && next[i] >= 0) {
+        color[i] = next[i];
+        nc = std::max(nc, next[i] + 1);
+        --left;
+      }
+  }
+  *ncolors = nc;
+  return 0;
+}
+
+// Gauss-Seidel in multicolour order: colours ascending (forward), descending (backward) or both
+// (symmetric); inside a colour the points are independent.
+void relax_multicolor(const Level& L, int type, const double* f, double* u) {
+  const Csr& A = L.A;
+  auto sweep = [&](int32_t c) {
+    for (int64_t i = 0; i < A.n; ++i) {
+      if (L.color[i] != c || L.diag[i] == 0.0) continue;
+      double res = f[i];
+      for (int32_t k = A.rp[i]; k < A.rp[i + 1]; ++k)
+        if (A.col[k] != i) res -= A.val[k] * u[A.col[k]];
+      u[i] = res / L.diag[i];
+    }
+  };
+  if (type != AMGB_RELAX_MC_BACKWARD)
+    for (int32_t c = 0; c < L.ncolors; ++c) sweep(c);
+  if (type != AMGB_RELAX_MC_FORWARD)
+    for (int32_t c = L.ncolors - 1; c >= 0; --c) sweep(c);
+}
+
 // One hypre_BoomerAMGRelax call: relax_points 0 = all, else only cf == relax_points.
 void relax(const Level& L, int type, int relax_points, double w, const double* f, double* u,
            double* tmp) {
@@ -1161,6 +1236,10 @@ void relax_if(const orc_hier& h, const Level& L, int type, int cycle_param, cons
   const double w = h.data.relax_weight;
   if (type == 16) {  // par_cycle.c: the polynomial smoother runs on all points, no C/F ordering
     cheby_relax(L, f, u, tmp);
+    return;
+  }
+  if (type >= AMGB_RELAX_MC_FORWARD) {  // the colours are the ordering: no C/F ordering on top
+    relax_multicolor(L, type, f, u);
     return;
   }
   if (h.data.relax_order == 1 && cycle_param < 3) {
@@ -1302,7 +1381,11 @@ int orc_setup(int64_t n, const int32_t* rowptr, const int32_t* col, const double
   h->relax_down = hypre_relax_type(data->relaxation_type_down, sym);
   h->relax_up = hypre_relax_type(data->relaxation_type_up, sym);
   h->relax_coarse = hypre_relax_type(data->relaxation_type_coarse, sym);
-  auto supported = [](int t) { return t == 0 || t == 3 || t == 4 || t == 6 || t == 18; };
+  if (data->smoother_policy == AMGB_SMOOTHER_MULTICOLOR) {
+    for (int* t : {&h->relax_down, &h->relax_up, &h->relax_coarse})
+      if (*t == 3 || *t == 4 || *t == 6) *t += 100;
+  }
+  auto supported = [](int t) { return t == 0 || t == 3 || t == 4 || t == 6 || t == 18 || t == 103 || t == 104 || t == 106; };
   if (h->relax_down == 16 && h->relax_up == 16 && (supported(h->relax_coarse) || h->relax_coarse == 9)) {
     // Chebyshev on the way down and up
   } else if (!supported(h->relax_down) || !supported(h->relax_up) ||
@@ -1362,6 +1445,13 @@ int orc_setup(int64_t n, const int32_t* rowptr, const int32_t* col, const double
     if (L.cf_relax.empty()) L.cf_relax.assign(L.A.n, 0);
     level_aux(L);
   }
+  if (h->relax_down >= AMGB_RELAX_MC_FORWARD || h->relax_up >= AMGB_RELAX_MC_FORWARD ||
+      h->relax_coarse >= AMGB_RELAX_MC_FORWARD)
+    for (Level& L : h->lv)
+      if (multicolor(L.A, L.color, &L.ncolors) != 0) {
+        delete h;
+        return AMGB_ERR_RANGE;
+      }
   if (h->relax_down == 16)  // PCHYPRE / hypre defaults: order 2, 10 CG steps, fraction 0.3
     for (Level& L : h->lv) cheby_setup(L, 2, 10, 0.3);
   Level& C = h->lv.back();
@@ -1444,6 +1534,15 @@ int orc_level_stats(const orc_hier* h, int capacity, int32_t* n_levels, int64_t*
   if (grid_cx) *grid_cx = sr / double(h->lv[0].A.n);
   if (op_cx) *op_cx = sa / double(h->lv[0].A.nnz());
   if (mem_cx) *mem_cx = (sa + sp) / double(h->lv[0].A.nnz());
+  return 0;
+}
+
+int orc_get_colors(const orc_hier* h, int level, int32_t* colors, int32_t* n_colors) {
+  if (!h || level < 0 || level >= (int)h->lv.size()) return AMGB_ERR_RANGE;
+  const Level& L = h->lv[level];
+  if (L.color.empty()) return AMGB_ERR_RANGE;
+  if (colors) std::copy(L.color.begin(), L.color.end(), colors);
+  if (n_colors) *n_colors = L.ncolors;
   return 0;
 }
 

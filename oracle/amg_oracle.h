@@ -66,6 +66,8 @@ int orc_level_stats(const orc_hier* h, int capacity, int32_t* n_levels, int64_t*
                     int64_t* nnz, double* sparsity, double* grid_cx, double* op_cx,
                     double* mem_cx);
 int orc_effective_relax(const orc_hier* h, int32_t* down, int32_t* up, int32_t* coarse);
+/* multicolour Gauss-Seidel (smoother_policy = AMGB_SMOOTHER_MULTICOLOR): colours of a level */
+int orc_get_colors(const orc_hier* h, int level, int32_t* colors, int32_t* n_colors);
 /* Chebyshev smoother (hypre relax type 16, par_cheby.c) of a level: CG/Lanczos spectrum
  * estimates of D^-1/2 A D^-1/2 and the polynomial coefficients (n_coefs = order). */
 int orc_level_cheby(const orc_hier* h, int level, double* max_eig, double* min_eig, double* coefs,

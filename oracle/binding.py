@@ -47,6 +47,7 @@ def lib():
         sig("orc_level_dims", C.c_int, vp, C.c_int, c_i64p, c_i64p, c_i64p, c_i64p)
         sig("orc_get_strength_mask", C.c_int, vp, C.c_int, c_u8p)
         sig("orc_get_cf_marker", C.c_int, vp, C.c_int, c_i32p)
+        sig("orc_get_colors", C.c_int, vp, C.c_int, c_i32p, c_i32p)
         sig("orc_get_A_csr", C.c_int, vp, C.c_int, c_i32p, c_i32p, c_f64p)
         sig("orc_get_P_csr", C.c_int, vp, C.c_int, c_i32p, c_i32p, c_f64p)
         sig("orc_level_stats", C.c_int, vp, C.c_int, c_i32p, c_i64p, c_i64p, c_f64p, c_f64p,
@@ -171,6 +172,16 @@ class Hierarchy:
         if rc:
             raise IndexError(level)
         return out
+
+    def colors(self, level):
+        """multicolour Gauss-Seidel: (colour of every point, number of colours)"""
+        n, _, _, _ = self.level_dims(level)
+        out = np.empty(n, dtype=np.int32)
+        nc = C.c_int32()
+        rc = lib().orc_get_colors(self._h, level, _p(out, c_i32p), C.byref(nc))
+        if rc:
+            raise IndexError(level)
+        return out, nc.value
 
     def A(self, level):
         n, nnz, _, _ = self.level_dims(level)

@@ -503,3 +503,43 @@ def test_cuthill_mckee_is_a_level_ordering():
     perm = ab.gen.cuthill_mckee(B.indptr, B.indices)
     assert sorted(perm) == list(range(2 * n)) and list(perm[:n]) == list(range(n))
     assert list(ab.gen.cuthill_mckee(B.indptr, B.indices, reversed=True)) == list(perm[::-1])
+
+
+def test_oracle_multicolour_gauss_seidel():
+    """smoother_policy = SMOOTHER_MULTICOLOR in the oracle: a valid greedy colouring on every level,
+    the multicolour sweep is the Gauss-Seidel sweep of the colour-ordered system (checked against a
+    dense triangular solve), and PCG needs fewer iterations than with the l1-Jacobi substitute."""
+    import amg_ann_b200 as ab
+    from oracle import binding as orc
+    from helpers import device_data, poisson
+    R = ab.RelaxationType
+    s = poisson(10, contrast=3.0)
+    data = device_data(0.25, relaxation_type_up=R.symmetricSORJacobi, relaxation_type_down=R.symmetricSORJacobi,
+                       smoother_policy=ab.SMOOTHER_MULTICOLOR, max_levels=1, relaxation_type_coarse=R.SORJacobi,
+                       n_sweeps_coarse=1)
+    H = orc.Hierarchy(s.rowptr32(), s.col, s.val, data.to_struct())
+    assert H.effective_relax() == (106, 106, 106)
+    col, nc = H.colors(0)
+    rp = s.rowptr32()
+    rows = np.repeat(np.arange(s.n), np.diff(rp))
+    off = rows != s.col
+    assert col.min() == 0 and col.max() == nc - 1 and not (col[rows[off]] == col[s.col[off]]).any()
+    # one level, one symmetric sweep from zero = (forward then backward Gauss-Seidel) in colour order
+    import scipy.sparse as sp
+    A = sp.csr_matrix((s.val, s.col, rp), shape=(s.n, s.n)).toarray()
+    order = np.lexsort((np.arange(s.n), col))
+    Ap = A[np.ix_(order, order)]
+    r = np.random.default_rng(0).standard_normal(s.n)
+    f = r[order]
+    Lo, Up, D = np.tril(Ap, -1), np.triu(Ap, 1), np.diag(np.diag(Ap))
+    u1 = np.linalg.solve(D + Lo, f)                      # forward from zero
+    u2 = np.linalg.solve(D + Up, f - Lo @ u1)            # backward
+    z = H.vmult(r)
+    assert np.abs(z[order] - u2).max() <= 1e-11 * np.abs(u2).max()
+    # full hierarchy: fewer iterations than C/F l1-Jacobi
+    s = poisson(14, contrast=3.0)
+    d_mc = device_data(0.25, relaxation_type_up=R.symmetricSORJacobi, relaxation_type_down=R.symmetricSORJacobi,
+                       smoother_policy=ab.SMOOTHER_MULTICOLOR)
+    it_mc = orc.Hierarchy(s.rowptr32(), s.col, s.val, d_mc.to_struct()).cg_solve(s.rhs, s.x0, abs_tol=1e-8)[2]
+    it_j = orc.Hierarchy(s.rowptr32(), s.col, s.val, device_data(0.25).to_struct()).cg_solve(s.rhs, s.x0, abs_tol=1e-8)[2]
+    assert it_mc < it_j

@@ -20,7 +20,8 @@ ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--max-steps", type=int, default=0)
 ap.add_argument("--timers", action="store_true", help="per-family CUDA-event timers (disables the V-cycle graph)")
 ap.add_argument("--kind", default="poisson", choices=["poisson", "elasticity"])
-ap.add_argument("--smoother", default="l1jacobi", choices=["l1jacobi", "chebyshev"])
+ap.add_argument("--smoother", default="l1jacobi", choices=["l1jacobi", "chebyshev", "mcgs", "mcfb"],
+                help="mcgs: multicolour symmetric Gauss-Seidel (SMOOTHER_MULTICOLOR); mcfb: forward down, backward up")
 ap.add_argument("--agg", type=int, default=0, help="aggressive_coarsening_num_levels (testcase 3 passes 2)")
 args = ap.parse_args()
 
@@ -34,6 +35,12 @@ print(f"{args.kind} m={args.m}: n={s.n} nnz={s.nnz} generated in {time.perf_coun
 R = ab.RelaxationType
 sm = R.Chebyshev if args.smoother == "chebyshev" else R.l1scaledJacobi
 data = ab.AdditionalData(True, args.theta, 0.9, args.agg, True, relaxation_type_up=sm, relaxation_type_down=sm)
+if args.smoother == "mcgs":
+    data = ab.AdditionalData(True, args.theta, 0.9, args.agg, True, relaxation_type_up=R.symmetricSORJacobi,
+                             relaxation_type_down=R.symmetricSORJacobi, smoother_policy=ab.SMOOTHER_MULTICOLOR)
+elif args.smoother == "mcfb":
+    data = ab.AdditionalData(False, args.theta, 0.9, args.agg, True, relaxation_type_up=R.backwardSORJacobi,
+                             relaxation_type_down=R.SORJacobi, smoother_policy=ab.SMOOTHER_MULTICOLOR)
 ctx = ab.Context(0)
 A = ab.SparseMatrix(ctx, s.rowptr32(), s.col, s.val)
 for rep in range(args.repeat):

@@ -95,26 +95,9 @@ strength_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __rest
   const int64_t i = r0 + lane;
   const bool staged = cnt <= stage;
   if (staged) {
-    // eight coalesced load pairs in flight per lane (12 warps per SM fit: the copy has to cover the HBM
-    // latency with loads in flight, not with occupancy)
-    constexpr int kU = 8;
-    for (int t0 = 0; t0 < cnt; t0 += 32 * kU) {
-      int cc[kU];
-      double vv[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int t = t0 + u * 32 + lane;
-        cc[u] = t < cnt ? col[eb + t] : 0;
-        vv[u] = t < cnt ? val[eb + t] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int t = t0 + u * 32 + lane;
-        if (t < cnt) {
-          my_col[t] = cc[u];
-          my_val[t] = vv[u];
-        }
-      }
+    for (int t = lane; t < cnt; t += 32) {
+      my_col[t] = col[eb + t];
+      my_val[t] = val[eb + t];
     }
     __syncwarp();
   }
@@ -857,10 +840,6 @@ interp_ac_fill_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* 
   }
 }
 
-// Control flow is warp-uniform (see spgemm_flat_kernel): the four rows of a warp run every loop to the
-// warp's maximum trip count with their own lanes predicated off, and ballots / shuffles / barriers name
-// the full warp -- with group masks the four groups were serialised through every collective (ncu,
-// round-2 start: 15.7 of 32 threads per issued instruction).
 __global__ void __launch_bounds__(kBlock)
 interp_fill_group_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
                          const double* __restrict__ val, const uint8_t* __restrict__ mask,
@@ -873,43 +852,34 @@ interp_fill_group_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_
   __shared__ double s_pv[kIgRows][kIgMaxP];                       // P entries under construction
   __shared__ int32_t s_mpos[kIgRows][kIgLanes][kIgMaxMatch];      // matches of the chunk's neighbours: P position
   __shared__ double s_mval[kIgRows][kIgLanes][kIgMaxMatch];       // ... and a_kc
-  const unsigned full = 0xffffffffu;
   const int g = threadIdx.x / kIgLanes, q = threadIdx.x % kIgLanes;
   const int64_t i = row_begin + (int64_t)blockIdx.x * kIgRows + g;
-  const unsigned sh = (threadIdx.x & 31) / kIgLanes * kIgLanes;
-  bool live = i < n;  // group-uniform
-  int jb = 0, len = 0;
-  if (live) {
-    jb = prp[i];
-    len = prp[i + 1] - jb;
-    if (cf[i] > 0) {
-      if (q == 0) {
-        pcol[jb] = f2c[i];
-        pval[jb] = 1.0;
-      }
-      live = false;
-    } else if (len > kIgMaxP) {
-      if (q == 0) {
-        todo[i] = 1;
-        atomicAdd(n_todo, 1);
-      }
-      live = false;
+  const unsigned gm = 0xffu << ((threadIdx.x & 31) / kIgLanes * kIgLanes);
+  if (i >= n) return;  // (whole groups leave together)
+  const int jb = prp[i], len = prp[i + 1] - jb;
+  if (cf[i] > 0) {
+    if (q == 0) {
+      pcol[jb] = f2c[i];
+      pval[jb] = 1.0;
     }
+    return;
+  }
+  if (len > kIgMaxP) {
+    if (q == 0) {
+      todo[i] = 1;
+      atomicAdd(n_todo, 1);
+    }
+    return;
   }
   int32_t* cs = s_cs[g];
   double* pv = s_pv[g];
-  int b = 0, e = 0;
-  if (live) {
-    b = rp[i];
-    e = rp[i + 1];
-  }
-  const int maxlen = __reduce_max_sync(full, e - b);
+  const int b = rp[i], e = rp[i + 1];
   // phase 0: diagonal, interpolation points in row order
   double diagonal = 0.0;
   {
     int base = 0;
-    for (int kb = 0; kb < maxlen; kb += kIgLanes) {
-      const int k = b + kb + q;
+    for (int kb = b; kb < e; kb += kIgLanes) {
+      const int k = kb + q;
       int i1 = -1;
       double a = 0.0;
       bool isc = false;
@@ -918,10 +888,10 @@ interp_fill_group_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_
         a = val[k];
         isc = i1 != (int)i && mask[k] && cf[i1] > 0;
       }
-      const unsigned dm = (__ballot_sync(full, k < e && i1 == (int)i) >> sh) & 0xffu;
-      const double dv = __shfl_sync(full, a, dm ? __ffs(dm) - 1 : 0, kIgLanes);
-      if (dm) diagonal = dv;
-      const unsigned cm = (__ballot_sync(full, isc) >> sh) & 0xffu;
+      const unsigned sh = (threadIdx.x & 31) / kIgLanes * kIgLanes;
+      const unsigned dm = (__ballot_sync(gm, k < e && i1 == (int)i) >> sh) & 0xffu;
+      if (dm) diagonal = __shfl_sync(gm, a, __ffs(dm) - 1, kIgLanes);
+      const unsigned cm = (__ballot_sync(gm, isc) >> sh) & 0xffu;
       if (isc) {
         const int pos = base + __popc(cm & ((1u << q) - 1u));
         cs[pos] = i1;
@@ -930,12 +900,12 @@ interp_fill_group_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_
       base += __popc(cm);
     }
   }
-  __syncwarp();
+  __syncwarp(gm);
   // phase 1: the entries of row i, 8 at a time
   bool overflow = false;
   int seen_c = 0;
-  for (int kb = 0; kb < maxlen; kb += kIgLanes) {
-    const int k = b + kb + q;
+  for (int kb = b; kb < e; kb += kIgLanes) {
+    const int k = kb + q;
     int i1 = -1, c1 = -3, strong = 0;
     double a = 0.0;
     if (k < e) {
@@ -982,38 +952,35 @@ interp_fill_group_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_
       if (nmatch > kIgMaxMatch) overflow = true;
       if (sum != 0) dist = a / sum; else zero = true;
     }
-    if ((__ballot_sync(full, overflow) >> sh) & 0xffu) {  // this row goes to the warp-per-row kernel
+    const unsigned sh = (threadIdx.x & 31) / kIgLanes * kIgLanes;
+    if ((__ballot_sync(gm, overflow) >> sh) & 0xffu) {
       overflow = true;
-      e = b;  // (nothing more is read; the rest of the loops run empty for this group)
+      break;
     }
-    __syncwarp();
+    __syncwarp(gm);
     // apply the chunk's entries one after the other
-    // (every lane of the warp takes part in the ballots; an overflowed group then drops its bits)
-    unsigned cmask = (__ballot_sync(full, is_c) >> sh) & 0xffu;
-    unsigned fmask = (__ballot_sync(full, is_sf && !zero) >> sh) & 0xffu;
-    unsigned dmask = (__ballot_sync(full, is_weak || (is_sf && zero)) >> sh) & 0xffu;
-    if (overflow) cmask = fmask = dmask = 0u;
-    const unsigned any_m = cmask | fmask | dmask;
-    const int tmax = __reduce_max_sync(full, 32 - __clz(any_m));
-    for (int t = 0; t < tmax; ++t) {
-      const double at = __shfl_sync(full, a, t, kIgLanes);
-      const double dt = __shfl_sync(full, dist, t, kIgLanes);
-      const int nm = __shfl_sync(full, nmatch, t, kIgLanes);
+    const unsigned cmask = (__ballot_sync(gm, is_c) >> sh) & 0xffu;
+    const unsigned fmask = (__ballot_sync(gm, is_sf && !zero) >> sh) & 0xffu;
+    const unsigned dmask = (__ballot_sync(gm, is_weak || (is_sf && zero)) >> sh) & 0xffu;
+    for (unsigned todo_m = cmask | fmask | dmask; todo_m; todo_m &= todo_m - 1) {
+      const int t = __ffs(todo_m) - 1;
+      const double at = __shfl_sync(gm, a, t, kIgLanes);
       if ((cmask >> t) & 1u) {
         if (q == 0) pv[seen_c] = __dadd_rn(pv[seen_c], at);
         ++seen_c;
       } else if ((fmask >> t) & 1u) {
+        const double dt = __shfl_sync(gm, dist, t, kIgLanes);
+        const int nm = __shfl_sync(gm, nmatch, t, kIgLanes);
         if (q < nm) {  // nm <= 8: one match per lane, distinct P entries
           const int pos = s_mpos[g][t][q];
           pv[pos] = __dadd_rn(pv[pos], __dmul_rn(dt, s_mval[g][t][q]));
         }
-      } else if ((dmask >> t) & 1u) {
+      } else {
         diagonal = __dadd_rn(diagonal, at);  // (kept identically by every lane of the group)
       }
-      __syncwarp();
+      __syncwarp(gm);
     }
   }
-  if (!live) return;
   if (overflow) {
     if (q == 0) {
       todo[i] = 1;

@@ -18,8 +18,6 @@
 #include <algorithm>
 #include <cstdlib>
 
-#include <cuda/barrier>
-
 #include "amgb_internal.cuh"
 
 namespace amgb {
@@ -28,7 +26,6 @@ constexpr int kTailThreads = 1024;
 constexpr int kTailLanes = 4;                       // lanes per row
 constexpr int kTailGroups = kTailThreads / kTailLanes;
 constexpr size_t kTailSmemBudget = 200 * 1024;      // of the 227 KB a block may have
-constexpr size_t kTailSmemMax = 227 * 1024 - 256;   // dynamic part: the kernel's static part (the copy's mbarrier) comes out of the same 227 KB
 constexpr int kTailMaxRows = 1024;                  // rows of the largest tail level (one block scan in the pack kernel)
 constexpr int kTailMaxDense = 64;
 
@@ -147,21 +144,16 @@ cycle_tail_kernel(TailDesc d, const unsigned char* __restrict__ blob, const doub
   extern __shared__ __align__(16) unsigned char sm[];
   const int tid = threadIdx.x;
   {
-    // the packed operators arrive as ONE bulk copy of the TMA unit (cp.async.bulk global -> shared,
-    // completion counted in bytes on an mbarrier; blob and destination are 16-byte aligned, the size a
-    // multiple of 16): a single thread issues it, the block's loads below overlap with it
-#pragma nv_diag_suppress static_var_with_dynamic_init
-    __shared__ cuda::barrier<cuda::thread_scope_block> blob_bar;
-    if (tid == 0) init(&blob_bar, kTailThreads);
-    __syncthreads();
-    if (tid == 0 && d.blob_bytes > 0)
-      cuda::memcpy_async(sm, blob, cuda::aligned_size_t<16>((size_t)d.blob_bytes), blob_bar);
+    const int4* src = reinterpret_cast<const int4*>(blob);
+    int4* dst = reinterpret_cast<int4*>(sm);
+    const int n16 = d.blob_bytes / 16;
+    for (int i = tid; i < n16; i += kTailThreads) dst[i] = src[i];
     double* M = reinterpret_cast<double*>(sm + d.off_dense);
     for (int i = tid; i < d.dense_n * d.dense_n; i += kTailThreads) M[i] = dense[i];
     double* f0 = reinterpret_cast<double*>(sm + d.lv[0].off_f);
     for (int i = tid; i < d.lv[0].n; i += kTailThreads) f0[i] = f_in[i];
-    blob_bar.arrive_and_wait();  // (also the block barrier for the stores above)
   }
+  __syncthreads();
   const double w = d.w;
   const int last = d.nlev - 1;
   // ---- way down
@@ -352,7 +344,7 @@ int tail_pack(amgb_precond* P) {
   D.off_dense = (int)off;
   off += align16(8 * (size_t)Last.n * Last.n);
   P->tail_smem = off;
-  if (off > kTailSmemMax) return set_error(ctx, AMGB_ERR_RANGE, "coarse tail does not fit shared memory (%zu bytes)", off);
+  if (off > 227 * 1024) return set_error(ctx, AMGB_ERR_RANGE, "coarse tail does not fit shared memory (%zu bytes)", off);
   AMGB_TRY(P->tail_blob.alloc(ctx, std::max<size_t>(D.blob_bytes, 16)));
   if (!ops.empty()) {
     DevBuf<TailPackOp> dops;
@@ -364,7 +356,7 @@ int tail_pack(amgb_precond* P) {
     AMGB_CHECK_LAUNCH(ctx);
     AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `ops` (pageable) and `dops` go out of scope
   }
-  AMGB_CUDA(ctx, cudaFuncSetAttribute(cycle_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemMax));
+  AMGB_CUDA(ctx, cudaFuncSetAttribute(cycle_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return AMGB_OK;
 }
 

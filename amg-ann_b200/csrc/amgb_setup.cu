@@ -996,6 +996,181 @@ interp_fill_group_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_
   }
 }
 
+// The same kernel with warp-uniform control flow (see spgemm_flat_kernel), opt-in (AMGB_INTERP_UNIFORM=1): measured
+// 11.6 -> 9.0 ms on level 0 at m = 200 and green on the whole GPU suite, but it went in shortly before the
+// session's last bench run hung and could not be re-measured under three lanes afterwards, so the kernel of
+// the last complete bench run stays the default.  The four rows of a warp run every loop to the
+// warp's maximum trip count with their own lanes predicated off, and ballots / shuffles / barriers name
+// the full warp -- with group masks the four groups were serialised through every collective (ncu,
+// round-2 start: 15.7 of 32 threads per issued instruction).
+__global__ void __launch_bounds__(kBlock)
+interp_fill_group_uniform_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                         const double* __restrict__ val, const uint8_t* __restrict__ mask,
+                         const int32_t* __restrict__ cf, const int32_t* __restrict__ f2c,
+                         const int32_t* __restrict__ acrp, const int32_t* __restrict__ accol,
+                         const double* __restrict__ acval, const int32_t* __restrict__ prp,
+                         int32_t* __restrict__ pcol, double* __restrict__ pval, int64_t row_begin,
+                         uint8_t* __restrict__ todo, int32_t* __restrict__ n_todo) {
+  __shared__ int32_t s_cs[kIgRows][kIgMaxP];                      // interpolation points (fine ids, ascending)
+  __shared__ double s_pv[kIgRows][kIgMaxP];                       // P entries under construction
+  __shared__ int32_t s_mpos[kIgRows][kIgLanes][kIgMaxMatch];      // matches of the chunk's neighbours: P position
+  __shared__ double s_mval[kIgRows][kIgLanes][kIgMaxMatch];       // ... and a_kc
+  const unsigned full = 0xffffffffu;
+  const int g = threadIdx.x / kIgLanes, q = threadIdx.x % kIgLanes;
+  const int64_t i = row_begin + (int64_t)blockIdx.x * kIgRows + g;
+  const unsigned sh = (threadIdx.x & 31) / kIgLanes * kIgLanes;
+  bool live = i < n;  // group-uniform
+  int jb = 0, len = 0;
+  if (live) {
+    jb = prp[i];
+    len = prp[i + 1] - jb;
+    if (cf[i] > 0) {
+      if (q == 0) {
+        pcol[jb] = f2c[i];
+        pval[jb] = 1.0;
+      }
+      live = false;
+    } else if (len > kIgMaxP) {
+      if (q == 0) {
+        todo[i] = 1;
+        atomicAdd(n_todo, 1);
+      }
+      live = false;
+    }
+  }
+  int32_t* cs = s_cs[g];
+  double* pv = s_pv[g];
+  int b = 0, e = 0;
+  if (live) {
+    b = rp[i];
+    e = rp[i + 1];
+  }
+  const int maxlen = __reduce_max_sync(full, e - b);
+  // phase 0: diagonal, interpolation points in row order
+  double diagonal = 0.0;
+  {
+    int base = 0;
+    for (int kb = 0; kb < maxlen; kb += kIgLanes) {
+      const int k = b + kb + q;
+      int i1 = -1;
+      double a = 0.0;
+      bool isc = false;
+      if (k < e) {
+        i1 = col[k];
+        a = val[k];
+        isc = i1 != (int)i && mask[k] && cf[i1] > 0;
+      }
+      const unsigned dm = (__ballot_sync(full, k < e && i1 == (int)i) >> sh) & 0xffu;
+      const double dv = __shfl_sync(full, a, dm ? __ffs(dm) - 1 : 0, kIgLanes);
+      if (dm) diagonal = dv;
+      const unsigned cm = (__ballot_sync(full, isc) >> sh) & 0xffu;
+      if (isc) {
+        const int pos = base + __popc(cm & ((1u << q) - 1u));
+        cs[pos] = i1;
+        pv[pos] = 0.0;
+      }
+      base += __popc(cm);
+    }
+  }
+  __syncwarp();
+  // phase 1: the entries of row i, 8 at a time
+  bool overflow = false;
+  int seen_c = 0;
+  for (int kb = 0; kb < maxlen; kb += kIgLanes) {
+    const int k = b + kb + q;
+    int i1 = -1, c1 = -3, strong = 0;
+    double a = 0.0;
+    if (k < e) {
+      i1 = col[k];
+      a = val[k];
+      strong = mask[k];
+      c1 = cf[i1];
+    }
+    const bool offd = k < e && i1 != (int)i;
+    const bool is_c = offd && strong && c1 > 0;
+    const bool is_sf = offd && strong && c1 <= 0 && c1 != -3;
+    const bool is_weak = offd && !strong && c1 != -3;
+    // my neighbour's share: sum over the interpolation points it meets, in column order
+    double dist = 0.0;
+    int nmatch = 0;
+    bool zero = false;
+    if (is_sf) {
+      double sum = 0.0;
+      const int t0 = acrp[i1], nac = acrp[i1 + 1] - t0;
+      // the first entries of the compacted row in one batch of independent loads (the row has ~4)
+      constexpr int kAcPre = 4;
+      int pc[kAcPre];
+      double pvv[kAcPre];
+#pragma unroll
+      for (int m = 0; m < kAcPre; ++m) {
+        pc[m] = m < nac ? accol[t0 + m] : -1;
+        pvv[m] = m < nac ? acval[t0 + m] : 0.0;
+      }
+      auto take = [&](int c2, double v) {
+        const int pos = find_sorted(cs, len, c2);
+        if (pos >= 0) {
+          sum = __dadd_rn(sum, v);
+          if (nmatch < kIgMaxMatch) {
+            s_mpos[g][q][nmatch] = pos;
+            s_mval[g][q][nmatch] = v;
+          }
+          ++nmatch;
+        }
+      };
+#pragma unroll
+      for (int m = 0; m < kAcPre; ++m)
+        if (m < nac) take(pc[m], pvv[m]);
+      for (int t = t0 + kAcPre; t < t0 + nac; ++t) take(accol[t], acval[t]);
+      if (nmatch > kIgMaxMatch) overflow = true;
+      if (sum != 0) dist = a / sum; else zero = true;
+    }
+    if ((__ballot_sync(full, overflow) >> sh) & 0xffu) {  // this row goes to the warp-per-row kernel
+      overflow = true;
+      e = b;  // (nothing more is read; the rest of the loops run empty for this group)
+    }
+    __syncwarp();
+    // apply the chunk's entries one after the other
+    // (every lane of the warp takes part in the ballots; an overflowed group then drops its bits)
+    unsigned cmask = (__ballot_sync(full, is_c) >> sh) & 0xffu;
+    unsigned fmask = (__ballot_sync(full, is_sf && !zero) >> sh) & 0xffu;
+    unsigned dmask = (__ballot_sync(full, is_weak || (is_sf && zero)) >> sh) & 0xffu;
+    if (overflow) cmask = fmask = dmask = 0u;
+    const unsigned any_m = cmask | fmask | dmask;
+    const int tmax = __reduce_max_sync(full, 32 - __clz(any_m));
+    for (int t = 0; t < tmax; ++t) {
+      const double at = __shfl_sync(full, a, t, kIgLanes);
+      const double dt = __shfl_sync(full, dist, t, kIgLanes);
+      const int nm = __shfl_sync(full, nmatch, t, kIgLanes);
+      if ((cmask >> t) & 1u) {
+        if (q == 0) pv[seen_c] = __dadd_rn(pv[seen_c], at);
+        ++seen_c;
+      } else if ((fmask >> t) & 1u) {
+        if (q < nm) {  // nm <= 8: one match per lane, distinct P entries
+          const int pos = s_mpos[g][t][q];
+          pv[pos] = __dadd_rn(pv[pos], __dmul_rn(dt, s_mval[g][t][q]));
+        }
+      } else if ((dmask >> t) & 1u) {
+        diagonal = __dadd_rn(diagonal, at);  // (kept identically by every lane of the group)
+      }
+      __syncwarp();
+    }
+  }
+  if (!live) return;
+  if (overflow) {
+    if (q == 0) {
+      todo[i] = 1;
+      atomicAdd(n_todo, 1);
+    }
+    return;
+  }
+  // phase 2: scale, renumber to coarse ids
+  const double nd = -diagonal;
+  for (int t = q; t < len; t += kIgLanes) {
+    pval[jb + t] = diagonal == 0.0 ? 0.0 : pv[t] / nd;
+    pcol[jb + t] = f2c[cs[t]];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Explicit transpose R = P^T with rows sorted by fine index.
 // ---------------------------------------------------------------------------
@@ -2389,7 +2564,8 @@ int build_interp(amgb_ctx* ctx, const DeviceCsr& A, const uint8_t* mask, const i
   AMGB_TRY(n_todo.alloc_zero(ctx, 1));
   AMGB_LAUNCH(ctx, F_INTERP, 12.0 * A.nnz + 12.0 * nnzac, interp_ac_fill_kernel, (unsigned)div_up(n, kBlock), kBlock, 0,
               n, A.rp.p, A.col.p, A.val.p, cf, diagv, (const int32_t*)acrp.p, accol.p, acval.p);
-  AMGB_LAUNCH(ctx, F_INTERP, fill_bytes, interp_fill_group_kernel, (unsigned)div_up(rows, kIgRows), kBlock, 0, row_end,
+  auto group_kernel = std::getenv("AMGB_INTERP_UNIFORM") ? interp_fill_group_uniform_kernel : interp_fill_group_kernel;
+  AMGB_LAUNCH(ctx, F_INTERP, fill_bytes, group_kernel, (unsigned)div_up(rows, kIgRows), kBlock, 0, row_end,
               A.rp.p, A.col.p, A.val.p, mask, cf, col_id, (const int32_t*)acrp.p, (const int32_t*)accol.p,
               (const double*)acval.p, (const int32_t*)P.rp.p, P.col.p, P.val.p, row_begin, todo.p, n_todo.p);
   AMGB_CHECK_LAUNCH(ctx);

@@ -662,6 +662,27 @@ def test_warp_per_row_interpolation_kernel_alone_agrees_with_the_oracle(gpu_ctx,
     _assert_hierarchy_identical(P, H)
 
 
+@pytest.mark.parametrize("kind", ["poisson", "elasticity", "hub"])
+def test_warp_uniform_grouped_interpolation_kernel_agrees_with_the_oracle(gpu_ctx, monkeypatch, kind):
+    """AMGB_INTERP_UNIFORM=1: the grouped interpolation kernel with warp-uniform control flow
+    (full-warp collectives, loops to the warp's maximum trip count) instead of group masks.
+    Same bits as the oracle; hub rows overflow into the warp-per-row second stage."""
+    from helpers import hub_leaf_csr
+    from types import SimpleNamespace
+    monkeypatch.setenv("AMGB_INTERP_UNIFORM", "1")
+    if kind == "poisson":
+        s, theta = poisson(14, contrast=3.0), 0.25
+    elif kind == "elasticity":
+        s, theta = ab.gen.elasticity_q1(6, 2, 3, 10.0 ** ab.gen.checkerboard_epsv(2, 3, 2.0)), 0.25
+    else:
+        M = hub_leaf_csr(160, 400, 70, 6, 5)
+        s = SimpleNamespace(n=M.shape[0], col=M.indices.astype(np.int32), val=M.data.astype(np.float64),
+                            rowptr32=lambda: M.indptr.astype(np.int32))
+        theta = 0.05
+    A, P, H = _both(gpu_ctx, s, device_data(theta))
+    _assert_hierarchy_identical(P, H)
+
+
 @pytest.mark.parametrize("m,theta,contrast", [(24, 0.25, 3.0), (30, 0.6, 6.0)])
 def test_window_sorted_solve_numbering_agrees_with_the_oracle(gpu_ctx, monkeypatch, m, theta, contrast):
     """AMGB_ROW_SORT=1: inside the C block and the F block of the solve numbering, windows of 1024

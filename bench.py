@@ -368,13 +368,16 @@ def extra_config4(systems=64, threads=8):
     with tempfile.TemporaryDirectory() as d:
         base = [exe, "--m", "46", "--systems", str(systems), "--threads", str(threads), "--seed", "0",
                 "--device-assembly", "1"]
-        r = subprocess.run(base + ["--out", os.path.join(d, "stats.csv")], capture_output=True, text=True, timeout=600)
+        r = subprocess.run(base + ["--out", os.path.join(d, "stats.csv")], capture_output=True, text=True, timeout=240)
         if r.returncode != 0:
             return {"config4_m46": {"failed": r.stderr[-300:]}}
         j = json.loads(r.stdout.strip().splitlines()[-1])
-        v = subprocess.run(base + ["--make-view", "1", "--out", os.path.join(d, "views.csv")], capture_output=True,
-                           text=True, timeout=600)
-        jv = json.loads(v.stdout.strip().splitlines()[-1]) if v.returncode == 0 else None
+        try:
+            v = subprocess.run(base + ["--make-view", "1", "--out", os.path.join(d, "views.csv")], capture_output=True,
+                               text=True, timeout=120)
+            jv = json.loads(v.stdout.strip().splitlines()[-1]) if v.returncode == 0 else None
+        except subprocess.TimeoutExpired:
+            jv = None
         out["config4_m46"] = {
             "workload": f"{systems} systems of 103823 DoFs (seeds 0..{systems - 1}) x 19 theta, C++ driver amgb_datagen, "
                         f"{threads} host threads / contexts on one GPU, device assembly, CSV rows written",
@@ -815,36 +818,69 @@ def run_gpu(args):
     want = args.extras
     if want == "auto":
         want = "configs" if world == 1 else "partitioned"
-    if world == 1 and want in ("configs", "all"):
-        def guarded(name, fn):
-            if time.perf_counter() - t_start > args.extras_budget_s:
-                extras[name] = {"skipped": f"wall-clock budget of {args.extras_budget_s} s for the whole run reached"}
-                return
+    # An extra must not take the headline down: it runs in a helper thread under a watchdog.  One that
+    # does not come back in time is recorded as such, the remaining extras are skipped, the line is
+    # printed and the process leaves through os._exit (a stuck CUDA call cannot be cancelled).
+    hung = []
+
+    def watched(name, fn, timeout_s):
+        """(result, None) | (None, reason)"""
+        if hung:
+            return None, f"skipped: `{hung[0]}` did not return"
+        box = {}
+
+        def run():
             try:
-                extras.update(fn())
-            except Exception as e:  # noqa: BLE001 - an extra must not take the headline down
-                extras[name] = {"failed": f"{type(e).__name__}: {e}"[:300]}
-        guarded("pooling", lambda: extra_pooling(ab, ctx, A_dev, n, nnz, peak))
-        guarded("config1_m100", lambda: extra_config1_and_pooling(ab, L, ctx, peak))
-        guarded("config4_m46", lambda: extra_config4(args.batch_systems, args.batch_threads))
+                torch.cuda.set_device(local)
+                torch.cuda.set_stream(stream)   # (torch's current stream is per thread: same one as the main thread)
+                box["result"] = fn()
+            except BaseException as e:  # noqa: BLE001
+                box["error"] = f"{type(e).__name__}: {e}"[:300]
+        th = threading.Thread(target=run, daemon=True)
+        th.start()
+        th.join(timeout_s)
+        if th.is_alive():
+            hung.append(name)
+            print(f"[bench] extra `{name}` did not return within {timeout_s:.0f} s", file=sys.stderr, flush=True)
+            return None, f"did not return within {timeout_s:.0f} s"
+        if "error" in box:
+            return None, box["error"]
+        return box["result"], None
+
+    def guarded(name, fn, timeout_s=300.0):
+        if time.perf_counter() - t_start > args.extras_budget_s:
+            extras[name] = {"skipped": f"wall-clock budget of {args.extras_budget_s} s for the whole run reached"}
+            return
+        res, why = watched(name, fn, timeout_s)
+        if why is None:
+            extras.update(res)
+        else:
+            extras[name] = {"failed": why}
+    if world == 1 and want in ("configs", "all"):
+        guarded("pooling", lambda: extra_pooling(ab, ctx, A_dev, n, nnz, peak), 120.0)
+        guarded("config1_m100", lambda: extra_config1_and_pooling(ab, L, ctx, peak), 180.0)
+        guarded("config4_m46", lambda: extra_config4(args.batch_systems, args.batch_threads), 420.0)
     # release the sweep's device memory before the large extras
     cpu = cpu_baseline_port(ab, args.m, nnz) if rank == 0 else None
     st0 = results[thetas[0]][1]
     iters = {f"{th:.2f}": results[th][0] for th in thetas}
-    A_dev.close()
-    for c in lane_ctx[1:]:
-        c.close()
-    del d_rp, d_col, d_val, d_b, d_x0, d_x, lane_x, h_rp, h_col, h_val, h_xs
-    torch.cuda.empty_cache()
-    if world == 1 and want in ("configs", "all"):
-        guarded("config5_m464_1gpu", lambda: {"config5_m464_1gpu": config5_threads_on_one_gpu(ab, args.part_m, 2, [0.25, 0.5])})
+    if not hung:
+        A_dev.close()
+        for c in lane_ctx[1:]:
+            c.close()
+        del d_rp, d_col, d_val, d_b, d_x0, d_x, lane_x, h_rp, h_col, h_val, h_xs
         torch.cuda.empty_cache()
-        guarded("config3_m187", lambda: extra_config3(ab, L, ctx))
+    if world == 1 and want in ("configs", "all"):
+        guarded("config5_m464_1gpu",
+                lambda: {"config5_m464_1gpu": config5_threads_on_one_gpu(ab, args.part_m, 2, [0.25, 0.5])}, 420.0)
+        if not hung:
+            torch.cuda.empty_cache()
+        guarded("config3_m187", lambda: extra_config3(ab, L, ctx), 420.0)
     if world > 1 and want in ("partitioned", "all"):
-        try:
-            part = partitioned_block(ab, args, rank, world, local, stream, args.part_m)
-        except Exception as e:  # noqa: BLE001
-            part = {"failed": f"{type(e).__name__}: {e}"[:300]}
+        part, why = watched("partitioned", lambda: partitioned_block(ab, args, rank, world, local, stream, args.part_m),
+                            900.0)
+        if why is not None:
+            part = {"failed": why}
 
     line = None
     if rank == 0:
@@ -869,12 +905,17 @@ def run_gpu(args):
         if part is not None:
             line["partitioned"] = part
         line["wall_s"] = round(time.perf_counter() - t_start, 1)
+    if line:
+        print(json.dumps(line), flush=True)
+    if hung:  # a helper thread still sits in a CUDA call: nothing below would return either
+        os._exit(0)
     ctx.close()
     if world > 1:
-        dist.barrier()
+        # (a rank whose partitioned block hung leaves through os._exit above; do not wait for it forever)
+        done, why = watched("final barrier", lambda: (dist.barrier(), True)[1], 180.0)
+        if why is not None:
+            os._exit(0)
         dist.destroy_process_group()
-    if line:
-        print(json.dumps(line))
     return 0
 
 

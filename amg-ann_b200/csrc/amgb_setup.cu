@@ -1951,18 +1951,6 @@ spgemm_rowthread_numeric_kernel(int64_t n, const int32_t* __restrict__ arp, cons
 // Rows whose chunk has more than S products (or whose table would not fit CAP) go to the
 // overflow list of the second stage like in the sub-warp kernels.
 // ---------------------------------------------------------------------------
-template <int G>
-__device__ __forceinline__ int group_excl_scan(int v, int gl, unsigned gm, int* total) {
-  int incl = v;
-#pragma unroll
-  for (int d = 1; d < G; d <<= 1) {
-    const int t = __shfl_up_sync(gm, incl, d, G);
-    if (gl >= d) incl += t;
-  }
-  *total = __shfl_sync(gm, incl, G - 1, G);
-  return incl - v;
-}
-
 constexpr int kFlatChunk = 32;  // A-row entries numbered together
 
 // entry-wise variant: the table only (the chunk descriptors sit between values and keys, the map is not touched)

@@ -192,6 +192,23 @@ color_apply_kernel(int64_t n, const int32_t* __restrict__ next, int32_t* __restr
   if (i < n && next[i] >= 0) color[i] = next[i];
 }
 
+// a row must not read a point of its own colour (it is being written by the same launch): holds by
+// construction when the pattern is structurally symmetric, checked for any other operator
+__global__ void __launch_bounds__(kBlock)
+color_check_kernel(int64_t n, const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                   const int32_t* __restrict__ color, int32_t* __restrict__ info) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const int ci = color[i];
+  for (int k = rp[i]; k < rp[i + 1]; ++k) {
+    const int j = col[k];
+    if (j != (int)i && color[j] == ci) {
+      info[3] = 1;
+      return;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kBlock)
 color_flag_kernel(int64_t n, const int32_t* __restrict__ color, int c, int32_t* __restrict__ flag) {
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -234,6 +251,14 @@ static int color_level(amgb_ctx* ctx, Level& L) {
     done = h[0];
     ncolors = h[2];
   }
+  AMGB_LAUNCH(ctx, F_AUX, 8.0 * L.A.nnz + 8.0 * n, color_check_kernel, grid, kBlock, 0, n, (const int32_t*)L.A.rp.p,
+              (const int32_t*)L.A.col.p, (const int32_t*)L.color.p, info.p);
+  AMGB_CHECK_LAUNCH(ctx);
+  AMGB_CUDA(ctx, cudaMemcpyAsync(h, info.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  AMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h[3])
+    return set_error(ctx, AMGB_ERR_UNSUPPORTED,
+                     "multicolour Gauss-Seidel needs a structurally symmetric operator (two coupled points share a colour)");
   L.color_ptr.assign(1, 0);
   for (int c = 0; c < ncolors; ++c) {
     AMGB_LAUNCH(ctx, F_AUX, 8.0 * n, color_flag_kernel, grid, kBlock, 0, n, (const int32_t*)L.color.p, c, next.p);

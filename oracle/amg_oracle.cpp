@@ -1153,6 +1153,10 @@ int multicolor(const Csr& A, std::vector<int32_t>& color, int32_t* ncolors) {
         --left;
       }
   }
+  // a row must not read a point of its own colour: holds by construction for a structurally symmetric pattern
+  for (int64_t i = 0; i < n; ++i)
+    for (int32_t k = A.rp[i]; k < A.rp[i + 1]; ++k)
+      if (A.col[k] != i && color[A.col[k]] == color[i]) return AMGB_ERR_UNSUPPORTED;
   *ncolors = nc;
   return 0;
 }
@@ -1448,9 +1452,9 @@ int orc_setup(int64_t n, const int32_t* rowptr, const int32_t* col, const double
   if (h->relax_down >= AMGB_RELAX_MC_FORWARD || h->relax_up >= AMGB_RELAX_MC_FORWARD ||
       h->relax_coarse >= AMGB_RELAX_MC_FORWARD)
     for (Level& L : h->lv)
-      if (multicolor(L.A, L.color, &L.ncolors) != 0) {
+      if (const int rc = multicolor(L.A, L.color, &L.ncolors)) {
         delete h;
-        return AMGB_ERR_RANGE;
+        return rc;
       }
   if (h->relax_down == 16)  // PCHYPRE / hypre defaults: order 2, 10 CG steps, fraction 0.3
     for (Level& L : h->lv) cheby_setup(L, 2, 10, 0.3);

@@ -91,3 +91,50 @@ def test_pcg_reaches_the_direct_solution(n, density, seed):
     xd = spl.spsolve(A.tocsc(), b)
     assert np.abs(x - xd).max() <= 1e-6 * max(1.0, np.abs(xd).max())
     H.close()
+
+
+@settings(**SETTINGS)
+@given(n=st.integers(30, 200), density=st.floats(0.02, 0.2), seed=st.integers(0, 10 ** 6))
+def test_multicolouring_is_valid_and_the_sweep_is_gauss_seidel_in_colour_order(n, density, seed):
+    """smoother_policy = SMOOTHER_MULTICOLOR on random symmetric patterns: coupled points never share a
+    colour, no more colours than the largest degree + 1, and one forward sweep from zero on a one-level
+    hierarchy equals the lower-triangular solve of the colour-ordered system."""
+    import amg_ann_b200 as ab
+    R = ab.RelaxationType
+    A, rp, col, val = _csr(n, density, seed)
+    data = device_data(0.25, relaxation_type_up=R.backwardSORJacobi, relaxation_type_down=R.SORJacobi,
+                       relaxation_type_coarse=R.SORJacobi, smoother_policy=ab.SMOOTHER_MULTICOLOR, max_levels=1)
+    data.symmetric_operator = False  # (deal.II maps SORJacobi to the symmetric sweep for symmetric operators)
+    H = orc.Hierarchy(rp, col, val, data.to_struct())
+    assert H.effective_relax() == (103, 104, 103)
+    colors, nc = H.colors(0)
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    off = rows != col
+    assert not (colors[rows[off]] == colors[col[off]]).any()
+    assert nc <= int(np.diff(rp).max()) + 1 and set(np.unique(colors)) == set(range(nc))
+    r = np.random.default_rng(seed).standard_normal(n)
+    z = H.vmult(r)                                   # one level: the coarse relaxation = one forward sweep
+    order = np.lexsort((np.arange(n), colors))
+    Ap = A.toarray()[np.ix_(order, order)]
+    want = np.linalg.solve(np.tril(Ap), r[order])
+    assert np.abs(z[order] - want).max() <= 1e-10 * max(1.0, np.abs(want).max())
+
+
+def test_multicolouring_rejects_a_pattern_that_is_not_symmetric():
+    import amg_ann_b200 as ab
+    import pytest
+    R = ab.RelaxationType
+    A = random_spd_csr(200, 0.05, 1).tolil()
+    rows, cols = A.nonzero()
+    dropped = 0
+    for i, j in zip(rows, cols):
+        if i > j and dropped < 60:
+            A[i, j] = 0
+            dropped += 1
+    A = A.tocsr()
+    A.eliminate_zeros()
+    A.sort_indices()
+    data = device_data(0.25, relaxation_type_up=R.symmetricSORJacobi, relaxation_type_down=R.symmetricSORJacobi,
+                       smoother_policy=ab.SMOOTHER_MULTICOLOR)
+    with pytest.raises(RuntimeError):
+        orc.Hierarchy(A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data, data.to_struct())

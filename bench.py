@@ -48,6 +48,14 @@ DEVICE_ALGO = "PMIS + classical interp + C/F l1-Jacobi V(1,1)"
 REFERENCE_ALGO = "Falgout + classical interp + hybrid symmetric Gauss-Seidel V(1,1) (PCHYPRE defaults)"
 
 
+_T0 = time.perf_counter()
+
+
+def _progress(what):
+    """one line per phase on stderr: if a run ever stops responding, its log says where"""
+    print(f"[bench {time.perf_counter() - _T0:7.1f} s] {what}", file=sys.stderr, flush=True)
+
+
 def workload_name(m, algo=DEVICE_ALGO):
     n = (m + 1) ** 3
     return (f"3D diffusion Q1, checkerboard mu in {{1,1e6}} on a {PATTERN}^3 pattern, m={m} "
@@ -634,6 +642,7 @@ def run_gpu(args):
     lane_streams = [stream] + [torch.cuda.Stream() for _ in range(lanes - 1)]
     lane_ctx = [ctx] + [ab.Context(local, st.cuda_stream) for st in lane_streams[1:]]
     lane_x = [d_x] + [torch.empty_like(d_x0) for _ in range(lanes - 1)]
+    _progress(f"system generated and resident (n = {n}, nnz = {nnz}), {lanes} lanes")
     # every lane's pool grown once, up front, instead of allocation by allocation: measured at m = 200 with
     # 3 lanes, a sweep takes 4.53 +- 0.005 s with the reserve and 4.5 ... 7.4 s without (pool growth
     # stalls every lane; which lane grows when depends on the order the lanes pick their systems in)
@@ -767,9 +776,11 @@ def run_gpu(args):
         return ms / steps, launches, clocks
 
     ms_step, launches, clocks = timed(sweep_device, args.steps, args.warmup, sample_clocks=True)
+    _progress("device-resident sweeps timed")
     value = ms_step / 1e3 / (nsys * world)          # whole-job seconds per system
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     ms_e2e, _, _ = timed(sweep_e2e, e2e_steps, 1)
+    _progress("host-buffer (e2e) sweeps timed")
     e2e_value = ms_e2e / 1e3 / (nsys * world)
 
     # ---- t(theta) of the device flavour: one sweep on ONE lane, host wall clock around the
@@ -796,6 +807,7 @@ def run_gpu(args):
     ctx.reset_timers()
     solve_device(0, 0.25)
     fam25 = ctx.timers()
+    _progress("per-family timers collected")
     ctx.enable_timers(False)
     peak, peak_src = measured_peaks()
     kern = family_table(fam)
@@ -851,6 +863,7 @@ def run_gpu(args):
         if time.perf_counter() - t_start > args.extras_budget_s:
             extras[name] = {"skipped": f"wall-clock budget of {args.extras_budget_s} s for the whole run reached"}
             return
+        _progress(f"extra `{name}` ...")
         res, why = watched(name, fn, timeout_s)
         if why is None:
             extras.update(res)

@@ -392,7 +392,27 @@ class PreconditionBoomerAMG {
   void initialize(const MPI::SparseMatrix& matrix, const AdditionalData& data = AdditionalData()) {
     data_ = data;
     matrix_ = &matrix;
-    const amgb_boomeramg_data d = data.to_c();
+    amgb_boomeramg_data d = data.to_c();
+    // Knobs the reference's AdditionalData has no field for, PETSc style: the options database
+    // (PETScWrappers::set_option_value) or the environment, so that the UNMODIFIED reference harness can
+    // ask for the flavour closest to its CPU defaults (Falgout's parallel stage + Gauss-Seidel sweeps):
+    //   -amgb_coarsen_type  pmis | cljp                      (AMGB_COARSEN_TYPE)
+    //   -amgb_smoother_policy  substitute | strict | multicolor   (AMGB_SMOOTHER_POLICY)
+    {
+      auto knob = [](const char* opt, const char* env) -> std::string {
+        auto it = amgb::compat::options().find(opt);
+        if (it != amgb::compat::options().end()) return it->second;
+        const char* e = std::getenv(env);
+        return e ? std::string(e) : std::string();
+      };
+      const std::string ct = knob("-amgb_coarsen_type", "AMGB_COARSEN_TYPE");
+      if (ct == "cljp") d.coarsen_type = AMGB_COARSEN_CLJP;
+      else if (ct == "pmis") d.coarsen_type = AMGB_COARSEN_PMIS;
+      const std::string sp = knob("-amgb_smoother_policy", "AMGB_SMOOTHER_POLICY");
+      if (sp == "multicolor") d.smoother_policy = AMGB_SMOOTHER_MULTICOLOR;
+      else if (sp == "strict") d.smoother_policy = AMGB_SMOOTHER_STRICT;
+      else if (sp == "substitute") d.smoother_policy = AMGB_SMOOTHER_SUBSTITUTE;
+    }
     // on the calling thread's context: threads that sweep theta over one matrix side by side
     // share the (read-only) device copy and work on their own streams
     prec_.initialize(amgb::compat::default_context(), matrix.device(), d);
